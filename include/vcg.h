@@ -1,0 +1,138 @@
+/*
+ * vcg.h — C ABI of libvcg_b200.so, the sm_100a implementation of the chapter-boundary scoring path of
+ * SeoYeonnLee/Video-Chapter-Generation (TwoStream point model: BERT-base text stream + ResNet-50-TSM vision
+ * stream + ChapterHead).
+ *
+ * The reference has no FFI of its own: its boundary is the Python module API
+ * (video_chapter_generation/model/fusion/two_stream.py:99-194).  This header is what the Python mirror of that
+ * API (video-chapter-generation_b200/model/...) binds with ctypes; every entry point names the reference code it
+ * replaces.  All pointers are plain device pointers unless a name ends in _host; no torch types cross the boundary.
+ * Every function returning int returns 0 on success and non-zero on failure, in which case vcg_last_error()
+ * holds the message (CUDA allocation failures contain the words "out of memory", which the reference's handler in
+ * convert2vision_emb.py:208-215 looks for).  An engine is not re-entrant; use one engine per host thread / device.
+ */
+#ifndef VCG_B200_H
+#define VCG_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define VCG_API __attribute__((visibility("default")))
+#else
+#define VCG_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vcg_engine vcg_engine;
+
+enum { VCG_HEAD_MLP = 0, VCG_HEAD_ATTN = 1 };       /* two_stream.py:63-68 head_type "mlp" / "attn"            */
+enum { VCG_PREC_BF16 = 0, VCG_PREC_FP32 = 1 };      /* bf16 tensor-core mode / 3xTF32 fp32-accurate mode       */
+enum { VCG_VISION_R50TSM = 0, VCG_VISION_NONE = 1 };/* resnet50_tsm.py:15-19 / precomputed vision embeddings   */
+enum { VCG_DTYPE_F32 = 0, VCG_DTYPE_I64 = 1 };
+enum { VCG_ACT_NONE = 0, VCG_ACT_RELU = 1, VCG_ACT_GELU = 2, VCG_ACT_TANH = 3 };
+
+typedef struct vcg_config {
+  int32_t clip_frames;   /* T: segment_size of TwoStream / n_segment of TemporalShift (two_stream.py:100-107)   */
+  int32_t max_tokens;    /* L: longest text_ids row the engine will see (reference: max_text_len = 100)         */
+  int32_t hidden_size;   /* ChapterHead hidden size, 128 in every reference caller                              */
+  int32_t head_type;     /* VCG_HEAD_*                                                                          */
+  int32_t precision;     /* VCG_PREC_*                                                                          */
+  int32_t vision;        /* VCG_VISION_*                                                                        */
+  int32_t max_batch;     /* clips scored per internal pass (workspace is sized for this)                        */
+  int32_t shift_div;     /* TSM fold divisor, 8 in the reference (resnet50_tsm.py:16)                           */
+} vcg_config;
+
+/* Lifetime ------------------------------------------------------------------------------------------------- */
+VCG_API int vcg_create(const vcg_config* cfg, vcg_engine** out);
+VCG_API void vcg_destroy(vcg_engine* e);
+VCG_API const char* vcg_last_error(void);
+VCG_API const char* vcg_version(void);
+
+/* Weights: one call per entry of TwoStream.state_dict() (key schema: SURVEY.md 8b; replaces
+ * nn.Module.load_state_dict at test_video_segment_point.py:102-105).  dev_ptr is fp32 (or int64 for
+ * num_batches_tracked, ignored).  The data is copied/repacked; the caller keeps ownership.
+ * vcg_finalize folds BatchNorm (eval mode, running statistics) into the conv weights, packs everything into the
+ * kernels' layouts and checks that no tensor is missing. */
+VCG_API int vcg_load_tensor(vcg_engine* e, const char* key, const void* dev_ptr, const int64_t* shape, int32_t ndim,
+                    int32_t dtype, void* stream);
+VCG_API int vcg_finalize(vcg_engine* e, void* stream);
+
+/* TwoStream.forward (two_stream.py:172-194).
+ *   img_clip     [B,T,3,224,224] fp32, already normalised (test_video_segment_point.py:142-145), or NULL
+ *   vision_emb   [B,T,2048] fp32 precomputed embeddings (convert2vision_emb.py output), used when img_clip is NULL
+ *   text_ids, attention_mask  [B,L] int64
+ *   logits, probs             [B,2] fp32 out
+ *   vision_emb_out [B,T,2048] fp32 out or NULL;  lang_emb_out [B,768] fp32 out or NULL   (return_emb=True)
+ * Work is enqueued on `stream` (a cudaStream_t); B may exceed max_batch (processed in passes). */
+VCG_API int vcg_forward(vcg_engine* e, const float* img_clip, const float* vision_emb, const int64_t* text_ids,
+                const int64_t* attention_mask, int32_t B, int32_t L, float* logits, float* probs,
+                float* vision_emb_out, float* lang_emb_out, void* stream);
+
+/* Sliding-window scoring of one video straight from decoded frames (replaces ToTensor+Normalize at
+ * test_video_segment_point.py:142-145, the clip gather of infer_youtube_video_dataset.py:117 and the forward).
+ *   frames_u8   [n_frames,224,224,3] uint8 HWC (device)
+ *   clip_start  [B] int32 (device): first frame of every candidate clip; clip b = frames start..start+T-1
+ *   the rest as vcg_forward. */
+VCG_API int vcg_score_clips_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames, const int32_t* clip_start,
+                       const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L, float* logits,
+                       float* probs, void* stream);
+
+/* Same, with HOST buffers (pinned for full speed): the host->device copies of frames / ids / mask and the
+ * device->host copy of logits+probs are issued inside the call; returns after the results are on the host. */
+VCG_API int vcg_score_clips_u8_host(vcg_engine* e, const uint8_t* frames_u8_host, int32_t n_frames,
+                            const int32_t* clip_start_host, const int64_t* text_ids_host,
+                            const int64_t* attention_mask_host, int32_t B, int32_t L, float* logits_host,
+                            float* probs_host, void* stream);
+
+/* Number of kernel launches issued by this engine since creation (bench.py's gpu_launches). */
+VCG_API int64_t vcg_launch_count(const vcg_engine* e);
+
+/* Stand-alone operators (what the engine is built from; used by the parity tests) ------------------------- */
+
+/* uint8 HWC frames -> normalised, zero-padded NHWC4 stem input [n,230,240,4] (bf16 or fp32):
+ * (x/255 - mean_c)/std_c, the ToTensor+Normalize of test_video_segment_point.py:142-145.  frame_index may be
+ * NULL (identity) or [n] int32 frame numbers to gather. */
+VCG_API int vcg_op_preprocess_u8(const uint8_t* frames_u8, const int32_t* frame_index, int32_t n, void* out_padded,
+                         int32_t precision, void* stream);
+/* fp32 NCHW [n,3,224,224] -> the same padded NHWC4 layout. */
+VCG_API int vcg_op_nchw_to_stem(const float* img, int32_t n, void* out_padded, int32_t precision, void* stream);
+
+/* out[M,N] = act(A[M,K] W[N,K]^T + bias (+ residual)) on tcgen05 tensor cores; element type bf16 (precision 0) or
+ * fp32 via 3xTF32 (precision 1); bias fp32.  lda/ld_res/ld_out in elements. */
+VCG_API int vcg_op_gemm(const void* A, int64_t lda, const void* W, const float* bias, const void* residual, int32_t ld_res,
+                void* out, int32_t ld_out, int32_t M, int32_t N, int32_t K, int32_t act, int32_t precision,
+                void* stream);
+
+/* NHWC convolution (k = 1 or 3, stride 1 or 2, pad k/2) as an implicit GEMM; weights [Cout][k][k][Cin].
+ * tsm_in (optional, 1x1 only): buffer [n*H*W, tsm_in_ch] that replaces input channels [0,tsm_in_ch) — the
+ * temporally shifted channels of ops/temporal_shift.py:34-51.  tsm_out (optional): the kernel also scatters output
+ * channels [0,fold) to frame t-1 and [fold,2*fold) to frame t+1 of this buffer [n*Ho*Wo, 2*fold]. */
+VCG_API int vcg_op_conv2d_nhwc(const void* in, int32_t n, int32_t H, int32_t W, int32_t Cin, const void* weight,
+                       const float* bias, const void* residual, void* out, int32_t Cout, int32_t k, int32_t stride,
+                       int32_t act, int32_t precision, const void* tsm_in, int32_t tsm_in_ch, void* tsm_out,
+                       int32_t tsm_fold, int32_t clip_frames, void* stream);
+
+/* ResNet stem conv (7x7/2, folded BN, ReLU) over the padded NHWC4 input; weight [64][7][W][4] with W = 16 (bf16)
+ * or 8 (fp32) window pixels; out NHWC [n,112,112,64]. */
+VCG_API int vcg_op_stem_conv(const void* in_padded, int32_t n, const void* weight, const float* bias, void* out,
+                     int32_t precision, void* stream);
+
+/* 3x3/2 max-pool NHWC [n,112,112,64] -> x [n,56,56,64] and its temporally shifted copy (fold = 64/shift_div). */
+VCG_API int vcg_op_maxpool_tsm(const void* in, int32_t n, void* out, void* out_shifted, int32_t clip_frames,
+                       int32_t shift_div, int32_t precision, void* stream);
+
+/* softmax(Q K^T / 8 + key mask) V for BERT: qkv [B*L, 2304] (Q|K|V, 12 heads x 64) -> ctx [B*L, 768]. */
+VCG_API int vcg_op_bert_attention(const void* qkv, const int64_t* attention_mask, void* ctx, int32_t B, int32_t L,
+                          int32_t precision, void* stream);
+
+/* y = LayerNorm(x) * gamma + beta over rows of 768, eps 1e-12 (modeling_bert.py BertSelfOutput/BertOutput). */
+VCG_API int vcg_op_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t cols,
+                     float eps, int32_t precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCG_B200_H */

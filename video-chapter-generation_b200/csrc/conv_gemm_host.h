@@ -1,0 +1,229 @@
+// Host-side builders for conv_gemm_kernel launches: tensor maps, patch geometry, tap tables.
+#pragma once
+#include "conv_gemm.cuh"
+#include "tensormap.h"
+#include <algorithm>
+#include <cstring>
+
+namespace vcg {
+
+struct ConvGemmLaunch {
+  ConvGemmParams p;
+  int block_n = 0;
+  bool fp32 = false;
+  int grid = 0;
+  double flops = 0;   // 2*M*N*K of useful work (for reporting)
+  const char* name = "";
+};
+
+int sm_count();   // engine.cu
+
+inline int elem_size(bool fp32) { return fp32 ? 4 : 2; }
+inline int block_k(bool fp32) { return fp32 ? 32 : 64; }
+
+inline int pick_block_n(int N, bool fp32) {
+  const int cap = fp32 ? 128 : 256;
+  if (N <= 64) return 64;
+  if (N <= 128 || cap == 128) return 128;
+  return 256;
+}
+
+inline int pow2_divisor(int x, int cap) {
+  int d = 1;
+  while (d * 2 <= cap && x % (d * 2) == 0) d *= 2;
+  return d;
+}
+
+// Output patch (bw, bh, nf) covered by one 128-row M tile.
+inline void pick_patch(int Wo, int Ho, int Nimg, int& bw, int& bh, int& nf) {
+  if (Ho == 1 && Nimg == 1) { bw = 128; bh = 1; nf = 1; return; }   // plain GEMM: W axis = rows
+  if (Wo % 2 == 1 && Wo * Ho <= 64 && Nimg % 128 != 0) {            // small odd maps (7x7), small batches
+    bw = Wo; bh = Ho; nf = 128 / (Wo * Ho);
+    return;
+  }
+  bw = pow2_divisor(Wo, 16);
+  bh = pow2_divisor(Ho, 128 / bw);
+  nf = 128 / (bw * bh);
+}
+
+inline void finish_launch(ConvGemmLaunch& L, int Wo, int Ho, int Nimg, int N, bool fp32) {
+  ConvGemmParams& p = L.p;
+  p.Wo = Wo; p.Ho = Ho; p.Nimg = Nimg; p.N = N;
+  p.tiles_w = (Wo + p.bw - 1) / p.bw;
+  p.tiles_h = (Ho + p.bh - 1) / p.bh;
+  p.tiles_n = (Nimg + p.nf - 1) / p.nf;
+  L.block_n = pick_block_n(N, fp32);
+  L.fp32 = fp32;
+  p.n_tiles = (N + L.block_n - 1) / L.block_n;
+  p.a_bytes = static_cast<uint32_t>(p.bw * p.bh * p.nf) * 128u;
+  p.b_bytes = static_cast<uint32_t>(L.block_n) * 128u;
+  const long total = static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n * p.n_tiles;
+  L.grid = static_cast<int>(std::min<long>(total, sm_count()));
+  VCG_REQUIRE(N % 8 == 0, "output channels must be a multiple of 8");
+  VCG_REQUIRE(p.bw * p.bh * p.nf <= 128, "patch larger than the M tile");
+}
+
+struct Epilogue {
+  const float* bias = nullptr;
+  const void* residual = nullptr;
+  int ld_res = 0;
+  int act = ACT_NONE;
+  void* tsm_out = nullptr;   // shifted copy of channels [0, 2*fold) for the next bottleneck
+  int tsm_ld = 0, tsm_fold = 0, T = 1;
+};
+
+inline void set_epilogue(ConvGemmLaunch& L, void* out, int ld_out, const Epilogue& e) {
+  ConvGemmParams& p = L.p;
+  p.out = out; p.ld_out = ld_out;
+  p.bias = e.bias; p.residual = e.residual; p.ld_res = e.ld_res; p.act = e.act;
+  p.tsm_out = e.tsm_out; p.tsm_ld = e.tsm_ld; p.tsm_fold = e.tsm_fold; p.T = e.T > 0 ? e.T : 1;
+  if (e.tsm_out) VCG_REQUIRE(e.tsm_fold % 32 == 0, "TSM fold must be a multiple of 32 channels");
+}
+
+inline CUtensorMap weight_map(const void* W, int N, int K, int block_n, bool fp32) {
+  const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+  const uint64_t str[1] = {static_cast<uint64_t>(K) * elem_size(fp32)};
+  const uint32_t box[2] = {static_cast<uint32_t>(block_k(fp32)), static_cast<uint32_t>(block_n)};
+  return make_tensor_map(W, fp32, 2, dims, str, box);
+}
+
+// Plain GEMM: out[M,N] = act(A[M,K] * W[N,K]^T + bias (+ residual)); lda in elements.
+inline ConvGemmLaunch build_gemm(const void* A, long lda, const void* W, void* out, int ld_out, int M, int N, int K,
+                                 bool fp32, const Epilogue& e, const char* name = "gemm") {
+  ConvGemmLaunch L;
+  memset(&L.p, 0, sizeof L.p);
+  L.name = name;
+  const int es = elem_size(fp32), bk = block_k(fp32);
+  VCG_REQUIRE(K % bk == 0, "GEMM K must be a multiple of the K block");
+  VCG_REQUIRE((lda * es) % 16 == 0, "GEMM row stride must be a multiple of 16 bytes");
+  ConvGemmParams& p = L.p;
+  p.bw = 128; p.bh = 1; p.nf = 1;
+  const uint64_t dims[5] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M), 1, 1, 1};
+  const uint64_t big = static_cast<uint64_t>(lda) * es * static_cast<uint64_t>(M);
+  const uint64_t plane = (big + 15) / 16 * 16;
+  const uint64_t str[4] = {static_cast<uint64_t>(lda) * es, plane, plane, plane};
+  const uint32_t box[5] = {static_cast<uint32_t>(bk), 128, 1, 1, 1};
+  p.a_map[0] = make_tensor_map(A, fp32, 5, dims, str, box);
+  for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+  p.n_taps = 1; p.cpt = K / bk;
+  p.taps[0] = TapDesc{0, 0, 0, 0, 0};
+  p.tsm_split_cb = 0; p.tsm_map = 0;
+  finish_launch(L, /*Wo=*/M, /*Ho=*/1, /*Nimg=*/1, N, fp32);
+  p.b_map = weight_map(W, N, K, L.block_n, fp32);
+  set_epilogue(L, out, ld_out, e);
+  L.flops = 2.0 * M * N * K;
+  return L;
+}
+
+// NHWC convolution, kernel k x k (1 or 3), stride 1 or 2, pad = k/2.  Weights packed [Cout][kh][kw][Cin].
+// tsm_in: optional shifted buffer [Nimg*H*W, tsm_in_ch] that replaces channels [0, tsm_in_ch) of the input
+// (temporal shift folded into the A-operand load; 1x1 stride-1 only).
+inline ConvGemmLaunch build_conv(const void* in, int Nimg, int H, int W, int Cin, const void* Wp, int Cout, int k,
+                                 int stride, void* out, bool fp32, const Epilogue& e, const void* tsm_in = nullptr,
+                                 int tsm_in_ch = 0, const char* name = "conv") {
+  ConvGemmLaunch L;
+  memset(&L.p, 0, sizeof L.p);
+  L.name = name;
+  const int es = elem_size(fp32), bk = block_k(fp32);
+  VCG_REQUIRE(Cin % bk == 0, "conv input channels must be a multiple of the K block");
+  VCG_REQUIRE(k == 1 || k == 3, "conv kernel must be 1x1 or 3x3");
+  VCG_REQUIRE(stride == 1 || stride == 2, "conv stride must be 1 or 2");
+  const int pad = k / 2;
+  const int Ho = H / stride, Wo = W / stride;
+  if (stride == 2) VCG_REQUIRE(H % 2 == 0 && W % 2 == 0, "stride-2 conv needs even input size");
+  ConvGemmParams& p = L.p;
+  pick_patch(Wo, Ho, Nimg, p.bw, p.bh, p.nf);
+  const uint32_t box[5] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), 1,
+                           static_cast<uint32_t>(p.nf)};
+  const uint64_t img = static_cast<uint64_t>(H) * W * Cin * es;
+  if (stride == 1) {
+    const uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H), 1,
+                              static_cast<uint64_t>(Nimg)};
+    const uint64_t str[4] = {static_cast<uint64_t>(Cin) * es, static_cast<uint64_t>(W) * Cin * es, img, img};
+    p.a_map[0] = make_tensor_map(in, fp32, 5, dims, str, box);
+    for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+  } else {
+    // four parity views: (row parity, col parity) -> every tap of a stride-2 conv is a dense box in one view
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const uint8_t* base = static_cast<const uint8_t*>(in) + (static_cast<uint64_t>(ph) * W + pw) * Cin * es;
+        const uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W / 2),
+                                  static_cast<uint64_t>(H / 2), 1, static_cast<uint64_t>(Nimg)};
+        const uint64_t str[4] = {2ull * Cin * es, 2ull * W * Cin * es, img, img};
+        p.a_map[ph * 2 + pw] = make_tensor_map(base, fp32, 5, dims, str, box);
+      }
+  }
+  p.n_taps = k * k;
+  p.cpt = Cin / bk;
+  for (int kh = 0; kh < k; ++kh)
+    for (int kw = 0; kw < k; ++kw) {
+      TapDesc t{};
+      const int oh = kh - pad, ow = kw - pad;
+      if (stride == 1) {
+        t.dh = static_cast<int16_t>(oh); t.dw = static_cast<int16_t>(ow); t.map = 0;
+      } else {
+        const int ph = oh & 1, pw = ow & 1;
+        t.dh = static_cast<int16_t>((oh - ph) / 2); t.dw = static_cast<int16_t>((ow - pw) / 2);
+        t.map = static_cast<int8_t>(ph * 2 + pw);
+      }
+      t.c_off = 0; t.plane = 0;
+      p.taps[kh * k + kw] = t;
+    }
+  p.tsm_split_cb = 0; p.tsm_map = 0;
+  if (tsm_in) {
+    VCG_REQUIRE(k == 1 && stride == 1, "temporal shift is folded into 1x1 stride-1 convs only");
+    VCG_REQUIRE(tsm_in_ch % bk == 0 && tsm_in_ch <= Cin, "shifted channel count must be a multiple of the K block");
+    const uint64_t simg = static_cast<uint64_t>(H) * W * tsm_in_ch * es;
+    const uint64_t dims[5] = {static_cast<uint64_t>(tsm_in_ch), static_cast<uint64_t>(W), static_cast<uint64_t>(H), 1,
+                              static_cast<uint64_t>(Nimg)};
+    const uint64_t str[4] = {static_cast<uint64_t>(tsm_in_ch) * es, static_cast<uint64_t>(W) * tsm_in_ch * es, simg,
+                             simg};
+    p.a_map[1] = make_tensor_map(tsm_in, fp32, 5, dims, str, box);
+    p.tsm_map = 1;
+    p.tsm_split_cb = tsm_in_ch / bk;
+  }
+  finish_launch(L, Wo, Ho, Nimg, Cout, fp32);
+  p.b_map = weight_map(Wp, Cout, k * k * Cin, L.block_n, fp32);
+  set_epilogue(L, out, Cout, e);
+  L.flops = 2.0 * Nimg * Ho * Wo * static_cast<double>(Cout) * k * k * Cin;
+  return L;
+}
+
+// ResNet stem: 7x7 stride-2 pad-3 conv over a zero-padded NHWC4 image [Nimg, Hp, Wp, 4] whose pixel (0,0) is the
+// input pixel (-3,-3).  One K block = one filter row: a window of 128 contiguous bytes (16 bf16 / 8 fp32 pixels x 4
+// channels) starting at pixel 2*wo; the tensor map's W dimension therefore has a 16-byte stride (overlapping
+// windows), and the stride-2 row walk is folded into an (H/2, parity) pair of dimensions.
+// Weights packed [Cout][7][window pixels][4], zero where kw >= 7 or c == 3.
+inline ConvGemmLaunch build_stem(const void* in_padded, int Nimg, int Hp, int Wp, int Ho, int Wo, const void* Wp_packed,
+                                 int Cout, void* out, bool fp32, const Epilogue& e) {
+  ConvGemmLaunch L;
+  memset(&L.p, 0, sizeof L.p);
+  L.name = "stem";
+  const int es = elem_size(fp32), bk = block_k(fp32);
+  VCG_REQUIRE(Hp % 2 == 0, "padded stem height must be even");
+  ConvGemmParams& p = L.p;
+  pick_patch(Wo, Ho, Nimg, p.bw, p.bh, p.nf);
+  const uint64_t pitch = static_cast<uint64_t>(Wp) * 4 * es;
+  const uint64_t dims[5] = {static_cast<uint64_t>(bk), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Hp / 2), 2,
+                            static_cast<uint64_t>(Nimg)};
+  const uint64_t str[4] = {2ull * 4 * es, 2 * pitch, pitch, pitch * Hp};
+  const uint32_t box[5] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), 1,
+                           static_cast<uint32_t>(p.nf)};
+  p.a_map[0] = make_tensor_map(in_padded, fp32, 5, dims, str, box);
+  for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+  p.n_taps = 7; p.cpt = 1;
+  for (int kh = 0; kh < 7; ++kh) {
+    TapDesc t{};
+    t.dw = 0; t.dh = static_cast<int16_t>(kh / 2); t.plane = static_cast<int8_t>(kh & 1); t.map = 0; t.c_off = 0;
+    p.taps[kh] = t;
+  }
+  finish_launch(L, Wo, Ho, Nimg, Cout, fp32);
+  p.b_map = weight_map(Wp_packed, Cout, 7 * bk, L.block_n, fp32);
+  set_epilogue(L, out, Cout, e);
+  L.flops = 2.0 * Nimg * Ho * Wo * static_cast<double>(Cout) * 147;
+  return L;
+}
+
+void launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream);   // conv_gemm.cu
+
+}  // namespace vcg

@@ -1,0 +1,714 @@
+// libvcg_b200.so — engine and C ABI (include/vcg.h).
+//
+// The engine owns packed weights and a workspace sized for `max_batch` clips, and builds (once per batch size) a
+// "plan": the ordered list of kernel launches — tcgen05 implicit-GEMM convs / GEMMs with their TMA tensor maps and
+// the memory-bound kernels between them — that scores a chunk of clips.  See DESIGN.md for the data layout.
+#include "../../include/vcg.h"
+#include "conv_gemm_host.h"
+#include "kernels.cuh"
+
+#include <cuda_bf16.h>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace vcg;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  void alloc(size_t n, bool zero = false) {
+    release();
+    if (n == 0) n = 16;
+    VCG_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+    if (zero) VCG_CUDA(cudaMemset(p, 0, n));
+  }
+  void ensure(size_t n) {
+    if (n > bytes) alloc(n);
+  }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct RawTensor {
+  std::unique_ptr<DevBuf> buf;
+  std::vector<int64_t> shape;
+  int dtype = VCG_DTYPE_F32;
+  long numel() const {
+    long n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+struct ConvW {
+  DevBuf w, bias;
+  int Cin = 0, Cout = 0, k = 1, stride = 1;
+};
+struct Bottleneck {
+  ConvW c1, c2, c3, ds;
+  bool has_ds = false;
+  int stride = 1, Cin = 0, planes = 0, H = 0;   // H = input spatial size
+};
+struct LinearW {
+  DevBuf w, bias;   // w: [N][K] in the activation element type, bias fp32
+  int N = 0, K = 0;
+};
+struct BertLayerW {
+  LinearW qkv, out, ffn1, ffn2;
+  DevBuf ln1_g, ln1_b, ln2_g, ln2_b;
+};
+
+// One step of a plan.
+struct Step {
+  enum Kind { CONV_GEMM, MAXPOOL, AVGPOOL, EMBED, LAYERNORM, ATTENTION } kind;
+  ConvGemmLaunch gemm;
+  // generic arguments for the small kernels
+  const void* in = nullptr;
+  void* out = nullptr;
+  void* out2 = nullptr;
+  const float* g = nullptr;
+  const float* b = nullptr;
+  int n = 0, a = 0, c = 0;
+};
+
+struct VisionPlan {
+  int B = 0;
+  std::vector<Step> steps;   // stem .. last bottleneck (avgpool is issued by the caller: its destination varies)
+  const void* final_act = nullptr;
+};
+struct BertPlan {
+  int B = 0, L = 0;
+  std::vector<Step> steps;   // everything after the embedding (whose ids pointer varies)
+};
+
+}  // namespace
+
+struct vcg_engine {
+  vcg_config cfg{};
+  bool fp32 = false;
+  bool finalized = false;
+  int T = 16, Lmax = 100, H = 128, Bv = 32, Bt = 256;
+  int64_t launches = 0;
+  std::unordered_map<std::string, RawTensor> raw;
+
+  // vision weights
+  ConvW stem;
+  std::vector<Bottleneck> blocks;
+  bool tsm = true;
+  // text weights
+  DevBuf word, pos, type, emb_g, emb_b;
+  std::vector<BertLayerW> layers;
+  // tail weights (fp32)
+  DevBuf pool_w_t, pool_b, lang_w_t, vis_w_t, head_w, head_b, q_w_t, q_b, k_w_t, k_b, v_w_t, v_b, proj_w, proj_b;
+
+  // vision workspace (sized for Bv clips)
+  DevBuf stem_in, stem_out, x0, xa, xb, dsbuf, mid1, mid2, vis_emb;
+  std::vector<std::unique_ptr<DevBuf>> shifted;   // one per bottleneck: its temporally shifted input channels
+  // text workspace (sized for Bt clips x Lmax tokens)
+  DevBuf hid, hid2, qkv, ctx, tmp, ffn;
+  // host-call staging
+  DevBuf st_frames, st_ids, st_mask, st_start, st_logits, st_probs;
+
+  std::map<int, VisionPlan> vplans;
+  std::map<std::pair<int, int>, BertPlan> bplans;
+
+  int es() const { return fp32 ? 4 : 2; }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ weights
+const RawTensor& need(vcg_engine* e, const std::string& key, std::initializer_list<int64_t> shape = {}) {
+  auto it = e->raw.find(key);
+  if (it == e->raw.end()) throw Error("vcg: missing state-dict tensor '" + key + "'");
+  if (shape.size()) {
+    std::vector<int64_t> s(shape);
+    if (s != it->second.shape) {
+      std::string got;
+      for (auto d : it->second.shape) got += std::to_string(d) + ",";
+      throw Error("vcg: tensor '" + key + "' has unexpected shape [" + got + "]");
+    }
+  }
+  return it->second;
+}
+const float* fptr(const RawTensor& t) { return t.buf->as<float>(); }
+
+void copy_f32(DevBuf& dst, const RawTensor& t, cudaStream_t s) {
+  dst.alloc(t.numel() * sizeof(float));
+  VCG_CUDA(cudaMemcpyAsync(dst.p, t.buf->p, t.numel() * sizeof(float), cudaMemcpyDeviceToDevice, s));
+}
+void convert_to(DevBuf& dst, const RawTensor& t, bool fp32, cudaStream_t s) {
+  dst.alloc(t.numel() * (fp32 ? 4 : 2));
+  launch_convert(fptr(t), dst.p, t.numel(), fp32, s);
+}
+void transpose_to(DevBuf& dst, const RawTensor& t, cudaStream_t s) {   // [r][c] -> [c][r], fp32
+  VCG_REQUIRE(t.shape.size() == 2, "transpose expects a matrix");
+  dst.alloc(t.numel() * sizeof(float));
+  launch_transpose(fptr(t), dst.as<float>(), static_cast<int>(t.shape[0]), static_cast<int>(t.shape[1]), s);
+}
+
+void pack_conv_bn(vcg_engine* e, ConvW& cw, const std::string& wkey, const std::string& bnkey, int Cin, int Cout, int k,
+                  int stride, cudaStream_t s) {
+  const RawTensor& w = need(e, wkey, {Cout, Cin, k, k});
+  const RawTensor& g = need(e, bnkey + ".weight", {Cout});
+  const RawTensor& b = need(e, bnkey + ".bias", {Cout});
+  const RawTensor& m = need(e, bnkey + ".running_mean", {Cout});
+  const RawTensor& v = need(e, bnkey + ".running_var", {Cout});
+  cw.Cin = Cin; cw.Cout = Cout; cw.k = k; cw.stride = stride;
+  cw.w.alloc(static_cast<size_t>(Cout) * Cin * k * k * e->es());
+  cw.bias.alloc(Cout * sizeof(float));
+  launch_pack_conv(fptr(w), fptr(g), fptr(b), fptr(m), fptr(v), 1e-5f, Cout, Cin, k, cw.w.p, cw.bias.as<float>(),
+                   e->fp32, s);
+}
+
+std::string conv1_key(vcg_engine* e, const std::string& prefix) {
+  // TemporalShift wraps conv1 (ops/temporal_shift.py:138), which inserts ".net" into the key
+  if (e->raw.count(prefix + ".conv1.net.weight")) return prefix + ".conv1.net.weight";
+  return prefix + ".conv1.weight";
+}
+
+void pack_linear(vcg_engine* e, LinearW& lw, const std::string& prefix, int N, int K, cudaStream_t s) {
+  const RawTensor& w = need(e, prefix + ".weight", {N, K});
+  const RawTensor& b = need(e, prefix + ".bias", {N});
+  lw.N = N; lw.K = K;
+  convert_to(lw.w, w, e->fp32, s);
+  copy_f32(lw.bias, b, s);
+}
+
+void finalize_vision(vcg_engine* e, cudaStream_t s) {
+  const std::string vm = "vision_model.";
+  {
+    const RawTensor& w = need(e, vm + "conv1.weight", {64, 3, 7, 7});
+    const RawTensor& g = need(e, vm + "bn1.weight", {64});
+    const RawTensor& b = need(e, vm + "bn1.bias", {64});
+    const RawTensor& m = need(e, vm + "bn1.running_mean", {64});
+    const RawTensor& v = need(e, vm + "bn1.running_var", {64});
+    const int win = e->fp32 ? 8 : 16;
+    e->stem.Cin = 3; e->stem.Cout = 64; e->stem.k = 7; e->stem.stride = 2;
+    e->stem.w.alloc(static_cast<size_t>(64) * 7 * win * 4 * e->es());
+    e->stem.bias.alloc(64 * sizeof(float));
+    launch_pack_stem(fptr(w), fptr(g), fptr(b), fptr(m), fptr(v), 1e-5f, e->stem.w.p, e->stem.bias.as<float>(), e->fp32, s);
+  }
+  const int nblocks[4] = {3, 4, 6, 3};
+  const int planes[4] = {64, 128, 256, 512};
+  int inplanes = 64, Hs = 56;
+  e->blocks.clear();
+  e->blocks.resize(16);
+  int bi = 0;
+  for (int st = 0; st < 4; ++st) {
+    for (int i = 0; i < nblocks[st]; ++i, ++bi) {
+      Bottleneck& bk = e->blocks[bi];
+      const std::string pre = vm + "layer" + std::to_string(st + 1) + "." + std::to_string(i);
+      bk.stride = (i == 0 && st > 0) ? 2 : 1;
+      bk.Cin = inplanes; bk.planes = planes[st]; bk.H = Hs;
+      bk.has_ds = (i == 0);
+      pack_conv_bn(e, bk.c1, conv1_key(e, pre), pre + ".bn1", inplanes, planes[st], 1, 1, s);
+      pack_conv_bn(e, bk.c2, pre + ".conv2.weight", pre + ".bn2", planes[st], planes[st], 3, bk.stride, s);
+      pack_conv_bn(e, bk.c3, pre + ".conv3.weight", pre + ".bn3", planes[st], planes[st] * 4, 1, 1, s);
+      if (bk.has_ds)
+        pack_conv_bn(e, bk.ds, pre + ".downsample.0.weight", pre + ".downsample.1", inplanes, planes[st] * 4, 1,
+                     bk.stride, s);
+      inplanes = planes[st] * 4;
+      Hs /= bk.stride;
+    }
+  }
+  // workspace
+  const size_t nF = static_cast<size_t>(e->Bv) * e->T, es = e->es();
+  e->stem_in.alloc(nF * kStemHp * kStemWp * 4 * es, /*zero=*/true);   // borders stay zero forever
+  e->stem_out.alloc(nF * 112 * 112 * 64 * es);
+  e->x0.alloc(nF * 56 * 56 * 64 * es);
+  e->xa.alloc(nF * 56 * 56 * 256 * es);
+  e->xb.alloc(nF * 56 * 56 * 256 * es);
+  e->dsbuf.alloc(nF * 56 * 56 * 256 * es);
+  e->mid1.alloc(nF * 56 * 56 * 128 * es);
+  e->mid2.alloc(nF * 56 * 56 * 64 * es);
+  e->shifted.clear();
+  for (int i = 0; i < 16; ++i) {
+    const Bottleneck& bk = e->blocks[i];
+    const int ch = (i == 0) ? 64 : bk.Cin / 4;
+    auto buf = std::make_unique<DevBuf>();
+    if (e->tsm) buf->alloc(nF * bk.H * bk.H * ch * es, /*zero=*/true);   // never-written edge frames stay zero
+    e->shifted.push_back(std::move(buf));
+  }
+}
+
+void finalize_text(vcg_engine* e, cudaStream_t s) {
+  const std::string lm = "lang_model.";
+  const RawTensor& word = need(e, lm + "embeddings.word_embeddings.weight");
+  VCG_REQUIRE(word.shape.size() == 2 && word.shape[1] == kBertHidden, "word embedding must be [vocab,768]");
+  const RawTensor& pos = need(e, lm + "embeddings.position_embeddings.weight");
+  VCG_REQUIRE(pos.shape.size() == 2 && pos.shape[1] == kBertHidden && pos.shape[0] >= e->Lmax,
+              "position embedding table shorter than max_tokens");
+  const RawTensor& type = need(e, lm + "embeddings.token_type_embeddings.weight");
+  convert_to(e->word, word, e->fp32, s);
+  convert_to(e->pos, pos, e->fp32, s);
+  convert_to(e->type, type, e->fp32, s);
+  copy_f32(e->emb_g, need(e, lm + "embeddings.LayerNorm.weight", {kBertHidden}), s);
+  copy_f32(e->emb_b, need(e, lm + "embeddings.LayerNorm.bias", {kBertHidden}), s);
+  int n_layers = 0;
+  while (e->raw.count(lm + "encoder.layer." + std::to_string(n_layers) + ".attention.self.query.weight")) ++n_layers;
+  VCG_REQUIRE(n_layers > 0, "no BERT encoder layers found in the state dict");
+  e->layers.clear();
+  e->layers.resize(n_layers);
+  for (int i = 0; i < n_layers; ++i) {
+    BertLayerW& lw = e->layers[i];
+    const std::string pre = lm + "encoder.layer." + std::to_string(i) + ".";
+    // fused QKV: rows [0,768) query, [768,1536) key, [1536,2304) value
+    lw.qkv.N = 3 * kBertHidden; lw.qkv.K = kBertHidden;
+    lw.qkv.w.alloc(static_cast<size_t>(3) * kBertHidden * kBertHidden * e->es());
+    lw.qkv.bias.alloc(3 * kBertHidden * sizeof(float));
+    const char* names[3] = {"query", "key", "value"};
+    for (int j = 0; j < 3; ++j) {
+      const RawTensor& w = need(e, pre + "attention.self." + names[j] + ".weight", {kBertHidden, kBertHidden});
+      const RawTensor& b = need(e, pre + "attention.self." + names[j] + ".bias", {kBertHidden});
+      launch_convert(fptr(w), static_cast<uint8_t*>(lw.qkv.w.p) + static_cast<size_t>(j) * kBertHidden * kBertHidden * e->es(),
+                     static_cast<long>(kBertHidden) * kBertHidden, e->fp32, s);
+      VCG_CUDA(cudaMemcpyAsync(lw.qkv.bias.as<float>() + j * kBertHidden, b.buf->p, kBertHidden * sizeof(float),
+                               cudaMemcpyDeviceToDevice, s));
+    }
+    pack_linear(e, lw.out, pre + "attention.output.dense", kBertHidden, kBertHidden, s);
+    copy_f32(lw.ln1_g, need(e, pre + "attention.output.LayerNorm.weight", {kBertHidden}), s);
+    copy_f32(lw.ln1_b, need(e, pre + "attention.output.LayerNorm.bias", {kBertHidden}), s);
+    pack_linear(e, lw.ffn1, pre + "intermediate.dense", kBertFfn, kBertHidden, s);
+    pack_linear(e, lw.ffn2, pre + "output.dense", kBertHidden, kBertFfn, s);
+    copy_f32(lw.ln2_g, need(e, pre + "output.LayerNorm.weight", {kBertHidden}), s);
+    copy_f32(lw.ln2_b, need(e, pre + "output.LayerNorm.bias", {kBertHidden}), s);
+  }
+  transpose_to(e->pool_w_t, need(e, lm + "pooler.dense.weight", {kBertHidden, kBertHidden}), s);
+  copy_f32(e->pool_b, need(e, lm + "pooler.dense.bias", {kBertHidden}), s);
+  // workspace: +128 rows of slack so that a TMA box starting at the last valid row never leaves the allocation
+  const size_t rows = static_cast<size_t>(e->Bt) * e->Lmax + 128, es = e->es();
+  e->hid.alloc(rows * kBertHidden * es);
+  e->hid2.alloc(rows * kBertHidden * es);
+  e->qkv.alloc(rows * 3 * kBertHidden * es);
+  e->ctx.alloc(rows * kBertHidden * es);
+  e->tmp.alloc(rows * kBertHidden * es);
+  e->ffn.alloc(rows * kBertFfn * es);
+}
+
+void finalize_head(vcg_engine* e, cudaStream_t s) {
+  const std::string fh = "fusion_head.";
+  const int H = e->H, T = e->T;
+  transpose_to(e->lang_w_t, need(e, fh + "lang_proj_head.weight", {H, kBertHidden}), s);
+  transpose_to(e->vis_w_t, need(e, fh + "vision_proj_head.weight", {H, kVisionDim}), s);
+  if (e->cfg.head_type == VCG_HEAD_MLP) {
+    copy_f32(e->head_w, need(e, fh + "head.weight", {2, static_cast<int64_t>(T + 1) * H}), s);
+    copy_f32(e->head_b, need(e, fh + "head.bias", {2}), s);
+  } else {
+    transpose_to(e->q_w_t, need(e, fh + "head.query.weight", {H, H}), s);
+    copy_f32(e->q_b, need(e, fh + "head.query.bias", {H}), s);
+    transpose_to(e->k_w_t, need(e, fh + "head.key.weight", {H, H}), s);
+    copy_f32(e->k_b, need(e, fh + "head.key.bias", {H}), s);
+    transpose_to(e->v_w_t, need(e, fh + "head.value.weight", {H, H}), s);
+    copy_f32(e->v_b, need(e, fh + "head.value.bias", {H}), s);
+    copy_f32(e->proj_w, need(e, fh + "head.proj.weight", {2, H}), s);
+    copy_f32(e->proj_b, need(e, fh + "head.proj.bias", {2}), s);
+  }
+  e->vis_emb.alloc(static_cast<size_t>(std::max(e->Bv, e->Bt)) * T * kVisionDim * sizeof(float));
+}
+
+// ------------------------------------------------------------------------------------------------ plans
+VisionPlan& vision_plan(vcg_engine* e, int B) {
+  auto it = e->vplans.find(B);
+  if (it != e->vplans.end()) return it->second;
+  VisionPlan plan;
+  plan.B = B;
+  const int N = B * e->T;
+  const bool fp = e->fp32;
+  {
+    Step st{};
+    st.kind = Step::CONV_GEMM;
+    Epilogue ep;
+    ep.bias = e->stem.bias.as<float>();
+    ep.act = ACT_RELU;
+    st.gemm = build_stem(e->stem_in.p, N, kStemHp, kStemWp, kStemOut, kStemOut, e->stem.w.p, 64, e->stem_out.p, fp, ep);
+    plan.steps.push_back(st);
+  }
+  {
+    Step st{};
+    st.kind = Step::MAXPOOL;
+    st.in = e->stem_out.p; st.out = e->x0.p; st.out2 = e->tsm ? e->shifted[0]->p : nullptr;
+    st.n = N; st.a = e->T; st.c = e->tsm ? 64 / e->cfg.shift_div : 0;
+    plan.steps.push_back(st);
+  }
+  const void* x = e->x0.p;
+  void* pingpong[2] = {e->xa.p, e->xb.p};
+  int pp = 0;
+  for (int i = 0; i < 16; ++i) {
+    const Bottleneck& bk = e->blocks[i];
+    const int H = bk.H, Ho = H / bk.stride, Cout = bk.planes * 4;
+    void* xnext = pingpong[pp];
+    pp ^= 1;
+    {   // conv1 1x1 (+ temporal shift folded into the operand load) + BN + ReLU
+      Step st{}; st.kind = Step::CONV_GEMM;
+      Epilogue ep; ep.bias = bk.c1.bias.as<float>(); ep.act = ACT_RELU;
+      const void* sh = e->tsm ? e->shifted[i]->p : nullptr;
+      const int sh_ch = e->tsm ? ((i == 0) ? 64 : 2 * (bk.Cin / e->cfg.shift_div)) : 0;
+      st.gemm = build_conv(x, N, H, H, bk.Cin, bk.c1.w.p, bk.planes, 1, 1, e->mid1.p, fp, ep, sh, sh_ch, "conv1");
+      plan.steps.push_back(st);
+    }
+    {   // conv2 3x3 (stride) + BN + ReLU
+      Step st{}; st.kind = Step::CONV_GEMM;
+      Epilogue ep; ep.bias = bk.c2.bias.as<float>(); ep.act = ACT_RELU;
+      st.gemm = build_conv(e->mid1.p, N, H, H, bk.planes, bk.c2.w.p, bk.planes, 3, bk.stride, e->mid2.p, fp, ep, nullptr, 0, "conv2");
+      plan.steps.push_back(st);
+    }
+    const void* identity = x;
+    if (bk.has_ds) {   // downsample 1x1 (stride) + BN on the un-shifted block input
+      Step st{}; st.kind = Step::CONV_GEMM;
+      Epilogue ep; ep.bias = bk.ds.bias.as<float>(); ep.act = ACT_NONE;
+      st.gemm = build_conv(x, N, H, H, bk.Cin, bk.ds.w.p, Cout, 1, bk.stride, e->dsbuf.p, fp, ep, nullptr, 0, "downsample");
+      plan.steps.push_back(st);
+      identity = e->dsbuf.p;
+    }
+    {   // conv3 1x1 + BN + residual + ReLU, scattering the next block's shifted channels
+      Step st{}; st.kind = Step::CONV_GEMM;
+      Epilogue ep; ep.bias = bk.c3.bias.as<float>(); ep.act = ACT_RELU;
+      ep.residual = identity; ep.ld_res = Cout;
+      if (e->tsm && i + 1 < 16) {
+        ep.tsm_out = e->shifted[i + 1]->p;
+        ep.tsm_fold = Cout / e->cfg.shift_div;
+        ep.tsm_ld = 2 * ep.tsm_fold;
+        ep.T = e->T;
+      }
+      st.gemm = build_conv(e->mid2.p, N, Ho, Ho, bk.planes, bk.c3.w.p, Cout, 1, 1, xnext, fp, ep, nullptr, 0, "conv3");
+      plan.steps.push_back(st);
+    }
+    x = xnext;
+  }
+  plan.final_act = x;
+  return e->vplans.emplace(B, std::move(plan)).first->second;
+}
+
+BertPlan& bert_plan(vcg_engine* e, int B, int L) {
+  auto key = std::make_pair(B, L);
+  auto it = e->bplans.find(key);
+  if (it != e->bplans.end()) return it->second;
+  BertPlan plan;
+  plan.B = B; plan.L = L;
+  const int M = B * L;
+  const bool fp = e->fp32;
+  auto gemm_step = [&](const void* A, const LinearW& w, void* out, int act, const void* res, const char* name) {
+    Step st{}; st.kind = Step::CONV_GEMM;
+    Epilogue ep; ep.bias = w.bias.as<float>(); ep.act = act; ep.residual = res; ep.ld_res = w.N;
+    st.gemm = build_gemm(A, w.K, w.w.p, out, w.N, M, w.N, w.K, fp, ep, name);
+    plan.steps.push_back(st);
+  };
+  auto ln_step = [&](const void* x, const DevBuf& g, const DevBuf& b, void* y) {
+    Step st{}; st.kind = Step::LAYERNORM;
+    st.in = x; st.out = y; st.g = g.as<float>(); st.b = b.as<float>(); st.n = M;
+    plan.steps.push_back(st);
+  };
+  for (size_t i = 0; i < e->layers.size(); ++i) {
+    const BertLayerW& lw = e->layers[i];
+    gemm_step(e->hid.p, lw.qkv, e->qkv.p, ACT_NONE, nullptr, "bert.qkv");
+    { Step st{}; st.kind = Step::ATTENTION; st.in = e->qkv.p; st.out = e->ctx.p; st.n = B; st.a = L; plan.steps.push_back(st); }
+    gemm_step(e->ctx.p, lw.out, e->tmp.p, ACT_NONE, e->hid.p, "bert.attn_out");
+    ln_step(e->tmp.p, lw.ln1_g, lw.ln1_b, e->hid2.p);
+    gemm_step(e->hid2.p, lw.ffn1, e->ffn.p, ACT_GELU, nullptr, "bert.ffn_in");
+    gemm_step(e->ffn.p, lw.ffn2, e->tmp.p, ACT_NONE, e->hid2.p, "bert.ffn_out");
+    ln_step(e->tmp.p, lw.ln2_g, lw.ln2_b, e->hid.p);
+  }
+  return e->bplans.emplace(key, std::move(plan)).first->second;
+}
+
+void run_steps(vcg_engine* e, const std::vector<Step>& steps, const int64_t* mask, cudaStream_t s) {
+  for (const Step& st : steps) {
+    switch (st.kind) {
+      case Step::CONV_GEMM: launch_conv_gemm(st.gemm, s); break;
+      case Step::MAXPOOL: launch_maxpool_tsm(st.in, st.n, st.out, st.out2, st.a, st.c, e->fp32, s); break;
+      case Step::LAYERNORM: launch_layernorm(st.in, st.g, st.b, st.out, st.n, kBertHidden, 1e-12f, e->fp32, s); break;
+      case Step::ATTENTION: launch_bert_attention(st.in, mask, st.out, st.n, st.a, e->fp32, s); break;
+      default: throw Error("vcg: unknown plan step");
+    }
+    ++e->launches;
+  }
+}
+
+struct FrameSource {
+  const float* img_clip = nullptr;     // [B,T,3,224,224] fp32
+  const uint8_t* frames_u8 = nullptr;  // [n_frames,224,224,3]
+  const int32_t* clip_start = nullptr; // [B]
+};
+
+// Scores B clips; any of the sources may be used for the vision stream (or precomputed embeddings).
+void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, const int64_t* ids, const int64_t* mask,
+           int B, int L, float* logits, float* probs, float* vision_emb_out, float* lang_emb_out, cudaStream_t s) {
+  VCG_REQUIRE(e->finalized, "vcg_finalize has not been called");
+  VCG_REQUIRE(B >= 0 && L >= 1 && L <= e->Lmax, "token count exceeds max_tokens of the engine");
+  const bool have_frames = src.img_clip || src.frames_u8;
+  VCG_REQUIRE(have_frames || vision_emb_in, "no vision input given");
+  if (have_frames) VCG_REQUIRE(e->cfg.vision == VCG_VISION_R50TSM, "engine was created without a vision backbone");
+  const int T = e->T;
+  for (int b0 = 0; b0 < B; b0 += e->Bt) {
+    const int bt = std::min(e->Bt, B - b0);
+    // ---- text stream for bt clips
+    launch_bert_embed_ln(ids + static_cast<long>(b0) * L, bt * L, L, e->word.p, e->pos.p, e->type.p, e->emb_g.as<float>(),
+                         e->emb_b.as<float>(), e->hid.p, e->fp32, s);
+    ++e->launches;
+    run_steps(e, bert_plan(e, bt, L).steps, mask + static_cast<long>(b0) * L, s);
+    // ---- vision stream + tail in sub-chunks
+    const int step = have_frames ? e->Bv : bt;
+    for (int c0 = 0; c0 < bt; c0 += step) {
+      const int bv = std::min(step, bt - c0);
+      const int g0 = b0 + c0;   // first clip of this sub-chunk in the caller's numbering
+      const float* vis = nullptr;
+      if (have_frames) {
+        if (src.img_clip)
+          launch_nchw_to_stem(src.img_clip + static_cast<long>(g0) * T * 3 * kImg * kImg, bv * T, e->stem_in.p, e->fp32, s);
+        else
+          launch_preprocess_u8_clips(src.frames_u8, src.clip_start + g0, bv, T, e->stem_in.p, e->fp32, s);
+        ++e->launches;
+        VisionPlan& vp = vision_plan(e, bv);
+        run_steps(e, vp.steps, nullptr, s);
+        float* dst = vision_emb_out ? vision_emb_out + static_cast<long>(g0) * T * kVisionDim : e->vis_emb.as<float>();
+        launch_avgpool(vp.final_act, bv * T, 49, kVisionDim, dst, s, e->fp32);
+        ++e->launches;
+        vis = dst;
+      } else {
+        vis = vision_emb_in + static_cast<long>(g0) * T * kVisionDim;
+        if (vision_emb_out)
+          VCG_CUDA(cudaMemcpyAsync(vision_emb_out + static_cast<long>(g0) * T * kVisionDim, vis,
+                                   static_cast<size_t>(bv) * T * kVisionDim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      }
+      TailParams tp{};
+      tp.hidden = static_cast<const uint8_t*>(e->hid.p) + static_cast<size_t>(c0) * L * kBertHidden * e->es();
+      tp.L = L; tp.vision = vis; tp.T = T; tp.H = e->H; tp.head_type = e->cfg.head_type;
+      tp.pool_w_t = e->pool_w_t.as<float>(); tp.pool_b = e->pool_b.as<float>();
+      tp.lang_w_t = e->lang_w_t.as<float>(); tp.vis_w_t = e->vis_w_t.as<float>();
+      tp.head_w = e->head_w.as<float>(); tp.head_b = e->head_b.as<float>();
+      tp.q_w_t = e->q_w_t.as<float>(); tp.q_b = e->q_b.as<float>();
+      tp.k_w_t = e->k_w_t.as<float>(); tp.k_b = e->k_b.as<float>();
+      tp.v_w_t = e->v_w_t.as<float>(); tp.v_b = e->v_b.as<float>();
+      tp.proj_w = e->proj_w.as<float>(); tp.proj_b = e->proj_b.as<float>();
+      tp.logits = logits + static_cast<long>(g0) * 2;
+      tp.probs = probs + static_cast<long>(g0) * 2;
+      tp.lang_emb = lang_emb_out ? lang_emb_out + static_cast<long>(g0) * kBertHidden : nullptr;
+      launch_tail(tp, bv, e->fp32, s);
+      ++e->launches;
+    }
+  }
+}
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& ex) {
+    g_last_error = ex.what();
+    cudaGetLastError();   // clear sticky-free errors so the next call starts clean
+    return 1;
+  } catch (...) {
+    g_last_error = "vcg: unknown error";
+    return 1;
+  }
+}
+
+}  // namespace
+
+// =================================================================================================== C ABI
+extern "C" {
+
+const char* vcg_last_error(void) { return g_last_error.c_str(); }
+const char* vcg_version(void) { return "vcg_b200 0.1 (sm_100a)"; }
+
+int vcg_create(const vcg_config* cfg, vcg_engine** out) {
+  return guarded([&] {
+    VCG_REQUIRE(cfg && out, "null argument");
+    VCG_REQUIRE(cfg->clip_frames >= 1 && cfg->clip_frames <= 39, "clip_frames must be in [1,39]");
+    VCG_REQUIRE(cfg->max_tokens >= 1 && cfg->max_tokens <= 512, "max_tokens must be in [1,512]");
+    VCG_REQUIRE(cfg->hidden_size == 128, "hidden_size must be 128");
+    if (cfg->head_type != VCG_HEAD_MLP && cfg->head_type != VCG_HEAD_ATTN)
+      throw Error("Unknown head_type " + std::to_string(cfg->head_type));   // two_stream.py:68
+    VCG_REQUIRE(cfg->precision == VCG_PREC_BF16 || cfg->precision == VCG_PREC_FP32, "unknown precision");
+    VCG_REQUIRE(cfg->max_batch >= 1, "max_batch must be positive");
+    VCG_REQUIRE(cfg->shift_div == 8 || cfg->shift_div == 4 || cfg->shift_div == 0, "shift_div must be 8, 4 or 0 (no shift)");
+    int dev = 0, major = 0, minor = 0;
+    VCG_CUDA(cudaGetDevice(&dev));
+    VCG_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    VCG_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    VCG_REQUIRE(major == 10, "libvcg_b200 needs a Blackwell (sm_100a) GPU; there is no fallback path");
+    auto e = std::make_unique<vcg_engine>();
+    e->cfg = *cfg;
+    e->fp32 = cfg->precision == VCG_PREC_FP32;
+    e->T = cfg->clip_frames; e->Lmax = cfg->max_tokens; e->H = cfg->hidden_size;
+    e->Bv = cfg->max_batch;
+    e->Bt = std::max(cfg->max_batch, 256);
+    e->tsm = cfg->shift_div != 0;
+    *out = e.release();
+  });
+}
+
+void vcg_destroy(vcg_engine* e) { delete e; }
+
+int vcg_load_tensor(vcg_engine* e, const char* key, const void* dev_ptr, const int64_t* shape, int32_t ndim,
+                    int32_t dtype, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e && key && dev_ptr && (shape || ndim == 0), "null argument");
+    RawTensor t;
+    t.shape.assign(shape, shape + ndim);
+    t.dtype = dtype;
+    const size_t bytes = static_cast<size_t>(t.numel()) * (dtype == VCG_DTYPE_I64 ? 8 : 4);
+    t.buf = std::make_unique<DevBuf>();
+    t.buf->alloc(bytes);
+    VCG_CUDA(cudaMemcpyAsync(t.buf->p, dev_ptr, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    e->raw[key] = std::move(t);
+    e->finalized = false;
+  });
+}
+
+int vcg_finalize(vcg_engine* e, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e, "null engine");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    e->vplans.clear();
+    e->bplans.clear();
+    if (e->cfg.vision == VCG_VISION_R50TSM) finalize_vision(e, s);
+    finalize_text(e, s);
+    finalize_head(e, s);
+    VCG_CUDA(cudaStreamSynchronize(s));
+    e->raw.clear();   // packed copies are all the kernels read
+    e->finalized = true;
+  });
+}
+
+int vcg_forward(vcg_engine* e, const float* img_clip, const float* vision_emb, const int64_t* text_ids,
+                const int64_t* attention_mask, int32_t B, int32_t L, float* logits, float* probs,
+                float* vision_emb_out, float* lang_emb_out, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e && text_ids && attention_mask && logits && probs, "null argument");
+    FrameSource src;
+    src.img_clip = img_clip;
+    score(e, src, vision_emb, text_ids, attention_mask, B, L, logits, probs, vision_emb_out, lang_emb_out,
+          static_cast<cudaStream_t>(stream));
+  });
+}
+
+int vcg_score_clips_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames, const int32_t* clip_start,
+                       const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L, float* logits,
+                       float* probs, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e && frames_u8 && clip_start && text_ids && attention_mask && logits && probs, "null argument");
+    (void)n_frames;
+    FrameSource src;
+    src.frames_u8 = frames_u8;
+    src.clip_start = clip_start;
+    score(e, src, nullptr, text_ids, attention_mask, B, L, logits, probs, nullptr, nullptr,
+          static_cast<cudaStream_t>(stream));
+  });
+}
+
+int vcg_score_clips_u8_host(vcg_engine* e, const uint8_t* frames_u8_host, int32_t n_frames,
+                            const int32_t* clip_start_host, const int64_t* text_ids_host,
+                            const int64_t* attention_mask_host, int32_t B, int32_t L, float* logits_host,
+                            float* probs_host, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e && frames_u8_host && clip_start_host && text_ids_host && attention_mask_host && logits_host && probs_host,
+                "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t fbytes = static_cast<size_t>(n_frames) * kImg * kImg * 3;
+    const size_t tbytes = static_cast<size_t>(B) * L * sizeof(int64_t);
+    e->st_frames.ensure(fbytes);
+    e->st_ids.ensure(tbytes);
+    e->st_mask.ensure(tbytes);
+    e->st_start.ensure(static_cast<size_t>(B) * sizeof(int32_t));
+    e->st_logits.ensure(static_cast<size_t>(B) * 2 * sizeof(float));
+    e->st_probs.ensure(static_cast<size_t>(B) * 2 * sizeof(float));
+    VCG_CUDA(cudaMemcpyAsync(e->st_frames.p, frames_u8_host, fbytes, cudaMemcpyHostToDevice, s));
+    VCG_CUDA(cudaMemcpyAsync(e->st_ids.p, text_ids_host, tbytes, cudaMemcpyHostToDevice, s));
+    VCG_CUDA(cudaMemcpyAsync(e->st_mask.p, attention_mask_host, tbytes, cudaMemcpyHostToDevice, s));
+    VCG_CUDA(cudaMemcpyAsync(e->st_start.p, clip_start_host, static_cast<size_t>(B) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    FrameSource src;
+    src.frames_u8 = e->st_frames.as<uint8_t>();
+    src.clip_start = e->st_start.as<int32_t>();
+    score(e, src, nullptr, e->st_ids.as<int64_t>(), e->st_mask.as<int64_t>(), B, L, e->st_logits.as<float>(),
+          e->st_probs.as<float>(), nullptr, nullptr, s);
+    VCG_CUDA(cudaMemcpyAsync(logits_host, e->st_logits.p, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    VCG_CUDA(cudaMemcpyAsync(probs_host, e->st_probs.p, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    VCG_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int64_t vcg_launch_count(const vcg_engine* e) { return e ? e->launches : 0; }
+
+// --------------------------------------------------------------------------------------------- operators
+int vcg_op_preprocess_u8(const uint8_t* frames_u8, const int32_t* frame_index, int32_t n, void* out_padded,
+                         int32_t precision, void* stream) {
+  return guarded([&] {
+    launch_preprocess_u8(frames_u8, frame_index, n, out_padded, precision == VCG_PREC_FP32, static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_nchw_to_stem(const float* img, int32_t n, void* out_padded, int32_t precision, void* stream) {
+  return guarded([&] { launch_nchw_to_stem(img, n, out_padded, precision == VCG_PREC_FP32, static_cast<cudaStream_t>(stream)); });
+}
+int vcg_op_gemm(const void* A, int64_t lda, const void* W, const float* bias, const void* residual, int32_t ld_res,
+                void* out, int32_t ld_out, int32_t M, int32_t N, int32_t K, int32_t act, int32_t precision,
+                void* stream) {
+  return guarded([&] {
+    Epilogue ep;
+    ep.bias = bias; ep.residual = residual; ep.ld_res = ld_res; ep.act = act;
+    ConvGemmLaunch L = build_gemm(A, lda, W, out, ld_out, M, N, K, precision == VCG_PREC_FP32, ep);
+    launch_conv_gemm(L, static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_conv2d_nhwc(const void* in, int32_t n, int32_t H, int32_t W, int32_t Cin, const void* weight,
+                       const float* bias, const void* residual, void* out, int32_t Cout, int32_t k, int32_t stride,
+                       int32_t act, int32_t precision, const void* tsm_in, int32_t tsm_in_ch, void* tsm_out,
+                       int32_t tsm_fold, int32_t clip_frames, void* stream) {
+  return guarded([&] {
+    Epilogue ep;
+    ep.bias = bias; ep.residual = residual; ep.ld_res = Cout; ep.act = act;
+    ep.tsm_out = tsm_out; ep.tsm_fold = tsm_fold; ep.tsm_ld = 2 * tsm_fold; ep.T = clip_frames;
+    ConvGemmLaunch L = build_conv(in, n, H, W, Cin, weight, Cout, k, stride, out, precision == VCG_PREC_FP32, ep, tsm_in, tsm_in_ch);
+    launch_conv_gemm(L, static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_stem_conv(const void* in_padded, int32_t n, const void* weight, const float* bias, void* out,
+                     int32_t precision, void* stream) {
+  return guarded([&] {
+    Epilogue ep;
+    ep.bias = bias; ep.act = ACT_RELU;
+    ConvGemmLaunch L = build_stem(in_padded, n, kStemHp, kStemWp, kStemOut, kStemOut, weight, 64, out, precision == VCG_PREC_FP32, ep);
+    launch_conv_gemm(L, static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_maxpool_tsm(const void* in, int32_t n, void* out, void* out_shifted, int32_t clip_frames,
+                       int32_t shift_div, int32_t precision, void* stream) {
+  return guarded([&] {
+    launch_maxpool_tsm(in, n, out, out_shifted, clip_frames, shift_div > 0 ? 64 / shift_div : 0, precision == VCG_PREC_FP32,
+                       static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_bert_attention(const void* qkv, const int64_t* attention_mask, void* ctx, int32_t B, int32_t L,
+                          int32_t precision, void* stream) {
+  return guarded([&] { launch_bert_attention(qkv, attention_mask, ctx, B, L, precision == VCG_PREC_FP32, static_cast<cudaStream_t>(stream)); });
+}
+int vcg_op_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t cols,
+                     float eps, int32_t precision, void* stream) {
+  return guarded([&] { launch_layernorm(x, gamma, beta, y, rows, cols, eps, precision == VCG_PREC_FP32, static_cast<cudaStream_t>(stream)); });
+}
+
+}  // extern "C"

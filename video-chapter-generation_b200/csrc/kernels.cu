@@ -1,0 +1,423 @@
+// HBM-bound kernels of the scoring path: frame preprocessing, max/avg pooling (with the temporal shift folded in),
+// BERT embedding + LayerNorm, LayerNorm, and weight packing.  All use 8/16-byte vector accesses with consecutive
+// threads on consecutive addresses; grids are sized from the element count (>= several waves at bench sizes).
+#include "kernels.cuh"
+#include "tensormap.h"
+#include <cuda_bf16.h>
+#include <type_traits>
+
+namespace vcg {
+
+namespace {
+
+template <bool FP32>
+using elem_t = typename std::conditional<FP32, float, __nv_bfloat16>::type;
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+
+// 8 consecutive elements as fp32
+template <bool FP32>
+__device__ __forceinline__ void load8(const elem_t<FP32>* p, float (&v)[8]) {
+  if constexpr (FP32) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    float2 f;
+    f = unpack_bf16x2(q.x); v[0] = f.x; v[1] = f.y;
+    f = unpack_bf16x2(q.y); v[2] = f.x; v[3] = f.y;
+    f = unpack_bf16x2(q.z); v[4] = f.x; v[5] = f.y;
+    f = unpack_bf16x2(q.w); v[6] = f.x; v[7] = f.y;
+  }
+}
+template <bool FP32>
+__device__ __forceinline__ void store8(elem_t<FP32>* p, const float (&v)[8]) {
+  if constexpr (FP32) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+    q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = q;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ preprocess
+// ToTensor + Normalize (test_video_segment_point.py:142-145): (u8/255 - mean)/std, HWC -> zero-padded NHWC4.
+// One thread = 4 pixels: 12 bytes in (three aligned 32-bit loads), 4 pixel stores out.
+__constant__ float c_mean[3] = {0.485f, 0.456f, 0.406f};
+__constant__ float c_std[3] = {0.229f, 0.224f, 0.225f};
+
+template <bool FP32>
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ frame_index,
+                                     const int32_t* __restrict__ clip_start, int T, long total,
+                                     elem_t<FP32>* __restrict__ out) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  constexpr int W4 = kImg / 4;
+  const int w4 = static_cast<int>(idx % W4);
+  const int h = static_cast<int>((idx / W4) % kImg);
+  const long n = idx / (W4 * kImg);
+  long f = n;
+  if (clip_start) f = clip_start[n / T] + (n % T);
+  else if (frame_index) f = frame_index[n];
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(frames + (f * kImg + h) * (kImg * 3L) + w4 * 12);
+  const uint32_t u0 = __ldg(src), u1 = __ldg(src + 1), u2 = __ldg(src + 2);
+  uint8_t b[12];
+  *reinterpret_cast<uint32_t*>(b) = u0;
+  *reinterpret_cast<uint32_t*>(b + 4) = u1;
+  *reinterpret_cast<uint32_t*>(b + 8) = u2;
+  elem_t<FP32>* dst = out + ((n * kStemHp + h + kStemPad) * kStemWp + (w4 * 4 + kStemPad)) * 4L;
+#pragma unroll
+  for (int px = 0; px < 4; ++px) {
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (static_cast<float>(b[px * 3 + c]) / 255.0f - c_mean[c]) / c_std[c];
+    if constexpr (FP32) {
+      *reinterpret_cast<float4*>(dst + px * 4) = make_float4(v[0], v[1], v[2], 0.f);
+    } else {
+      uint2 q;
+      q.x = pack_bf16x2(v[0], v[1]);
+      q.y = pack_bf16x2(v[2], 0.f);
+      *reinterpret_cast<uint2*>(dst + px * 4) = q;
+    }
+  }
+}
+
+// fp32 NCHW (already normalised, the reference's img_clip) -> padded NHWC4
+template <bool FP32>
+__global__ void nchw_to_stem_kernel(const float* __restrict__ img, long total, elem_t<FP32>* __restrict__ out) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int w = static_cast<int>(idx % kImg);
+  const int h = static_cast<int>((idx / kImg) % kImg);
+  const long n = idx / (kImg * kImg);
+  const float* src = img + n * 3L * kImg * kImg + h * kImg + w;
+  const float r = __ldg(src), g = __ldg(src + kImg * kImg), b = __ldg(src + 2 * kImg * kImg);
+  elem_t<FP32>* dst = out + ((n * kStemHp + h + kStemPad) * kStemWp + (w + kStemPad)) * 4L;
+  if constexpr (FP32) {
+    *reinterpret_cast<float4*>(dst) = make_float4(r, g, b, 0.f);
+  } else {
+    uint2 q;
+    q.x = pack_bf16x2(r, g);
+    q.y = pack_bf16x2(b, 0.f);
+    *reinterpret_cast<uint2*>(dst) = q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ max pool + TSM
+// MaxPool2d(3, stride 2, pad 1) over NHWC [n,112,112,64]; writes x and the temporally shifted copy that layer1.0.conv1
+// consumes (ops/temporal_shift.py:34-51): channels [0,fold) of frame t land in frame t-1, [fold,2*fold) in frame t+1.
+// One thread = 8 channels of one output pixel.
+template <bool FP32>
+__global__ void maxpool_tsm_kernel(const elem_t<FP32>* __restrict__ in, long total, elem_t<FP32>* __restrict__ out,
+                                   elem_t<FP32>* __restrict__ shifted, int T, int fold) {
+  constexpr int C = 64, HI = kStemOut, HO = kStemOut / 2;
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % (C / 8));
+  const int wo = static_cast<int>((idx / (C / 8)) % HO);
+  const int ho = static_cast<int>((idx / (C / 8 * HO)) % HO);
+  const long n = idx / (C / 8 * HO * HO);
+  float m[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int y = 2 * ho + dy;
+    if (y < 0 || y >= HI) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int x = 2 * wo + dx;
+      if (x < 0 || x >= HI) continue;
+      float v[8];
+      load8<FP32>(in + ((n * HI + y) * HI + x) * C + c8 * 8, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+    }
+  }
+  const long pix = (n * HO + ho) * HO + wo;
+  store8<FP32>(out + pix * C + c8 * 8, m);
+  if (shifted) {
+    const int c0 = c8 * 8;
+    const int t = static_cast<int>(n % T);
+    long dpix = pix;
+    bool ok = true;
+    if (c0 < fold) { ok = t >= 1; dpix = pix - HO * HO; }
+    else if (c0 < 2 * fold) { ok = t + 1 < T; dpix = pix + HO * HO; }
+    if (ok) store8<FP32>(shifted + dpix * C + c0, m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ avg pool
+// AdaptiveAvgPool2d(1) over NHWC [n, hw, C] -> fp32 [n, C]
+template <bool FP32>
+__global__ void avgpool_kernel(const elem_t<FP32>* __restrict__ in, long total, int hw, int C,
+                               float* __restrict__ out) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % (C / 8));
+  const long n = idx / (C / 8);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = 0; p < hw; ++p) {
+    float v[8];
+    load8<FP32>(in + (n * hw + p) * C + c8 * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] += v[e];
+  }
+  const float d = static_cast<float>(hw);
+  float* o = out + n * C + c8 * 8;
+  *reinterpret_cast<float4*>(o) = make_float4(s[0] / d, s[1] / d, s[2] / d, s[3] / d);
+  *reinterpret_cast<float4*>(o + 4) = make_float4(s[4] / d, s[5] / d, s[6] / d, s[7] / d);
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// One warp per row of 768: 3 chunks of 8 elements per lane, statistics in fp32 with warp-shuffle reductions.
+template <bool FP32>
+__device__ __forceinline__ void ln_row_768(float (&x)[3][8], const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, float eps, elem_t<FP32>* __restrict__ y,
+                                           int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += x[c][e];
+  const float mean = warp_sum(s) * (1.0f / 768.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float d = x[c][e] - mean; q += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / 768.0f) + eps);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int col = c * 256 + lane * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = (x[c][e] - mean) * rstd * g[e] + b[e];
+    store8<FP32>(y + col, o);
+  }
+}
+
+template <bool FP32>
+__global__ void layernorm768_kernel(const elem_t<FP32>* __restrict__ x, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, elem_t<FP32>* __restrict__ y, int rows,
+                                    float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) load8<FP32>(x + row * 768L + c * 256 + lane * 8, v[c]);
+  ln_row_768<FP32>(v, gamma, beta, eps, y + row * 768L, lane);
+}
+
+// BertEmbeddings (modeling_bert.py:72-113): word[id] + position[pos] + token_type[0], LayerNorm(eps 1e-12)
+template <bool FP32>
+__global__ void bert_embed_ln_kernel(const int64_t* __restrict__ ids, int rows, int L,
+                                     const elem_t<FP32>* __restrict__ word, const elem_t<FP32>* __restrict__ pos,
+                                     const elem_t<FP32>* __restrict__ type, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, elem_t<FP32>* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long id = ids[row];
+  const int p = row % L;
+  float v[3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int col = c * 256 + lane * 8;
+    float a[8], b[8], t[8];
+    load8<FP32>(word + id * 768L + col, a);
+    load8<FP32>(pos + p * 768L + col, b);
+    load8<FP32>(type + col, t);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[c][e] = (a[e] + t[e]) + b[e];   // HF order: (inputs + token_type) + position
+  }
+  ln_row_768<FP32>(v, gamma, beta, 1e-12f, out + row * 768L, lane);
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// conv weight [Cout,Cin,k,k] fp32 + eval-mode BatchNorm -> [Cout][k][k][Cin] (scaled) and bias[Cout]
+template <bool FP32>
+__global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
+                                 const float* __restrict__ bn_b, const float* __restrict__ bn_mean,
+                                 const float* __restrict__ bn_var, float eps, int Cout, int Cin, int k,
+                                 elem_t<FP32>* __restrict__ w_out, float* __restrict__ bias_out) {
+  const long total = static_cast<long>(Cout) * Cin * k * k;
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int ci = static_cast<int>(idx % Cin);
+  const int kk = static_cast<int>((idx / Cin) % (k * k));
+  const int co = static_cast<int>(idx / (static_cast<long>(Cin) * k * k));
+  const float scale = bn_w[co] / sqrtf(bn_var[co] + eps);
+  const float v = w[(static_cast<long>(co) * Cin + ci) * k * k + kk] * scale;
+  if constexpr (FP32) w_out[idx] = v; else w_out[idx] = __float2bfloat16_rn(v);
+  if (ci == 0 && kk == 0) bias_out[co] = bn_b[co] - bn_mean[co] * scale;
+}
+
+// stem weight [64,3,7,7] -> [64][7][win][4], win = 16 (bf16) / 8 (fp32) pixels, zero for kw >= 7 or c == 3
+template <bool FP32>
+__global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
+                                 const float* __restrict__ bn_b, const float* __restrict__ bn_mean,
+                                 const float* __restrict__ bn_var, float eps, elem_t<FP32>* __restrict__ w_out,
+                                 float* __restrict__ bias_out) {
+  constexpr int win = FP32 ? 8 : 16;
+  const int total = 64 * 7 * win * 4;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = idx % 4;
+  const int kw = (idx / 4) % win;
+  const int kh = (idx / (4 * win)) % 7;
+  const int co = idx / (4 * win * 7);
+  const float scale = bn_w[co] / sqrtf(bn_var[co] + eps);
+  float v = 0.f;
+  if (c < 3 && kw < 7) v = w[((co * 3 + c) * 7 + kh) * 7 + kw] * scale;
+  if constexpr (FP32) w_out[idx] = v; else w_out[idx] = __float2bfloat16_rn(v);
+  if (idx % (7 * win * 4) == 0) bias_out[co] = bn_b[co] - bn_mean[co] * scale;
+}
+
+template <bool FP32>
+__global__ void convert_kernel(const float* __restrict__ in, elem_t<FP32>* __restrict__ out, long n) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= n) return;
+  if constexpr (FP32) out[idx] = in[idx]; else out[idx] = __float2bfloat16_rn(in[idx]);
+}
+template <bool FP32>
+__global__ void cast_to_f32_kernel(const elem_t<FP32>* __restrict__ in, float* __restrict__ out, long n) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= n) return;
+  if constexpr (FP32) out[idx] = in[idx]; else out[idx] = __bfloat162float(in[idx]);
+}
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y)
+    if (x < cols && y0 + j < rows) tile[j][threadIdx.x] = in[static_cast<long>(y0 + j) * cols + x];
+  __syncthreads();
+  const int ox = blockIdx.y * 32 + threadIdx.x;   // row index of input = col of output
+  const int oy0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y)
+    if (ox < rows && oy0 + j < cols) out[static_cast<long>(oy0 + j) * rows + ox] = tile[threadIdx.x][j];
+}
+
+inline unsigned blocks_for(long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+}  // namespace
+
+#define VCG_DISPATCH(fp32, ...)                 \
+  do {                                          \
+    if (fp32) { constexpr bool FP = true; __VA_ARGS__; } \
+    else { constexpr bool FP = false; __VA_ARGS__; }     \
+  } while (0)
+
+void launch_preprocess_u8(const uint8_t* frames, const int32_t* frame_index, int n, void* out, bool fp32,
+                          cudaStream_t s) {
+  const long total = static_cast<long>(n) * kImg * (kImg / 4);
+  if (total == 0) return;
+  VCG_DISPATCH(fp32, (preprocess_u8_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(
+                         frames, frame_index, nullptr, 1, total, static_cast<elem_t<FP>*>(out))));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_preprocess_u8_clips(const uint8_t* frames, const int32_t* clip_start, int B, int T, void* out, bool fp32,
+                                cudaStream_t s) {
+  const long total = static_cast<long>(B) * T * kImg * (kImg / 4);
+  if (total == 0) return;
+  VCG_DISPATCH(fp32, (preprocess_u8_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(
+                         frames, nullptr, clip_start, T, total, static_cast<elem_t<FP>*>(out))));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_nchw_to_stem(const float* img, int n, void* out, bool fp32, cudaStream_t s) {
+  const long total = static_cast<long>(n) * kImg * kImg;
+  if (total == 0) return;
+  VCG_DISPATCH(fp32, (nchw_to_stem_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(
+                         img, total, static_cast<elem_t<FP>*>(out))));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_maxpool_tsm(const void* in, int n, void* out, void* out_shifted, int T, int fold, bool fp32,
+                        cudaStream_t s) {
+  VCG_REQUIRE(out_shifted == nullptr || (fold % 8 == 0 && fold > 0), "TSM fold of the stem output must be a multiple of 8");
+  const long total = static_cast<long>(n) * 56 * 56 * 8;
+  if (total == 0) return;
+  VCG_DISPATCH(fp32, (maxpool_tsm_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(
+                         static_cast<const elem_t<FP>*>(in), total, static_cast<elem_t<FP>*>(out),
+                         static_cast<elem_t<FP>*>(out_shifted), T, fold)));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_avgpool(const void* in, int n, int hw, int C, float* out, cudaStream_t s, bool fp32) {
+  const long total = static_cast<long>(n) * (C / 8);
+  if (total == 0) return;
+  VCG_DISPATCH(fp32, (avgpool_kernel<FP><<<blocks_for(total, 128), 128, 0, s>>>(static_cast<const elem_t<FP>*>(in),
+                                                                                 total, hw, C, out)));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const void* word, const void* pos, const void* type,
+                          const float* gamma, const float* beta, void* out, bool fp32, cudaStream_t s) {
+  if (rows == 0) return;
+  VCG_DISPATCH(fp32, (bert_embed_ln_kernel<FP><<<blocks_for(rows, 8), 256, 0, s>>>(
+                         ids, rows, L, static_cast<const elem_t<FP>*>(word), static_cast<const elem_t<FP>*>(pos),
+                         static_cast<const elem_t<FP>*>(type), gamma, beta, static_cast<elem_t<FP>*>(out))));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_layernorm(const void* x, const float* gamma, const float* beta, void* y, int rows, int cols, float eps,
+                      bool fp32, cudaStream_t s) {
+  VCG_REQUIRE(cols == 768, "LayerNorm kernel is specialised for 768 columns");
+  if (rows == 0) return;
+  VCG_DISPATCH(fp32, (layernorm768_kernel<FP><<<blocks_for(rows, 8), 256, 0, s>>>(
+                         static_cast<const elem_t<FP>*>(x), gamma, beta, static_cast<elem_t<FP>*>(y), rows, eps)));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_pack_conv(const float* w, const float* bn_w, const float* bn_b, const float* bn_mean, const float* bn_var,
+                      float eps, int Cout, int Cin, int k, void* w_out, float* bias_out, bool fp32, cudaStream_t s) {
+  const long total = static_cast<long>(Cout) * Cin * k * k;
+  VCG_DISPATCH(fp32, (pack_conv_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(
+                         w, bn_w, bn_b, bn_mean, bn_var, eps, Cout, Cin, k, static_cast<elem_t<FP>*>(w_out),
+                         bias_out)));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_pack_stem(const float* w, const float* bn_w, const float* bn_b, const float* bn_mean, const float* bn_var,
+                      float eps, void* w_out, float* bias_out, bool fp32, cudaStream_t s) {
+  const int total = 64 * 7 * (fp32 ? 8 : 16) * 4;
+  VCG_DISPATCH(fp32, (pack_stem_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(
+                         w, bn_w, bn_b, bn_mean, bn_var, eps, static_cast<elem_t<FP>*>(w_out), bias_out)));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_convert(const float* in, void* out, long n, bool fp32, cudaStream_t s) {
+  if (n == 0) return;
+  VCG_DISPATCH(fp32, (convert_kernel<FP><<<blocks_for(n, 256), 256, 0, s>>>(in, static_cast<elem_t<FP>*>(out), n)));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_cast_to_f32(const void* in, float* out, long n, bool fp32, cudaStream_t s) {
+  if (n == 0) return;
+  VCG_DISPATCH(fp32, (cast_to_f32_kernel<FP><<<blocks_for(n, 256), 256, 0, s>>>(static_cast<const elem_t<FP>*>(in),
+                                                                                 out, n)));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t s) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, s>>>(in, out, rows, cols);
+  VCG_CUDA(cudaGetLastError());
+}
+
+}  // namespace vcg

@@ -1,0 +1,71 @@
+// Launchers of the memory-bound / small kernels around the tcgen05 GEMMs (definitions in kernels.cu, attention.cu,
+// tail.cu, pack.cu).  `fp32` selects the element type of activations: false = bf16, true = fp32.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace vcg {
+
+// geometry of the zero-padded NHWC4 stem input (pixel (0,0) of the buffer is input pixel (-3,-3))
+constexpr int kImg = 224;
+constexpr int kStemPad = 3;
+constexpr int kStemHp = 230;
+constexpr int kStemWp = 240;
+constexpr int kStemOut = 112;
+constexpr int kBertHidden = 768;
+constexpr int kBertHeads = 12;
+constexpr int kBertFfn = 3072;
+constexpr int kVisionDim = 2048;
+
+void launch_preprocess_u8(const uint8_t* frames, const int32_t* frame_index, int n, void* out, bool fp32,
+                          cudaStream_t s);
+// clip-structured gather: image i = (b, t) reads frame clip_start[b] + t
+void launch_preprocess_u8_clips(const uint8_t* frames, const int32_t* clip_start, int B, int T, void* out, bool fp32,
+                                cudaStream_t s);
+void launch_nchw_to_stem(const float* img, int n, void* out, bool fp32, cudaStream_t s);
+void launch_maxpool_tsm(const void* in, int n, void* out, void* out_shifted, int T, int fold, bool fp32,
+                        cudaStream_t s);
+void launch_avgpool(const void* in, int n, int hw, int C, float* out, cudaStream_t s, bool fp32);
+void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const void* word, const void* pos, const void* type,
+                          const float* gamma, const float* beta, void* out, bool fp32, cudaStream_t s);
+void launch_layernorm(const void* x, const float* gamma, const float* beta, void* y, int rows, int cols, float eps,
+                      bool fp32, cudaStream_t s);
+void launch_bert_attention(const void* qkv, const int64_t* mask, void* ctx, int B, int L, bool fp32, cudaStream_t s);
+
+struct TailParams {
+  // inputs
+  const void* hidden;      // final BERT hidden states [B*L, 768] (element type per `fp32`)
+  int L;
+  const float* vision;     // [B, T, 2048] fp32
+  int T, H;                // frames per clip, head hidden size (128)
+  int head_type;           // 0 mlp, 1 attn
+  // weights (fp32; *_t are transposed to [in][out])
+  const float* pool_w_t;   // [768][768]
+  const float* pool_b;     // [768]
+  const float* lang_w_t;   // [768][H]
+  const float* vis_w_t;    // [2048][H]
+  const float* head_w;     // mlp: [2][(T+1)*H]
+  const float* head_b;     // mlp: [2]
+  const float* q_w_t; const float* q_b;   // attn: [H][H], [H]
+  const float* k_w_t; const float* k_b;
+  const float* v_w_t; const float* v_b;
+  const float* proj_w; const float* proj_b;  // [2][H], [2]
+  // outputs
+  float* logits;           // [B,2]
+  float* probs;            // [B,2]
+  float* lang_emb;         // [B,768] or nullptr
+};
+void launch_tail(const TailParams& p, int B, bool fp32, cudaStream_t s);
+
+// weight packing (fp32 state-dict tensors -> kernel layouts)
+void launch_pack_conv(const float* w /*[Cout,Cin,k,k]*/, const float* bn_w, const float* bn_b, const float* bn_mean,
+                      const float* bn_var, float eps, int Cout, int Cin, int k, void* w_out /*[Cout][k][k][Cin]*/,
+                      float* bias_out, bool fp32, cudaStream_t s);
+void launch_pack_stem(const float* w /*[64,3,7,7]*/, const float* bn_w, const float* bn_b, const float* bn_mean,
+                      const float* bn_var, float eps, void* w_out /*[64][7][win][4]*/, float* bias_out, bool fp32,
+                      cudaStream_t s);
+void launch_convert(const float* in, void* out, long n, bool fp32, cudaStream_t s);       // fp32 -> T copy
+void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t s);    // [r][c] -> [c][r]
+void launch_cast_to_f32(const void* in, float* out, long n, bool fp32, cudaStream_t s);
+
+}  // namespace vcg

@@ -1,0 +1,92 @@
+"""ctypes binding of libvcg_b200.so (C ABI: include/vcg.h).
+
+The library is built in-tree (``csrc/Makefile`` -> ``lib/libvcg_b200.so``).  Loading it needs no GPU; every compute
+entry point needs a Blackwell GPU and fails loudly otherwise — there is no CPU or PyTorch fallback.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(PKG_ROOT, "lib", "libvcg_b200.so")
+CSRC_DIR = os.path.join(PKG_ROOT, "csrc")
+
+HEAD_MLP, HEAD_ATTN = 0, 1
+PREC_BF16, PREC_FP32 = 0, 1
+VISION_R50TSM, VISION_NONE = 0, 1
+DTYPE_F32, DTYPE_I64 = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
+
+
+class VcgConfig(ctypes.Structure):
+    _fields_ = [
+        ("clip_frames", ctypes.c_int32),
+        ("max_tokens", ctypes.c_int32),
+        ("hidden_size", ctypes.c_int32),
+        ("head_type", ctypes.c_int32),
+        ("precision", ctypes.c_int32),
+        ("vision", ctypes.c_int32),
+        ("max_batch", ctypes.c_int32),
+        ("shift_div", ctypes.c_int32),
+    ]
+
+
+_vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+
+# name -> (restype, argtypes); must list every symbol declared in include/vcg.h (checked by tests/test_abi.py)
+PROTOTYPES = {
+    "vcg_create": (ctypes.c_int, [ctypes.POINTER(VcgConfig), ctypes.POINTER(_vp)]),
+    "vcg_destroy": (None, [_vp]),
+    "vcg_last_error": (ctypes.c_char_p, []),
+    "vcg_version": (ctypes.c_char_p, []),
+    "vcg_load_tensor": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(_i64), _i32, _i32, _vp]),
+    "vcg_finalize": (ctypes.c_int, [_vp, _vp]),
+    "vcg_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "vcg_score_clips_u8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "vcg_score_clips_u8_host": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "vcg_launch_count": (_i64, [_vp]),
+    "vcg_op_preprocess_u8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),
+    "vcg_op_nchw_to_stem": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp]),
+    "vcg_op_gemm": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "vcg_op_conv2d_nhwc": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
+                                          _i32, _vp, _i32, _vp, _i32, _i32, _vp]),
+    "vcg_op_stem_conv": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "vcg_op_maxpool_tsm": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "vcg_op_bert_attention": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "vcg_op_layernorm": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _vp]),
+}
+
+_lib = None
+
+
+def build_library(force=False):
+    """Compile libvcg_b200.so for sm_100a with nvcc (no GPU needed)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.run(["make", "-C", CSRC_DIR, "-j8"], check=True)
+    return LIB_PATH
+
+
+def load_library():
+    """dlopen the library and attach prototypes.  Raises if it has not been built — never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `make -C {CSRC_DIR}` (or __graft_entry__.build()). "
+            "There is no fallback implementation.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status):
+    """Map a non-zero C status to RuntimeError carrying vcg_last_error()."""
+    if status != 0:
+        msg = load_library().vcg_last_error()
+        raise RuntimeError(msg.decode("utf-8", "replace") if msg else "vcg: unknown error")

@@ -1,0 +1,125 @@
+"""Torch-tensor front ends of the stand-alone C-ABI operators (vcg_op_*).
+
+torch is used for device memory and the current stream only; all arithmetic happens in libvcg_b200.so.
+Activation tensors are NHWC (channels-last, contiguous), bf16 (precision 0) or fp32 (precision 1).
+"""
+import torch
+
+from . import binding as _b
+
+STEM_HP, STEM_WP = 230, 240
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _prec(t):
+    if t.dtype == torch.bfloat16:
+        return _b.PREC_BF16
+    if t.dtype == torch.float32:
+        return _b.PREC_FP32
+    raise TypeError(f"unsupported activation dtype {t.dtype}")
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vcg_b200 operators need CUDA tensors: there is no CPU fallback")
+
+
+def gemm(a, w, bias=None, residual=None, act=_b.ACT_NONE, out=None):
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias (+ residual)).  a may be a strided row view (stride(1) == 1)."""
+    _need_cuda(a, w, bias, residual)
+    M, K = a.shape
+    N = w.shape[0]
+    assert a.stride(1) == 1 and w.is_contiguous() and w.shape[1] == K and w.dtype == a.dtype
+    if out is None:
+        out = torch.empty(M, N, dtype=a.dtype, device=a.device)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_gemm(a.data_ptr(), a.stride(0), w.data_ptr(), _ptr(bias), _ptr(residual),
+                             0 if residual is None else residual.stride(0), out.data_ptr(), out.stride(0), M, N, K,
+                             act, _prec(a), _stream()))
+    return out
+
+
+def conv2d_nhwc(x, w, bias=None, residual=None, stride=1, act=_b.ACT_NONE, tsm_in=None, tsm_out=None, tsm_fold=0,
+                clip_frames=1):
+    """x [n,H,W,Cin], w [Cout,k,k,Cin] -> [n,H/stride,W/stride,Cout]."""
+    _need_cuda(x, w, bias, residual, tsm_in, tsm_out)
+    n, H, W, Cin = x.shape
+    Cout, k = w.shape[0], w.shape[1]
+    assert x.is_contiguous() and w.is_contiguous() and w.dtype == x.dtype
+    out = torch.empty(n, H // stride, W // stride, Cout, dtype=x.dtype, device=x.device)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_conv2d_nhwc(x.data_ptr(), n, H, W, Cin, w.data_ptr(), _ptr(bias), _ptr(residual),
+                                    out.data_ptr(), Cout, k, stride, act, _prec(x), _ptr(tsm_in),
+                                    0 if tsm_in is None else tsm_in.shape[-1], _ptr(tsm_out), tsm_fold, clip_frames,
+                                    _stream()))
+    return out
+
+
+def preprocess_u8(frames, frame_index=None, dtype=torch.bfloat16):
+    """uint8 [n,224,224,3] -> normalised, zero-padded NHWC4 [n,230,240,4]."""
+    _need_cuda(frames, frame_index)
+    n = frames.shape[0] if frame_index is None else frame_index.shape[0]
+    out = torch.zeros(n, STEM_HP, STEM_WP, 4, dtype=dtype, device=frames.device)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_preprocess_u8(frames.data_ptr(), _ptr(frame_index), n, out.data_ptr(), _prec(out), _stream()))
+    return out
+
+
+def nchw_to_stem(img, dtype=torch.bfloat16):
+    """fp32 [n,3,224,224] (normalised) -> zero-padded NHWC4 [n,230,240,4]."""
+    _need_cuda(img)
+    n = img.shape[0]
+    out = torch.zeros(n, STEM_HP, STEM_WP, 4, dtype=dtype, device=img.device)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_nchw_to_stem(img.data_ptr(), n, out.data_ptr(), _prec(out), _stream()))
+    return out
+
+
+def stem_conv(x_padded, w_packed, bias):
+    """padded NHWC4 -> relu(conv7x7/2 + bias) as NHWC [n,112,112,64]; w_packed [64,7,win,4]."""
+    _need_cuda(x_padded, w_packed, bias)
+    n = x_padded.shape[0]
+    out = torch.empty(n, 112, 112, 64, dtype=x_padded.dtype, device=x_padded.device)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_stem_conv(x_padded.data_ptr(), n, w_packed.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                  _prec(x_padded), _stream()))
+    return out
+
+
+def maxpool_tsm(x, clip_frames, shift_div=8):
+    """[n,112,112,64] -> (pooled [n,56,56,64], temporally shifted copy [n,56,56,64])."""
+    _need_cuda(x)
+    n = x.shape[0]
+    out = torch.empty(n, 56, 56, 64, dtype=x.dtype, device=x.device)
+    shifted = torch.zeros_like(out)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_maxpool_tsm(x.data_ptr(), n, out.data_ptr(), shifted.data_ptr(), clip_frames, shift_div,
+                                    _prec(x), _stream()))
+    return out, shifted
+
+
+def bert_attention(qkv, attention_mask, B, L):
+    """qkv [B*L, 2304], attention_mask int64 [B,L] -> ctx [B*L, 768]."""
+    _need_cuda(qkv, attention_mask)
+    ctx = torch.empty(B * L, 768, dtype=qkv.dtype, device=qkv.device)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_bert_attention(qkv.data_ptr(), attention_mask.data_ptr(), ctx.data_ptr(), B, L, _prec(qkv),
+                                       _stream()))
+    return ctx
+
+
+def layernorm(x, gamma, beta, eps=1e-12):
+    _need_cuda(x, gamma, beta)
+    y = torch.empty_like(x)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), x.shape[0],
+                                  x.shape[1], eps, _prec(x), _stream()))
+    return y
