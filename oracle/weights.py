@@ -1,0 +1,147 @@
+"""TEST INFRASTRUCTURE — deterministic random weights and synthetic inputs for the chapter-boundary scorer.
+
+The reference ships no checkpoint and there is no network, so parity runs on random-init weights.  This module builds
+a state dict with exactly the key schema and shapes of the reference's ``TwoStream.state_dict()``
+(video_chapter_generation/model/fusion/two_stream.py:99-124 wiring ``BertModel`` + torchvision ResNet-50 with
+``TemporalShift`` wrappers (ops/temporal_shift.py:138 -> ``conv1.net.weight``) + ``ChapterHead``), from a seeded CPU
+generator, so the same tensors can be regenerated on any machine with the same torch build instead of committing
+533 MB of weights.  ``oracle/make_golden.py`` loads this dict into the unmodified reference with
+``load_state_dict(strict=True)``, which is what pins the schema.
+
+BatchNorm statistics/affine and LayerNorm affine are randomised so that activations stay O(1) through
+the 16 residual blocks and every parameter influences the output.
+
+Only tests/, bench.py's cpu_baseline / --impl reference legs and __graft_entry__.smoke() may import this package.
+"""
+import math
+
+import torch
+
+BERT_HIDDEN = 768
+BERT_FFN = 3072
+VOCAB = 30522
+MAX_POS = 512
+
+
+def _gen(seed):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+def make_state_dict(clip_frames=16, head_type="mlp", hidden_size=128, seed=123, bert_layers=12, tsm=True,
+                    include_vision=True):
+    """Returns an OrderedDict-like dict of fp32 CPU tensors keyed like the reference TwoStream.state_dict()."""
+    g = _gen(seed)
+    sd = {}
+
+    def normal(shape, std):
+        return torch.randn(shape, generator=g) * std
+
+    def uniform(shape, lo, hi):
+        return torch.rand(shape, generator=g) * (hi - lo) + lo
+
+    # ---------------- text stream: transformers BertModel (bert-base-uncased geometry)
+    lm = "lang_model."
+    sd[lm + "embeddings.word_embeddings.weight"] = normal((VOCAB, BERT_HIDDEN), 0.02)
+    sd[lm + "embeddings.position_embeddings.weight"] = normal((MAX_POS, BERT_HIDDEN), 0.02)
+    sd[lm + "embeddings.token_type_embeddings.weight"] = normal((2, BERT_HIDDEN), 0.02)
+    sd[lm + "embeddings.LayerNorm.weight"] = uniform((BERT_HIDDEN,), 0.8, 1.2)
+    sd[lm + "embeddings.LayerNorm.bias"] = normal((BERT_HIDDEN,), 0.05)
+    for i in range(bert_layers):
+        p = f"{lm}encoder.layer.{i}."
+        for name in ("query", "key", "value"):
+            # std 0.05 (not 0.02) so that attention is not uniform and the softmax path is really exercised
+            sd[p + f"attention.self.{name}.weight"] = normal((BERT_HIDDEN, BERT_HIDDEN), 0.05)
+            sd[p + f"attention.self.{name}.bias"] = normal((BERT_HIDDEN,), 0.02)
+        sd[p + "attention.output.dense.weight"] = normal((BERT_HIDDEN, BERT_HIDDEN), 0.02)
+        sd[p + "attention.output.dense.bias"] = normal((BERT_HIDDEN,), 0.02)
+        sd[p + "attention.output.LayerNorm.weight"] = uniform((BERT_HIDDEN,), 0.8, 1.2)
+        sd[p + "attention.output.LayerNorm.bias"] = normal((BERT_HIDDEN,), 0.05)
+        sd[p + "intermediate.dense.weight"] = normal((BERT_FFN, BERT_HIDDEN), 0.02)
+        sd[p + "intermediate.dense.bias"] = normal((BERT_FFN,), 0.02)
+        sd[p + "output.dense.weight"] = normal((BERT_HIDDEN, BERT_FFN), 0.02)
+        sd[p + "output.dense.bias"] = normal((BERT_HIDDEN,), 0.02)
+        sd[p + "output.LayerNorm.weight"] = uniform((BERT_HIDDEN,), 0.8, 1.2)
+        sd[p + "output.LayerNorm.bias"] = normal((BERT_HIDDEN,), 0.05)
+    sd[lm + "pooler.dense.weight"] = normal((BERT_HIDDEN, BERT_HIDDEN), 0.02)
+    sd[lm + "pooler.dense.bias"] = normal((BERT_HIDDEN,), 0.02)
+
+    # ---------------- vision stream: torchvision resnet50 (v1.5), fc = Identity, TemporalShift on every conv1
+    if include_vision:
+        vm = "vision_model."
+
+        def conv(key, cout, cin, k):
+            sd[key] = normal((cout, cin, k, k), math.sqrt(2.0 / (cout * k * k)))   # kaiming_normal_(fan_out, relu)
+
+        def bn(prefix, c, last=False):
+            # the last BN of a block gets a smaller gain so the residual sum does not blow up over 16 blocks
+            sd[prefix + ".weight"] = uniform((c,), 0.2, 0.6) if last else uniform((c,), 0.5, 1.5)
+            sd[prefix + ".bias"] = normal((c,), 0.1)
+            sd[prefix + ".running_mean"] = normal((c,), 0.1)
+            sd[prefix + ".running_var"] = uniform((c,), 0.5, 1.5)
+            sd[prefix + ".num_batches_tracked"] = torch.tensor(100, dtype=torch.long)
+
+        conv(vm + "conv1.weight", 64, 3, 7)
+        bn(vm + "bn1", 64)
+        inplanes = 64
+        for stage, (blocks, planes) in enumerate(zip((3, 4, 6, 3), (64, 128, 256, 512)), start=1):
+            for i in range(blocks):
+                p = f"{vm}layer{stage}.{i}."
+                conv(p + ("conv1.net.weight" if tsm else "conv1.weight"), planes, inplanes, 1)
+                bn(p + "bn1", planes)
+                conv(p + "conv2.weight", planes, planes, 3)
+                bn(p + "bn2", planes)
+                conv(p + "conv3.weight", planes * 4, planes, 1)
+                bn(p + "bn3", planes * 4, last=True)
+                if i == 0:
+                    conv(p + "downsample.0.weight", planes * 4, inplanes, 1)
+                    bn(p + "downsample.1", planes * 4)
+                inplanes = planes * 4
+
+    # ---------------- fusion head (two_stream.py:51-68)
+    fh = "fusion_head."
+
+    def linear_w(out_f, in_f):
+        b = 1.0 / math.sqrt(in_f)
+        return uniform((out_f, in_f), -b, b)
+
+    sd[fh + "lang_proj_head.weight"] = linear_w(hidden_size, BERT_HIDDEN)
+    sd[fh + "vision_proj_head.weight"] = linear_w(hidden_size, 2048)
+    if head_type == "mlp":
+        n_in = (clip_frames + 1) * hidden_size
+        sd[fh + "head.weight"] = linear_w(2, n_in)
+        sd[fh + "head.bias"] = uniform((2,), -1.0 / math.sqrt(n_in), 1.0 / math.sqrt(n_in))
+    elif head_type == "attn":
+        for name in ("key", "query", "value"):
+            sd[fh + f"head.{name}.weight"] = linear_w(hidden_size, hidden_size)
+            sd[fh + f"head.{name}.bias"] = uniform((hidden_size,), -0.08, 0.08)
+        sd[fh + "head.proj.weight"] = linear_w(2, hidden_size)
+        sd[fh + "head.proj.bias"] = uniform((2,), -0.08, 0.08)
+    else:
+        raise RuntimeError(f"Unknown head_type {head_type}")
+    return sd
+
+
+def make_text(batch, max_len, seed=123):
+    """Synthetic token ids / attention mask: [CLS]=101 first, len ~ U{10..L}, pad id 0."""
+    g = _gen(seed + 1)
+    lo = min(10, max_len)
+    lens = torch.randint(lo, max_len + 1, (batch,), generator=g)
+    ids = torch.randint(1000, VOCAB, (batch, max_len), generator=g)
+    ids[:, 0] = 101
+    ar = torch.arange(max_len)[None, :]
+    mask = (ar < lens[:, None]).long()
+    ids = ids * mask
+    return ids, mask
+
+
+def make_frames_u8(n_frames, seed=123):
+    """uint8 HWC frames [n,224,224,3], uniform in [0,255]."""
+    g = _gen(seed + 2)
+    return torch.randint(0, 256, (n_frames, 224, 224, 3), generator=g, dtype=torch.uint8)
+
+
+def clip_starts(n_frames, clip_frames, stride=4):
+    """Candidate clips of a video: range(0, n_frames - T, stride) (infer_youtube_video_dataset.py:117)."""
+    return list(range(0, n_frames - clip_frames, stride))

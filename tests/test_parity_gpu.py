@@ -1,0 +1,119 @@
+"""GPU parity tests proper: the CUDA path (through the reference-facing TwoStream API and the C ABI underneath)
+against the reference's own outputs (tests/golden/*.npz, produced by oracle/make_golden.py from the unmodified
+reference) and against the oracle restatement on fresh inputs.
+
+Tolerances (BASELINE.json north_star): logits within 1e-4 relative (max|delta| / max|ref|) in fp32 mode, 2e-2 in
+bf16 mode; predicted labels / cut points identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def build_model(T, head_type, precision, sd=None, vision=True, chunk=None):
+    from model.fusion import two_stream
+    from model.lang import bert_hugface
+    from model.vision import resnet50_tsm
+    from ops.basic_ops import Identity
+    from oracle import weights as W
+    if sd is None:
+        sd = W.make_state_dict(T, head_type, seed=123)
+    lang = bert_hugface.BertHugface(pretrain_stage=False)
+    if vision:
+        vis = resnet50_tsm.Resnet50TSM(segments_size=T, shift_div=8, pretrain_stage=False)
+        model = two_stream.TwoStream(lang.base_model, vis.base_model, lang.embed_size, vis.feature_dim, T, 128)
+    else:
+        model = two_stream.TwoStream(lang.base_model, Identity(), lang.embed_size, 2048, T, 128)
+        sd = {k: v for k, v in sd.items() if not k.startswith("vision_model.")}
+    model.build_chapter_head(output_size=2, head_type=head_type)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(0).eval()
+    model.precision = precision
+    if chunk:
+        model.vision_chunk = chunk
+    return model, sd
+
+
+def golden_inputs(g):
+    from oracle import two_stream_oracle as orc
+    from oracle import weights as W
+    T, L, B, seed = [int(x) for x in g["meta"][:4]]
+    ids, mask = W.make_text(B, L, seed=seed)
+    assert np.array_equal(ids.numpy(), g["text_ids"]) and np.array_equal(mask.numpy(), g["attention_mask"])
+    starts = [int(s) for s in g["clip_starts"]]
+    frames = W.make_frames_u8(4 * (B - 1) + T, seed=seed)
+    img = orc.gather_clips(orc.preprocess_u8(frames), starts, T)
+    return T, L, B, ids, mask, frames, starts, img
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case,head", [("mlp_T16_L100_B2", "mlp"), ("attn_T8_L32_B2", "attn")])
+def test_forward_matches_reference_golden(golden_dir, case, head, precision):
+    g = np.load(f"{golden_dir}/two_stream_{case}.npz")
+    T, L, B, ids, mask, frames, starts, img = golden_inputs(g)
+    model, _ = build_model(T, head, precision)
+    logits, probs, vis, lang = model(img.cuda(), ids.cuda(), mask.cuda(), return_emb=True)
+    torch.cuda.synchronize()
+    tol = TOL[precision]
+    errs = {"lang_emb": rel(lang, torch.from_numpy(g["lang_emb"])),
+            "vision_emb": rel(vis, torch.from_numpy(g["vision_emb"])),
+            "logits": rel(logits, torch.from_numpy(g["logits"])),
+            "probs": rel(probs, torch.from_numpy(g["probs"]))}
+    print(case, precision, errs)
+    assert errs["logits"] <= tol, errs
+    assert errs["lang_emb"] <= tol and errs["vision_emb"] <= tol and errs["probs"] <= tol, errs
+    assert logits.topk(1, 1, True, True)[1].view(-1).tolist() == g["labels"].tolist()
+    # the 2-tuple form and the engine launch counter
+    l2, p2 = model(img.cuda(), ids.cuda(), mask.cuda())
+    assert torch.equal(l2, logits) and torch.equal(p2, probs)
+    assert model.engine.launch_count > 0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_precomputed_vision_embeddings(golden_dir, precision):
+    """BASELINE.json config 2: Identity vision model fed [B,T,2048,1,1] embeddings."""
+    g = np.load(f"{golden_dir}/two_stream_mlp_T16_L100_B2.npz")
+    T, L, B, ids, mask, *_ = golden_inputs(g)
+    model, _ = build_model(T, "mlp", precision, vision=False)
+    emb = torch.from_numpy(g["vision_emb"]).cuda().view(B, T, 2048, 1, 1)
+    logits, probs = model(emb, ids.cuda(), mask.cuda())
+    assert rel(logits, torch.from_numpy(g["logits"])) <= TOL[precision]
+
+
+def test_u8_pipeline_and_chunking_match_oracle():
+    """uint8 frames -> preprocess -> scorer on device (ragged batch, several internal passes) vs the CPU oracle;
+    the host-buffer entry point must give bit-identical results to the device-buffer one."""
+    from oracle import two_stream_oracle as orc
+    from oracle import weights as W
+    T, L, B = 8, 40, 5
+    model, sd = build_model(T, "mlp", "fp32", chunk=2)
+    frames = W.make_frames_u8(4 * (B - 1) + T, seed=7)
+    starts = [4 * b for b in range(B)]
+    ids, mask = W.make_text(B, L, seed=7)
+    img = orc.gather_clips(orc.preprocess_u8(frames), starts, T)
+    ref_logits, ref_probs, _, _ = orc.two_stream_forward(sd, img, ids, mask, T)
+    model(img[:1].cuda(), ids[:1].cuda(), mask[:1].cuda())     # creates the engine
+    eng = model.engine
+    lg, pr = eng.score_clips_u8(frames.cuda(), torch.tensor(starts, dtype=torch.int32).cuda(), ids.cuda(), mask.cuda())
+    assert rel(lg, ref_logits) <= TOL["fp32"], (lg, ref_logits)
+    assert orc.predict_labels(lg.cpu()) == orc.predict_labels(ref_logits)
+    lg2, pr2 = model(img.cuda(), ids.cuda(), mask.cuda())
+    assert rel(lg2, ref_logits) <= TOL["fp32"]
+    lh, ph = eng.score_clips_u8_host(frames.pin_memory(), torch.tensor(starts, dtype=torch.int32).pin_memory(),
+                                     ids.pin_memory(), mask.pin_memory())
+    assert torch.equal(lh, lg.cpu()) and torch.equal(ph, pr.cpu())
+
+
+def test_no_cpu_fallback():
+    model, _ = build_model(8, "mlp", "bf16")
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 8, 3, 224, 224), torch.zeros(1, 16, dtype=torch.long), torch.ones(1, 16, dtype=torch.long))

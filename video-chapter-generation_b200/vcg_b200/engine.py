@@ -1,0 +1,152 @@
+"""Engine: Python handle on a ``vcg_engine`` (include/vcg.h).
+
+Takes a reference-schema state dict whose tensors live on the GPU, hands every entry to
+``vcg_load_tensor`` and finalises (BatchNorm folding / repacking happen inside the library).  torch is used only to
+own device memory and to name the current stream.
+"""
+import ctypes
+
+import torch
+
+from . import binding as _b
+
+_HEADS = {"mlp": _b.HEAD_MLP, "attn": _b.HEAD_ATTN}
+_PRECS = {"bf16": _b.PREC_BF16, "fp32": _b.PREC_FP32}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Engine:
+    def __init__(self, clip_frames, head_type="mlp", precision="bf16", vision=True, max_tokens=128, max_batch=32,
+                 hidden_size=128, shift_div=8, device=None):
+        if head_type not in _HEADS:
+            raise RuntimeError(f"Unknown head_type {head_type}")
+        if precision not in _PRECS:
+            raise RuntimeError(f"Unknown precision {precision}")
+        if not torch.cuda.is_available():
+            raise RuntimeError("vcg_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.clip_frames, self.head_type, self.precision = clip_frames, head_type, precision
+        self.vision, self.max_tokens, self.max_batch = vision, max_tokens, max_batch
+        self._lib = _b.load_library()
+        cfg = _b.VcgConfig(clip_frames, max_tokens, hidden_size, _HEADS[head_type], _PRECS[precision],
+                           _b.VISION_R50TSM if vision else _b.VISION_NONE, max_batch, shift_div)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _b.check(self._lib.vcg_create(ctypes.byref(cfg), ctypes.byref(handle)))
+        self._h = handle
+        self._keep = []   # pinned staging tensors etc.
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vcg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict):
+        """state_dict: reference key schema; CPU tensors are moved to the GPU one at a time."""
+        with torch.cuda.device(self.device):
+            for key, t in state_dict.items():
+                if not (key.startswith("lang_model.") or key.startswith("fusion_head.") or
+                        (self.vision and key.startswith("vision_model."))):
+                    continue
+                if key.endswith("num_batches_tracked"):
+                    continue
+                t = t.detach()
+                if t.dtype != torch.float32:
+                    t = t.float()
+                t = t.to(self.device, non_blocking=False).contiguous()
+                shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+                _b.check(self._lib.vcg_load_tensor(self._h, key.encode(), t.data_ptr(), shape, t.dim(),
+                                                   _b.DTYPE_F32, _stream()))
+                torch.cuda.current_stream().synchronize()   # `t` may be a temporary
+            _b.check(self._lib.vcg_finalize(self._h, _stream()))
+
+    # ------------------------------------------------------------------ scoring
+    def _text(self, text_ids, attention_mask):
+        if not (text_ids.is_cuda and attention_mask.is_cuda):
+            raise RuntimeError("vcg_b200: inputs must be CUDA tensors (no CPU fallback)")
+        ids = text_ids.long().contiguous()
+        mask = attention_mask.long().contiguous()
+        B, L = ids.shape
+        if L > self.max_tokens:
+            raise RuntimeError(f"vcg_b200: {L} tokens exceed the engine's max_tokens={self.max_tokens}")
+        return ids, mask, B, L
+
+    def forward(self, img_clip, text_ids, attention_mask, return_emb=False, vision_emb=None):
+        """TwoStream.forward: img_clip [B,T,3,224,224] fp32 (normalised) or vision_emb [B,T,2048] fp32."""
+        ids, mask, B, L = self._text(text_ids, attention_mask)
+        dev = ids.device
+        logits = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        probs = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        ve = le = None
+        img_ptr = emb_ptr = 0
+        if vision_emb is not None:
+            vision_emb = vision_emb.float().contiguous().view(B, self.clip_frames, 2048)
+            emb_ptr = vision_emb.data_ptr()
+        else:
+            if not img_clip.is_cuda:
+                raise RuntimeError("vcg_b200: inputs must be CUDA tensors (no CPU fallback)")
+            img_clip = img_clip.float().contiguous()
+            if tuple(img_clip.shape[1:]) != (self.clip_frames, 3, 224, 224):
+                raise RuntimeError(f"vcg_b200: img_clip must be [B,{self.clip_frames},3,224,224], got {tuple(img_clip.shape)}")
+            img_ptr = img_clip.data_ptr()
+        if return_emb:
+            ve = torch.empty(B, self.clip_frames, 2048, dtype=torch.float32, device=dev)
+            le = torch.empty(B, 768, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _b.check(self._lib.vcg_forward(self._h, img_ptr, emb_ptr, ids.data_ptr(), mask.data_ptr(), B, L,
+                                           logits.data_ptr(), probs.data_ptr(), 0 if ve is None else ve.data_ptr(),
+                                           0 if le is None else le.data_ptr(), _stream()))
+        if return_emb:
+            return logits, probs, ve, le
+        return logits, probs
+
+    def score_clips_u8(self, frames_u8, clip_start, text_ids, attention_mask, out=None):
+        """Device-resident uint8 HWC frames [n,224,224,3] + int32 clip starts [B] -> (logits, probs)."""
+        ids, mask, B, L = self._text(text_ids, attention_mask)
+        assert frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+        clip_start = clip_start.to(torch.int32).contiguous()
+        assert clip_start.is_cuda and clip_start.numel() == B
+        dev = ids.device
+        if out is None:
+            logits = torch.empty(B, 2, dtype=torch.float32, device=dev)
+            probs = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        else:
+            logits, probs = out
+        with torch.cuda.device(dev):
+            _b.check(self._lib.vcg_score_clips_u8(self._h, frames_u8.data_ptr(), frames_u8.shape[0],
+                                                  clip_start.data_ptr(), ids.data_ptr(), mask.data_ptr(), B, L,
+                                                  logits.data_ptr(), probs.data_ptr(), _stream()))
+        return logits, probs
+
+    def score_clips_u8_host(self, frames_u8, clip_start, text_ids, attention_mask, out=None):
+        """HOST tensors in (pinned for full speed), host tensors out; H2D/D2H copies happen inside the call."""
+        for t in (frames_u8, clip_start, text_ids, attention_mask):
+            assert not t.is_cuda and t.is_contiguous()
+        assert frames_u8.dtype == torch.uint8 and clip_start.dtype == torch.int32
+        assert text_ids.dtype == torch.int64 and attention_mask.dtype == torch.int64
+        B, L = text_ids.shape
+        if out is None:
+            logits = torch.empty(B, 2, dtype=torch.float32).pin_memory()
+            probs = torch.empty(B, 2, dtype=torch.float32).pin_memory()
+        else:
+            logits, probs = out
+        with torch.cuda.device(self.device):
+            _b.check(self._lib.vcg_score_clips_u8_host(self._h, frames_u8.data_ptr(), frames_u8.shape[0],
+                                                       clip_start.data_ptr(), text_ids.data_ptr(),
+                                                       attention_mask.data_ptr(), B, L, logits.data_ptr(),
+                                                       probs.data_ptr(), _stream()))
+        return logits, probs
+
+    @property
+    def launch_count(self):
+        return int(self._lib.vcg_launch_count(self._h))
