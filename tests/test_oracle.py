@@ -1,0 +1,73 @@
+"""The oracle (test infrastructure) against the committed golden vectors, which oracle/make_golden.py produced by
+running the UNMODIFIED reference in the build container.  Runs on CPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import two_stream_oracle as orc
+from oracle import weights as W
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+@pytest.fixture(scope="module")
+def golden_attn(golden_dir):
+    return np.load(f"{golden_dir}/two_stream_attn_T8_L32_B2.npz")
+
+
+def test_oracle_reproduces_reference_outputs(golden_attn):
+    g = golden_attn
+    T, L, B, seed = [int(x) for x in g["meta"][:4]]
+    sd = W.make_state_dict(T, "attn", seed=seed)
+    ids, mask = W.make_text(B, L, seed=seed)
+    assert np.array_equal(ids.numpy(), g["text_ids"])
+    frames = W.make_frames_u8(4 * (B - 1) + T, seed=seed)
+    img = orc.gather_clips(orc.preprocess_u8(frames), [int(s) for s in g["clip_starts"]], T)
+    taps = {}
+    with torch.no_grad():
+        logits, probs, vis, lang = orc.two_stream_forward(sd, img, ids, mask, T, 128, "attn", 8, taps=taps)
+    assert rel(logits, torch.from_numpy(g["logits"])) <= 1e-5
+    assert rel(probs, torch.from_numpy(g["probs"])) <= 1e-5
+    assert rel(vis, torch.from_numpy(g["vision_emb"])) <= 1e-5
+    assert rel(lang, torch.from_numpy(g["lang_emb"])) <= 1e-5
+    assert orc.predict_labels(logits) == g["labels"].tolist()
+    for k, v in taps.items():
+        ref = g["tap/" + k]
+        t = v.float().reshape(-1)
+        got = np.array([t.mean().item(), t.abs().mean().item(), t.abs().max().item(),
+                        t.double().pow(2).sum().sqrt().item()])
+        assert np.allclose(got, ref, rtol=1e-4, atol=1e-6), (k, got, ref)
+
+
+def test_cut_points_known_answers(golden_dir):
+    g = np.load(f"{golden_dir}/cut_points.npz", allow_pickle=True)
+    for labels, T, cuts in zip(g["labels"], g["T"], g["cuts"]):
+        assert orc.convert_clip_label2cut_point(list(labels), int(T), 2) == list(cuts)
+    vec = [1, 0, 0, 0, 1, 1, 0, 0, 1, 1, 1, 1, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]
+    assert orc.convert_clip_label2cut_point(vec, 8, 2) == [4, 22, 44, 60]
+    assert orc.convert_clip_label2cut_point(vec, 16, 2) == [8, 26, 48, 64]
+    assert orc.convert_clip_label2cut_point(vec, 32, 2) == [16, 34, 56, 72]
+    assert orc.convert_clip_label2cut_point([0, 1, 1], 16, 2) == []
+    assert orc.calculate_pr([10, 50, 100], [10, 52, 96, 200]) == tuple(g["pr"])
+    with pytest.raises(ZeroDivisionError):
+        orc.calculate_pr([], [1])
+
+
+def test_temporal_shift_restatement():
+    x = torch.arange(2 * 4 * 16 * 1 * 1, dtype=torch.float32).view(8, 16, 1, 1)
+    y = orc.temporal_shift(x, 4, 8).view(2, 4, 16)
+    xv = x.view(2, 4, 16)
+    assert torch.equal(y[:, :-1, :2], xv[:, 1:, :2]) and torch.all(y[:, -1, :2] == 0)
+    assert torch.equal(y[:, 1:, 2:4], xv[:, :-1, 2:4]) and torch.all(y[:, 0, 2:4] == 0)
+    assert torch.equal(y[:, :, 4:], xv[:, :, 4:])
+
+
+def test_preprocess_matches_totensor_normalize():
+    frames = W.make_frames_u8(2, seed=5)
+    x = orc.preprocess_u8(frames)
+    assert x.shape == (2, 3, 224, 224)
+    f = frames[1, 10, 20].float() / 255.0
+    exp = (f - torch.tensor(orc.IMAGENET_MEAN)) / torch.tensor(orc.IMAGENET_STD)
+    assert torch.allclose(x[1, :, 10, 20], exp, atol=1e-6)

@@ -63,8 +63,13 @@ struct ConvGemmCfg {
   static constexpr int kBBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = (kABytes + kBBytes) * (TF32X3 ? 2 : 1);
   static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-  static constexpr int kTmemCols = 2 * BLOCK_N <= 32 ? 32 : 2 * BLOCK_N <= 64 ? 64 : 2 * BLOCK_N <= 128 ? 128
-                                   : 2 * BLOCK_N <= 256 ? 256 : 512;
+  // bf16: two accumulators (tile i+1 accumulates while tile i drains).  TF32x3: the tensor core truncates on every
+  // accumulate, so long fp32 sums pick up a bias ~ (#MMAs) * ulp/2; the 512 TMEM columns are used as 512/BLOCK_N
+  // partial accumulators instead (number 0 takes the small lo*hi + hi*lo terms, the others take hi*hi round-robin
+  // over K blocks) and the epilogue adds them with round-to-nearest fp32 adds.
+  static constexpr int kNumAcc = TF32X3 ? 512 / BLOCK_N : 2;
+  static constexpr int kTmemCols = TF32X3 ? 512 : (2 * BLOCK_N <= 32 ? 32 : 2 * BLOCK_N <= 64 ? 64 : 2 * BLOCK_N <= 128 ? 128
+                                   : 2 * BLOCK_N <= 256 ? 256 : 512);
   static constexpr int kThreads = TF32X3 ? 512 : 384;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -162,8 +167,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        const int acc = TF32X3 ? 0 : (it & 1);
+        mbar_wait(&tmem_empty[acc], (TF32X3 ? (it & 1) : ((it >> 1) & 1)) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -178,9 +183,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             if constexpr (TF32X3) {
               const uint64_t da_lo = umma_desc_sw128(smem_u32(sA_lo + stage * Cfg::kABytes) + k * 32);
               const uint64_t db_lo = umma_desc_sw128(smem_u32(sB_lo + stage * Cfg::kBBytes) + k * 32);
-              umma_tf32(d_tmem, da_lo, db, idesc, (kb | k) != 0);   // small terms first
-              umma_tf32(d_tmem, da, db_lo, idesc, 1);
-              umma_tf32(d_tmem, da, db, idesc, 1);
+              constexpr int kHiAcc = Cfg::kNumAcc - 1;
+              const uint32_t d_hi = tmem_base + (1 + kb % kHiAcc) * BLOCK_N;
+              umma_tf32(tmem_base, da_lo, db, idesc, (kb | k) != 0);      // accumulator 0: correction terms
+              umma_tf32(tmem_base, da, db_lo, idesc, 1);
+              umma_tf32(d_hi, da, db, idesc, (kb >= kHiAcc) || (k != 0));  // hi*hi partial sums
             } else {
               umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
             }
@@ -212,21 +219,40 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int w = iw * p.bw + dw, h = ih * p.bh + dh, n = in * p.nf + dn;
       const bool row_ok = (dn < p.nf) && (w < p.Wo) && (h < p.Ho) && (n < p.Nimg);
       const long grow = (static_cast<long>(n) * p.Ho + h) * p.Wo + w;
-      const int acc = it & 1;
-      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      const int acc = TF32X3 ? 0 : (it & 1);
+      mbar_wait(&tmem_full[acc], TF32X3 ? (it & 1) : ((it >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
       for (int chunk = half; chunk < BLOCK_N / 32; chunk += 2) {
         uint32_t r[32];
-        tmem_ld_32x32(taddr + chunk * 32, r);
-        tmem_ld_wait();
+        float v[32];
+        if constexpr (TF32X3) {
+          // sum the hi*hi partial accumulators (round-to-nearest adds), then the correction accumulator
+          const int n_hi = min(Cfg::kNumAcc - 1, num_kb);
+          tmem_ld_32x32(taddr + BLOCK_N + chunk * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          for (int a = 2; a <= n_hi; ++a) {
+            tmem_ld_32x32(taddr + a * BLOCK_N + chunk * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+          }
+          tmem_ld_32x32(taddr + chunk * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+        } else {
+          tmem_ld_32x32(taddr + chunk * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
         const int col0 = n_blk * BLOCK_N + chunk * 32;
         if (row_ok && col0 < p.N) {
           const int ncols = min(32, p.N - col0);   // multiple of 8 by contract
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
