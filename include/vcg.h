@@ -87,6 +87,26 @@ VCG_API int vcg_score_clips_u8_host(vcg_engine* e, const uint8_t* frames_u8_host
                             const int64_t* attention_mask_host, int32_t B, int32_t L, float* logits_host,
                             float* probs_host, void* stream);
 
+/* TwoStream.forward with HOST buffers (pinned for full speed): img_clip_host [B,T,3,224,224] fp32 or, when it is
+ * NULL, vision_emb_host [B,T,2048] fp32; ids / mask [B,L] int64; results land in logits_host / probs_host [B,2].
+ * All host<->device copies are issued inside the call, which returns once the results are on the host. */
+VCG_API int vcg_forward_host(vcg_engine* e, const float* img_clip_host, const float* vision_emb_host,
+                     const int64_t* text_ids_host, const int64_t* attention_mask_host, int32_t B, int32_t L,
+                     float* logits_host, float* probs_host, void* stream);
+
+/* Per-kernel CUDA-event profile (bench.py's roofline): between begin and end every launch is bracketed by events
+ * on the launching stream; end synchronises and returns one entry per "<kernel>|<layer>" name with the summed
+ * device time and the algorithmic FLOPs / bytes of those launches. */
+typedef struct vcg_profile_entry {
+  char name[64];
+  int64_t launches;
+  double ms;
+  double flops;
+  double bytes;
+} vcg_profile_entry;
+VCG_API int vcg_profile_begin(vcg_engine* e);
+VCG_API int vcg_profile_end(vcg_engine* e, void* stream, vcg_profile_entry* out, int32_t max_entries, int32_t* n_out);
+
 /* Number of kernel launches issued by this engine since creation (bench.py's gpu_launches). */
 VCG_API int64_t vcg_launch_count(const vcg_engine* e);
 

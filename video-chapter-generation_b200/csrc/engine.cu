@@ -93,6 +93,13 @@ struct Step {
   int n = 0, a = 0, c = 0;
 };
 
+// CUDA-event profile of one launch (collected between vcg_profile_begin / vcg_profile_end)
+struct ProfRec {
+  std::string name;     // "<kernel>|<layer>"
+  double flops = 0, bytes = 0;
+  cudaEvent_t start = nullptr, stop = nullptr;
+};
+
 struct VisionPlan {
   int B = 0;
   std::vector<Step> steps;   // stem .. last bottleneck (avgpool is issued by the caller: its destination varies)
@@ -133,6 +140,23 @@ struct vcg_engine {
 
   std::map<int, VisionPlan> vplans;
   std::map<std::pair<int, int>, BertPlan> bplans;
+
+  // profiling
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
+  size_t events_used = 0;
+  cudaEvent_t next_event() {
+    if (events_used == event_pool.size()) {
+      cudaEvent_t ev;
+      VCG_CUDA(cudaEventCreate(&ev));
+      event_pool.push_back(ev);
+    }
+    return event_pool[events_used++];
+  }
+  ~vcg_engine() {
+    for (auto ev : event_pool) cudaEventDestroy(ev);
+  }
 
   int es() const { return fp32 ? 4 : 2; }
 };
@@ -434,16 +458,56 @@ BertPlan& bert_plan(vcg_engine* e, int B, int L) {
   return e->bplans.emplace(key, std::move(plan)).first->second;
 }
 
+// Brackets one kernel launch with CUDA events on the launching stream when profiling is on.
+struct ProfScope {
+  vcg_engine* e;
+  cudaStream_t s;
+  ProfRec rec;
+  bool on;
+  ProfScope(vcg_engine* e_, cudaStream_t s_, std::string name, double flops, double bytes) : e(e_), s(s_), on(e_->profiling) {
+    ++e->launches;
+    if (!on) return;
+    rec.name = std::move(name); rec.flops = flops; rec.bytes = bytes;
+    rec.start = e->next_event(); rec.stop = e->next_event();
+    VCG_CUDA(cudaEventRecord(rec.start, s));
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(rec.stop, s);
+    e->prof.push_back(std::move(rec));
+  }
+};
+
+std::string gemm_kernel_name(const ConvGemmLaunch& L) {
+  return std::string("conv_gemm_") + (L.fp32 ? "tf32x3" : "bf16") + "_n" + std::to_string(L.block_n) + "|" + L.name;
+}
+
 void run_steps(vcg_engine* e, const std::vector<Step>& steps, const int64_t* mask, cudaStream_t s) {
+  const double es = e->es();
   for (const Step& st : steps) {
     switch (st.kind) {
-      case Step::CONV_GEMM: launch_conv_gemm(st.gemm, s); break;
-      case Step::MAXPOOL: launch_maxpool_tsm(st.in, st.n, st.out, st.out2, st.a, st.c, e->fp32, s); break;
-      case Step::LAYERNORM: launch_layernorm(st.in, st.g, st.b, st.out, st.n, kBertHidden, 1e-12f, e->fp32, s); break;
-      case Step::ATTENTION: launch_bert_attention(st.in, mask, st.out, st.n, st.a, e->fp32, s); break;
+      case Step::CONV_GEMM: {
+        ProfScope ps(e, s, gemm_kernel_name(st.gemm), st.gemm.flops, 0);
+        launch_conv_gemm(st.gemm, s);
+        break;
+      }
+      case Step::MAXPOOL: {
+        ProfScope ps(e, s, "maxpool_tsm|maxpool", 0, st.n * (112.0 * 112 * 64 + (st.out2 ? 2 : 1) * 56.0 * 56 * 64) * es);
+        launch_maxpool_tsm(st.in, st.n, st.out, st.out2, st.a, st.c, e->fp32, s);
+        break;
+      }
+      case Step::LAYERNORM: {
+        ProfScope ps(e, s, "layernorm768|bert.ln", 0, st.n * 768.0 * 2 * es);
+        launch_layernorm(st.in, st.g, st.b, st.out, st.n, kBertHidden, 1e-12f, e->fp32, s);
+        break;
+      }
+      case Step::ATTENTION: {
+        ProfScope ps(e, s, "bert_attention|bert.attn", 4.0 * st.n * kBertHeads * static_cast<double>(st.a) * st.a * 64, 0);
+        launch_bert_attention(st.in, mask, st.out, st.n, st.a, e->fp32, s);
+        break;
+      }
       default: throw Error("vcg: unknown plan step");
     }
-    ++e->launches;
   }
 }
 
@@ -465,9 +529,11 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
   for (int b0 = 0; b0 < B; b0 += e->Bt) {
     const int bt = std::min(e->Bt, B - b0);
     // ---- text stream for bt clips
-    launch_bert_embed_ln(ids + static_cast<long>(b0) * L, bt * L, L, e->word.p, e->pos.p, e->type.p, e->emb_g.as<float>(),
-                         e->emb_b.as<float>(), e->hid.p, e->fp32, s);
-    ++e->launches;
+    {
+      ProfScope ps(e, s, "bert_embed_ln|bert.embed", 0, static_cast<double>(bt) * L * 768 * 4 * e->es());
+      launch_bert_embed_ln(ids + static_cast<long>(b0) * L, bt * L, L, e->word.p, e->pos.p, e->type.p,
+                           e->emb_g.as<float>(), e->emb_b.as<float>(), e->hid.p, e->fp32, s);
+    }
     run_steps(e, bert_plan(e, bt, L).steps, mask + static_cast<long>(b0) * L, s);
     // ---- vision stream + tail in sub-chunks
     const int step = have_frames ? e->Bv : bt;
@@ -476,16 +542,20 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
       const int g0 = b0 + c0;   // first clip of this sub-chunk in the caller's numbering
       const float* vis = nullptr;
       if (have_frames) {
-        if (src.img_clip)
+        if (src.img_clip) {
+          ProfScope ps(e, s, "nchw_to_stem|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (4 + e->es()));
           launch_nchw_to_stem(src.img_clip + static_cast<long>(g0) * T * 3 * kImg * kImg, bv * T, e->stem_in.p, e->fp32, s);
-        else
+        } else {
+          ProfScope ps(e, s, "preprocess_u8|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (1 + e->es()));
           launch_preprocess_u8_clips(src.frames_u8, src.clip_start + g0, bv, T, e->stem_in.p, e->fp32, s);
-        ++e->launches;
+        }
         VisionPlan& vp = vision_plan(e, bv);
         run_steps(e, vp.steps, nullptr, s);
         float* dst = vision_emb_out ? vision_emb_out + static_cast<long>(g0) * T * kVisionDim : e->vis_emb.as<float>();
-        launch_avgpool(vp.final_act, bv * T, 49, kVisionDim, dst, s, e->fp32);
-        ++e->launches;
+        {
+          ProfScope ps(e, s, "avgpool|avgpool", 0, static_cast<double>(bv) * T * kVisionDim * (49 * e->es() + 4));
+          launch_avgpool(vp.final_act, bv * T, 49, kVisionDim, dst, s, e->fp32);
+        }
         vis = dst;
       } else {
         vis = vision_emb_in + static_cast<long>(g0) * T * kVisionDim;
@@ -506,8 +576,10 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
       tp.logits = logits + static_cast<long>(g0) * 2;
       tp.probs = probs + static_cast<long>(g0) * 2;
       tp.lang_emb = lang_emb_out ? lang_emb_out + static_cast<long>(g0) * kBertHidden : nullptr;
-      launch_tail(tp, bv, e->fp32, s);
-      ++e->launches;
+      {
+        ProfScope ps(e, s, "tail|head", 2.0 * bv * (768.0 * 768 + 768 * 128 + T * 2048.0 * 128 + (T + 1) * 128 * 2), 0);
+        launch_tail(tp, bv, e->fp32, s);
+      }
     }
   }
 }
@@ -652,7 +724,75 @@ int vcg_score_clips_u8_host(vcg_engine* e, const uint8_t* frames_u8_host, int32_
   });
 }
 
+int vcg_forward_host(vcg_engine* e, const float* img_clip_host, const float* vision_emb_host,
+                     const int64_t* text_ids_host, const int64_t* attention_mask_host, int32_t B, int32_t L,
+                     float* logits_host, float* probs_host, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e && (img_clip_host || vision_emb_host) && text_ids_host && attention_mask_host && logits_host && probs_host,
+                "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t vbytes = img_clip_host ? static_cast<size_t>(B) * e->T * 3 * kImg * kImg * sizeof(float)
+                                        : static_cast<size_t>(B) * e->T * kVisionDim * sizeof(float);
+    const size_t tbytes = static_cast<size_t>(B) * L * sizeof(int64_t);
+    e->st_frames.ensure(vbytes);
+    e->st_ids.ensure(tbytes);
+    e->st_mask.ensure(tbytes);
+    e->st_logits.ensure(static_cast<size_t>(B) * 2 * sizeof(float));
+    e->st_probs.ensure(static_cast<size_t>(B) * 2 * sizeof(float));
+    VCG_CUDA(cudaMemcpyAsync(e->st_frames.p, img_clip_host ? img_clip_host : vision_emb_host, vbytes, cudaMemcpyHostToDevice, s));
+    VCG_CUDA(cudaMemcpyAsync(e->st_ids.p, text_ids_host, tbytes, cudaMemcpyHostToDevice, s));
+    VCG_CUDA(cudaMemcpyAsync(e->st_mask.p, attention_mask_host, tbytes, cudaMemcpyHostToDevice, s));
+    FrameSource src;
+    if (img_clip_host) src.img_clip = e->st_frames.as<float>();
+    score(e, src, img_clip_host ? nullptr : e->st_frames.as<float>(), e->st_ids.as<int64_t>(), e->st_mask.as<int64_t>(), B, L,
+          e->st_logits.as<float>(), e->st_probs.as<float>(), nullptr, nullptr, s);
+    VCG_CUDA(cudaMemcpyAsync(logits_host, e->st_logits.p, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    VCG_CUDA(cudaMemcpyAsync(probs_host, e->st_probs.p, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    VCG_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
 int64_t vcg_launch_count(const vcg_engine* e) { return e ? e->launches : 0; }
+
+int vcg_profile_begin(vcg_engine* e) {
+  return guarded([&] {
+    VCG_REQUIRE(e, "null engine");
+    e->prof.clear();
+    e->events_used = 0;
+    e->profiling = true;
+  });
+}
+
+int vcg_profile_end(vcg_engine* e, void* stream, vcg_profile_entry* out, int32_t max_entries, int32_t* n_out) {
+  return guarded([&] {
+    VCG_REQUIRE(e && n_out, "null argument");
+    e->profiling = false;
+    VCG_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    std::map<std::string, vcg_profile_entry> agg;
+    for (const ProfRec& r : e->prof) {
+      float ms = 0.f;
+      VCG_CUDA(cudaEventElapsedTime(&ms, r.start, r.stop));
+      auto it = agg.find(r.name);
+      if (it == agg.end()) {
+        vcg_profile_entry en{};
+        snprintf(en.name, sizeof en.name, "%s", r.name.c_str());
+        it = agg.emplace(r.name, en).first;
+      }
+      it->second.launches += 1;
+      it->second.ms += ms;
+      it->second.flops += r.flops;
+      it->second.bytes += r.bytes;
+    }
+    int n = 0;
+    for (auto& kv : agg) {
+      if (out && n < max_entries) out[n] = kv.second;
+      ++n;
+    }
+    *n_out = n;
+    e->prof.clear();
+    e->events_used = 0;
+  });
+}
 
 // --------------------------------------------------------------------------------------------- operators
 int vcg_op_preprocess_u8(const uint8_t* frames_u8, const int32_t* frame_index, int32_t n, void* out_padded,

@@ -32,6 +32,11 @@ class VcgConfig(ctypes.Structure):
     ]
 
 
+class VcgProfileEntry(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 64), ("launches", ctypes.c_int64), ("ms", ctypes.c_double),
+                ("flops", ctypes.c_double), ("bytes", ctypes.c_double)]
+
+
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 
 # name -> (restype, argtypes); must list every symbol declared in include/vcg.h (checked by tests/test_abi.py)
@@ -45,6 +50,9 @@ PROTOTYPES = {
     "vcg_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vcg_score_clips_u8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vcg_score_clips_u8_host": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "vcg_forward_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "vcg_profile_begin": (ctypes.c_int, [_vp]),
+    "vcg_profile_end": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(VcgProfileEntry), _i32, ctypes.POINTER(_i32)]),
     "vcg_launch_count": (_i64, [_vp]),
     "vcg_op_preprocess_u8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),
     "vcg_op_nchw_to_stem": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp]),

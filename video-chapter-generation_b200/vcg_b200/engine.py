@@ -147,6 +147,41 @@ class Engine:
                                                        probs.data_ptr(), _stream()))
         return logits, probs
 
+    def forward_host(self, vision_emb, text_ids, attention_mask, img_clip=None, out=None):
+        """HOST tensors in, host tensors out (TwoStream.forward through vcg_forward_host)."""
+        src = img_clip if img_clip is not None else vision_emb
+        for t in (src, text_ids, attention_mask):
+            assert not t.is_cuda and t.is_contiguous()
+        assert src.dtype == torch.float32 and text_ids.dtype == torch.int64 and attention_mask.dtype == torch.int64
+        B, L = text_ids.shape
+        if out is None:
+            logits = torch.empty(B, 2, dtype=torch.float32).pin_memory()
+            probs = torch.empty(B, 2, dtype=torch.float32).pin_memory()
+        else:
+            logits, probs = out
+        with torch.cuda.device(self.device):
+            _b.check(self._lib.vcg_forward_host(self._h, 0 if img_clip is None else img_clip.data_ptr(),
+                                                0 if img_clip is not None else vision_emb.data_ptr(),
+                                                text_ids.data_ptr(), attention_mask.data_ptr(), B, L,
+                                                logits.data_ptr(), probs.data_ptr(), _stream()))
+        return logits, probs
+
+    def profile_begin(self):
+        _b.check(self._lib.vcg_profile_begin(self._h))
+
+    def profile_end(self):
+        """-> list of dicts {kernel, layer, launches, ms, flops, bytes}, one per '<kernel>|<layer>' name."""
+        n = ctypes.c_int32(0)
+        buf = (_b.VcgProfileEntry * 256)()
+        with torch.cuda.device(self.device):
+            _b.check(self._lib.vcg_profile_end(self._h, _stream(), buf, 256, ctypes.byref(n)))
+        out = []
+        for i in range(min(n.value, 256)):
+            kernel, _, layer = buf[i].name.decode().partition("|")
+            out.append({"kernel": kernel, "layer": layer, "launches": int(buf[i].launches), "ms": buf[i].ms,
+                        "flops": buf[i].flops, "bytes": buf[i].bytes})
+        return out
+
     @property
     def launch_count(self):
         return int(self._lib.vcg_launch_count(self._h))
