@@ -6,14 +6,20 @@
 // M-tile is a (bw x bh x nf) patch of output pixels, and the K loop walks (filter tap, channel block) pairs, every
 // step being one TMA box load whose origin is the patch origin plus the tap offset.  Out-of-bounds box elements are
 // zero-filled by TMA, which is exactly conv zero padding.  Plain GEMMs are the degenerate case bw=128, bh=nf=1,
-// one tap.  W is [N, K] K-major.  tcgen05.mma accumulates 128 x BLOCK_N fp32 tiles in TMEM (double buffered), the
-// epilogue warps drain them with tcgen05.ld and apply bias / residual / activation, and optionally scatter the
-// first C/4 channels into the next bottleneck's temporally shifted input (TSM).
+// one tap.  W is [N, K] K-major.  tcgen05.mma accumulates 128 x BLOCK_N fp32 tiles in TMEM.
 //
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 idle,
-// warps 4..11 epilogue (two warps per 32-lane TMEM quarter, interleaved over 32-column chunks).
-// In the TF32x3 variant (fp32 verification mode) warps 12..15 split every landed fp32 stage into
-// (hi, lo) TF32 parts in shared memory and the MMA warp issues hi*hi + hi*lo + lo*hi.
+// bf16 variant (the product path), 384 threads:
+//   warp 0      TMA producer of the A/B stage ring
+//   warp 1      MMA issuer (one elected lane), two TMEM accumulators so tile i+1 runs under tile i's epilogue
+//   warp 2      TMEM allocator
+//   warp 3      "C" producer: a ring of four 128x64 bf16 smem tiles; for layers with a residual it prefetches the
+//               residual tile by TMA (the residual layers are HBM-bound: the ring keeps 64 KB per SM in flight)
+//   warps 4-11  epilogue: tcgen05.ld -> +bias (+residual from smem) -> activation -> bf16 into the same smem tile
+//               (TMA 128-byte swizzle, conflict-free) -> one TMA store per 128x64 tile; the first C/4 channels are
+//               additionally scattered into the next bottleneck's temporally shifted input (TSM).
+// TF32x3 variant (fp32 verification mode), 512 threads: warps 12-15 split every landed fp32 stage into (hi, lo) TF32
+// parts in shared memory, the MMA warp issues hi*hi + hi*lo + lo*hi into several partial accumulators, and the
+// epilogue uses plain row-per-lane global accesses.
 #pragma once
 #include "ptx.cuh"
 #include <cuda_bf16.h>
@@ -32,6 +38,8 @@ struct TapDesc {
 struct ConvGemmParams {
   CUtensorMap a_map[4];
   CUtensorMap b_map;
+  CUtensorMap out_map;         // bf16 path: output [Nimg, Ho, Wo, ld_out] as (C, W, H, 1, N), box (64, bw, bh, 1, nf)
+  CUtensorMap res_map;         // bf16 path: residual, same geometry
   TapDesc taps[16];
   int n_taps, cpt;             // taps; channel blocks (of BLOCK_K elements) per tap
   int tsm_split_cb, tsm_map;   // channel blocks below tsm_split_cb are read through a_map[tsm_map]
@@ -53,6 +61,8 @@ struct ConvGemmParams {
 constexpr int kBlockM = 128;
 constexpr int kNumEpiWarps = 8;
 constexpr int kFirstEpiWarp = 4;
+constexpr int kCSlots = 4;               // smem C-tile ring (bf16 path)
+constexpr int kCBytes = kBlockM * 128;   // one 128 x 64 bf16 tile
 
 template <int BLOCK_N, bool TF32X3>
 struct ConvGemmCfg {
@@ -62,7 +72,9 @@ struct ConvGemmCfg {
   static constexpr int kABytes = kBlockM * 128;
   static constexpr int kBBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = (kABytes + kBBytes) * (TF32X3 ? 2 : 1);
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kCRingBytes = TF32X3 ? 0 : kCSlots * kCBytes;
+  static constexpr int kBudget = 224 * 1024;
+  static constexpr int kStages = (kBudget - kCRingBytes) / kStageBytes > 8 ? 8 : (kBudget - kCRingBytes) / kStageBytes;
   // bf16: two accumulators (tile i+1 accumulates while tile i drains).  TF32x3: the tensor core truncates on every
   // accumulate, so long fp32 sums pick up a bias ~ (#MMAs) * ulp/2; the 512 TMEM columns are used as 512/BLOCK_N
   // partial accumulators instead (number 0 takes the small lo*hi + hi*lo terms, the others take hi*hi round-robin
@@ -71,21 +83,46 @@ struct ConvGemmCfg {
   static constexpr int kTmemCols = TF32X3 ? 512 : (2 * BLOCK_N <= 32 ? 32 : 2 * BLOCK_N <= 64 ? 64 : 2 * BLOCK_N <= 128 ? 128
                                    : 2 * BLOCK_N <= 256 ? 256 : 512);
   static constexpr int kThreads = TF32X3 ? 512 : 384;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kCRingBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+  static_assert(kStages >= 2, "need at least two pipeline stages");
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-  if (act == ACT_TANH) return tanhf(v);
-  return v;
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one MUFU.RCP, one MUFU.EX2 and a 5-term Horner chain — a
+// third of the instructions of erff(), which matters because the FFN-in epilogue is ALU-bound.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(e, x);
+}
+
+// Activation over a register tile; the switch is hoisted out of the element loop.
+template <bool EXACT>
+__device__ __forceinline__ void apply_act32(float (&v)[32], int act) {
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if constexpr (EXACT) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+      else v[j] = 0.5f * v[j] * (1.f + erf_fast(v[j] * 0.70710678118654752440f));
+    }
+  } else if (act == ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+  }
 }
 
 template <int BLOCK_N, bool TF32X3>
 __global__ void __launch_bounds__(ConvGemmCfg<BLOCK_N, TF32X3>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using Cfg = ConvGemmCfg<BLOCK_N, TF32X3>;
-  using OutT = typename std::conditional<TF32X3, float, __nv_bfloat16>::type;
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -94,13 +131,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   uint8_t* sB = sA + kStages * Cfg::kABytes;           // [stage][BLOCK_N rows][128 B]
   uint8_t* sA_lo = sB + kStages * Cfg::kBBytes;        // TF32X3 only
   uint8_t* sB_lo = sA_lo + kStages * Cfg::kABytes;     // TF32X3 only
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* sC = smem + kStages * Cfg::kStageBytes;     // bf16 only: [kCSlots][128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kCRingBytes);
   uint64_t* full_bar = bars;                  // TMA -> (splitter | MMA)
   uint64_t* empty_bar = bars + kStages;       // MMA -> TMA
   uint64_t* split_bar = bars + 2 * kStages;   // splitter -> MMA (TF32X3)
   uint64_t* tmem_full = bars + 3 * kStages;   // MMA -> epilogue   [2]
   uint64_t* tmem_empty = tmem_full + 2;       // epilogue -> MMA   [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* c_full = tmem_empty + 2;          // C producer -> epilogue [kCSlots]
+  uint64_t* c_empty = c_full + kCSlots;       // epilogue -> C producer [kCSlots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_empty + kCSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,6 +148,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
     tma_prefetch_desc(&p.b_map);
+    if (!TF32X3) {
+      tma_prefetch_desc(&p.out_map);
+      tma_prefetch_desc(&p.res_map);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -118,6 +162,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], kNumEpiWarps);
+    }
+    for (int i = 0; i < kCSlots; ++i) {
+      mbar_init(&c_full[i], 1);
+      mbar_init(&c_empty[i], kNumEpiWarps);
     }
     fence_mbar_init();
   }
@@ -135,7 +183,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const int total_tiles = m_tiles * p.n_tiles;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (A/B stages)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -198,19 +246,42 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         umma_commit(&tmem_full[acc]);
       }
     }
+  } else if (!TF32X3 && warp == 3) {
+    // ------------------------------------------------------------ C producer (bf16): residual prefetch ring
+    if (elect_one()) {
+      const bool has_res = p.residual != nullptr;
+      int c_it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
+        const int iw = m_blk % p.tiles_w;
+        const int ih = (m_blk / p.tiles_w) % p.tiles_h;
+        const int in = m_blk / (p.tiles_w * p.tiles_h);
+        const int n_sub = min(BLOCK_N / 64, (p.N - n_blk * BLOCK_N + 63) / 64);
+        for (int j = 0; j < n_sub; ++j, ++c_it) {
+          const int slot = c_it % kCSlots;
+          mbar_wait(&c_empty[slot], ((c_it / kCSlots) & 1) ^ 1);
+          if (has_res) {
+            mbar_expect_tx(&c_full[slot], p.a_bytes);   // same box extents as the A patch: rows x 128 B
+            tma_load_5d(sC + slot * kCBytes, &p.res_map, &c_full[slot], n_blk * BLOCK_N + j * 64, iw * p.bw, ih * p.bh,
+                        0, in * p.nf);
+          } else {
+            mbar_arrive(&c_full[slot]);
+          }
+        }
+      }
+    }
   } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + kNumEpiWarps) {
     // ------------------------------------------------------------ epilogue
     const int quarter = warp & 3;                       // TMEM lanes [32*quarter, +32)
-    const int half = (warp - kFirstEpiWarp) >> 2;       // which 32-column chunks (even / odd)
+    const int half = (warp - kFirstEpiWarp) >> 2;       // which 32-column half of a 64-column C tile
     const int row = quarter * 32 + lane;
     const int dw = row % p.bw;
     const int dh = (row / p.bw) % p.bh;
     const int dn = row / (p.bw * p.bh);
     const int HW = p.Ho * p.Wo;
-    OutT* out = reinterpret_cast<OutT*>(p.out);
-    const OutT* res = reinterpret_cast<const OutT*>(p.residual);
-    OutT* tsm = reinterpret_cast<OutT*>(p.tsm_out);
     int it = 0;
+    [[maybe_unused]] int c_it = 0;
+    [[maybe_unused]] int prev_slot = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
       const int iw = m_blk % p.tiles_w;
@@ -218,16 +289,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int in = m_blk / (p.tiles_w * p.tiles_h);
       const int w = iw * p.bw + dw, h = ih * p.bh + dh, n = in * p.nf + dn;
       const bool row_ok = (dn < p.nf) && (w < p.Wo) && (h < p.Ho) && (n < p.Nimg);
-      const long grow = (static_cast<long>(n) * p.Ho + h) * p.Wo + w;
+      const long grow = row_ok ? (static_cast<long>(n) * p.Ho + h) * p.Wo + w : -1;
       const int acc = TF32X3 ? 0 : (it & 1);
       mbar_wait(&tmem_full[acc], TF32X3 ? (it & 1) : ((it >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+
+      if constexpr (TF32X3) {
+        // ---- fp32 verification path: direct row-per-lane accesses
+        float* out = reinterpret_cast<float*>(p.out);
+        const float* res = reinterpret_cast<const float*>(p.residual);
+        float* tsm = reinterpret_cast<float*>(p.tsm_out);
 #pragma unroll 1
-      for (int chunk = half; chunk < BLOCK_N / 32; chunk += 2) {
-        uint32_t r[32];
-        float v[32];
-        if constexpr (TF32X3) {
+        for (int chunk = half; chunk < BLOCK_N / 32; chunk += 2) {
+          uint32_t r[32];
+          float v[32];
           // sum the hi*hi partial accumulators (round-to-nearest adds), then the correction accumulator
           const int n_hi = min(Cfg::kNumAcc - 1, num_kb);
           tmem_ld_32x32(taddr + BLOCK_N + chunk * 32, r);
@@ -244,27 +320,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
-        } else {
-          tmem_ld_32x32(taddr + chunk * 32, r);
-          tmem_ld_wait();
+          const int col0 = n_blk * BLOCK_N + chunk * 32;
+          if (row_ok && col0 < p.N) {
+            const int ncols = min(32, p.N - col0);   // multiple of 8 by contract
+            if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        }
-        const int col0 = n_blk * BLOCK_N + chunk * 32;
-        if (row_ok && col0 < p.N) {
-          const int ncols = min(32, p.N - col0);   // multiple of 8 by contract
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              for (int j = 0; j < 32; j += 4) {
+                if (j < ncols) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
               }
             }
-          }
-          if (res) {
-            const OutT* rp = res + grow * p.ld_res + col0;
-            if constexpr (TF32X3) {
+            if (res) {
+              const float* rp = res + grow * p.ld_res + col0;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 if (j < ncols) {
@@ -272,37 +341,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                   v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
                 }
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (j < ncols) {
-                  const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
-                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(h2[e]);
-                    v[j + 2 * e] += f.x; v[j + 2 * e + 1] += f.y;
-                  }
-                }
+            }
+            apply_act32<true>(v, p.act);
+            float* dst = out + grow * p.ld_out + col0;
+            float* dst2 = nullptr;
+            if (tsm && col0 < 2 * p.tsm_fold) {
+              const int t = static_cast<int>((grow / HW) % p.T);
+              if (col0 < p.tsm_fold) {             // out[t-1, c] = x[t, c]   (shift left in time)
+                if (t >= 1) dst2 = tsm + (grow - HW) * p.tsm_ld + col0;
+              } else {                             // out[t+1, c] = x[t, c]   (shift right in time)
+                if (t + 1 < p.T) dst2 = tsm + (grow + HW) * p.tsm_ld + col0;
               }
             }
-          }
-          if (p.act != ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-          }
-          // destination rows: the output itself, plus (TSM) the neighbouring frame's slot in the shifted buffer
-          OutT* dst = out + grow * p.ld_out + col0;
-          OutT* dst2 = nullptr;
-          if (tsm && col0 < 2 * p.tsm_fold) {
-            const int t = static_cast<int>((grow / HW) % p.T);
-            if (col0 < p.tsm_fold) {             // out[t-1, c] = x[t, c]   (shift left in time)
-              if (t >= 1) dst2 = tsm + (grow - HW) * p.tsm_ld + col0;
-            } else {                             // out[t+1, c] = x[t, c]   (shift right in time)
-              if (t + 1 < p.T) dst2 = tsm + (grow + HW) * p.tsm_ld + col0;
-            }
-          }
-          if constexpr (TF32X3) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (j < ncols) {
@@ -311,24 +361,107 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 if (dst2) *reinterpret_cast<float4*>(dst2 + j) = o;
               }
             }
-          } else {
+          }
+        }
+      } else {
+        // ---- bf16 path: 128x64 C tiles through the smem ring, TMA store
+        __nv_bfloat16* tsm = reinterpret_cast<__nv_bfloat16*>(p.tsm_out);
+        const bool has_res = p.residual != nullptr;
+        const int srow = lane >> 2, spiece = lane & 3;    // TSM scatter: rows srow + 8*i of the warp, 16-byte piece
+        long g_i[4];
+        int t_i[4];
+        if (tsm) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < ncols) {
-                uint4 o;
-                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+          for (int i = 0; i < 4; ++i) {
+            g_i[i] = __shfl_sync(0xffffffffu, grow, srow + 8 * i);
+            t_i[i] = g_i[i] >= 0 ? static_cast<int>((g_i[i] / HW) % p.T) : 0;
+          }
+        }
+        const int n_sub = min(BLOCK_N / 64, (p.N - n_blk * BLOCK_N + 63) / 64);
+#pragma unroll 1
+        for (int j = 0; j < n_sub; ++j, ++c_it) {
+          const int slot = c_it % kCSlots;
+          uint8_t* ctile = sC + slot * kCBytes;
+          uint8_t* crow = ctile + row * 128;
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + j * 64 + half * 32, r);      // asynchronous until tmem_ld_wait
+          const int col0 = n_blk * BLOCK_N + j * 64 + half * 32;
+          mbar_wait(&c_full[slot], (c_it / kCSlots) & 1);    // residual landed / slot free
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(dst + j) = o;
-                if (dst2) *reinterpret_cast<uint4*>(dst2 + j) = o;
+          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+          if (col0 < p.N) {
+            if (p.bias) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + e));   // N % 32 == 0 (host check)
+                v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
               }
             }
+            if (has_res) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {      // logical 16-byte chunk 4*half + c, XOR-swizzled with row % 8
+                const uint4 q = *reinterpret_cast<const uint4*>(crow + (((half * 4 + c) ^ (row & 7)) << 4));
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h2[e]);
+                  v[c * 8 + 2 * e] += f.x; v[c * 8 + 2 * e + 1] += f.y;
+                }
+              }
+            }
+            apply_act32<false>(v, p.act);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 o;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(crow + (((half * 4 + c) ^ (row & 7)) << 4)) = o;
+          }
+          fence_proxy_async_smem();                       // generic-proxy writes -> visible to the TMA store
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // all 8 epilogue warps finished this C tile
+          if (warp == kFirstEpiWarp && lane == 0) {
+            tma_store_5d(ctile, &p.out_map, n_blk * BLOCK_N + j * 64, iw * p.bw, ih * p.bh, 0, in * p.nf);
+            tma_store_commit();
+          }
+          // TSM: this warp's 32 rows x 32 columns, re-read with 4 lanes per row for coalesced 64-byte segments
+          const bool zone_a = tsm && col0 < p.tsm_fold;
+          const bool zone_b = tsm && !zone_a && col0 < 2 * p.tsm_fold;
+          if (zone_a || zone_b) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = quarter * 32 + srow + 8 * i;
+              if (g_i[i] >= 0) {
+                const uint4 o = *reinterpret_cast<const uint4*>(ctile + rr * 128 + (((half * 4 + spiece) ^ (rr & 7)) << 4));
+                if (zone_a && t_i[i] >= 1)           // out[t-1, c] = x[t, c]   (shift left in time)
+                  *reinterpret_cast<uint4*>(tsm + (g_i[i] - HW) * p.tsm_ld + col0 + spiece * 8) = o;
+                if (zone_b && t_i[i] + 1 < p.T)      // out[t+1, c] = x[t, c]   (shift right in time)
+                  *reinterpret_cast<uint4*>(tsm + (g_i[i] + HW) * p.tsm_ld + col0 + spiece * 8) = o;
+              }
+            }
+          }
+          // release the slot: the storing warp defers its arrival until the bulk store has finished reading smem
+          __syncwarp();
+          if (warp == kFirstEpiWarp) {
+            if (lane == 0 && prev_slot >= 0) {
+              tma_store_wait_read<1>();
+              mbar_arrive(&c_empty[prev_slot]);
+            }
+            prev_slot = slot;
+          } else if (lane == 0) {
+            mbar_arrive(&c_empty[slot]);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    if constexpr (!TF32X3) {
+      if (warp == kFirstEpiWarp && lane == 0) tma_store_wait_all();   // stores complete before the CTA exits
     }
   } else if (TF32X3 && warp >= 12) {
     // ------------------------------------------------------------ TF32 hi/lo splitter (fp32 verification mode)

@@ -72,12 +72,29 @@ struct Epilogue {
   int tsm_ld = 0, tsm_fold = 0, T = 1;
 };
 
+// [Nimg, Ho, Wo, ld] bf16 tensor seen as (C, W, H, 1, N) with a (64 x bw x bh x 1 x nf) box: the C tiles of the epilogue
+inline CUtensorMap c_tile_map(const void* ptr, long ld, const ConvGemmParams& p) {
+  const uint64_t dims[5] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.Wo), static_cast<uint64_t>(p.Ho), 1,
+                            static_cast<uint64_t>(p.Nimg)};
+  const uint64_t row = static_cast<uint64_t>(ld) * 2;
+  const uint64_t img = row * p.Wo * p.Ho;
+  const uint64_t str[4] = {row, row * p.Wo, img, img};
+  const uint32_t box[5] = {64, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), 1, static_cast<uint32_t>(p.nf)};
+  return make_tensor_map(ptr, false, 5, dims, str, box);
+}
+
 inline void set_epilogue(ConvGemmLaunch& L, void* out, int ld_out, const Epilogue& e) {
   ConvGemmParams& p = L.p;
   p.out = out; p.ld_out = ld_out;
   p.bias = e.bias; p.residual = e.residual; p.ld_res = e.ld_res; p.act = e.act;
   p.tsm_out = e.tsm_out; p.tsm_ld = e.tsm_ld; p.tsm_fold = e.tsm_fold; p.T = e.T > 0 ? e.T : 1;
   if (e.tsm_out) VCG_REQUIRE(e.tsm_fold % 32 == 0, "TSM fold must be a multiple of 32 channels");
+  if (!L.fp32) {
+    VCG_REQUIRE(p.N % 32 == 0, "bf16 path: output channels must be a multiple of 32");
+    VCG_REQUIRE(ld_out % 8 == 0 && (e.residual == nullptr || e.ld_res % 8 == 0), "row strides must be multiples of 16 bytes");
+    p.out_map = c_tile_map(out, ld_out, p);
+    p.res_map = e.residual ? c_tile_map(e.residual, e.ld_res, p) : p.out_map;
+  }
 }
 
 inline CUtensorMap weight_map(const void* W, int N, int K, int block_n, bool fp32) {

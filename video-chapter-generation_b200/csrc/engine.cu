@@ -131,7 +131,7 @@ struct vcg_engine {
   DevBuf pool_w_t, pool_b, lang_w_t, vis_w_t, head_w, head_b, q_w_t, q_b, k_w_t, k_b, v_w_t, v_b, proj_w, proj_b;
 
   // vision workspace (sized for Bv clips)
-  DevBuf stem_in, stem_out, x0, xa, xb, dsbuf, mid1, mid2, vis_emb;
+  DevBuf stem_in, stem_out, x0, xa, xb, dsbuf, mid1, mid2, vis_emb, vis_out, lang_out;
   std::vector<std::unique_ptr<DevBuf>> shifted;   // one per bottleneck: its temporally shifted input channels
   // text workspace (sized for Bt clips x Lmax tokens)
   DevBuf hid, hid2, qkv, ctx, tmp, ffn;
@@ -351,6 +351,8 @@ void finalize_head(vcg_engine* e, cudaStream_t s) {
     copy_f32(e->proj_b, need(e, fh + "head.proj.bias", {2}), s);
   }
   e->vis_emb.alloc(static_cast<size_t>(std::max(e->Bv, e->Bt)) * T * kVisionDim * sizeof(float));
+  e->vis_out.alloc(static_cast<size_t>(std::max(e->Bv, e->Bt)) * T * H * sizeof(float));
+  e->lang_out.alloc(static_cast<size_t>(e->Bt) * H * sizeof(float));
 }
 
 // ------------------------------------------------------------------------------------------------ plans
@@ -535,7 +537,24 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
                            e->emb_g.as<float>(), e->emb_b.as<float>(), e->hid.p, e->fp32, s);
     }
     run_steps(e, bert_plan(e, bt, L).steps, mask + static_cast<long>(b0) * L, s);
-    // ---- vision stream + tail in sub-chunks
+    // ---- pooler + lang projection for the bt clips
+    TailParams tp{};
+    tp.L = L; tp.T = T; tp.H = e->H; tp.head_type = e->cfg.head_type;
+    tp.pool_w_t = e->pool_w_t.as<float>(); tp.pool_b = e->pool_b.as<float>();
+    tp.lang_w_t = e->lang_w_t.as<float>(); tp.vis_w_t = e->vis_w_t.as<float>();
+    tp.head_w = e->head_w.as<float>(); tp.head_b = e->head_b.as<float>();
+    tp.q_w_t = e->q_w_t.as<float>(); tp.q_b = e->q_b.as<float>();
+    tp.k_w_t = e->k_w_t.as<float>(); tp.k_b = e->k_b.as<float>();
+    tp.v_w_t = e->v_w_t.as<float>(); tp.v_b = e->v_b.as<float>();
+    tp.proj_w = e->proj_w.as<float>(); tp.proj_b = e->proj_b.as<float>();
+    tp.hidden = e->hid.p;
+    tp.lang_out = e->lang_out.as<float>();
+    tp.lang_emb = lang_emb_out ? lang_emb_out + static_cast<long>(b0) * kBertHidden : nullptr;
+    {
+      ProfScope ps(e, s, "lang_tail|head", 2.0 * bt * (768.0 * 768 + 768 * 128), 0);
+      launch_lang_tail(tp, bt, e->fp32, s);
+    }
+    // ---- vision stream + head in sub-chunks
     const int step = have_frames ? e->Bv : bt;
     for (int c0 = 0; c0 < bt; c0 += step) {
       const int bv = std::min(step, bt - c0);
@@ -563,22 +582,18 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
           VCG_CUDA(cudaMemcpyAsync(vision_emb_out + static_cast<long>(g0) * T * kVisionDim, vis,
                                    static_cast<size_t>(bv) * T * kVisionDim * sizeof(float), cudaMemcpyDeviceToDevice, s));
       }
-      TailParams tp{};
-      tp.hidden = static_cast<const uint8_t*>(e->hid.p) + static_cast<size_t>(c0) * L * kBertHidden * e->es();
-      tp.L = L; tp.vision = vis; tp.T = T; tp.H = e->H; tp.head_type = e->cfg.head_type;
-      tp.pool_w_t = e->pool_w_t.as<float>(); tp.pool_b = e->pool_b.as<float>();
-      tp.lang_w_t = e->lang_w_t.as<float>(); tp.vis_w_t = e->vis_w_t.as<float>();
-      tp.head_w = e->head_w.as<float>(); tp.head_b = e->head_b.as<float>();
-      tp.q_w_t = e->q_w_t.as<float>(); tp.q_b = e->q_b.as<float>();
-      tp.k_w_t = e->k_w_t.as<float>(); tp.k_b = e->k_b.as<float>();
-      tp.v_w_t = e->v_w_t.as<float>(); tp.v_b = e->v_b.as<float>();
-      tp.proj_w = e->proj_w.as<float>(); tp.proj_b = e->proj_b.as<float>();
-      tp.logits = logits + static_cast<long>(g0) * 2;
-      tp.probs = probs + static_cast<long>(g0) * 2;
-      tp.lang_emb = lang_emb_out ? lang_emb_out + static_cast<long>(g0) * kBertHidden : nullptr;
       {
-        ProfScope ps(e, s, "tail|head", 2.0 * bv * (768.0 * 768 + 768 * 128 + T * 2048.0 * 128 + (T + 1) * 128 * 2), 0);
-        launch_tail(tp, bv, e->fp32, s);
+        ProfScope ps(e, s, "vision_proj|head", 2.0 * bv * T * 2048.0 * 128, 0);
+        launch_vision_proj(vis, e->vis_w_t.as<float>(), e->vis_out.as<float>(), bv * T, e->H, s);
+      }
+      TailParams hp = tp;
+      hp.vis_out = e->vis_out.as<float>();
+      hp.lang_out = e->lang_out.as<float>() + static_cast<long>(c0) * e->H;
+      hp.logits = logits + static_cast<long>(g0) * 2;
+      hp.probs = probs + static_cast<long>(g0) * 2;
+      {
+        ProfScope ps(e, s, "head_final|head", 2.0 * bv * (T + 1) * 128 * 2, 0);
+        launch_head_final(hp, bv, s);
       }
     }
   }

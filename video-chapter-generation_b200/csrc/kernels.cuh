@@ -36,8 +36,9 @@ struct TailParams {
   // inputs
   const void* hidden;      // final BERT hidden states [B*L, 768] (element type per `fp32`)
   int L;
-  const float* vision;     // [B, T, 2048] fp32
   int T, H;                // frames per clip, head hidden size (128)
+  float* lang_out;         // [B, H]    relu(W_l lang_emb)          (written by lang_tail, read by head_final)
+  const float* vis_out;    // [B*T, H]  relu(W_v vision_emb[t])     (written by vision_proj, read by head_final)
   int head_type;           // 0 mlp, 1 attn
   // weights (fp32; *_t are transposed to [in][out])
   const float* pool_w_t;   // [768][768]
@@ -55,7 +56,10 @@ struct TailParams {
   float* probs;            // [B,2]
   float* lang_emb;         // [B,768] or nullptr
 };
-void launch_tail(const TailParams& p, int B, bool fp32, cudaStream_t s);
+void launch_lang_tail(const TailParams& p, int B, bool fp32, cudaStream_t s);     // pooler + lang projection
+void launch_vision_proj(const float* vision /*[n,2048]*/, const float* vis_w_t, float* vis_out /*[n,H]*/, int n_frames,
+                        int H, cudaStream_t s);
+void launch_head_final(const TailParams& p, int B, cudaStream_t s);                // head + softmax
 
 // weight packing (fp32 state-dict tensors -> kernel layouts)
 void launch_pack_conv(const float* w /*[Cout,Cin,k,k]*/, const float* bn_w, const float* bn_b, const float* bn_mean,
