@@ -48,7 +48,7 @@ def bert_forward(sd, ids, mask, prefix="lang_model.", taps=None):
     if taps is not None:
         taps["bert.embeddings"] = x
     # additive key mask: 0 where attention_mask == 1, -inf-like elsewhere (modeling_bert.py:115-140 via sdpa)
-    add = torch.zeros(B, 1, 1, L).masked_fill(mask[:, None, None, :] == 0, float("-inf"))
+    add = torch.zeros(B, 1, 1, L, device=ids.device).masked_fill(mask[:, None, None, :] == 0, float("-inf"))
     n_layers = 0
     while f"{p}encoder.layer.{n_layers}.attention.self.query.weight" in sd:
         n_layers += 1
