@@ -112,7 +112,9 @@ VCG_API int64_t vcg_launch_count(const vcg_engine* e);
 
 /* Stand-alone operators (what the engine is built from; used by the parity tests) ------------------------- */
 
-/* uint8 HWC frames -> normalised, zero-padded NHWC4 stem input [n,230,240,4] (bf16 or fp32):
+/* uint8 HWC frames -> normalised, zero-padded stem input (4 channels per pixel, channel 3 = 0; pixel (0,0) of the
+ * buffer is input pixel (-3,-3)): fp32 plain NHWC4 [n,230,240,4]; bf16 with row pairs interleaved per pixel
+ * [n,115,240,2,4] (one stem K block = 8 pixels x 2 rows = 128 contiguous bytes):
  * (x/255 - mean_c)/std_c, the ToTensor+Normalize of test_video_segment_point.py:142-145.  frame_index may be
  * NULL (identity) or [n] int32 frame numbers to gather. */
 VCG_API int vcg_op_preprocess_u8(const uint8_t* frames_u8, const int32_t* frame_index, int32_t n, void* out_padded,
@@ -135,8 +137,8 @@ VCG_API int vcg_op_conv2d_nhwc(const void* in, int32_t n, int32_t H, int32_t W, 
                        int32_t act, int32_t precision, const void* tsm_in, int32_t tsm_in_ch, void* tsm_out,
                        int32_t tsm_fold, int32_t clip_frames, void* stream);
 
-/* ResNet stem conv (7x7/2, folded BN, ReLU) over the padded NHWC4 input; weight [64][7][W][4] with W = 16 (bf16)
- * or 8 (fp32) window pixels; out NHWC [n,112,112,64]. */
+/* ResNet stem conv (7x7/2, folded BN, ReLU) over the padded stem input; weight bf16 [64][4 row pairs][8 px][2 rows][4 ch],
+ * fp32 [64][7 rows][8 px][4 ch] (zero for row 7, pixel 7, channel 3); out NHWC [n,112,112,64]. */
 VCG_API int vcg_op_stem_conv(const void* in_padded, int32_t n, const void* weight, const float* bias, void* out,
                      int32_t precision, void* stream);
 

@@ -93,10 +93,18 @@ def t_tsm(dtype, B_, T, H, C, planes):
         report(f"tsm-scatter {dtype} B{B_} T{T} H{H} C{C}", (tsm_out.float() - exp.view(n, H, H, 2 * fold).float()).abs().max().item(), 0.0)
     run(f"tsm {dtype}", f)
 
+def stem_to_nhwc4(xp, dtype):
+    """stem input buffer -> plain padded NHWC4 view [n,230,240,4] (bf16 stores row pairs interleaved per pixel)."""
+    if dtype == torch.bfloat16:
+        n = xp.shape[0]
+        return xp.view(n, 115, 240, 2, 4).permute(0, 1, 3, 2, 4).reshape(n, 230, 240, 4)
+    return xp
+
 def t_stem(dtype, n):
     def f():
         frames = torch.randint(0, 256, (n, 224, 224, 3), device=dev, dtype=torch.uint8)
-        xp = ops.preprocess_u8(frames, None, dtype)
+        xp_raw = ops.preprocess_u8(frames, None, dtype)
+        xp = stem_to_nhwc4(xp_raw, dtype)
         mean = torch.tensor([0.485, 0.456, 0.406], device=dev); std = torch.tensor([0.229, 0.224, 0.225], device=dev)
         img = ((frames.float() / 255.0) - mean) / std            # NHWC fp32
         interior = xp[:, 3:227, 3:227, :3].float()
@@ -104,16 +112,22 @@ def t_stem(dtype, n):
         border = xp.clone(); border[:, 3:227, 3:227, :] = 0
         report(f"preprocess border zero {dtype}", border.float().abs().max().item() + xp[..., 3].float().abs().max().item(), 0.0)
         xp2 = ops.nchw_to_stem(img.permute(0, 3, 1, 2).contiguous(), dtype)
-        report(f"nchw_to_stem == preprocess {dtype}", (xp2.float() - xp.float()).abs().max().item(), 4e-2 if dtype == torch.bfloat16 else 1e-6)
+        report(f"nchw_to_stem == preprocess {dtype}", (xp2.float() - xp_raw.float()).abs().max().item(), 4e-2 if dtype == torch.bfloat16 else 1e-6)
         w = torch.randn(64, 3, 7, 7, device=dev) / 147 ** 0.5
         b = torch.randn(64, device=dev)
-        win = 16 if dtype == torch.bfloat16 else 8
-        wp = torch.zeros(64, 7, win, 4, device=dev)
-        wp[:, :, :7, :3] = w.permute(0, 2, 3, 1)
-        wp = wp.to(dtype)
-        out = ops.stem_conv(xp, wp, b)
+        if dtype == torch.bfloat16:      # [64][4 row pairs][8 px][2 rows][4 ch]
+            w8 = torch.zeros(64, 8, 8, 4, device=dev)          # [co][kh][kw][c], kh = 7 / kw = 7 / c = 3 zero
+            w8[:, :7, :7, :3] = w.permute(0, 2, 3, 1)
+            wp = w8.view(64, 4, 2, 8, 4).permute(0, 1, 3, 2, 4).contiguous().to(dtype)
+            wq = w8[:, :7, :7, :3].to(dtype).float()
+        else:                            # [64][7][8 px][4 ch]
+            w7 = torch.zeros(64, 7, 8, 4, device=dev)
+            w7[:, :, :7, :3] = w.permute(0, 2, 3, 1)
+            wp = w7.contiguous()
+            wq = w7[:, :, :7, :3]
+        out = ops.stem_conv(xp_raw, wp, b)
         xin = xp[:, 3:227, 3:227, :3].float().permute(0, 3, 1, 2)
-        ref = F.relu(F.conv2d(xin, wp[:, :, :7, :3].float().permute(0, 3, 1, 2), b, stride=2, padding=3)).permute(0, 2, 3, 1)
+        ref = F.relu(F.conv2d(xin, wq.permute(0, 3, 1, 2), b, stride=2, padding=3)).permute(0, 2, 3, 1)
         report(f"stem conv {dtype} n{n}", rel(out, ref), 1e-2 if dtype == torch.bfloat16 else 2e-5)
         T = 4 if n % 4 == 0 else 1
         pooled, shifted = ops.maxpool_tsm(out, T, 8)

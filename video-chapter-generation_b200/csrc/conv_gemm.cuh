@@ -8,13 +8,14 @@
 // zero-filled by TMA, which is exactly conv zero padding.  Plain GEMMs are the degenerate case bw=128, bh=nf=1,
 // one tap.  W is [N, K] K-major.  tcgen05.mma accumulates 128 x BLOCK_N fp32 tiles in TMEM.
 //
-// bf16 variant (the product path), 384 threads:
+// bf16 variant (the product path), 640 threads:
 //   warp 0      TMA producer of the A/B stage ring
 //   warp 1      MMA issuer (one elected lane), two TMEM accumulators so tile i+1 runs under tile i's epilogue
 //   warp 2      TMEM allocator
 //   warp 3      "C" producer: a ring of four 128x64 bf16 smem tiles; for layers with a residual it prefetches the
 //               residual tile by TMA (the residual layers are HBM-bound: the ring keeps 64 KB per SM in flight)
-//   warps 4-11  epilogue: tcgen05.ld -> +bias (+residual from smem) -> activation -> bf16 into the same smem tile
+//   warps 4-19  epilogue, four groups of four warps (one per TMEM lane quarter) that split the tile's columns and run
+//               concurrently: tcgen05.ld -> +bias (+residual from smem) -> activation -> bf16 into the same smem tile
 //               (TMA 128-byte swizzle, conflict-free) -> one TMA store per 128x64 tile; the first C/4 channels are
 //               additionally scattered into the next bottleneck's temporally shifted input (TSM).
 // TF32x3 variant (fp32 verification mode), 512 threads: warps 12-15 split every landed fp32 stage into (hi, lo) TF32
@@ -43,6 +44,7 @@ struct ConvGemmParams {
   TapDesc taps[16];
   int n_taps, cpt;             // taps; channel blocks (of BLOCK_K elements) per tap
   int tsm_split_cb, tsm_map;   // channel blocks below tsm_split_cb are read through a_map[tsm_map]
+  int n_stages, n_cslots;      // bf16 path: split of the smem budget between the A/B stage ring and the C-tile ring
   int bw, bh, nf;              // patch extents; bw*bh*nf <= 128 rows
   int Wo, Ho, Nimg;            // output geometry
   int tiles_w, tiles_h, tiles_n, n_tiles;
@@ -59,9 +61,12 @@ struct ConvGemmParams {
 };
 
 constexpr int kBlockM = 128;
-constexpr int kNumEpiWarps = 8;
 constexpr int kFirstEpiWarp = 4;
-constexpr int kCSlots = 4;               // smem C-tile ring (bf16 path)
+constexpr int kEpiWarpsBf16 = 16;        // bf16: four warps per TMEM lane quarter, 16 columns of a 64-column C tile each
+constexpr int kEpiWarpsTf32 = 8;
+constexpr int kMaxStages = 8;
+constexpr int kMaxCSlots = 12;           // smem C-tile ring (bf16 path); the host picks n_stages / n_cslots per layer
+constexpr int kMinCSlots = 4;
 constexpr int kCBytes = kBlockM * 128;   // one 128 x 64 bf16 tile
 
 template <int BLOCK_N, bool TF32X3>
@@ -72,9 +77,10 @@ struct ConvGemmCfg {
   static constexpr int kABytes = kBlockM * 128;
   static constexpr int kBBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = (kABytes + kBBytes) * (TF32X3 ? 2 : 1);
-  static constexpr int kCRingBytes = TF32X3 ? 0 : kCSlots * kCBytes;
-  static constexpr int kBudget = 224 * 1024;
-  static constexpr int kStages = (kBudget - kCRingBytes) / kStageBytes > 8 ? 8 : (kBudget - kCRingBytes) / kStageBytes;
+  static constexpr int kCRingBytes = TF32X3 ? 0 : kMinCSlots * kCBytes;
+  static constexpr int kBudget = 224 * 1024;   // stage ring + C ring
+  // default split: as many stages as fit next to the minimum C ring
+  static constexpr int kStages = (kBudget - kCRingBytes) / kStageBytes > kMaxStages ? kMaxStages : (kBudget - kCRingBytes) / kStageBytes;
   // bf16: two accumulators (tile i+1 accumulates while tile i drains).  TF32x3: the tensor core truncates on every
   // accumulate, so long fp32 sums pick up a bias ~ (#MMAs) * ulp/2; the 512 TMEM columns are used as 512/BLOCK_N
   // partial accumulators instead (number 0 takes the small lo*hi + hi*lo terms, the others take hi*hi round-robin
@@ -82,8 +88,9 @@ struct ConvGemmCfg {
   static constexpr int kNumAcc = TF32X3 ? 512 / BLOCK_N : 2;
   static constexpr int kTmemCols = TF32X3 ? 512 : (2 * BLOCK_N <= 32 ? 32 : 2 * BLOCK_N <= 64 ? 64 : 2 * BLOCK_N <= 128 ? 128
                                    : 2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int kThreads = TF32X3 ? 512 : 384;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kCRingBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int kNumEpiWarps = TF32X3 ? kEpiWarpsTf32 : kEpiWarpsBf16;
+  static constexpr int kThreads = TF32X3 ? 512 : (kFirstEpiWarp + kEpiWarpsBf16) * 32;
+  static constexpr int kSmemBytes = kBudget + 1024 /*align*/ + 512 /*barriers*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
   static_assert(kStages >= 2, "need at least two pipeline stages");
 };
@@ -119,11 +126,26 @@ __device__ __forceinline__ void apply_act32(float (&v)[32], int act) {
   }
 }
 
+// 16-wide variant for the bf16 epilogue (fast erf)
+__device__ __forceinline__ void apply_act16(float (&v)[16], int act) {
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erf_fast(v[j] * 0.70710678118654752440f));
+  } else if (act == ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j]);
+  }
+}
+
 template <int BLOCK_N, bool TF32X3>
 __global__ void __launch_bounds__(ConvGemmCfg<BLOCK_N, TF32X3>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using Cfg = ConvGemmCfg<BLOCK_N, TF32X3>;
-  constexpr int kStages = Cfg::kStages;
+  const int kStages = TF32X3 ? Cfg::kStages : p.n_stages;
+  const int kCSlots = TF32X3 ? kMinCSlots : p.n_cslots;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -132,15 +154,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   uint8_t* sA_lo = sB + kStages * Cfg::kBBytes;        // TF32X3 only
   uint8_t* sB_lo = sA_lo + kStages * Cfg::kABytes;     // TF32X3 only
   uint8_t* sC = smem + kStages * Cfg::kStageBytes;     // bf16 only: [kCSlots][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kCRingBytes);
-  uint64_t* full_bar = bars;                  // TMA -> (splitter | MMA)
-  uint64_t* empty_bar = bars + kStages;       // MMA -> TMA
-  uint64_t* split_bar = bars + 2 * kStages;   // splitter -> MMA (TF32X3)
-  uint64_t* tmem_full = bars + 3 * kStages;   // MMA -> epilogue   [2]
-  uint64_t* tmem_empty = tmem_full + 2;       // epilogue -> MMA   [2]
-  uint64_t* c_full = tmem_empty + 2;          // C producer -> epilogue [kCSlots]
-  uint64_t* c_empty = c_full + kCSlots;       // epilogue -> C producer [kCSlots]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_empty + kCSlots);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBudget);
+  uint64_t* full_bar = bars;                     // TMA -> (splitter | MMA)
+  uint64_t* empty_bar = bars + kMaxStages;       // MMA -> TMA
+  uint64_t* split_bar = bars + 2 * kMaxStages;   // splitter -> MMA (TF32X3)
+  uint64_t* tmem_full = bars + 3 * kMaxStages;   // MMA -> epilogue   [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // epilogue -> MMA   [2]
+  uint64_t* c_full = tmem_empty + 2;             // C producer -> epilogue [kCSlots]
+  uint64_t* c_empty = c_full + kMaxCSlots;       // epilogue -> C producer [kCSlots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_empty + kMaxCSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -161,11 +183,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kNumEpiWarps);
+      mbar_init(&tmem_empty[i], Cfg::kNumEpiWarps);
     }
     for (int i = 0; i < kCSlots; ++i) {
       mbar_init(&c_full[i], 1);
-      mbar_init(&c_empty[i], kNumEpiWarps);
+      mbar_init(&c_empty[i], TF32X3 ? 1 : (4 / (BLOCK_N / 64)) * 4);   // warps sharing one C tile
     }
     fence_mbar_init();
   }
@@ -270,10 +292,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
       }
     }
-  } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + kNumEpiWarps) {
+  } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + Cfg::kNumEpiWarps) {
     // ------------------------------------------------------------ epilogue
     const int quarter = warp & 3;                       // TMEM lanes [32*quarter, +32)
-    const int half = (warp - kFirstEpiWarp) >> 2;       // which 32-column half of a 64-column C tile
+    const int half = (warp - kFirstEpiWarp) >> 2;       // TF32x3: even/odd 32-column chunks; bf16: 16-column group 0..3
     const int row = quarter * 32 + lane;
     const int dw = row % p.bw;
     const int dh = (row / p.bw) % p.bh;
@@ -281,7 +303,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const int HW = p.Ho * p.Wo;
     int it = 0;
     [[maybe_unused]] int c_it = 0;
-    [[maybe_unused]] int prev_slot = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
       const int iw = m_blk % p.tiles_w;
@@ -364,104 +385,124 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
       } else {
-        // ---- bf16 path: 128x64 C tiles through the smem ring, TMA store
+        // ---- bf16 path: 128x64 C tiles through the smem ring, TMA store.  The 16 epilogue warps form four groups of
+        //      four (one warp per TMEM lane quarter); the groups split the tile's BLOCK_N columns, so with
+        //      BLOCK_N = 256 the four C tiles of an output tile drain concurrently (each chain of
+        //      tcgen05.ld -> math -> st.shared -> fence -> barrier -> TMA store is latency-bound).
+        constexpr int kSub = BLOCK_N / 64;          // C tiles (ring slots) per output tile
+        constexpr int kGps = 4 / kSub;              // groups sharing one C tile
+        constexpr int kCg = BLOCK_N / 4;            // columns per group: 64, 32 or 16
+        const int group = half;                     // (warp - kFirstEpiWarp) >> 2
+        const int my_sub = group / kGps;
+        const int col_in_sub = (group % kGps) * kCg;
+        const bool storer = (quarter == 0) && (group % kGps == 0);
         __nv_bfloat16* tsm = reinterpret_cast<__nv_bfloat16*>(p.tsm_out);
         const bool has_res = p.residual != nullptr;
-        const int srow = lane >> 2, spiece = lane & 3;    // TSM scatter: rows srow + 8*i of the warp, 16-byte piece
-        long g_i[4];
-        int t_i[4];
+        const int srow = lane >> 1, spiece = lane & 1;    // TSM scatter: rows srow + 16*i of the warp, 16-byte piece
+        long g_i[2];
+        int t_i[2];
         if (tsm) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            g_i[i] = __shfl_sync(0xffffffffu, grow, srow + 8 * i);
+          for (int i = 0; i < 2; ++i) {
+            g_i[i] = __shfl_sync(0xffffffffu, grow, srow + 16 * i);
             t_i[i] = g_i[i] >= 0 ? static_cast<int>((g_i[i] / HW) % p.T) : 0;
           }
         }
-        const int n_sub = min(BLOCK_N / 64, (p.N - n_blk * BLOCK_N + 63) / 64);
-#pragma unroll 1
-        for (int j = 0; j < n_sub; ++j, ++c_it) {
-          const int slot = c_it % kCSlots;
+        const int n_sub = min(kSub, (p.N - n_blk * BLOCK_N + 63) / 64);
+        if (my_sub < n_sub) {
+          const int my_it = c_it + my_sub;
+          const int slot = my_it % kCSlots;
           uint8_t* ctile = sC + slot * kCBytes;
           uint8_t* crow = ctile + row * 128;
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + j * 64 + half * 32, r);      // asynchronous until tmem_ld_wait
-          const int col0 = n_blk * BLOCK_N + j * 64 + half * 32;
-          mbar_wait(&c_full[slot], (c_it / kCSlots) & 1);    // residual landed / slot free
-          tmem_ld_wait();
-          float v[32];
+          mbar_wait(&c_full[slot], (my_it / kCSlots) & 1);    // residual landed / slot free
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
-          if (col0 < p.N) {
-            if (p.bias) {
+          for (int pass = 0; pass < kCg / 16; ++pass) {
+            const int cs = col_in_sub + pass * 16;            // first column inside the C tile
+            const int col0 = n_blk * BLOCK_N + my_sub * 64 + cs;
+            uint32_t r[16];
+            tmem_ld_32x16(taddr + my_sub * 64 + cs, r);
+            tmem_ld_wait();
+            float v[16];
 #pragma unroll
-              for (int e = 0; e < 32; e += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + e));   // N % 32 == 0 (host check)
-                v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+            if (col0 < p.N) {
+              if (p.bias) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + e));   // N % 32 == 0 (host check)
+                  v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+                }
               }
+              if (has_res) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {      // logical 16-byte chunk cs/8 + c, XOR-swizzled with row % 8
+                  const uint4 q = *reinterpret_cast<const uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4));
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    v[c * 8 + 2 * e] += f.x; v[c * 8 + 2 * e + 1] += f.y;
+                  }
+                }
+              }
+              apply_act16(v, p.act);
             }
-            if (has_res) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {      // logical 16-byte chunk 4*half + c, XOR-swizzled with row % 8
-                const uint4 q = *reinterpret_cast<const uint4*>(crow + (((half * 4 + c) ^ (row & 7)) << 4));
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+            for (int c = 0; c < 2; ++c) {
+              uint4 o;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(h2[e]);
-                  v[c * 8 + 2 * e] += f.x; v[c * 8 + 2 * e + 1] += f.y;
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4)) = o;
+            }
+          }
+          fence_proxy_async_smem();                       // generic-proxy writes -> visible to the TMA store
+          // every warp that shares this C tile has finished it
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + my_sub), "n"(kGps * 128) : "memory");
+          if (storer && lane == 0) {
+            tma_store_5d(ctile, &p.out_map, n_blk * BLOCK_N + my_sub * 64, iw * p.bw, ih * p.bh, 0, in * p.nf);
+            tma_store_commit();
+          }
+          // TSM: this warp's 32 rows x kCg columns, re-read with 2 lanes per row (32-byte segments)
+          if (tsm) {
+#pragma unroll
+            for (int pass = 0; pass < kCg / 16; ++pass) {
+              const int cs = col_in_sub + pass * 16;
+              const int col0 = n_blk * BLOCK_N + my_sub * 64 + cs;
+              const bool zone_a = col0 < p.tsm_fold;
+              const bool zone_b = !zone_a && col0 < 2 * p.tsm_fold;
+              if (zone_a || zone_b) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const int rr = quarter * 32 + srow + 16 * i;
+                  if (g_i[i] >= 0) {
+                    const uint4 o = *reinterpret_cast<const uint4*>(ctile + rr * 128 + ((((cs >> 3) + spiece) ^ (rr & 7)) << 4));
+                    if (zone_a && t_i[i] >= 1)           // out[t-1, c] = x[t, c]   (shift left in time)
+                      *reinterpret_cast<uint4*>(tsm + (g_i[i] - HW) * p.tsm_ld + col0 + spiece * 8) = o;
+                    if (zone_b && t_i[i] + 1 < p.T)      // out[t+1, c] = x[t, c]   (shift right in time)
+                      *reinterpret_cast<uint4*>(tsm + (g_i[i] + HW) * p.tsm_ld + col0 + spiece * 8) = o;
+                  }
                 }
               }
             }
-            apply_act32<false>(v, p.act);
           }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 o;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1]);
-            *reinterpret_cast<uint4*>(crow + (((half * 4 + c) ^ (row & 7)) << 4)) = o;
-          }
-          fence_proxy_async_smem();                       // generic-proxy writes -> visible to the TMA store
-          asm volatile("bar.sync 1, 256;" ::: "memory");  // all 8 epilogue warps finished this C tile
-          if (warp == kFirstEpiWarp && lane == 0) {
-            tma_store_5d(ctile, &p.out_map, n_blk * BLOCK_N + j * 64, iw * p.bw, ih * p.bh, 0, in * p.nf);
-            tma_store_commit();
-          }
-          // TSM: this warp's 32 rows x 32 columns, re-read with 4 lanes per row for coalesced 64-byte segments
-          const bool zone_a = tsm && col0 < p.tsm_fold;
-          const bool zone_b = tsm && !zone_a && col0 < 2 * p.tsm_fold;
-          if (zone_a || zone_b) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = quarter * 32 + srow + 8 * i;
-              if (g_i[i] >= 0) {
-                const uint4 o = *reinterpret_cast<const uint4*>(ctile + rr * 128 + (((half * 4 + spiece) ^ (rr & 7)) << 4));
-                if (zone_a && t_i[i] >= 1)           // out[t-1, c] = x[t, c]   (shift left in time)
-                  *reinterpret_cast<uint4*>(tsm + (g_i[i] - HW) * p.tsm_ld + col0 + spiece * 8) = o;
-                if (zone_b && t_i[i] + 1 < p.T)      // out[t+1, c] = x[t, c]   (shift right in time)
-                  *reinterpret_cast<uint4*>(tsm + (g_i[i] + HW) * p.tsm_ld + col0 + spiece * 8) = o;
-              }
-            }
-          }
-          // release the slot: the storing warp defers its arrival until the bulk store has finished reading smem
+          // release the slot; the storing warp first waits until its bulk store has finished READING the tile (the
+          // TSM scatter above gave it time).  Releasing one tile late instead would chain the four groups together:
+          // each group's next slot is the one its neighbour group has just used.
           __syncwarp();
-          if (warp == kFirstEpiWarp) {
-            if (lane == 0 && prev_slot >= 0) {
-              tma_store_wait_read<1>();
-              mbar_arrive(&c_empty[prev_slot]);
-            }
-            prev_slot = slot;
-          } else if (lane == 0) {
+          if (lane == 0) {
+            if (storer) tma_store_wait_read<0>();
             mbar_arrive(&c_empty[slot]);
           }
         }
+        c_it += n_sub;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
     if constexpr (!TF32X3) {
-      if (warp == kFirstEpiWarp && lane == 0) tma_store_wait_all();   // stores complete before the CTA exits
+      if (lane == 0) tma_store_wait_all();   // (storing warps) stores complete before the CTA exits
     }
   } else if (TF32X3 && warp >= 12) {
     // ------------------------------------------------------------ TF32 hi/lo splitter (fp32 verification mode)

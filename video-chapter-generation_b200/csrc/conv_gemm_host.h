@@ -90,6 +90,15 @@ inline void set_epilogue(ConvGemmLaunch& L, void* out, int ld_out, const Epilogu
   p.tsm_out = e.tsm_out; p.tsm_ld = e.tsm_ld; p.tsm_fold = e.tsm_fold; p.T = e.T > 0 ? e.T : 1;
   if (e.tsm_out) VCG_REQUIRE(e.tsm_fold % 32 == 0, "TSM fold must be a multiple of 32 channels");
   if (!L.fp32) {
+    // smem split: residual layers are HBM-bound -> short K loops get few A/B stages and a deep residual-prefetch ring
+    const int stage_bytes = kBlockM * 128 + L.block_n * 128;
+    const int budget = 224 * 1024;
+    const int min_slots = std::max(kMinCSlots, L.block_n / 64 + 1);   // at least one C tile of prefetch beyond a tile
+    const int max_stages = std::min(kMaxStages, (budget - min_slots * kCBytes) / stage_bytes);
+    const int num_kb = p.n_taps * p.cpt;
+    p.n_stages = e.residual ? std::max(2, std::min(max_stages, num_kb + 1)) : max_stages;
+    p.n_cslots = std::min(kMaxCSlots, (budget - p.n_stages * stage_bytes) / kCBytes);
+    VCG_REQUIRE(p.n_stages >= 2 && p.n_cslots >= min_slots, "shared-memory split failed");
     VCG_REQUIRE(p.N % 32 == 0, "bf16 path: output channels must be a multiple of 32");
     VCG_REQUIRE(ld_out % 8 == 0 && (e.residual == nullptr || e.ld_res % 8 == 0), "row strides must be multiples of 16 bytes");
     p.out_map = c_tile_map(out, ld_out, p);
@@ -206,36 +215,52 @@ inline ConvGemmLaunch build_conv(const void* in, int Nimg, int H, int W, int Cin
   return L;
 }
 
-// ResNet stem: 7x7 stride-2 pad-3 conv over a zero-padded NHWC4 image [Nimg, Hp, Wp, 4] whose pixel (0,0) is the
-// input pixel (-3,-3).  One K block = one filter row: a window of 128 contiguous bytes (16 bf16 / 8 fp32 pixels x 4
-// channels) starting at pixel 2*wo; the tensor map's W dimension therefore has a 16-byte stride (overlapping
-// windows), and the stride-2 row walk is folded into an (H/2, parity) pair of dimensions.
-// Weights packed [Cout][7][window pixels][4], zero where kw >= 7 or c == 3.
+// ResNet stem: 7x7 stride-2 pad-3 conv over the zero-padded stem input (kernels.cuh: pixel (0,0) of the buffer is input
+// pixel (-3,-3)).  The filter rows are walked by TMA boxes over *overlapping* windows: the tensor map's W dimension
+// has a 2-pixel stride while a window is 8 pixels wide.
+//   bf16: the image is stored with ROW PAIRS interleaved per pixel, [N][Hp/2][Wp][2 rows][4 ch], so that a window of
+//         8 pixels x 2 rows x 4 channels is 128 contiguous bytes = one K block of 64; the stride-2 row walk becomes a
+//         unit walk over row pairs: map (64, Wo [32 B], Hp/2, 1, N), 4 K blocks (K = 256, 147 useful);
+//         weights packed [Cout][4 row pairs][8 px][2][4], zero for kh = 7, kw = 7, c = 3.
+//   fp32: plain NHWC4 [N][Hp][Wp][4]; a window of 8 pixels is one K block of 32: map (32, Wo [32 B], Hp/2, parity, N),
+//         7 K blocks (K = 224); weights packed [Cout][7][8 px][4].
 inline ConvGemmLaunch build_stem(const void* in_padded, int Nimg, int Hp, int Wp, int Ho, int Wo, const void* Wp_packed,
                                  int Cout, void* out, bool fp32, const Epilogue& e) {
   ConvGemmLaunch L;
   memset(&L.p, 0, sizeof L.p);
   L.name = "stem";
-  const int es = elem_size(fp32), bk = block_k(fp32);
   VCG_REQUIRE(Hp % 2 == 0, "padded stem height must be even");
   ConvGemmParams& p = L.p;
   pick_patch(Wo, Ho, Nimg, p.bw, p.bh, p.nf);
-  const uint64_t pitch = static_cast<uint64_t>(Wp) * 4 * es;
-  const uint64_t dims[5] = {static_cast<uint64_t>(bk), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Hp / 2), 2,
-                            static_cast<uint64_t>(Nimg)};
-  const uint64_t str[4] = {2ull * 4 * es, 2 * pitch, pitch, pitch * Hp};
-  const uint32_t box[5] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), 1,
+  const uint32_t box[5] = {static_cast<uint32_t>(block_k(fp32)), static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), 1,
                            static_cast<uint32_t>(p.nf)};
-  p.a_map[0] = make_tensor_map(in_padded, fp32, 5, dims, str, box);
-  for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
-  p.n_taps = 7; p.cpt = 1;
-  for (int kh = 0; kh < 7; ++kh) {
-    TapDesc t{};
-    t.dw = 0; t.dh = static_cast<int16_t>(kh / 2); t.plane = static_cast<int8_t>(kh & 1); t.map = 0; t.c_off = 0;
-    p.taps[kh] = t;
+  if (!fp32) {
+    const uint64_t pair_pitch = static_cast<uint64_t>(Wp) * 8 * 2;   // one row pair: Wp pixels x (2 rows x 4 ch) bf16
+    const uint64_t img = pair_pitch * (Hp / 2);
+    const uint64_t dims[5] = {64, static_cast<uint64_t>(Wo), static_cast<uint64_t>(Hp / 2), 1, static_cast<uint64_t>(Nimg)};
+    const uint64_t str[4] = {2 * 16, pair_pitch, img, img};            // W step: 2 pixels x 16 B
+    p.a_map[0] = make_tensor_map(in_padded, false, 5, dims, str, box);
+    p.n_taps = 4; p.cpt = 1;
+    for (int j = 0; j < 4; ++j) {
+      TapDesc t{};
+      t.dh = static_cast<int16_t>(j);
+      p.taps[j] = t;
+    }
+  } else {
+    const uint64_t pitch = static_cast<uint64_t>(Wp) * 4 * 4;
+    const uint64_t dims[5] = {32, static_cast<uint64_t>(Wo), static_cast<uint64_t>(Hp / 2), 2, static_cast<uint64_t>(Nimg)};
+    const uint64_t str[4] = {2 * 16, 2 * pitch, pitch, pitch * Hp};
+    p.a_map[0] = make_tensor_map(in_padded, true, 5, dims, str, box);
+    p.n_taps = 7; p.cpt = 1;
+    for (int kh = 0; kh < 7; ++kh) {
+      TapDesc t{};
+      t.dh = static_cast<int16_t>(kh / 2); t.plane = static_cast<int8_t>(kh & 1);
+      p.taps[kh] = t;
+    }
   }
+  for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
   finish_launch(L, Wo, Ho, Nimg, Cout, fp32);
-  p.b_map = weight_map(Wp_packed, Cout, 7 * bk, L.block_n, fp32);
+  p.b_map = weight_map(Wp_packed, Cout, fp32 ? 7 * 32 : 4 * 64, L.block_n, fp32);
   set_epilogue(L, out, Cout, e);
   L.flops = 2.0 * Nimg * Ho * Wo * static_cast<double>(Cout) * 147;
   return L;

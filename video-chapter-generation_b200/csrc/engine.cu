@@ -128,10 +128,12 @@ struct vcg_engine {
   DevBuf word, pos, type, emb_g, emb_b;
   std::vector<BertLayerW> layers;
   // tail weights (fp32)
-  DevBuf pool_w_t, pool_b, lang_w_t, vis_w_t, head_w, head_b, q_w_t, q_b, k_w_t, k_b, v_w_t, v_b, proj_w, proj_b;
+  LinearW pooler;                       // [768][768] + bias, activation type (tcgen05 GEMM, tanh epilogue)
+  DevBuf lang_w, vis_w;                 // bias-free projections [128][768], [128][2048], activation type
+  DevBuf head_w, head_b, q_w_t, q_b, k_w_t, k_b, v_w_t, v_b, proj_w, proj_b;   // head, fp32
 
   // vision workspace (sized for Bv clips)
-  DevBuf stem_in, stem_out, x0, xa, xb, dsbuf, mid1, mid2, vis_emb, vis_out, lang_out;
+  DevBuf stem_in, stem_out, x0, xa, xb, dsbuf, mid1, mid2, vis_emb, vis_emb_act, vis_out, lang_out, pooled;
   std::vector<std::unique_ptr<DevBuf>> shifted;   // one per bottleneck: its temporally shifted input channels
   // text workspace (sized for Bt clips x Lmax tokens)
   DevBuf hid, hid2, qkv, ctx, tmp, ffn;
@@ -140,6 +142,8 @@ struct vcg_engine {
 
   std::map<int, VisionPlan> vplans;
   std::map<std::pair<int, int>, BertPlan> bplans;
+  std::map<std::pair<int, int>, std::vector<ConvGemmLaunch>> lang_tail_plans;   // (clips, L) -> pooler, lang projection
+  std::map<int, ConvGemmLaunch> vis_proj_plans;                                 // frames -> vision projection
 
   // profiling
   bool profiling = false;
@@ -229,9 +233,8 @@ void finalize_vision(vcg_engine* e, cudaStream_t s) {
     const RawTensor& b = need(e, vm + "bn1.bias", {64});
     const RawTensor& m = need(e, vm + "bn1.running_mean", {64});
     const RawTensor& v = need(e, vm + "bn1.running_var", {64});
-    const int win = e->fp32 ? 8 : 16;
     e->stem.Cin = 3; e->stem.Cout = 64; e->stem.k = 7; e->stem.stride = 2;
-    e->stem.w.alloc(static_cast<size_t>(64) * 7 * win * 4 * e->es());
+    e->stem.w.alloc(static_cast<size_t>(64) * (e->fp32 ? 7 * 32 : 4 * 64) * e->es());
     e->stem.bias.alloc(64 * sizeof(float));
     launch_pack_stem(fptr(w), fptr(g), fptr(b), fptr(m), fptr(v), 1e-5f, e->stem.w.p, e->stem.bias.as<float>(), e->fp32, s);
   }
@@ -320,8 +323,7 @@ void finalize_text(vcg_engine* e, cudaStream_t s) {
     copy_f32(lw.ln2_g, need(e, pre + "output.LayerNorm.weight", {kBertHidden}), s);
     copy_f32(lw.ln2_b, need(e, pre + "output.LayerNorm.bias", {kBertHidden}), s);
   }
-  transpose_to(e->pool_w_t, need(e, lm + "pooler.dense.weight", {kBertHidden, kBertHidden}), s);
-  copy_f32(e->pool_b, need(e, lm + "pooler.dense.bias", {kBertHidden}), s);
+  pack_linear(e, e->pooler, lm + "pooler.dense", kBertHidden, kBertHidden, s);
   // workspace: +128 rows of slack so that a TMA box starting at the last valid row never leaves the allocation
   const size_t rows = static_cast<size_t>(e->Bt) * e->Lmax + 128, es = e->es();
   e->hid.alloc(rows * kBertHidden * es);
@@ -335,8 +337,8 @@ void finalize_text(vcg_engine* e, cudaStream_t s) {
 void finalize_head(vcg_engine* e, cudaStream_t s) {
   const std::string fh = "fusion_head.";
   const int H = e->H, T = e->T;
-  transpose_to(e->lang_w_t, need(e, fh + "lang_proj_head.weight", {H, kBertHidden}), s);
-  transpose_to(e->vis_w_t, need(e, fh + "vision_proj_head.weight", {H, kVisionDim}), s);
+  convert_to(e->lang_w, need(e, fh + "lang_proj_head.weight", {H, kBertHidden}), e->fp32, s);
+  convert_to(e->vis_w, need(e, fh + "vision_proj_head.weight", {H, kVisionDim}), e->fp32, s);
   if (e->cfg.head_type == VCG_HEAD_MLP) {
     copy_f32(e->head_w, need(e, fh + "head.weight", {2, static_cast<int64_t>(T + 1) * H}), s);
     copy_f32(e->head_b, need(e, fh + "head.bias", {2}), s);
@@ -350,9 +352,12 @@ void finalize_head(vcg_engine* e, cudaStream_t s) {
     copy_f32(e->proj_w, need(e, fh + "head.proj.weight", {2, H}), s);
     copy_f32(e->proj_b, need(e, fh + "head.proj.bias", {2}), s);
   }
-  e->vis_emb.alloc(static_cast<size_t>(std::max(e->Bv, e->Bt)) * T * kVisionDim * sizeof(float));
-  e->vis_out.alloc(static_cast<size_t>(std::max(e->Bv, e->Bt)) * T * H * sizeof(float));
-  e->lang_out.alloc(static_cast<size_t>(e->Bt) * H * sizeof(float));
+  const size_t max_frames = static_cast<size_t>(std::max(e->Bv, e->Bt)) * T;
+  e->vis_emb.alloc(max_frames * kVisionDim * sizeof(float));
+  if (!e->fp32) e->vis_emb_act.alloc(max_frames * kVisionDim * e->es());   // bf16 copy: A operand of the projection
+  e->vis_out.alloc((max_frames + 128) * H * e->es());
+  e->lang_out.alloc((static_cast<size_t>(e->Bt) + 128) * H * e->es());
+  e->pooled.alloc((static_cast<size_t>(e->Bt) + 128) * kBertHidden * e->es());
 }
 
 // ------------------------------------------------------------------------------------------------ plans
@@ -382,8 +387,13 @@ VisionPlan& vision_plan(vcg_engine* e, int B) {
   const void* x = e->x0.p;
   void* pingpong[2] = {e->xa.p, e->xb.p};
   int pp = 0;
+  static const char* const kNames[4][4] = {{"l1.conv1", "l1.conv2", "l1.conv3", "l1.downsample"},
+                                           {"l2.conv1", "l2.conv2", "l2.conv3", "l2.downsample"},
+                                           {"l3.conv1", "l3.conv2", "l3.conv3", "l3.downsample"},
+                                           {"l4.conv1", "l4.conv2", "l4.conv3", "l4.downsample"}};
   for (int i = 0; i < 16; ++i) {
     const Bottleneck& bk = e->blocks[i];
+    const int stage = i < 3 ? 0 : i < 7 ? 1 : i < 13 ? 2 : 3;
     const int H = bk.H, Ho = H / bk.stride, Cout = bk.planes * 4;
     void* xnext = pingpong[pp];
     pp ^= 1;
@@ -392,20 +402,20 @@ VisionPlan& vision_plan(vcg_engine* e, int B) {
       Epilogue ep; ep.bias = bk.c1.bias.as<float>(); ep.act = ACT_RELU;
       const void* sh = e->tsm ? e->shifted[i]->p : nullptr;
       const int sh_ch = e->tsm ? ((i == 0) ? 64 : 2 * (bk.Cin / e->cfg.shift_div)) : 0;
-      st.gemm = build_conv(x, N, H, H, bk.Cin, bk.c1.w.p, bk.planes, 1, 1, e->mid1.p, fp, ep, sh, sh_ch, "conv1");
+      st.gemm = build_conv(x, N, H, H, bk.Cin, bk.c1.w.p, bk.planes, 1, 1, e->mid1.p, fp, ep, sh, sh_ch, kNames[stage][0]);
       plan.steps.push_back(st);
     }
     {   // conv2 3x3 (stride) + BN + ReLU
       Step st{}; st.kind = Step::CONV_GEMM;
       Epilogue ep; ep.bias = bk.c2.bias.as<float>(); ep.act = ACT_RELU;
-      st.gemm = build_conv(e->mid1.p, N, H, H, bk.planes, bk.c2.w.p, bk.planes, 3, bk.stride, e->mid2.p, fp, ep, nullptr, 0, "conv2");
+      st.gemm = build_conv(e->mid1.p, N, H, H, bk.planes, bk.c2.w.p, bk.planes, 3, bk.stride, e->mid2.p, fp, ep, nullptr, 0, kNames[stage][1]);
       plan.steps.push_back(st);
     }
     const void* identity = x;
     if (bk.has_ds) {   // downsample 1x1 (stride) + BN on the un-shifted block input
       Step st{}; st.kind = Step::CONV_GEMM;
       Epilogue ep; ep.bias = bk.ds.bias.as<float>(); ep.act = ACT_NONE;
-      st.gemm = build_conv(x, N, H, H, bk.Cin, bk.ds.w.p, Cout, 1, bk.stride, e->dsbuf.p, fp, ep, nullptr, 0, "downsample");
+      st.gemm = build_conv(x, N, H, H, bk.Cin, bk.ds.w.p, Cout, 1, bk.stride, e->dsbuf.p, fp, ep, nullptr, 0, kNames[stage][3]);
       plan.steps.push_back(st);
       identity = e->dsbuf.p;
     }
@@ -419,7 +429,7 @@ VisionPlan& vision_plan(vcg_engine* e, int B) {
         ep.tsm_ld = 2 * ep.tsm_fold;
         ep.T = e->T;
       }
-      st.gemm = build_conv(e->mid2.p, N, Ho, Ho, bk.planes, bk.c3.w.p, Cout, 1, 1, xnext, fp, ep, nullptr, 0, "conv3");
+      st.gemm = build_conv(e->mid2.p, N, Ho, Ho, bk.planes, bk.c3.w.p, Cout, 1, 1, xnext, fp, ep, nullptr, 0, kNames[stage][2]);
       plan.steps.push_back(st);
     }
     x = xnext;
@@ -537,29 +547,43 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
                            e->emb_g.as<float>(), e->emb_b.as<float>(), e->hid.p, e->fp32, s);
     }
     run_steps(e, bert_plan(e, bt, L).steps, mask + static_cast<long>(b0) * L, s);
-    // ---- pooler + lang projection for the bt clips
+    // ---- BertPooler (tanh) + lang projection (ReLU) for the bt clips: two small tcgen05 GEMMs over the [CLS] rows
+    {
+      auto key = std::make_pair(bt, L);
+      auto it = e->lang_tail_plans.find(key);
+      if (it == e->lang_tail_plans.end()) {
+        std::vector<ConvGemmLaunch> v;
+        Epilogue ep1; ep1.bias = e->pooler.bias.as<float>(); ep1.act = ACT_TANH;
+        v.push_back(build_gemm(e->hid.p, static_cast<long>(L) * kBertHidden, e->pooler.w.p, e->pooled.p, kBertHidden, bt,
+                               kBertHidden, kBertHidden, e->fp32, ep1, "head.pooler"));
+        Epilogue ep2; ep2.act = ACT_RELU;
+        v.push_back(build_gemm(e->pooled.p, kBertHidden, e->lang_w.p, e->lang_out.p, e->H, bt, e->H, kBertHidden, e->fp32, ep2,
+                               "head.lang_proj"));
+        it = e->lang_tail_plans.emplace(key, std::move(v)).first;
+      }
+      for (const ConvGemmLaunch& g : it->second) {
+        ProfScope ps(e, s, gemm_kernel_name(g), g.flops, 0);
+        launch_conv_gemm(g, s);
+      }
+      if (lang_emb_out) {
+        ProfScope ps(e, s, "cast_to_f32|head.lang_emb", 0, static_cast<double>(bt) * kBertHidden * (4 + e->es()));
+        launch_cast_to_f32(e->pooled.p, lang_emb_out + static_cast<long>(b0) * kBertHidden, static_cast<long>(bt) * kBertHidden,
+                           e->fp32, s);
+      }
+    }
     TailParams tp{};
-    tp.L = L; tp.T = T; tp.H = e->H; tp.head_type = e->cfg.head_type;
-    tp.pool_w_t = e->pool_w_t.as<float>(); tp.pool_b = e->pool_b.as<float>();
-    tp.lang_w_t = e->lang_w_t.as<float>(); tp.vis_w_t = e->vis_w_t.as<float>();
+    tp.T = T; tp.H = e->H; tp.head_type = e->cfg.head_type;
     tp.head_w = e->head_w.as<float>(); tp.head_b = e->head_b.as<float>();
     tp.q_w_t = e->q_w_t.as<float>(); tp.q_b = e->q_b.as<float>();
     tp.k_w_t = e->k_w_t.as<float>(); tp.k_b = e->k_b.as<float>();
     tp.v_w_t = e->v_w_t.as<float>(); tp.v_b = e->v_b.as<float>();
     tp.proj_w = e->proj_w.as<float>(); tp.proj_b = e->proj_b.as<float>();
-    tp.hidden = e->hid.p;
-    tp.lang_out = e->lang_out.as<float>();
-    tp.lang_emb = lang_emb_out ? lang_emb_out + static_cast<long>(b0) * kBertHidden : nullptr;
-    {
-      ProfScope ps(e, s, "lang_tail|head", 2.0 * bt * (768.0 * 768 + 768 * 128), 0);
-      launch_lang_tail(tp, bt, e->fp32, s);
-    }
     // ---- vision stream + head in sub-chunks
     const int step = have_frames ? e->Bv : bt;
     for (int c0 = 0; c0 < bt; c0 += step) {
       const int bv = std::min(step, bt - c0);
       const int g0 = b0 + c0;   // first clip of this sub-chunk in the caller's numbering
-      const float* vis = nullptr;
+      const void* vis_act = nullptr;   // [bv*T, 2048] in the activation type
       if (have_frames) {
         if (src.img_clip) {
           ProfScope ps(e, s, "nchw_to_stem|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (4 + e->es()));
@@ -570,30 +594,54 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
         }
         VisionPlan& vp = vision_plan(e, bv);
         run_steps(e, vp.steps, nullptr, s);
+        // fp32 embeddings go to the caller's buffer when asked for; in fp32 mode they are also the GEMM operand
         float* dst = vision_emb_out ? vision_emb_out + static_cast<long>(g0) * T * kVisionDim : e->vis_emb.as<float>();
         {
           ProfScope ps(e, s, "avgpool|avgpool", 0, static_cast<double>(bv) * T * kVisionDim * (49 * e->es() + 4));
-          launch_avgpool(vp.final_act, bv * T, 49, kVisionDim, dst, s, e->fp32);
+          launch_avgpool(vp.final_act, bv * T, 49, kVisionDim, dst, e->fp32 ? nullptr : e->vis_emb_act.p, s, e->fp32);
         }
-        vis = dst;
+        vis_act = e->fp32 ? static_cast<const void*>(dst) : e->vis_emb_act.p;
+        if (e->fp32 && vision_emb_out) {   // keep the GEMM operand at a fixed address (cached tensor maps)
+          VCG_CUDA(cudaMemcpyAsync(e->vis_emb.p, dst, static_cast<size_t>(bv) * T * kVisionDim * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s));
+          vis_act = e->vis_emb.p;
+        }
       } else {
-        vis = vision_emb_in + static_cast<long>(g0) * T * kVisionDim;
+        const float* vis = vision_emb_in + static_cast<long>(g0) * T * kVisionDim;
         if (vision_emb_out)
           VCG_CUDA(cudaMemcpyAsync(vision_emb_out + static_cast<long>(g0) * T * kVisionDim, vis,
                                    static_cast<size_t>(bv) * T * kVisionDim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        // caller's fp32 embeddings -> activation type at the fixed operand address
+        ProfScope ps(e, s, "convert|head.vision_emb_in", 0, static_cast<double>(bv) * T * kVisionDim * (4 + e->es()));
+        if (e->fp32) {
+          VCG_CUDA(cudaMemcpyAsync(e->vis_emb.p, vis, static_cast<size_t>(bv) * T * kVisionDim * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s));
+          vis_act = e->vis_emb.p;
+        } else {
+          launch_convert(vis, e->vis_emb_act.p, static_cast<long>(bv) * T * kVisionDim, false, s);
+          vis_act = e->vis_emb_act.p;
+        }
       }
       {
-        ProfScope ps(e, s, "vision_proj|head", 2.0 * bv * T * 2048.0 * 128, 0);
-        launch_vision_proj(vis, e->vis_w_t.as<float>(), e->vis_out.as<float>(), bv * T, e->H, s);
+        auto it = e->vis_proj_plans.find(bv * T);
+        if (it == e->vis_proj_plans.end()) {
+          Epilogue ep; ep.act = ACT_RELU;
+          const void* a = e->fp32 ? e->vis_emb.p : e->vis_emb_act.p;
+          it = e->vis_proj_plans.emplace(bv * T, build_gemm(a, kVisionDim, e->vis_w.p, e->vis_out.p, e->H, bv * T, e->H,
+                                                            kVisionDim, e->fp32, ep, "head.vision_proj")).first;
+        }
+        (void)vis_act;
+        ProfScope ps(e, s, gemm_kernel_name(it->second), it->second.flops, 0);
+        launch_conv_gemm(it->second, s);
       }
       TailParams hp = tp;
-      hp.vis_out = e->vis_out.as<float>();
-      hp.lang_out = e->lang_out.as<float>() + static_cast<long>(c0) * e->H;
+      hp.vis_out = e->vis_out.p;
+      hp.lang_out = static_cast<const uint8_t*>(e->lang_out.p) + static_cast<size_t>(c0) * e->H * e->es();
       hp.logits = logits + static_cast<long>(g0) * 2;
       hp.probs = probs + static_cast<long>(g0) * 2;
       {
-        ProfScope ps(e, s, "head_final|head", 2.0 * bv * (T + 1) * 128 * 2, 0);
-        launch_head_final(hp, bv, s);
+        ProfScope ps(e, s, "head_final|head.final", 2.0 * bv * (T + 1) * 128 * 2, 0);
+        launch_head_final(hp, bv, e->fp32, s);
       }
     }
   }
@@ -673,6 +721,8 @@ int vcg_finalize(vcg_engine* e, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     e->vplans.clear();
     e->bplans.clear();
+    e->lang_tail_plans.clear();
+    e->vis_proj_plans.clear();
     if (e->cfg.vision == VCG_VISION_R50TSM) finalize_vision(e, s);
     finalize_text(e, s);
     finalize_head(e, s);

@@ -56,6 +56,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Element offset of padded pixel (hp, wp) of image n in the stem input.  fp32: plain NHWC4 [n][Hp][Wp][4];
+// bf16: row pairs interleaved per pixel, [n][Hp/2][Wp][2][4] (one stem K block = 8 pixels x 2 rows, conv_gemm_host.h).
+template <bool FP32>
+__device__ __forceinline__ long stem_offset(long n, int hp, int wp) {
+  if constexpr (FP32) return ((n * kStemHp + hp) * kStemWp + wp) * 4L;
+  else return (((n * (kStemHp / 2) + (hp >> 1)) * kStemWp + wp) * 2L + (hp & 1)) * 4L;
+}
+
 // ------------------------------------------------------------------------------------------------ preprocess
 // ToTensor + Normalize (test_video_segment_point.py:142-145): (u8/255 - mean)/std, HWC -> zero-padded NHWC4.
 // One thread = 4 pixels: 12 bytes in (three aligned 32-bit loads), 4 pixel stores out.
@@ -81,19 +89,19 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ frames, const i
   *reinterpret_cast<uint32_t*>(b) = u0;
   *reinterpret_cast<uint32_t*>(b + 4) = u1;
   *reinterpret_cast<uint32_t*>(b + 8) = u2;
-  elem_t<FP32>* dst = out + ((n * kStemHp + h + kStemPad) * kStemWp + (w4 * 4 + kStemPad)) * 4L;
 #pragma unroll
   for (int px = 0; px < 4; ++px) {
     float v[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[c] = (static_cast<float>(b[px * 3 + c]) / 255.0f - c_mean[c]) / c_std[c];
+    elem_t<FP32>* dst = out + stem_offset<FP32>(n, h + kStemPad, w4 * 4 + px + kStemPad);
     if constexpr (FP32) {
-      *reinterpret_cast<float4*>(dst + px * 4) = make_float4(v[0], v[1], v[2], 0.f);
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], 0.f);
     } else {
       uint2 q;
       q.x = pack_bf16x2(v[0], v[1]);
       q.y = pack_bf16x2(v[2], 0.f);
-      *reinterpret_cast<uint2*>(dst + px * 4) = q;
+      *reinterpret_cast<uint2*>(dst) = q;
     }
   }
 }
@@ -108,7 +116,7 @@ __global__ void nchw_to_stem_kernel(const float* __restrict__ img, long total, e
   const long n = idx / (kImg * kImg);
   const float* src = img + n * 3L * kImg * kImg + h * kImg + w;
   const float r = __ldg(src), g = __ldg(src + kImg * kImg), b = __ldg(src + 2 * kImg * kImg);
-  elem_t<FP32>* dst = out + ((n * kStemHp + h + kStemPad) * kStemWp + (w + kStemPad)) * 4L;
+  elem_t<FP32>* dst = out + stem_offset<FP32>(n, h + kStemPad, w + kStemPad);
   if constexpr (FP32) {
     *reinterpret_cast<float4*>(dst) = make_float4(r, g, b, 0.f);
   } else {
@@ -167,7 +175,7 @@ __global__ void maxpool_tsm_kernel(const elem_t<FP32>* __restrict__ in, long tot
 // AdaptiveAvgPool2d(1) over NHWC [n, hw, C] -> fp32 [n, C]
 template <bool FP32>
 __global__ void avgpool_kernel(const elem_t<FP32>* __restrict__ in, long total, int hw, int C,
-                               float* __restrict__ out) {
+                               float* __restrict__ out, elem_t<FP32>* __restrict__ out_act) {
   const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   const int c8 = static_cast<int>(idx % (C / 8));
@@ -183,6 +191,12 @@ __global__ void avgpool_kernel(const elem_t<FP32>* __restrict__ in, long total, 
   float* o = out + n * C + c8 * 8;
   *reinterpret_cast<float4*>(o) = make_float4(s[0] / d, s[1] / d, s[2] / d, s[3] / d);
   *reinterpret_cast<float4*>(o + 4) = make_float4(s[4] / d, s[5] / d, s[6] / d, s[7] / d);
+  if (out_act) {
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = s[e] / d;
+    store8<FP32>(out_act + n * C + c8 * 8, m);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
@@ -276,25 +290,28 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
   if (ci == 0 && kk == 0) bias_out[co] = bn_b[co] - bn_mean[co] * scale;
 }
 
-// stem weight [64,3,7,7] -> [64][7][win][4], win = 16 (bf16) / 8 (fp32) pixels, zero for kw >= 7 or c == 3
+// stem weight [64,3,7,7] -> fp32: [64][7][8 px][4]; bf16: [64][4 row pairs][8 px][2 rows][4]; zero where kh = 7, kw = 7, c = 3
 template <bool FP32>
 __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
                                  const float* __restrict__ bn_b, const float* __restrict__ bn_mean,
                                  const float* __restrict__ bn_var, float eps, elem_t<FP32>* __restrict__ w_out,
                                  float* __restrict__ bias_out) {
-  constexpr int win = FP32 ? 8 : 16;
-  const int total = 64 * 7 * win * 4;
+  constexpr int per_co = FP32 ? 7 * 32 : 4 * 64;
+  const int total = 64 * per_co;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int c = idx % 4;
-  const int kw = (idx / 4) % win;
-  const int kh = (idx / (4 * win)) % 7;
-  const int co = idx / (4 * win * 7);
+  const int co = idx / per_co, k = idx % per_co;
+  int c, kw, kh;
+  if constexpr (FP32) {
+    c = k % 4; kw = (k / 4) % 8; kh = k / 32;
+  } else {
+    c = k % 4; kh = 2 * (k / 64) + ((k / 4) % 2); kw = (k / 8) % 8;
+  }
   const float scale = bn_w[co] / sqrtf(bn_var[co] + eps);
   float v = 0.f;
-  if (c < 3 && kw < 7) v = w[((co * 3 + c) * 7 + kh) * 7 + kw] * scale;
+  if (c < 3 && kw < 7 && kh < 7) v = w[((co * 3 + c) * 7 + kh) * 7 + kw] * scale;
   if constexpr (FP32) w_out[idx] = v; else w_out[idx] = __float2bfloat16_rn(v);
-  if (idx % (7 * win * 4) == 0) bias_out[co] = bn_b[co] - bn_mean[co] * scale;
+  if (k == 0) bias_out[co] = bn_b[co] - bn_mean[co] * scale;
 }
 
 template <bool FP32>
@@ -365,11 +382,11 @@ void launch_maxpool_tsm(const void* in, int n, void* out, void* out_shifted, int
                          static_cast<elem_t<FP>*>(out_shifted), T, fold)));
   VCG_CUDA(cudaGetLastError());
 }
-void launch_avgpool(const void* in, int n, int hw, int C, float* out, cudaStream_t s, bool fp32) {
+void launch_avgpool(const void* in, int n, int hw, int C, float* out, void* out_act, cudaStream_t s, bool fp32) {
   const long total = static_cast<long>(n) * (C / 8);
   if (total == 0) return;
-  VCG_DISPATCH(fp32, (avgpool_kernel<FP><<<blocks_for(total, 128), 128, 0, s>>>(static_cast<const elem_t<FP>*>(in),
-                                                                                 total, hw, C, out)));
+  VCG_DISPATCH(fp32, (avgpool_kernel<FP><<<blocks_for(total, 128), 128, 0, s>>>(
+                         static_cast<const elem_t<FP>*>(in), total, hw, C, out, static_cast<elem_t<FP>*>(out_act))));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const void* word, const void* pos, const void* type,
@@ -398,7 +415,7 @@ void launch_pack_conv(const float* w, const float* bn_w, const float* bn_b, cons
 }
 void launch_pack_stem(const float* w, const float* bn_w, const float* bn_b, const float* bn_mean, const float* bn_var,
                       float eps, void* w_out, float* bias_out, bool fp32, cudaStream_t s) {
-  const int total = 64 * 7 * (fp32 ? 8 : 16) * 4;
+  const int total = 64 * (fp32 ? 7 * 32 : 4 * 64);
   VCG_DISPATCH(fp32, (pack_stem_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(
                          w, bn_w, bn_b, bn_mean, bn_var, eps, static_cast<elem_t<FP>*>(w_out), bias_out)));
   VCG_CUDA(cudaGetLastError());

@@ -25,7 +25,8 @@ void launch_preprocess_u8_clips(const uint8_t* frames, const int32_t* clip_start
 void launch_nchw_to_stem(const float* img, int n, void* out, bool fp32, cudaStream_t s);
 void launch_maxpool_tsm(const void* in, int n, void* out, void* out_shifted, int T, int fold, bool fp32,
                         cudaStream_t s);
-void launch_avgpool(const void* in, int n, int hw, int C, float* out, cudaStream_t s, bool fp32);
+// out: fp32 [n, C]; out_act (optional): the same values in the activation type (GEMM operand of the vision projection)
+void launch_avgpool(const void* in, int n, int hw, int C, float* out, void* out_act, cudaStream_t s, bool fp32);
 void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const void* word, const void* pos, const void* type,
                           const float* gamma, const float* beta, void* out, bool fp32, cudaStream_t s);
 void launch_layernorm(const void* x, const float* gamma, const float* beta, void* y, int rows, int cols, float eps,
@@ -34,17 +35,11 @@ void launch_bert_attention(const void* qkv, const int64_t* mask, void* ctx, int 
 
 struct TailParams {
   // inputs
-  const void* hidden;      // final BERT hidden states [B*L, 768] (element type per `fp32`)
-  int L;
   int T, H;                // frames per clip, head hidden size (128)
-  float* lang_out;         // [B, H]    relu(W_l lang_emb)          (written by lang_tail, read by head_final)
-  const float* vis_out;    // [B*T, H]  relu(W_v vision_emb[t])     (written by vision_proj, read by head_final)
+  const void* lang_out;    // [B, H]    relu(W_l lang_emb)       activation type (bf16 / fp32), written by a GEMM
+  const void* vis_out;     // [B*T, H]  relu(W_v vision_emb[t])  activation type, written by a GEMM
   int head_type;           // 0 mlp, 1 attn
-  // weights (fp32; *_t are transposed to [in][out])
-  const float* pool_w_t;   // [768][768]
-  const float* pool_b;     // [768]
-  const float* lang_w_t;   // [768][H]
-  const float* vis_w_t;    // [2048][H]
+  // head weights (fp32; *_t are transposed to [in][out])
   const float* head_w;     // mlp: [2][(T+1)*H]
   const float* head_b;     // mlp: [2]
   const float* q_w_t; const float* q_b;   // attn: [H][H], [H]
@@ -54,19 +49,15 @@ struct TailParams {
   // outputs
   float* logits;           // [B,2]
   float* probs;            // [B,2]
-  float* lang_emb;         // [B,768] or nullptr
 };
-void launch_lang_tail(const TailParams& p, int B, bool fp32, cudaStream_t s);     // pooler + lang projection
-void launch_vision_proj(const float* vision /*[n,2048]*/, const float* vis_w_t, float* vis_out /*[n,H]*/, int n_frames,
-                        int H, cudaStream_t s);
-void launch_head_final(const TailParams& p, int B, cudaStream_t s);                // head + softmax
+void launch_head_final(const TailParams& p, int B, bool fp32, cudaStream_t s);     // head + softmax
 
 // weight packing (fp32 state-dict tensors -> kernel layouts)
 void launch_pack_conv(const float* w /*[Cout,Cin,k,k]*/, const float* bn_w, const float* bn_b, const float* bn_mean,
                       const float* bn_var, float eps, int Cout, int Cin, int k, void* w_out /*[Cout][k][k][Cin]*/,
                       float* bias_out, bool fp32, cudaStream_t s);
 void launch_pack_stem(const float* w /*[64,3,7,7]*/, const float* bn_w, const float* bn_b, const float* bn_mean,
-                      const float* bn_var, float eps, void* w_out /*[64][7][win][4]*/, float* bias_out, bool fp32,
+                      const float* bn_var, float eps, void* w_out /*[64][R][8][4]*/, float* bias_out, bool fp32,
                       cudaStream_t s);
 void launch_convert(const float* in, void* out, long n, bool fp32, cudaStream_t s);       // fp32 -> T copy
 void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t s);    // [r][c] -> [c][r]

@@ -64,7 +64,8 @@ def conv2d_nhwc(x, w, bias=None, residual=None, stride=1, act=_b.ACT_NONE, tsm_i
 
 
 def preprocess_u8(frames, frame_index=None, dtype=torch.bfloat16):
-    """uint8 [n,224,224,3] -> normalised, zero-padded NHWC4 [n,230,240,4]."""
+    """uint8 [n,224,224,3] -> normalised, zero-padded stem input (fp32: NHWC4 [n,230,240,4]; bf16: the same bytes
+    count with row pairs interleaved per pixel, i.e. [n,115,240,2,4] viewed as [n,230,240,4])."""
     _need_cuda(frames, frame_index)
     n = frames.shape[0] if frame_index is None else frame_index.shape[0]
     out = torch.zeros(n, STEM_HP, STEM_WP, 4, dtype=dtype, device=frames.device)
@@ -84,7 +85,7 @@ def nchw_to_stem(img, dtype=torch.bfloat16):
 
 
 def stem_conv(x_padded, w_packed, bias):
-    """padded NHWC4 -> relu(conv7x7/2 + bias) as NHWC [n,112,112,64]; w_packed [64,7,win,4]."""
+    """padded NHWC4 -> relu(conv7x7/2 + bias) as NHWC [n,112,112,64]; w_packed bf16 [64,4,8,2,4] / fp32 [64,7,8,4]."""
     _need_cuda(x_padded, w_packed, bias)
     n = x_padded.shape[0]
     out = torch.empty(n, 112, 112, 64, dtype=x_padded.dtype, device=x_padded.device)
