@@ -179,7 +179,7 @@ def run_reference(args):
                              "sample": f"{CPU_SAMPLE_CLIPS} clips per step of the same workload (oracle restatement of "
                                        "the reference forward, torch fp32 CPU)"},
             "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def pipeline_extra(args, peaks):
@@ -235,6 +235,15 @@ def pipeline_extra(args, peaks):
             "e2e": {"value": B * steps / sec_e2e, "unit": "clips/s", "h2d_bytes_per_step": int(frames_h.numel() + ids_h.numel() * 16 + starts_h.numel() * 4),
                     "d2h_bytes_per_step": B * 16},
             "kernels": summary, "layers": lsummary}
+
+
+def emit(line):
+    """The contract is ONE JSON line on stdout: libraries (NCCL prints its version there) are kept off it."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)          # anything else that writes to fd 1 goes to stderr
 
 
 def main():
@@ -334,9 +343,12 @@ def main():
                      "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": traffic,
                      "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                      "share_of_step": dom["ms"] / tot_ms, "launches_per_step": dom["launches"] // args.steps,
-                     "how": "algorithmic 2*M*N*K FLOPs of every launch of this kernel / its CUDA-event time"},
+                     "how": "executed 2*M*N*K FLOPs of every launch of this kernel (M = packed token rows) / its CUDA-event time"},
+        # algorithmic = SURVEY.md 8d (full padded length L); executed = what the kernels really did (the text stream
+        # drops masked tokens, which is exact: synthetic lengths are U{10..L})
         "whole_path": {"tflops": value / n_gpus * fl / 1e12, "frac_of_sustained_bf16_peak": value / n_gpus * fl / 1e12 / peaks["tf_sustained"],
-                       "flops_per_clip": fl},
+                       "flops_per_clip": fl,
+                       "tflops_executed": sum(k["flops"] for k in kern.values()) / args.steps / (sec / args.steps) / 1e12},
         "kernels": {n: {"share": round(k["ms"] / tot_ms, 4), "tflops": round(k["flops"] / k["ms"] / 1e9, 1) if k["flops"] else None,
                         "launches_per_step": k["launches"] // args.steps} for n, k in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
     }
@@ -354,7 +366,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
 
 
 if __name__ == "__main__":

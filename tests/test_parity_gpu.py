@@ -117,6 +117,29 @@ def test_u8_pipeline_and_chunking_match_oracle():
     assert torch.equal(lh, lg.cpu()) and torch.equal(ph, pr.cpu())
 
 
+def test_token_packing_irregular_masks():
+    """The text stream drops masked tokens (exact: they are masked as keys everywhere and only h[:,0] is read).
+    Masks with holes, a masked [CLS] position and full-length rows must all match the dense oracle."""
+    from oracle import two_stream_oracle as orc
+    from oracle import weights as W
+    T, L, B = 8, 48, 6
+    model, sd = build_model(T, "mlp", "fp32", vision=False)
+    ids, mask = W.make_text(B, L, seed=21)
+    g = torch.Generator().manual_seed(21)
+    mask[1] = (torch.rand(L, generator=g) > 0.4).long(); mask[1, 0] = 1          # holes
+    mask[2] = 1                                                                     # full length
+    mask[3] = (torch.rand(L, generator=g) > 0.5).long(); mask[3, 0] = 0; mask[3, 5] = 1   # [CLS] itself masked as a key
+    mask[4] = 0; mask[4, 0] = 1                                                     # a single token
+    emb = torch.rand(B, T, 2048, generator=g)
+    ref_logits, _, _, ref_lang = orc.two_stream_forward(sd, None, ids, mask, T, vision_emb=emb)
+    logits, probs, _, lang = model(emb.cuda().view(B, T, 2048, 1, 1), ids.cuda(), mask.cuda(), return_emb=True)
+    assert rel(lang, ref_lang) <= 1e-4, rel(lang, ref_lang)
+    assert rel(logits, ref_logits) <= 1e-4, (logits, ref_logits)
+    model.precision = "bf16"
+    logits_bf16, _ = model(emb.cuda().view(B, T, 2048, 1, 1), ids.cuda(), mask.cuda())
+    assert rel(logits_bf16, ref_logits) <= TOL["bf16"]
+
+
 def test_no_cpu_fallback():
     model, _ = build_model(8, "mlp", "bf16")
     with pytest.raises(RuntimeError):

@@ -1,6 +1,6 @@
 // BERT self-attention  ctx = softmax(Q K^T / sqrt(64) + key_mask) V   (modeling_bert.py:115-140, 12 heads x 64).
 //
-// bf16 path: one CTA per (clip, head, 128-query block); K, V and the Q block are staged in shared memory (rows padded
+// bf16 path: one CTA per (clip, head, 64-query block); K, V and the Q block are staged in shared memory (rows padded
 // to 144 B so ldmatrix is bank-conflict free), each warp owns 16 query rows and walks the keys in blocks of 64 with an
 // online softmax (fp32 statistics, quad shuffles for the row reductions); QK^T and PV run on mma.sync m16n8k16.
 // Attention is 2 % of the path's FLOPs at L=100 (10 % at L=512), so it stays on the legacy tensor path for now.
@@ -15,7 +15,7 @@ namespace {
 
 constexpr int kHeadDim = 64;
 constexpr int kRowPad = 72;   // bf16 elements per padded smem row (144 B)
-constexpr int kQBlock = 128;
+constexpr int kQBlock = 64;    // queries per CTA (4 warps x 16 rows)
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
   const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -38,18 +38,24 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(256) bert_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv,
+// Packed (variable-length) mode: cu[b] .. cu[b+1] are the rows of clip b in the token-packed activation matrices and
+// key_ok[row] says whether that token may be attended to; cu == nullptr: rows b*L .. b*L+L-1 and the int64 mask.
+__global__ void __launch_bounds__(128) bert_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                   const int64_t* __restrict__ mask,
-                                                                  __nv_bfloat16* __restrict__ ctx, int L, int Lp) {
+                                                                  const int32_t* __restrict__ cu,
+                                                                  const uint8_t* __restrict__ key_ok,
+                                                                  __nv_bfloat16* __restrict__ ctx, int Lmax, int Lp_max) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
-  __nv_bfloat16* sV = sK + Lp * kRowPad;
-  __nv_bfloat16* sQ = sV + Lp * kRowPad;
-  float* sMask = reinterpret_cast<float*>(sQ + kQBlock * kRowPad);
-
   const int head = blockIdx.x, b = blockIdx.y, q0 = blockIdx.z * kQBlock;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long row_base = static_cast<long>(b) * L;
+  const long row_base = cu ? cu[b] : static_cast<long>(b) * Lmax;
+  const int L = cu ? (cu[b + 1] - cu[b]) : Lmax;
+  if (q0 >= L) return;                              // (uniform) nothing to do for this query block
+  const int Lp = (L + 63) / 64 * 64;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sV = sK + Lp_max * kRowPad;
+  __nv_bfloat16* sQ = sV + Lp_max * kRowPad;
+  float* sMask = reinterpret_cast<float*>(sQ + kQBlock * kRowPad);
   const int ld = 3 * kBertHidden;
 
   // stage K, V (all keys) and the Q block; rows beyond L are zero (their probabilities are exactly 0)
@@ -70,8 +76,11 @@ __global__ void __launch_bounds__(256) bert_attention_bf16_kernel(const __nv_bfl
     if (q0 + r < L) q4 = *reinterpret_cast<const uint4*>(qkv + (row_base + q0 + r) * ld + head * kHeadDim + c);
     *reinterpret_cast<uint4*>(sQ + r * kRowPad + c) = q4;
   }
-  for (int j = tid; j < Lp; j += blockDim.x)
-    sMask[j] = (j < L && mask[row_base + j] != 0) ? 0.f : -INFINITY;
+  for (int j = tid; j < Lp; j += blockDim.x) {
+    bool ok = j < L;
+    if (ok) ok = cu ? (key_ok[row_base + j] != 0) : (mask[row_base + j] != 0);
+    sMask[j] = ok ? 0.f : -INFINITY;
+  }
   __syncthreads();
 
   const int qrow = warp * 16;                 // this warp's 16 query rows within the block
@@ -177,13 +186,16 @@ __global__ void __launch_bounds__(256) bert_attention_bf16_kernel(const __nv_bfl
 // fp32 verification path: one warp per query row, keys/values straight from L2.
 __global__ void __launch_bounds__(128) bert_attention_fp32_kernel(const float* __restrict__ qkv,
                                                                   const int64_t* __restrict__ mask,
-                                                                  float* __restrict__ ctx, int L) {
+                                                                  const int32_t* __restrict__ cu,
+                                                                  const uint8_t* __restrict__ key_ok,
+                                                                  float* __restrict__ ctx, int Lmax) {
   extern __shared__ float fsm[];
   const int head = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* sq = fsm + warp * (kHeadDim + L);
+  float* sq = fsm + warp * (kHeadDim + Lmax);
   float* sp = sq + kHeadDim;
-  const long row_base = static_cast<long>(b) * L;
+  const long row_base = cu ? cu[b] : static_cast<long>(b) * Lmax;
+  const int L = cu ? (cu[b + 1] - cu[b]) : Lmax;
   const int ld = 3 * kBertHidden;
   for (int q = blockIdx.z * 4 + warp; q < L; q += gridDim.z * 4) {
     const float* qp = qkv + (row_base + q) * ld + head * kHeadDim;
@@ -196,7 +208,8 @@ __global__ void __launch_bounds__(128) bert_attention_fp32_kernel(const float* _
       float acc = 0.f;
 #pragma unroll 16
       for (int d = 0; d < kHeadDim; ++d) acc = fmaf(sq[d], kp[d], acc);
-      acc = acc * 0.125f + (mask[row_base + j] != 0 ? 0.f : -INFINITY);
+      const bool ok = cu ? (key_ok[row_base + j] != 0) : (mask[row_base + j] != 0);
+      acc = acc * 0.125f + (ok ? 0.f : -INFINITY);
       sp[j] = acc;
       mx = fmaxf(mx, acc);
     }
@@ -228,7 +241,8 @@ __global__ void __launch_bounds__(128) bert_attention_fp32_kernel(const float* _
 
 }  // namespace
 
-void launch_bert_attention(const void* qkv, const int64_t* mask, void* ctx, int B, int L, bool fp32, cudaStream_t s) {
+void launch_bert_attention(const void* qkv, const int64_t* mask, const int32_t* cu, const uint8_t* key_ok, void* ctx, int B,
+                           int L, bool fp32, cudaStream_t s) {
   if (B == 0) return;
   VCG_REQUIRE(L >= 1 && L <= 512, "BERT sequence length must be in [1, 512]");
   if (!fp32) {
@@ -241,12 +255,12 @@ void launch_bert_attention(const void* qkv, const int64_t* mask, void* ctx, int 
       configured = smem;
     }
     dim3 grid(kBertHeads, B, (L + kQBlock - 1) / kQBlock);
-    bert_attention_bf16_kernel<<<grid, 256, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv), mask,
+    bert_attention_bf16_kernel<<<grid, 128, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv), mask, cu, key_ok,
                                                        static_cast<__nv_bfloat16*>(ctx), L, Lp);
   } else {
     const size_t smem = static_cast<size_t>(4) * (kHeadDim + L) * sizeof(float);
     dim3 grid(kBertHeads, B, (L + 31) / 32);
-    bert_attention_fp32_kernel<<<grid, 128, smem, s>>>(static_cast<const float*>(qkv), mask,
+    bert_attention_fp32_kernel<<<grid, 128, smem, s>>>(static_cast<const float*>(qkv), mask, cu, key_ok,
                                                        static_cast<float*>(ctx), L);
   }
   VCG_CUDA(cudaGetLastError());

@@ -45,6 +45,7 @@ struct ConvGemmParams {
   int n_taps, cpt;             // taps; channel blocks (of BLOCK_K elements) per tap
   int tsm_split_cb, tsm_map;   // channel blocks below tsm_split_cb are read through a_map[tsm_map]
   int n_stages, n_cslots;      // bf16 path: split of the smem budget between the A/B stage ring and the C-tile ring
+  const int* m_dev;            // plain GEMM only: number of valid rows lives on the device (token-packed BERT)
   int bw, bh, nf;              // patch extents; bw*bh*nf <= 128 rows
   int Wo, Ho, Nimg;            // output geometry
   int tiles_w, tiles_h, tiles_n, n_tiles;
@@ -201,7 +202,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_kb = p.n_taps * p.cpt;
-  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  // rows beyond *m_dev are never needed: only the M tiles that hold valid rows are computed
+  const int m_tiles = p.m_dev ? (min(__ldg(p.m_dev), p.Wo) + kBlockM - 1) / kBlockM : p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles;
 
   if (warp == 0) {

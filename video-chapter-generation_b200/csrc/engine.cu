@@ -97,6 +97,7 @@ struct Step {
 struct ProfRec {
   std::string name;     // "<kernel>|<layer>"
   double flops = 0, bytes = 0;
+  bool packed = false;   // work scales with the number of packed BERT tokens (resolved at profile end)
   cudaEvent_t start = nullptr, stop = nullptr;
 };
 
@@ -136,7 +137,10 @@ struct vcg_engine {
   DevBuf stem_in, stem_out, x0, xa, xb, dsbuf, mid1, mid2, vis_emb, vis_emb_act, vis_out, lang_out, pooled;
   std::vector<std::unique_ptr<DevBuf>> shifted;   // one per bottleneck: its temporally shifted input channels
   // text workspace (sized for Bt clips x Lmax tokens)
-  DevBuf hid, hid2, qkv, ctx, tmp, ffn;
+  DevBuf hid, hid2, qkv, ctx, tmp, ffn, cls;
+  // token packing (variable-length BERT): cu [Bt+1], tok_src / key_ok [Bt*Lmax], m_total [1]
+  DevBuf pk_cu, pk_src, pk_ok, pk_total;
+  int last_bert_rows = 0;   // bt*L of the most recent BERT pass (profile scaling)
   // host-call staging
   DevBuf st_frames, st_ids, st_mask, st_start, st_logits, st_probs;
 
@@ -332,6 +336,11 @@ void finalize_text(vcg_engine* e, cudaStream_t s) {
   e->ctx.alloc(rows * kBertHidden * es);
   e->tmp.alloc(rows * kBertHidden * es);
   e->ffn.alloc(rows * kBertFfn * es);
+  e->cls.alloc((static_cast<size_t>(e->Bt) + 128) * kBertHidden * es);
+  e->pk_cu.alloc((e->Bt + 1) * sizeof(int32_t));
+  e->pk_src.alloc(rows * sizeof(int32_t));
+  e->pk_ok.alloc(rows);
+  e->pk_total.alloc(sizeof(int32_t), /*zero=*/true);
 }
 
 void finalize_head(vcg_engine* e, cudaStream_t s) {
@@ -450,6 +459,7 @@ BertPlan& bert_plan(vcg_engine* e, int B, int L) {
     Step st{}; st.kind = Step::CONV_GEMM;
     Epilogue ep; ep.bias = w.bias.as<float>(); ep.act = act; ep.residual = res; ep.ld_res = w.N;
     st.gemm = build_gemm(A, w.K, w.w.p, out, w.N, M, w.N, w.K, fp, ep, name);
+    st.gemm.p.m_dev = e->pk_total.as<int32_t>();   // only the packed rows are computed
     plan.steps.push_back(st);
   };
   auto ln_step = [&](const void* x, const DevBuf& g, const DevBuf& b, void* y) {
@@ -476,10 +486,11 @@ struct ProfScope {
   cudaStream_t s;
   ProfRec rec;
   bool on;
-  ProfScope(vcg_engine* e_, cudaStream_t s_, std::string name, double flops, double bytes) : e(e_), s(s_), on(e_->profiling) {
+  ProfScope(vcg_engine* e_, cudaStream_t s_, std::string name, double flops, double bytes, bool packed = false)
+      : e(e_), s(s_), on(e_->profiling) {
     ++e->launches;
     if (!on) return;
-    rec.name = std::move(name); rec.flops = flops; rec.bytes = bytes;
+    rec.name = std::move(name); rec.flops = flops; rec.bytes = bytes; rec.packed = packed;
     rec.start = e->next_event(); rec.stop = e->next_event();
     VCG_CUDA(cudaEventRecord(rec.start, s));
   }
@@ -499,7 +510,7 @@ void run_steps(vcg_engine* e, const std::vector<Step>& steps, const int64_t* mas
   for (const Step& st : steps) {
     switch (st.kind) {
       case Step::CONV_GEMM: {
-        ProfScope ps(e, s, gemm_kernel_name(st.gemm), st.gemm.flops, 0);
+        ProfScope ps(e, s, gemm_kernel_name(st.gemm), st.gemm.flops, 0, st.gemm.p.m_dev != nullptr);
         launch_conv_gemm(st.gemm, s);
         break;
       }
@@ -509,13 +520,13 @@ void run_steps(vcg_engine* e, const std::vector<Step>& steps, const int64_t* mas
         break;
       }
       case Step::LAYERNORM: {
-        ProfScope ps(e, s, "layernorm768|bert.ln", 0, st.n * 768.0 * 2 * es);
-        launch_layernorm(st.in, st.g, st.b, st.out, st.n, kBertHidden, 1e-12f, e->fp32, s);
+        ProfScope ps(e, s, "layernorm768|bert.ln", 0, st.n * 768.0 * 2 * es, true);
+        launch_layernorm(st.in, st.g, st.b, st.out, st.n, kBertHidden, 1e-12f, e->fp32, s, e->pk_total.as<int32_t>());
         break;
       }
       case Step::ATTENTION: {
-        ProfScope ps(e, s, "bert_attention|bert.attn", 4.0 * st.n * kBertHeads * static_cast<double>(st.a) * st.a * 64, 0);
-        launch_bert_attention(st.in, mask, st.out, st.n, st.a, e->fp32, s);
+        ProfScope ps(e, s, "bert_attention|bert.attn", 4.0 * st.n * kBertHeads * static_cast<double>(st.a) * st.a * 64, 0, true);
+        launch_bert_attention(st.in, mask, e->pk_cu.as<int32_t>(), e->pk_ok.as<uint8_t>(), st.out, st.n, st.a, e->fp32, s);
         break;
       }
       default: throw Error("vcg: unknown plan step");
@@ -542,9 +553,15 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
     const int bt = std::min(e->Bt, B - b0);
     // ---- text stream for bt clips
     {
-      ProfScope ps(e, s, "bert_embed_ln|bert.embed", 0, static_cast<double>(bt) * L * 768 * 4 * e->es());
-      launch_bert_embed_ln(ids + static_cast<long>(b0) * L, bt * L, L, e->word.p, e->pos.p, e->type.p,
-                           e->emb_g.as<float>(), e->emb_b.as<float>(), e->hid.p, e->fp32, s);
+      ProfScope ps(e, s, "bert_pack|bert.pack", 0, static_cast<double>(bt) * L * 13);
+      launch_bert_pack(mask + static_cast<long>(b0) * L, bt, L, e->pk_cu.as<int32_t>(), e->pk_src.as<int32_t>(),
+                       e->pk_ok.as<uint8_t>(), e->pk_total.as<int32_t>(), s);
+    }
+    e->last_bert_rows = bt * L;
+    {
+      ProfScope ps(e, s, "bert_embed_ln|bert.embed", 0, static_cast<double>(bt) * L * 768 * 4 * e->es(), true);
+      launch_bert_embed_ln(ids + static_cast<long>(b0) * L, bt * L, L, e->pk_src.as<int32_t>(), e->pk_total.as<int32_t>(),
+                           e->word.p, e->pos.p, e->type.p, e->emb_g.as<float>(), e->emb_b.as<float>(), e->hid.p, e->fp32, s);
     }
     run_steps(e, bert_plan(e, bt, L).steps, mask + static_cast<long>(b0) * L, s);
     // ---- BertPooler (tanh) + lang projection (ReLU) for the bt clips: two small tcgen05 GEMMs over the [CLS] rows
@@ -554,12 +571,16 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
       if (it == e->lang_tail_plans.end()) {
         std::vector<ConvGemmLaunch> v;
         Epilogue ep1; ep1.bias = e->pooler.bias.as<float>(); ep1.act = ACT_TANH;
-        v.push_back(build_gemm(e->hid.p, static_cast<long>(L) * kBertHidden, e->pooler.w.p, e->pooled.p, kBertHidden, bt,
-                               kBertHidden, kBertHidden, e->fp32, ep1, "head.pooler"));
+        v.push_back(build_gemm(e->cls.p, kBertHidden, e->pooler.w.p, e->pooled.p, kBertHidden, bt, kBertHidden, kBertHidden,
+                               e->fp32, ep1, "head.pooler"));
         Epilogue ep2; ep2.act = ACT_RELU;
         v.push_back(build_gemm(e->pooled.p, kBertHidden, e->lang_w.p, e->lang_out.p, e->H, bt, e->H, kBertHidden, e->fp32, ep2,
                                "head.lang_proj"));
         it = e->lang_tail_plans.emplace(key, std::move(v)).first;
+      }
+      {
+        ProfScope ps(e, s, "gather_rows768|head.cls", 0, static_cast<double>(bt) * kBertHidden * 2 * e->es());
+        launch_gather_rows768(e->hid.p, e->pk_cu.as<int32_t>(), L, bt, e->cls.p, e->fp32, s);
       }
       for (const ConvGemmLaunch& g : it->second) {
         ProfScope ps(e, s, gemm_kernel_name(g), g.flops, 0);
@@ -833,6 +854,13 @@ int vcg_profile_end(vcg_engine* e, void* stream, vcg_profile_entry* out, int32_t
     VCG_REQUIRE(e && n_out, "null argument");
     e->profiling = false;
     VCG_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    // executed work of the token-packed BERT kernels: scale the padded figures by packed rows / padded rows
+    double pack_ratio = 1.0;
+    if (e->last_bert_rows > 0) {
+      int32_t total = 0;
+      VCG_CUDA(cudaMemcpy(&total, e->pk_total.p, sizeof total, cudaMemcpyDeviceToHost));
+      pack_ratio = static_cast<double>(total) / e->last_bert_rows;
+    }
     std::map<std::string, vcg_profile_entry> agg;
     for (const ProfRec& r : e->prof) {
       float ms = 0.f;
@@ -845,8 +873,8 @@ int vcg_profile_end(vcg_engine* e, void* stream, vcg_profile_entry* out, int32_t
       }
       it->second.launches += 1;
       it->second.ms += ms;
-      it->second.flops += r.flops;
-      it->second.bytes += r.bytes;
+      it->second.flops += r.flops * (r.packed ? pack_ratio : 1.0);
+      it->second.bytes += r.bytes * (r.packed ? pack_ratio : 1.0);
     }
     int n = 0;
     for (auto& kv : agg) {
@@ -909,7 +937,7 @@ int vcg_op_maxpool_tsm(const void* in, int32_t n, void* out, void* out_shifted, 
 }
 int vcg_op_bert_attention(const void* qkv, const int64_t* attention_mask, void* ctx, int32_t B, int32_t L,
                           int32_t precision, void* stream) {
-  return guarded([&] { launch_bert_attention(qkv, attention_mask, ctx, B, L, precision == VCG_PREC_FP32, static_cast<cudaStream_t>(stream)); });
+  return guarded([&] { launch_bert_attention(qkv, attention_mask, nullptr, nullptr, ctx, B, L, precision == VCG_PREC_FP32, static_cast<cudaStream_t>(stream)); });
 }
 int vcg_op_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t cols,
                      float eps, int32_t precision, void* stream) {

@@ -236,9 +236,10 @@ __device__ __forceinline__ void ln_row_768(float (&x)[3][8], const float* __rest
 template <bool FP32>
 __global__ void layernorm768_kernel(const elem_t<FP32>* __restrict__ x, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, elem_t<FP32>* __restrict__ y, int rows,
-                                    float eps) {
+                                    const int32_t* __restrict__ rows_dev, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  if (rows_dev) rows = min(rows, *rows_dev);     // token-packed BERT: only the packed rows exist
   if (row >= rows) return;
   float v[3][8];
 #pragma unroll
@@ -249,14 +250,17 @@ __global__ void layernorm768_kernel(const elem_t<FP32>* __restrict__ x, const fl
 // BertEmbeddings (modeling_bert.py:72-113): word[id] + position[pos] + token_type[0], LayerNorm(eps 1e-12)
 template <bool FP32>
 __global__ void bert_embed_ln_kernel(const int64_t* __restrict__ ids, int rows, int L,
+                                     const int32_t* __restrict__ tok_src, const int32_t* __restrict__ rows_dev,
                                      const elem_t<FP32>* __restrict__ word, const elem_t<FP32>* __restrict__ pos,
                                      const elem_t<FP32>* __restrict__ type, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, elem_t<FP32>* __restrict__ out) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  if (rows_dev) rows = min(rows, *rows_dev);
   if (row >= rows) return;
-  const long id = ids[row];
-  const int p = row % L;
+  const int src = tok_src ? tok_src[row] : row;   // packed row -> b*L + j
+  const long id = ids[src];
+  const int p = src % L;
   float v[3][8];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -269,6 +273,65 @@ __global__ void bert_embed_ln_kernel(const int64_t* __restrict__ ids, int rows, 
     for (int e = 0; e < 8; ++e) v[c][e] = (a[e] + t[e]) + b[e];   // HF order: (inputs + token_type) + position
   }
   ln_row_768<FP32>(v, gamma, beta, 1e-12f, out + row * 768L, lane);
+}
+
+// ------------------------------------------------------------------------------------------------ token packing
+// Variable-length BERT: padded positions are masked as keys in every layer and only h[:,0] is consumed, so tokens with
+// attention_mask == 0 never influence the output and are dropped (token 0 is always kept as a query).  One CTA:
+//   cu[b]      first packed row of clip b (cu[B] = number of packed rows, also written to *total)
+//   tok_src[m] b*L + j of packed row m;  key_ok[m] = attention_mask[b, j] != 0
+__global__ void __launch_bounds__(1024) bert_pack_kernel(const int64_t* __restrict__ mask, int B, int L,
+                                                          int32_t* __restrict__ cu, int32_t* __restrict__ tok_src,
+                                                          uint8_t* __restrict__ key_ok, int32_t* __restrict__ total) {
+  extern __shared__ int s_cnt[];   // [B + 1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int b = warp; b < B; b += nwarps) {
+    int c = 0;
+    for (int j0 = 0; j0 < L; j0 += 32) {
+      const int j = j0 + lane;
+      const bool v = j < L && (mask[static_cast<long>(b) * L + j] != 0 || j == 0);
+      c += __popc(__ballot_sync(0xffffffffu, v));
+    }
+    if (lane == 0) s_cnt[b] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {          // B <= a few hundred: a serial scan is negligible
+    int acc = 0;
+    for (int b = 0; b < B; ++b) { const int c = s_cnt[b]; s_cnt[b] = acc; cu[b] = acc; acc += c; }
+    s_cnt[B] = acc; cu[B] = acc; *total = acc;
+  }
+  __syncthreads();
+  for (int b = warp; b < B; b += nwarps) {
+    int base = s_cnt[b];
+    for (int j0 = 0; j0 < L; j0 += 32) {
+      const int j = j0 + lane;
+      const bool m = j < L && mask[static_cast<long>(b) * L + j] != 0;
+      const bool v = m || j == 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, v);
+      if (v) {
+        const int dst = base + __popc(bal & ((1u << lane) - 1));
+        tok_src[dst] = b * L + j;
+        key_ok[dst] = m ? 1 : 0;
+      }
+      base += __popc(bal);
+    }
+  }
+}
+
+// [CLS] rows of the packed hidden states -> dense [B, 768] (the pooler GEMM's A operand)
+template <bool FP32>
+__global__ void gather_rows768_kernel(const elem_t<FP32>* __restrict__ x, const int32_t* __restrict__ row_of, int stride,
+                                      int B, elem_t<FP32>* __restrict__ out) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const long src = row_of ? row_of[b] : static_cast<long>(b) * stride;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v[8];
+    load8<FP32>(x + src * 768 + c * 256 + lane * 8, v);
+    store8<FP32>(out + static_cast<long>(b) * 768 + c * 256 + lane * 8, v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
@@ -389,20 +452,33 @@ void launch_avgpool(const void* in, int n, int hw, int C, float* out, void* out_
                          static_cast<const elem_t<FP>*>(in), total, hw, C, out, static_cast<elem_t<FP>*>(out_act))));
   VCG_CUDA(cudaGetLastError());
 }
-void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const void* word, const void* pos, const void* type,
-                          const float* gamma, const float* beta, void* out, bool fp32, cudaStream_t s) {
+void launch_bert_pack(const int64_t* mask, int B, int L, int32_t* cu, int32_t* tok_src, uint8_t* key_ok, int32_t* total,
+                      cudaStream_t s) {
+  if (B == 0) return;
+  bert_pack_kernel<<<1, 1024, (B + 1) * sizeof(int), s>>>(mask, B, L, cu, tok_src, key_ok, total);
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_gather_rows768(const void* x, const int32_t* row_of, int stride, int B, void* out, bool fp32, cudaStream_t s) {
+  if (B == 0) return;
+  VCG_DISPATCH(fp32, (gather_rows768_kernel<FP><<<blocks_for(B, 8), 256, 0, s>>>(
+                         static_cast<const elem_t<FP>*>(x), row_of, stride, B, static_cast<elem_t<FP>*>(out))));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const int32_t* tok_src, const int32_t* rows_dev,
+                          const void* word, const void* pos, const void* type, const float* gamma, const float* beta,
+                          void* out, bool fp32, cudaStream_t s) {
   if (rows == 0) return;
   VCG_DISPATCH(fp32, (bert_embed_ln_kernel<FP><<<blocks_for(rows, 8), 256, 0, s>>>(
-                         ids, rows, L, static_cast<const elem_t<FP>*>(word), static_cast<const elem_t<FP>*>(pos),
+                         ids, rows, L, tok_src, rows_dev, static_cast<const elem_t<FP>*>(word), static_cast<const elem_t<FP>*>(pos),
                          static_cast<const elem_t<FP>*>(type), gamma, beta, static_cast<elem_t<FP>*>(out))));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_layernorm(const void* x, const float* gamma, const float* beta, void* y, int rows, int cols, float eps,
-                      bool fp32, cudaStream_t s) {
+                      bool fp32, cudaStream_t s, const int32_t* rows_dev) {
   VCG_REQUIRE(cols == 768, "LayerNorm kernel is specialised for 768 columns");
   if (rows == 0) return;
   VCG_DISPATCH(fp32, (layernorm768_kernel<FP><<<blocks_for(rows, 8), 256, 0, s>>>(
-                         static_cast<const elem_t<FP>*>(x), gamma, beta, static_cast<elem_t<FP>*>(y), rows, eps)));
+                         static_cast<const elem_t<FP>*>(x), gamma, beta, static_cast<elem_t<FP>*>(y), rows, rows_dev, eps)));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_pack_conv(const float* w, const float* bn_w, const float* bn_b, const float* bn_mean, const float* bn_var,

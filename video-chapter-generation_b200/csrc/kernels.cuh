@@ -27,11 +27,20 @@ void launch_maxpool_tsm(const void* in, int n, void* out, void* out_shifted, int
                         cudaStream_t s);
 // out: fp32 [n, C]; out_act (optional): the same values in the activation type (GEMM operand of the vision projection)
 void launch_avgpool(const void* in, int n, int hw, int C, float* out, void* out_act, cudaStream_t s, bool fp32);
-void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const void* word, const void* pos, const void* type,
-                          const float* gamma, const float* beta, void* out, bool fp32, cudaStream_t s);
+// token packing for variable-length BERT (kernels.cu): cu [B+1], tok_src / key_ok [B*L], total [1]
+void launch_bert_pack(const int64_t* mask, int B, int L, int32_t* cu, int32_t* tok_src, uint8_t* key_ok, int32_t* total,
+                      cudaStream_t s);
+// out[b] = x[row_of ? row_of[b] : b*stride]  (rows of 768)
+void launch_gather_rows768(const void* x, const int32_t* row_of, int stride, int B, void* out, bool fp32, cudaStream_t s);
+// tok_src / rows_dev are nullptr in the un-packed layout (row m = token m of the [B, L] matrix)
+void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const int32_t* tok_src, const int32_t* rows_dev,
+                          const void* word, const void* pos, const void* type, const float* gamma, const float* beta,
+                          void* out, bool fp32, cudaStream_t s);
 void launch_layernorm(const void* x, const float* gamma, const float* beta, void* y, int rows, int cols, float eps,
-                      bool fp32, cudaStream_t s);
-void launch_bert_attention(const void* qkv, const int64_t* mask, void* ctx, int B, int L, bool fp32, cudaStream_t s);
+                      bool fp32, cudaStream_t s, const int32_t* rows_dev = nullptr);
+// cu / key_ok: packed layout (nullptr: rows b*L.., int64 mask)
+void launch_bert_attention(const void* qkv, const int64_t* mask, const int32_t* cu, const uint8_t* key_ok, void* ctx, int B,
+                           int L, bool fp32, cudaStream_t s);
 
 struct TailParams {
   // inputs
