@@ -32,6 +32,7 @@ void launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     switch (L.block_n) {
       case 64: launch_t<64, false>(L, stream); break;
       case 128: launch_t<128, false>(L, stream); break;
+      case 192: launch_t<192, false>(L, stream); break;
       case 256: launch_t<256, false>(L, stream); break;
       default: throw Error("vcg: unsupported BLOCK_N");
     }

@@ -392,8 +392,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         //      BLOCK_N = 256 the four C tiles of an output tile drain concurrently (each chain of
         //      tcgen05.ld -> math -> st.shared -> fence -> barrier -> TMA store is latency-bound).
         constexpr int kSub = BLOCK_N / 64;          // C tiles (ring slots) per output tile
-        constexpr int kGps = 4 / kSub;              // groups sharing one C tile
-        constexpr int kCg = BLOCK_N / 4;            // columns per group: 64, 32 or 16
+        constexpr int kGps = 4 / kSub;              // groups sharing one C tile (BLOCK_N = 192: three groups work, one idles)
+        constexpr int kCg = 64 / kGps;              // columns per group: 64, 32 or 16
         const int group = half;                     // (warp - kFirstEpiWarp) >> 2
         const int my_sub = group / kGps;
         const int col_in_sub = (group % kGps) * kCg;

@@ -25,6 +25,9 @@ inline int pick_block_n(int N, bool fp32) {
   const int cap = fp32 ? 128 : 256;
   if (N <= 64) return 64;
   if (N <= 128 || cap == 128) return 128;
+  // N = 768 (BERT hidden): four 192-wide N tiles instead of three 256-wide ones -> 1/3 more tiles of 3/4 the size,
+  // which fills the 148 SMs' last wave much better (330 tiles = 2.2 waves vs 440 tiles = 2.97 waves at 14 k rows)
+  if (N == 768) return 192;
   return 256;
 }
 

@@ -149,6 +149,22 @@ struct vcg_engine {
   std::map<std::pair<int, int>, std::vector<ConvGemmLaunch>> lang_tail_plans;   // (clips, L) -> pooler, lang projection
   std::map<int, ConvGemmLaunch> vis_proj_plans;                                 // frames -> vision projection
 
+  // host-buffer entry points: copies run on a side stream and overlap the compute stream
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;
+  cudaEvent_t copy_event(size_t i) {
+    while (copy_events.size() <= i) {
+      cudaEvent_t ev;
+      VCG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      copy_events.push_back(ev);
+    }
+    return copy_events[i];
+  }
+  cudaStream_t get_copy_stream() {
+    if (!copy_stream) VCG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    return copy_stream;
+  }
+
   // profiling
   bool profiling = false;
   std::vector<ProfRec> prof;
@@ -164,6 +180,8 @@ struct vcg_engine {
   }
   ~vcg_engine() {
     for (auto ev : event_pool) cudaEventDestroy(ev);
+    for (auto ev : copy_events) cudaEventDestroy(ev);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
   }
 
   int es() const { return fp32 ? 4 : 2; }
@@ -540,9 +558,32 @@ struct FrameSource {
   const int32_t* clip_start = nullptr; // [B]
 };
 
+// Progress of an asynchronous host->device copy of the vision input (side stream): `ready[i]` = (units on the device
+// once event i has fired, event); units are frames when clip_start_host is given, clips otherwise.
+struct HostFeed {
+  const int32_t* clip_start_host = nullptr;
+  int T = 0;
+  std::vector<std::pair<long, cudaEvent_t>> ready;
+  // make `s` wait until the vision input of clips [g0, g1) is on the device
+  void wait_for(cudaStream_t s, int g0, int g1) const {
+    long need = g1;
+    if (clip_start_host) {
+      need = 0;
+      for (int g = g0; g < g1; ++g) need = std::max<long>(need, static_cast<long>(clip_start_host[g]) + T);
+    }
+    for (const auto& r : ready)
+      if (r.first >= need) {
+        VCG_CUDA(cudaStreamWaitEvent(s, r.second, 0));
+        return;
+      }
+    if (!ready.empty()) VCG_CUDA(cudaStreamWaitEvent(s, ready.back().second, 0));
+  }
+};
+
 // Scores B clips; any of the sources may be used for the vision stream (or precomputed embeddings).
 void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, const int64_t* ids, const int64_t* mask,
-           int B, int L, float* logits, float* probs, float* vision_emb_out, float* lang_emb_out, cudaStream_t s) {
+           int B, int L, float* logits, float* probs, float* vision_emb_out, float* lang_emb_out, cudaStream_t s,
+           const HostFeed* feed = nullptr) {
   VCG_REQUIRE(e->finalized, "vcg_finalize has not been called");
   VCG_REQUIRE(B >= 0 && L >= 1 && L <= e->Lmax, "token count exceeds max_tokens of the engine");
   const bool have_frames = src.img_clip || src.frames_u8;
@@ -605,6 +646,7 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
       const int bv = std::min(step, bt - c0);
       const int g0 = b0 + c0;   // first clip of this sub-chunk in the caller's numbering
       const void* vis_act = nullptr;   // [bv*T, 2048] in the activation type
+      if (feed) feed->wait_for(s, g0, g0 + bv);
       if (have_frames) {
         if (src.img_clip) {
           ProfScope ps(e, s, "nchw_to_stem|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (4 + e->es()));
@@ -795,15 +837,29 @@ int vcg_score_clips_u8_host(vcg_engine* e, const uint8_t* frames_u8_host, int32_
     e->st_start.ensure(static_cast<size_t>(B) * sizeof(int32_t));
     e->st_logits.ensure(static_cast<size_t>(B) * 2 * sizeof(float));
     e->st_probs.ensure(static_cast<size_t>(B) * 2 * sizeof(float));
-    VCG_CUDA(cudaMemcpyAsync(e->st_frames.p, frames_u8_host, fbytes, cudaMemcpyHostToDevice, s));
     VCG_CUDA(cudaMemcpyAsync(e->st_ids.p, text_ids_host, tbytes, cudaMemcpyHostToDevice, s));
     VCG_CUDA(cudaMemcpyAsync(e->st_mask.p, attention_mask_host, tbytes, cudaMemcpyHostToDevice, s));
     VCG_CUDA(cudaMemcpyAsync(e->st_start.p, clip_start_host, static_cast<size_t>(B) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    // frames go up on a side stream in pieces of 128 frames (19 MB); a vision pass waits only for the frames it reads
+    cudaStream_t cs = e->get_copy_stream();
+    HostFeed feed;
+    feed.clip_start_host = clip_start_host;
+    feed.T = e->T;
+    const size_t frame_bytes = static_cast<size_t>(kImg) * kImg * 3;
+    size_t ev_i = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += 128, ++ev_i) {
+      const int n = std::min(128, n_frames - f0);
+      VCG_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(e->st_frames.p) + f0 * frame_bytes, frames_u8_host + f0 * frame_bytes,
+                               n * frame_bytes, cudaMemcpyHostToDevice, cs));
+      cudaEvent_t ev = e->copy_event(ev_i);
+      VCG_CUDA(cudaEventRecord(ev, cs));
+      feed.ready.emplace_back(f0 + n, ev);
+    }
     FrameSource src;
     src.frames_u8 = e->st_frames.as<uint8_t>();
     src.clip_start = e->st_start.as<int32_t>();
     score(e, src, nullptr, e->st_ids.as<int64_t>(), e->st_mask.as<int64_t>(), B, L, e->st_logits.as<float>(),
-          e->st_probs.as<float>(), nullptr, nullptr, s);
+          e->st_probs.as<float>(), nullptr, nullptr, s, &feed);
     VCG_CUDA(cudaMemcpyAsync(logits_host, e->st_logits.p, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
     VCG_CUDA(cudaMemcpyAsync(probs_host, e->st_probs.p, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
     VCG_CUDA(cudaStreamSynchronize(s));
@@ -825,13 +881,28 @@ int vcg_forward_host(vcg_engine* e, const float* img_clip_host, const float* vis
     e->st_mask.ensure(tbytes);
     e->st_logits.ensure(static_cast<size_t>(B) * 2 * sizeof(float));
     e->st_probs.ensure(static_cast<size_t>(B) * 2 * sizeof(float));
-    VCG_CUDA(cudaMemcpyAsync(e->st_frames.p, img_clip_host ? img_clip_host : vision_emb_host, vbytes, cudaMemcpyHostToDevice, s));
     VCG_CUDA(cudaMemcpyAsync(e->st_ids.p, text_ids_host, tbytes, cudaMemcpyHostToDevice, s));
     VCG_CUDA(cudaMemcpyAsync(e->st_mask.p, attention_mask_host, tbytes, cudaMemcpyHostToDevice, s));
+    // the vision input is copied on a side stream in pieces of max_batch clips: the text stream (and earlier vision
+    // passes) run underneath; every vision pass waits only for its own piece
+    cudaStream_t cs = e->get_copy_stream();
+    HostFeed feed;
+    const size_t clip_bytes = vbytes / std::max(B, 1);
+    const int piece = img_clip_host ? e->Bv : std::max(B, 1);
+    const uint8_t* hsrc = reinterpret_cast<const uint8_t*>(img_clip_host ? img_clip_host : vision_emb_host);
+    size_t ev_i = 0;
+    for (int c0 = 0; c0 < B; c0 += piece, ++ev_i) {
+      const int n = std::min(piece, B - c0);
+      VCG_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(e->st_frames.p) + c0 * clip_bytes, hsrc + c0 * clip_bytes, n * clip_bytes,
+                               cudaMemcpyHostToDevice, cs));
+      cudaEvent_t ev = e->copy_event(ev_i);
+      VCG_CUDA(cudaEventRecord(ev, cs));
+      feed.ready.emplace_back(c0 + n, ev);
+    }
     FrameSource src;
     if (img_clip_host) src.img_clip = e->st_frames.as<float>();
     score(e, src, img_clip_host ? nullptr : e->st_frames.as<float>(), e->st_ids.as<int64_t>(), e->st_mask.as<int64_t>(), B, L,
-          e->st_logits.as<float>(), e->st_probs.as<float>(), nullptr, nullptr, s);
+          e->st_logits.as<float>(), e->st_probs.as<float>(), nullptr, nullptr, s, &feed);
     VCG_CUDA(cudaMemcpyAsync(logits_host, e->st_logits.p, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
     VCG_CUDA(cudaMemcpyAsync(probs_host, e->st_probs.p, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
     VCG_CUDA(cudaStreamSynchronize(s));
