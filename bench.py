@@ -200,11 +200,11 @@ def pipeline_extra(args, peaks):
     starts_h = torch.tensor(starts, dtype=torch.int32).pin_memory()
     frames_d, ids_d, mask_d, starts_d = frames_h.cuda(), ids_h.cuda(), mask_h.cuda(), starts_h.cuda()
     steps, warm = max(2, min(args.steps, 5)), 1
-    sec = timed(lambda: eng.score_clips_u8(frames_d, starts_d, ids_d, mask_d), steps, warm, False)
+    sec = timed(lambda: eng.score_video_u8(frames_d, 0, 4, ids_d, mask_d), steps, warm, False)
     out = (torch.empty(B, 2).pin_memory(), torch.empty(B, 2).pin_memory())
     sec_e2e = timed(lambda: eng.score_clips_u8_host(frames_h, starts_h, ids_h, mask_h, out=out), steps, warm, False)
     eng.profile_begin()
-    eng.score_clips_u8(frames_d, starts_d, ids_d, mask_d)
+    eng.score_video_u8(frames_d, 0, 4, ids_d, mask_d)
     prof = eng.profile_end()
     cps = B * steps / sec
     fl = flops_per_clip(T, L, True)

@@ -80,6 +80,14 @@ VCG_API int vcg_score_clips_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t 
                        const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L, float* logits,
                        float* probs, void* stream);
 
+/* Same for clips on a regular grid — clip b = frames first_start + b*clip_stride .. +T-1, the reference's
+ * range(0, n_frames - T, 4) (infer_youtube_video_dataset.py:117).  Overlapping clips share frames, so pre-processing,
+ * the ResNet stem, the max-pool and layer1.0's downsample run once per UNIQUE frame (TSM makes everything after
+ * layer1.0.conv1 clip-specific).  Results equal vcg_score_clips_u8 up to fp32 summation order. */
+VCG_API int vcg_score_video_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames, int32_t first_start,
+                       int32_t clip_stride, const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L,
+                       float* logits, float* probs, void* stream);
+
 /* Same, with HOST buffers (pinned for full speed): the host->device copies of frames / ids / mask and the
  * device->host copy of logits+probs are issued inside the call; returns after the results are on the host. */
 VCG_API int vcg_score_clips_u8_host(vcg_engine* e, const uint8_t* frames_u8_host, int32_t n_frames,

@@ -117,6 +117,30 @@ def test_u8_pipeline_and_chunking_match_oracle():
     assert torch.equal(lh, lg.cpu()) and torch.equal(ph, pr.cpu())
 
 
+def test_shared_stem_for_overlapping_clips():
+    """Clips on a regular grid share frames: the shared-stem path (stem once per unique frame, layer1.0.conv1 as a
+    3-tap temporal conv over clip views) must agree with the per-clip path and with the oracle (bf16 mode)."""
+    from oracle import two_stream_oracle as orc
+    from oracle import weights as W
+    T, L, B = 8, 24, 7
+    model, sd = build_model(T, "mlp", "bf16", chunk=3)          # 7 clips -> passes of 3, 3, 1
+    frames = W.make_frames_u8(4 * (B - 1) + T + 3, seed=9)
+    starts = [2 + 4 * b for b in range(B)]
+    ids, mask = W.make_text(B, L, seed=9)
+    img = orc.gather_clips(orc.preprocess_u8(frames), starts, T)
+    ref_logits, _, _, _ = orc.two_stream_forward(sd, img, ids, mask, T)
+    model(img[:1].cuda(), ids[:1].cuda(), mask[:1].cuda())
+    eng = model.engine
+    st = torch.tensor(starts, dtype=torch.int32)
+    per_clip, _ = eng.score_clips_u8(frames.cuda(), st.cuda(), ids.cuda(), mask.cuda())
+    shared, _ = eng.score_video_u8(frames.cuda(), starts[0], 4, ids.cuda(), mask.cuda())
+    host, _ = eng.score_clips_u8_host(frames.pin_memory(), st.pin_memory(), ids.pin_memory(), mask.pin_memory())
+    print("shared vs per-clip", rel(shared, per_clip), "vs oracle", rel(shared, ref_logits), rel(per_clip, ref_logits))
+    assert rel(per_clip, ref_logits) <= TOL["bf16"] and rel(shared, ref_logits) <= TOL["bf16"]
+    assert rel(shared, per_clip) <= 5e-3
+    assert torch.equal(host, shared.cpu())      # the host entry point detects the regular grid itself
+
+
 def test_token_packing_irregular_masks():
     """The text stream drops masked tokens (exact: they are masked as keys everywhere and only h[:,0] is read).
     Masks with holes, a masked [CLS] position and full-length rows must all match the dense oracle."""
@@ -138,6 +162,31 @@ def test_token_packing_irregular_masks():
     model.precision = "bf16"
     logits_bf16, _ = model(emb.cuda().view(B, T, 2048, 1, 1), ids.cuda(), mask.cuda())
     assert rel(logits_bf16, ref_logits) <= TOL["bf16"]
+
+
+@pytest.mark.parametrize("T,L,B,head", [(8, 128, 3, "mlp"), (32, 512, 1, "mlp"), (16, 256, 2, "attn"), (6, 20, 3, "mlp"),
+                                        (12, 77, 2, "attn")])
+def test_shape_sweep_bf16_vs_oracle(T, L, B, head):
+    """BASELINE.json configs[4]: window sizes x token counts (plus the odd clip_frame_num values the reference's shell
+    scripts list), bf16 mode against the CPU oracle: logits within 2e-2, identical labels (margins permitting)."""
+    from oracle import two_stream_oracle as orc
+    from oracle import weights as W
+    model, sd = build_model(T, head, "bf16", chunk=2)
+    frames = W.make_frames_u8(4 * (B - 1) + T, seed=T + L)
+    starts = [4 * b for b in range(B)]
+    ids, mask = W.make_text(B, L, seed=T + L)
+    img = orc.gather_clips(orc.preprocess_u8(frames), starts, T)
+    with torch.no_grad():
+        ref_logits, _, ref_vis, ref_lang = orc.two_stream_forward(sd, img, ids, mask, T, 128, head)
+    logits, probs, vis, lang = model(img.cuda(), ids.cuda(), mask.cuda(), return_emb=True)
+    errs = {"logits": rel(logits, ref_logits), "vision_emb": rel(vis, ref_vis), "lang_emb": rel(lang, ref_lang)}
+    print((T, L, B, head), errs)
+    assert errs["logits"] <= TOL["bf16"], errs
+    assert errs["vision_emb"] <= EMB_TOL["bf16"] and errs["lang_emb"] <= EMB_TOL["bf16"], errs
+    margin = (ref_logits[:, 1] - ref_logits[:, 0]).abs()
+    safe = margin > 4 * TOL["bf16"] * ref_logits.abs().max()
+    got, exp = orc.predict_labels(logits.cpu()), orc.predict_labels(ref_logits)
+    assert all(g == x for g, x, ok in zip(got, exp, safe.tolist()) if ok)
 
 
 def test_no_cpu_fallback():

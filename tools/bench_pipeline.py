@@ -18,14 +18,14 @@ st = torch.tensor(starts, dtype=torch.int32).cuda()
 for chunk in chunks:
     eng = Engine(T, "mlp", "bf16", vision=True, max_tokens=128, max_batch=chunk)
     eng.load_state_dict(sd)
-    for _ in range(2): eng.score_clips_u8(frames, st, ids, mask)
+    for _ in range(2): eng.score_video_u8(frames, 0, 4, ids, mask)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); n = 3
-    for _ in range(n): eng.score_clips_u8(frames, st, ids, mask)
+    for _ in range(n): eng.score_video_u8(frames, 0, 4, ids, mask)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    eng.profile_begin(); eng.score_clips_u8(frames, st, ids, mask); prof = eng.profile_end()
+    eng.profile_begin(); eng.score_video_u8(frames, 0, 4, ids, mask); prof = eng.profile_end()
     lay = {}
     for r in prof:
         k = lay.setdefault(r["layer"], [0.0, 0.0, 0]); k[0] += r["ms"]; k[1] += r["flops"]; k[2] += r["launches"]

@@ -46,6 +46,9 @@ struct ConvGemmParams {
   int tsm_split_cb, tsm_map;   // channel blocks below tsm_split_cb are read through a_map[tsm_map]
   int n_stages, n_cslots;      // bf16 path: split of the smem budget between the A/B stage ring and the C-tile ring
   const int* m_dev;            // plain GEMM only: number of valid rows lives on the device (token-packed BERT)
+  // "clip view" of a per-unique-frame tensor (frames shared by overlapping clips): map dims (C, W, H, T, clip) with
+  // box (.., nf, 1); image index n = clip*T + t.  0 = ordinary (C, W, H, plane, image) addressing.
+  int a_clip_T, res_clip_T;
   int bw, bh, nf;              // patch extents; bw*bh*nf <= 128 rows
   int Wo, Ho, Nimg;            // output geometry
   int tiles_w, tiles_h, tiles_n, n_tiles;
@@ -223,8 +226,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
           const TapDesc t = p.taps[tap];
           const int map = (cb < p.tsm_split_cb) ? p.tsm_map : t.map;
-          tma_load_5d(sA + stage * Cfg::kABytes, &p.a_map[map], &full_bar[stage], cb * Cfg::kBlockK + t.c_off,
-                      w0 + t.dw, h0 + t.dh, t.plane, n0);
+          if (p.a_clip_T == 0)
+            tma_load_5d(sA + stage * Cfg::kABytes, &p.a_map[map], &full_bar[stage], cb * Cfg::kBlockK + t.c_off,
+                        w0 + t.dw, h0 + t.dh, t.plane, n0);
+          else   // plane = temporal tap offset (frame t-1 / t / t+1 of the same clip; out of range -> zero fill)
+            tma_load_5d(sA + stage * Cfg::kABytes, &p.a_map[map], &full_bar[stage], cb * Cfg::kBlockK + t.c_off,
+                        w0 + t.dw, h0 + t.dh, n0 % p.a_clip_T + t.plane, n0 / p.a_clip_T);
           tma_load_2d(sB + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * Cfg::kBlockK, n_blk * BLOCK_N);
           if (++cb == p.cpt) { cb = 0; ++tap; }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -286,8 +293,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           mbar_wait(&c_empty[slot], ((c_it / kCSlots) & 1) ^ 1);
           if (has_res) {
             mbar_expect_tx(&c_full[slot], p.a_bytes);   // same box extents as the A patch: rows x 128 B
-            tma_load_5d(sC + slot * kCBytes, &p.res_map, &c_full[slot], n_blk * BLOCK_N + j * 64, iw * p.bw, ih * p.bh,
-                        0, in * p.nf);
+            const int n0 = in * p.nf;
+            if (p.res_clip_T == 0)
+              tma_load_5d(sC + slot * kCBytes, &p.res_map, &c_full[slot], n_blk * BLOCK_N + j * 64, iw * p.bw, ih * p.bh,
+                          0, n0);
+            else
+              tma_load_5d(sC + slot * kCBytes, &p.res_map, &c_full[slot], n_blk * BLOCK_N + j * 64, iw * p.bw, ih * p.bh,
+                          n0 % p.res_clip_T, n0 / p.res_clip_T);
           } else {
             mbar_arrive(&c_full[slot]);
           }

@@ -73,7 +73,22 @@ struct Epilogue {
   int act = ACT_NONE;
   void* tsm_out = nullptr;   // shifted copy of channels [0, 2*fold) for the next bottleneck
   int tsm_ld = 0, tsm_fold = 0, T = 1;
+  // residual given per UNIQUE frame and shared by overlapping clips: image (clip b, frame t) reads frame b*stride + t
+  int res_clip_T = 0, res_clip_stride = 0;
 };
+
+// (C, W, H, T, clip) view of a per-unique-frame NHWC tensor: clip b, frame t -> unique frame b*clip_stride + t
+inline CUtensorMap clip_view_map(const void* ptr, int C, int W, int H, int T, int n_clips, int clip_stride, int box_c,
+                                 int bw, int bh, int nf, bool fp32) {
+  const uint64_t es = elem_size(fp32);
+  const uint64_t img = static_cast<uint64_t>(H) * W * C * es;
+  const uint64_t dims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                            static_cast<uint64_t>(T), static_cast<uint64_t>(n_clips)};
+  const uint64_t str[4] = {static_cast<uint64_t>(C) * es, static_cast<uint64_t>(W) * C * es, img, img * clip_stride};
+  const uint32_t box[5] = {static_cast<uint32_t>(box_c), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh),
+                           static_cast<uint32_t>(nf), 1};
+  return make_tensor_map(ptr, fp32, 5, dims, str, box);
+}
 
 // [Nimg, Ho, Wo, ld] bf16 tensor seen as (C, W, H, 1, N) with a (64 x bw x bh x 1 x nf) box: the C tiles of the epilogue
 inline CUtensorMap c_tile_map(const void* ptr, long ld, const ConvGemmParams& p) {
@@ -106,6 +121,12 @@ inline void set_epilogue(ConvGemmLaunch& L, void* out, int ld_out, const Epilogu
     VCG_REQUIRE(ld_out % 8 == 0 && (e.residual == nullptr || e.ld_res % 8 == 0), "row strides must be multiples of 16 bytes");
     p.out_map = c_tile_map(out, ld_out, p);
     p.res_map = e.residual ? c_tile_map(e.residual, e.ld_res, p) : p.out_map;
+    if (e.residual && e.res_clip_T > 0) {
+      VCG_REQUIRE(e.res_clip_T % p.nf == 0 && p.Nimg % e.res_clip_T == 0 && e.ld_res == p.N, "clip-view residual: tile frames must stay inside a clip");
+      p.res_map = clip_view_map(e.residual, p.N, p.Wo, p.Ho, e.res_clip_T, p.Nimg / e.res_clip_T, e.res_clip_stride, 64, p.bw,
+                                p.bh, p.nf, false);
+      p.res_clip_T = e.res_clip_T;
+    }
   }
 }
 
@@ -266,6 +287,37 @@ inline ConvGemmLaunch build_stem(const void* in_padded, int Nimg, int Hp, int Wp
   p.b_map = weight_map(Wp_packed, Cout, fp32 ? 7 * 32 : 4 * 64, L.block_n, fp32);
   set_epilogue(L, out, Cout, e);
   L.flops = 2.0 * Nimg * Ho * Wo * static_cast<double>(Cout) * 147;
+  return L;
+}
+
+// layer1.0.conv1 over a per-unique-frame input x0u [U, H, W, Cin] shared by overlapping clips (clip b = frames
+// b*clip_stride .. +T-1), with the temporal shift expressed as three temporal taps with channel-masked weights:
+//   tap dt=0 -> channels [2f, Cin), dt=+1 -> channels [0, f), dt=-1 -> channels [f, 2f)   (f = Cin / shift_div)
+// weights packed [Cout][3][Cin] in that tap order; frames outside the clip are TMA zero fill.  bf16 only.
+inline ConvGemmLaunch build_conv1_shared(const void* x0u, int n_clips, int T, int clip_stride, int H, int W, int Cin,
+                                         const void* Wp, int Cout, void* out, const Epilogue& e, const char* name) {
+  ConvGemmLaunch L;
+  memset(&L.p, 0, sizeof L.p);
+  L.name = name;
+  VCG_REQUIRE(Cin % 64 == 0, "conv input channels must be a multiple of the K block");
+  ConvGemmParams& p = L.p;
+  const int Nimg = n_clips * T;
+  pick_patch(W, H, Nimg, p.bw, p.bh, p.nf);
+  VCG_REQUIRE(T % p.nf == 0, "shared-stem conv1: the frames of one tile must belong to one clip");
+  p.a_map[0] = clip_view_map(x0u, Cin, W, H, T, n_clips, clip_stride, 64, p.bw, p.bh, p.nf, false);
+  for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+  p.a_clip_T = T;
+  p.n_taps = 3; p.cpt = Cin / 64;
+  const int dts[3] = {0, 1, -1};
+  for (int i = 0; i < 3; ++i) {
+    TapDesc t{};
+    t.plane = static_cast<int8_t>(dts[i]);
+    p.taps[i] = t;
+  }
+  finish_launch(L, W, H, Nimg, Cout, false);
+  p.b_map = weight_map(Wp, Cout, 3 * Cin, L.block_n, false);
+  set_epilogue(L, out, Cout, e);
+  L.flops = 2.0 * Nimg * H * W * static_cast<double>(Cout) * Cin;
   return L;
 }
 

@@ -68,6 +68,7 @@ struct ConvW {
 };
 struct Bottleneck {
   ConvW c1, c2, c3, ds;
+  ConvW c1_shared;   // block 0 only: conv1 as three temporal taps over per-unique-frame input (bf16, TSM)
   bool has_ds = false;
   int stride = 1, Cin = 0, planes = 0, H = 0;   // H = input spatial size
 };
@@ -145,6 +146,7 @@ struct vcg_engine {
   DevBuf st_frames, st_ids, st_mask, st_start, st_logits, st_probs;
 
   std::map<int, VisionPlan> vplans;
+  std::map<std::pair<int, int>, VisionPlan> vplans_shared;   // (clips, clip stride): stem computed once per unique frame
   std::map<std::pair<int, int>, BertPlan> bplans;
   std::map<std::pair<int, int>, std::vector<ConvGemmLaunch>> lang_tail_plans;   // (clips, L) -> pooler, lang projection
   std::map<int, ConvGemmLaunch> vis_proj_plans;                                 // frames -> vision projection
@@ -283,6 +285,17 @@ void finalize_vision(vcg_engine* e, cudaStream_t s) {
       Hs /= bk.stride;
     }
   }
+  if (e->tsm && !e->fp32) {   // layer1.0.conv1 as a 3-tap temporal conv for the shared-stem path
+    Bottleneck& b0 = e->blocks[0];
+    const std::string pre = vm + "layer1.0";
+    const RawTensor& w = need(e, conv1_key(e, pre), {64, 64, 1, 1});
+    b0.c1_shared.Cin = 64; b0.c1_shared.Cout = 64; b0.c1_shared.k = 1; b0.c1_shared.stride = 1;
+    b0.c1_shared.w.alloc(static_cast<size_t>(64) * 3 * 64 * 2);
+    b0.c1_shared.bias.alloc(64 * sizeof(float));
+    launch_pack_conv1_shared(fptr(w), fptr(need(e, pre + ".bn1.weight")), fptr(need(e, pre + ".bn1.bias")),
+                             fptr(need(e, pre + ".bn1.running_mean")), fptr(need(e, pre + ".bn1.running_var")), 1e-5f, 64, 64,
+                             64 / e->cfg.shift_div, b0.c1_shared.w.p, b0.c1_shared.bias.as<float>(), s);
+  }
   // workspace
   const size_t nF = static_cast<size_t>(e->Bv) * e->T, es = e->es();
   e->stem_in.alloc(nF * kStemHp * kStemWp * 4 * es, /*zero=*/true);   // borders stay zero forever
@@ -388,12 +401,27 @@ void finalize_head(vcg_engine* e, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------ plans
-VisionPlan& vision_plan(vcg_engine* e, int B) {
-  auto it = e->vplans.find(B);
-  if (it != e->vplans.end()) return it->second;
+// Can the stem / max-pool / layer1.0 downsample be computed once per unique frame for clips start0 + b*stride ?
+bool shared_stem_ok(const vcg_engine* e, int stride) {
+  return e->tsm && !e->fp32 && stride >= 1 && stride < e->T && e->T % 2 == 0;
+}
+
+// clip_stride == 0: every clip brings its own T frames (N = B*T images everywhere).
+// clip_stride  > 0: clips overlap (clip b = unique frames b*stride .. +T-1): stem, max-pool and layer1.0's downsample run
+//                   once per unique frame; layer1.0.conv1 and the residual of layer1.0.conv3 read them through clip views.
+VisionPlan& vision_plan(vcg_engine* e, int B, int clip_stride = 0) {
+  const bool shared = clip_stride > 0;
+  if (shared) {
+    auto it = e->vplans_shared.find({B, clip_stride});
+    if (it != e->vplans_shared.end()) return it->second;
+  } else {
+    auto it = e->vplans.find(B);
+    if (it != e->vplans.end()) return it->second;
+  }
   VisionPlan plan;
   plan.B = B;
   const int N = B * e->T;
+  const int U = shared ? clip_stride * (B - 1) + e->T : N;   // images through the stem
   const bool fp = e->fp32;
   {
     Step st{};
@@ -401,14 +429,14 @@ VisionPlan& vision_plan(vcg_engine* e, int B) {
     Epilogue ep;
     ep.bias = e->stem.bias.as<float>();
     ep.act = ACT_RELU;
-    st.gemm = build_stem(e->stem_in.p, N, kStemHp, kStemWp, kStemOut, kStemOut, e->stem.w.p, 64, e->stem_out.p, fp, ep);
+    st.gemm = build_stem(e->stem_in.p, U, kStemHp, kStemWp, kStemOut, kStemOut, e->stem.w.p, 64, e->stem_out.p, fp, ep);
     plan.steps.push_back(st);
   }
   {
     Step st{};
     st.kind = Step::MAXPOOL;
-    st.in = e->stem_out.p; st.out = e->x0.p; st.out2 = e->tsm ? e->shifted[0]->p : nullptr;
-    st.n = N; st.a = e->T; st.c = e->tsm ? 64 / e->cfg.shift_div : 0;
+    st.in = e->stem_out.p; st.out = e->x0.p; st.out2 = (e->tsm && !shared) ? e->shifted[0]->p : nullptr;
+    st.n = U; st.a = e->T; st.c = e->tsm ? 64 / e->cfg.shift_div : 0;
     plan.steps.push_back(st);
   }
   const void* x = e->x0.p;
@@ -429,7 +457,13 @@ VisionPlan& vision_plan(vcg_engine* e, int B) {
       Epilogue ep; ep.bias = bk.c1.bias.as<float>(); ep.act = ACT_RELU;
       const void* sh = e->tsm ? e->shifted[i]->p : nullptr;
       const int sh_ch = e->tsm ? ((i == 0) ? 64 : 2 * (bk.Cin / e->cfg.shift_div)) : 0;
-      st.gemm = build_conv(x, N, H, H, bk.Cin, bk.c1.w.p, bk.planes, 1, 1, e->mid1.p, fp, ep, sh, sh_ch, kNames[stage][0]);
+      if (shared && i == 0) {
+        ep.bias = bk.c1_shared.bias.as<float>();
+        st.gemm = build_conv1_shared(x, B, e->T, clip_stride, H, H, bk.Cin, bk.c1_shared.w.p, bk.planes, e->mid1.p, ep,
+                                     kNames[stage][0]);
+      } else {
+        st.gemm = build_conv(x, N, H, H, bk.Cin, bk.c1.w.p, bk.planes, 1, 1, e->mid1.p, fp, ep, sh, sh_ch, kNames[stage][0]);
+      }
       plan.steps.push_back(st);
     }
     {   // conv2 3x3 (stride) + BN + ReLU
@@ -442,7 +476,8 @@ VisionPlan& vision_plan(vcg_engine* e, int B) {
     if (bk.has_ds) {   // downsample 1x1 (stride) + BN on the un-shifted block input
       Step st{}; st.kind = Step::CONV_GEMM;
       Epilogue ep; ep.bias = bk.ds.bias.as<float>(); ep.act = ACT_NONE;
-      st.gemm = build_conv(x, N, H, H, bk.Cin, bk.ds.w.p, Cout, 1, bk.stride, e->dsbuf.p, fp, ep, nullptr, 0, kNames[stage][3]);
+      st.gemm = build_conv(x, (shared && i == 0) ? U : N, H, H, bk.Cin, bk.ds.w.p, Cout, 1, bk.stride, e->dsbuf.p, fp, ep, nullptr,
+                           0, kNames[stage][3]);
       plan.steps.push_back(st);
       identity = e->dsbuf.p;
     }
@@ -450,6 +485,7 @@ VisionPlan& vision_plan(vcg_engine* e, int B) {
       Step st{}; st.kind = Step::CONV_GEMM;
       Epilogue ep; ep.bias = bk.c3.bias.as<float>(); ep.act = ACT_RELU;
       ep.residual = identity; ep.ld_res = Cout;
+      if (shared && i == 0) { ep.res_clip_T = e->T; ep.res_clip_stride = clip_stride; }
       if (e->tsm && i + 1 < 16) {
         ep.tsm_out = e->shifted[i + 1]->p;
         ep.tsm_fold = Cout / e->cfg.shift_div;
@@ -462,6 +498,7 @@ VisionPlan& vision_plan(vcg_engine* e, int B) {
     x = xnext;
   }
   plan.final_act = x;
+  if (shared) return e->vplans_shared.emplace(std::make_pair(B, clip_stride), std::move(plan)).first->second;
   return e->vplans.emplace(B, std::move(plan)).first->second;
 }
 
@@ -555,7 +592,8 @@ void run_steps(vcg_engine* e, const std::vector<Step>& steps, const int64_t* mas
 struct FrameSource {
   const float* img_clip = nullptr;     // [B,T,3,224,224] fp32
   const uint8_t* frames_u8 = nullptr;  // [n_frames,224,224,3]
-  const int32_t* clip_start = nullptr; // [B]
+  const int32_t* clip_start = nullptr; // [B] (device)
+  int grid_start = 0, grid_stride = 0; // clips on a regular grid: clip b starts at grid_start + b*grid_stride (0 = unknown)
 };
 
 // Progress of an asynchronous host->device copy of the vision input (side stream): `ready[i]` = (units on the device
@@ -651,11 +689,17 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
         if (src.img_clip) {
           ProfScope ps(e, s, "nchw_to_stem|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (4 + e->es()));
           launch_nchw_to_stem(src.img_clip + static_cast<long>(g0) * T * 3 * kImg * kImg, bv * T, e->stem_in.p, e->fp32, s);
+        } else if (shared_stem_ok(e, src.grid_stride)) {
+          // overlapping clips: every unique frame of this pass is pre-processed (and run through the stem) once
+          const int U = src.grid_stride * (bv - 1) + T;
+          const long f0 = src.grid_start + static_cast<long>(src.grid_stride) * g0;
+          ProfScope ps(e, s, "preprocess_u8|preprocess", 0, static_cast<double>(U) * kImg * kImg * 3 * (1 + e->es()));
+          launch_preprocess_u8(src.frames_u8 + f0 * kImg * kImg * 3, nullptr, U, e->stem_in.p, e->fp32, s);
         } else {
           ProfScope ps(e, s, "preprocess_u8|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (1 + e->es()));
           launch_preprocess_u8_clips(src.frames_u8, src.clip_start + g0, bv, T, e->stem_in.p, e->fp32, s);
         }
-        VisionPlan& vp = vision_plan(e, bv);
+        VisionPlan& vp = vision_plan(e, bv, (src.frames_u8 && shared_stem_ok(e, src.grid_stride)) ? src.grid_stride : 0);
         run_steps(e, vp.steps, nullptr, s);
         // fp32 embeddings go to the caller's buffer when asked for; in fp32 mode they are also the GEMM operand
         float* dst = vision_emb_out ? vision_emb_out + static_cast<long>(g0) * T * kVisionDim : e->vis_emb.as<float>();
@@ -783,6 +827,7 @@ int vcg_finalize(vcg_engine* e, void* stream) {
     VCG_REQUIRE(e, "null engine");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     e->vplans.clear();
+    e->vplans_shared.clear();
     e->bplans.clear();
     e->lang_tail_plans.clear();
     e->vis_proj_plans.clear();
@@ -818,6 +863,29 @@ int vcg_score_clips_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames
     src.clip_start = clip_start;
     score(e, src, nullptr, text_ids, attention_mask, B, L, logits, probs, nullptr, nullptr,
           static_cast<cudaStream_t>(stream));
+  });
+}
+
+int vcg_score_video_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames, int32_t first_start, int32_t clip_stride,
+                       const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L, float* logits,
+                       float* probs, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e && frames_u8 && text_ids && attention_mask && logits && probs, "null argument");
+    VCG_REQUIRE(clip_stride >= 1 && first_start >= 0 && (B == 0 || first_start + static_cast<long>(clip_stride) * (B - 1) + e->T <= n_frames),
+                "clip grid exceeds the frame buffer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // device-side start table for the passes that cannot share the stem
+    std::vector<int32_t> starts(B);
+    for (int b = 0; b < B; ++b) starts[b] = first_start + b * clip_stride;
+    e->st_start.ensure(static_cast<size_t>(std::max(B, 1)) * sizeof(int32_t));
+    VCG_CUDA(cudaMemcpyAsync(e->st_start.p, starts.data(), static_cast<size_t>(B) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    VCG_CUDA(cudaStreamSynchronize(s));   // `starts` is a temporary
+    FrameSource src;
+    src.frames_u8 = frames_u8;
+    src.clip_start = e->st_start.as<int32_t>();
+    src.grid_start = first_start;
+    src.grid_stride = clip_stride;
+    score(e, src, nullptr, text_ids, attention_mask, B, L, logits, probs, nullptr, nullptr, s);
   });
 }
 
@@ -858,6 +926,15 @@ int vcg_score_clips_u8_host(vcg_engine* e, const uint8_t* frames_u8_host, int32_
     FrameSource src;
     src.frames_u8 = e->st_frames.as<uint8_t>();
     src.clip_start = e->st_start.as<int32_t>();
+    if (B >= 2) {   // regular grid of clips (the reference's range(0, n - T, 4)) -> shared-stem path
+      const int stride = clip_start_host[1] - clip_start_host[0];
+      bool regular = stride >= 1;
+      for (int b = 2; b < B && regular; ++b) regular = clip_start_host[b] - clip_start_host[b - 1] == stride;
+      if (regular && clip_start_host[0] >= 0 && clip_start_host[B - 1] + e->T <= n_frames) {
+        src.grid_start = clip_start_host[0];
+        src.grid_stride = stride;
+      }
+    }
     score(e, src, nullptr, e->st_ids.as<int64_t>(), e->st_mask.as<int64_t>(), B, L, e->st_logits.as<float>(),
           e->st_probs.as<float>(), nullptr, nullptr, s, &feed);
     VCG_CUDA(cudaMemcpyAsync(logits_host, e->st_logits.p, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));

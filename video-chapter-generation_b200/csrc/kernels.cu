@@ -353,6 +353,22 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
   if (ci == 0 && kk == 0) bias_out[co] = bn_b[co] - bn_mean[co] * scale;
 }
 
+// layer1.0.conv1 for the shared-stem path: [Cout,Cin,1,1] + BN -> [Cout][3 temporal taps][Cin] with channel masks
+// (tap 0 = same frame: channels >= 2f; tap 1 = frame t+1: channels < f; tap 2 = frame t-1: channels [f, 2f)), bf16
+__global__ void pack_conv1_shared_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
+                                         const float* __restrict__ bn_b, const float* __restrict__ bn_mean,
+                                         const float* __restrict__ bn_var, float eps, int Cout, int Cin, int fold,
+                                         __nv_bfloat16* __restrict__ w_out, float* __restrict__ bias_out) {
+  const int total = Cout * 3 * Cin;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ci = idx % Cin, tap = (idx / Cin) % 3, co = idx / (3 * Cin);
+  const float scale = bn_w[co] / sqrtf(bn_var[co] + eps);
+  const bool keep = tap == 0 ? ci >= 2 * fold : tap == 1 ? ci < fold : (ci >= fold && ci < 2 * fold);
+  w_out[idx] = __float2bfloat16_rn(keep ? w[co * Cin + ci] * scale : 0.f);
+  if (ci == 0 && tap == 0) bias_out[co] = bn_b[co] - bn_mean[co] * scale;
+}
+
 // stem weight [64,3,7,7] -> fp32: [64][7][8 px][4]; bf16: [64][4 row pairs][8 px][2 rows][4]; zero where kh = 7, kw = 7, c = 3
 template <bool FP32>
 __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
@@ -487,6 +503,14 @@ void launch_pack_conv(const float* w, const float* bn_w, const float* bn_b, cons
   VCG_DISPATCH(fp32, (pack_conv_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(
                          w, bn_w, bn_b, bn_mean, bn_var, eps, Cout, Cin, k, static_cast<elem_t<FP>*>(w_out),
                          bias_out)));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_pack_conv1_shared(const float* w, const float* bn_w, const float* bn_b, const float* bn_mean,
+                              const float* bn_var, float eps, int Cout, int Cin, int fold, void* w_out, float* bias_out,
+                              cudaStream_t s) {
+  const int total = Cout * 3 * Cin;
+  pack_conv1_shared_kernel<<<blocks_for(total, 256), 256, 0, s>>>(w, bn_w, bn_b, bn_mean, bn_var, eps, Cout, Cin, fold,
+                                                                  static_cast<__nv_bfloat16*>(w_out), bias_out);
   VCG_CUDA(cudaGetLastError());
 }
 void launch_pack_stem(const float* w, const float* bn_w, const float* bn_b, const float* bn_mean, const float* bn_var,

@@ -65,6 +65,9 @@ void launch_head_final(const TailParams& p, int B, bool fp32, cudaStream_t s);  
 void launch_pack_conv(const float* w /*[Cout,Cin,k,k]*/, const float* bn_w, const float* bn_b, const float* bn_mean,
                       const float* bn_var, float eps, int Cout, int Cin, int k, void* w_out /*[Cout][k][k][Cin]*/,
                       float* bias_out, bool fp32, cudaStream_t s);
+void launch_pack_conv1_shared(const float* w /*[Cout,Cin,1,1]*/, const float* bn_w, const float* bn_b, const float* bn_mean,
+                              const float* bn_var, float eps, int Cout, int Cin, int fold, void* w_out /*[Cout][3][Cin] bf16*/,
+                              float* bias_out, cudaStream_t s);
 void launch_pack_stem(const float* w /*[64,3,7,7]*/, const float* bn_w, const float* bn_b, const float* bn_mean,
                       const float* bn_var, float eps, void* w_out /*[64][R][8][4]*/, float* bias_out, bool fp32,
                       cudaStream_t s);

@@ -128,6 +128,23 @@ class Engine:
                                                   logits.data_ptr(), probs.data_ptr(), _stream()))
         return logits, probs
 
+    def score_video_u8(self, frames_u8, first_start, clip_stride, text_ids, attention_mask, out=None):
+        """Clips on a regular grid (clip b = frames first_start + b*clip_stride ..): shares the stem between
+        overlapping clips.  Device-resident uint8 HWC frames -> (logits, probs)."""
+        ids, mask, B, L = self._text(text_ids, attention_mask)
+        assert frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+        dev = ids.device
+        if out is None:
+            logits = torch.empty(B, 2, dtype=torch.float32, device=dev)
+            probs = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        else:
+            logits, probs = out
+        with torch.cuda.device(dev):
+            _b.check(self._lib.vcg_score_video_u8(self._h, frames_u8.data_ptr(), frames_u8.shape[0], first_start,
+                                                  clip_stride, ids.data_ptr(), mask.data_ptr(), B, L,
+                                                  logits.data_ptr(), probs.data_ptr(), _stream()))
+        return logits, probs
+
     def score_clips_u8_host(self, frames_u8, clip_start, text_ids, attention_mask, out=None):
         """HOST tensors in (pinned for full speed), host tensors out; H2D/D2H copies happen inside the call."""
         for t in (frames_u8, clip_start, text_ids, attention_mask):
