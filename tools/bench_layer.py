@@ -11,6 +11,7 @@ from vcg_b200 import ops, binding as B
 dev = "cuda"
 NF = int(os.environ.get("NF", "512"))   # frames (32 clips x 16)
 T = 16
+GEMM_M = int(os.environ.get("GEMM_M", "25600"))   # rows of the BERT GEMMs (256 clips x 100 tokens; ~14080 when packed)
 
 def conv_case(H, Cin, Cout, k, stride, res, tsm_out, tsm_in, act=B.ACT_RELU, nbuf=3):
     xs = [torch.randn(NF, H, H, Cin, device=dev).to(torch.bfloat16) for _ in range(nbuf)]
@@ -51,10 +52,10 @@ CASES = {
     "conv1_l4": lambda: conv_case(7, 2048, 512, 1, 1, False, False, True),
     "conv2_l4": lambda: conv_case(7, 512, 512, 3, 1, False, False, False),
     "ds_l2": lambda: conv_case(56, 256, 512, 1, 2, False, False, False, act=B.ACT_NONE),
-    "qkv": lambda: gemm_case(25600, 2304, 768, B.ACT_NONE, False),
-    "attn_out": lambda: gemm_case(25600, 768, 768, B.ACT_NONE, True),
-    "ffn_in": lambda: gemm_case(25600, 3072, 768, B.ACT_GELU, False),
-    "ffn_out": lambda: gemm_case(25600, 768, 3072, B.ACT_NONE, True),
+    "qkv": lambda: gemm_case(GEMM_M, 2304, 768, B.ACT_NONE, False),
+    "attn_out": lambda: gemm_case(GEMM_M, 768, 768, B.ACT_NONE, True),
+    "ffn_in": lambda: gemm_case(GEMM_M, 3072, 768, B.ACT_GELU, False),
+    "ffn_out": lambda: gemm_case(GEMM_M, 768, 3072, B.ACT_NONE, True),
 }
 
 def main():

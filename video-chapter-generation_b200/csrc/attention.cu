@@ -6,6 +6,7 @@
 // Attention is 2 % of the path's FLOPs at L=100 (10 % at L=512), so it stays on the legacy tensor path for now.
 // fp32 path (verification mode): straightforward SIMT kernel, one warp per query row.
 #include "kernels.cuh"
+#include "launch.cuh"
 #include "tensormap.h"
 #include <cuda_bf16.h>
 
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(128) bert_attention_bf16_kernel(const __nv_bfl
                                                                   const uint8_t* __restrict__ key_ok,
                                                                   __nv_bfloat16* __restrict__ ctx, int Lmax, int Lp_max) {
   extern __shared__ __align__(16) uint8_t smem[];
+  pdl_enter();
   const int head = blockIdx.x, b = blockIdx.y, q0 = blockIdx.z * kQBlock;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long row_base = cu ? cu[b] : static_cast<long>(b) * Lmax;
@@ -190,6 +192,7 @@ __global__ void __launch_bounds__(128) bert_attention_fp32_kernel(const float* _
                                                                   const uint8_t* __restrict__ key_ok,
                                                                   float* __restrict__ ctx, int Lmax) {
   extern __shared__ float fsm[];
+  pdl_enter();
   const int head = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sq = fsm + warp * (kHeadDim + Lmax);
@@ -255,13 +258,13 @@ void launch_bert_attention(const void* qkv, const int64_t* mask, const int32_t* 
       configured = smem;
     }
     dim3 grid(kBertHeads, B, (L + kQBlock - 1) / kQBlock);
-    bert_attention_bf16_kernel<<<grid, 128, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv), mask, cu, key_ok,
-                                                       static_cast<__nv_bfloat16*>(ctx), L, Lp);
+    launch_pdl(bert_attention_bf16_kernel, grid, 128, smem, s, static_cast<const __nv_bfloat16*>(qkv), mask, cu, key_ok,
+               static_cast<__nv_bfloat16*>(ctx), L, Lp);
   } else {
     const size_t smem = static_cast<size_t>(4) * (kHeadDim + L) * sizeof(float);
     dim3 grid(kBertHeads, B, (L + 31) / 32);
-    bert_attention_fp32_kernel<<<grid, 128, smem, s>>>(static_cast<const float*>(qkv), mask, cu, key_ok,
-                                                       static_cast<float*>(ctx), L);
+    launch_pdl(bert_attention_fp32_kernel, grid, 128, smem, s, static_cast<const float*>(qkv), mask, cu, key_ok,
+               static_cast<float*>(ctx), L);
   }
   VCG_CUDA(cudaGetLastError());
 }

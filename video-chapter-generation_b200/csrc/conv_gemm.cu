@@ -1,5 +1,6 @@
 // Instantiations and launcher of the tcgen05 implicit-GEMM kernel.
 #include "conv_gemm_host.h"
+#include <cstdlib>
 
 namespace vcg {
 
@@ -13,6 +14,27 @@ int sm_count() {
   return n;
 }
 
+int cg2_policy() {
+  static int pol = -2;
+  if (pol == -2) {
+    const char* v = getenv("VCG_CG2");
+    pol = v ? atoi(v) : -1;
+  }
+  return pol;
+}
+
+template <int BLOCK_N>
+static void launch_pair_t(const ConvGemmLaunch& L, cudaStream_t stream) {
+  using Cfg = ConvGemmCfg<BLOCK_N, false>;
+  static bool configured = false;
+  if (!configured) {
+    VCG_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
+    configured = true;
+  }
+  launch_pdl(conv_gemm_pair_kernel<BLOCK_N>, L.grid, Cfg::kThreads, Cfg::kSmemBytes, stream, L.p);   // __cluster_dims__(2,1,1)
+}
+
 template <int BLOCK_N, bool TF32X3>
 static void launch_t(const ConvGemmLaunch& L, cudaStream_t stream) {
   using Cfg = ConvGemmCfg<BLOCK_N, TF32X3>;
@@ -22,13 +44,21 @@ static void launch_t(const ConvGemmLaunch& L, cudaStream_t stream) {
                                   Cfg::kSmemBytes));
     configured = true;
   }
-  conv_gemm_kernel<BLOCK_N, TF32X3><<<L.grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(L.p);
-  VCG_CUDA(cudaGetLastError());
+  launch_pdl(conv_gemm_kernel<BLOCK_N, TF32X3>, L.grid, Cfg::kThreads, Cfg::kSmemBytes, stream, L.p);
 }
 
 void launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
   if (L.grid <= 0) return;
-  if (!L.fp32) {
+  if (L.cg2) {
+    VCG_REQUIRE(!L.fp32 && L.grid % 2 == 0, "CTA-pair launch needs bf16 and an even grid");
+    switch (L.block_n) {
+      case 64: launch_pair_t<64>(L, stream); break;
+      case 128: launch_pair_t<128>(L, stream); break;
+      case 192: launch_pair_t<192>(L, stream); break;
+      case 256: launch_pair_t<256>(L, stream); break;
+      default: throw Error("vcg: unsupported BLOCK_N");
+    }
+  } else if (!L.fp32) {
     switch (L.block_n) {
       case 64: launch_t<64, false>(L, stream); break;
       case 128: launch_t<128, false>(L, stream); break;

@@ -23,6 +23,7 @@
 // epilogue uses plain row-per-lane global accesses.
 #pragma once
 #include "ptx.cuh"
+#include "launch.cuh"
 #include <cuda_bf16.h>
 
 namespace vcg {
@@ -130,34 +131,68 @@ __device__ __forceinline__ void apply_act32(float (&v)[32], int act) {
   }
 }
 
-// 16-wide variant for the bf16 epilogue (fast erf)
-__device__ __forceinline__ void apply_act16(float (&v)[16], int act) {
+// GELU for the bf16 epilogue: x * Phi(x) with Phi(x) - 1/2 = u * P(u^2), u = clamp(x, +-3.75), P a degree-6 minimax
+// polynomial (max |error| of the GELU value 2.5e-4, an eighth of a bf16 ulp at 1; the fp32 verification mode uses
+// erff).  No MUFU, and two elements per instruction on the packed fp32x2 pipe (FMUL2 / FFMA2): the FFN-in epilogue is
+// issue-bound, the A&S erf it replaces cost 13 FMA-pipe + 2 MUFU instructions per element.
+__device__ __forceinline__ float2 gelu_poly2(float2 x) {
+  constexpr float c = 3.75f;
+  const float2 u = make_float2(fminf(fmaxf(x.x, -c), c), fminf(fmaxf(x.y, -c), c));
+  const float2 t = __fmul2_rn(u, u);
+  float2 p = __ffma2_rn(t, make_float2(3.419050747872096e-08f, 3.419050747872096e-08f),
+                        make_float2(-2.1325091891693936e-06f, -2.1325091891693936e-06f));
+  p = __ffma2_rn(p, t, make_float2(5.764379563294139e-05f, 5.764379563294139e-05f));
+  p = __ffma2_rn(p, t, make_float2(-0.0008995933840409692f, -0.0008995933840409692f));
+  p = __ffma2_rn(p, t, make_float2(0.009149351282721695f, 0.009149351282721695f));
+  p = __ffma2_rn(p, t, make_float2(-0.06531965073372963f, -0.06531965073372963f));
+  p = __ffma2_rn(p, t, make_float2(0.3983374174621377f, 0.3983374174621377f));
+  return __fmul2_rn(x, __ffma2_rn(u, p, make_float2(0.5f, 0.5f)));
+}
+
+// Activation over eight fp32 pairs (the bf16 epilogue works on packed pairs throughout)
+__device__ __forceinline__ void apply_act8x2(float2 (&v)[8], int act) {
   if (act == ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    for (int j = 0; j < 8; ++j) v[j] = make_float2(fmaxf(v[j].x, 0.f), fmaxf(v[j].y, 0.f));
   } else if (act == ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erf_fast(v[j] * 0.70710678118654752440f));
+    for (int j = 0; j < 8; ++j) v[j] = gelu_poly2(v[j]);
   } else if (act == ACT_TANH) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j]);
+    for (int j = 0; j < 8; ++j) v[j] = make_float2(tanhf(v[j].x), tanhf(v[j].y));
   }
 }
 
-template <int BLOCK_N, bool TF32X3>
-__global__ void __launch_bounds__(ConvGemmCfg<BLOCK_N, TF32X3>::kThreads, 1)
-conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+// CG2 = CTA-pair mode (bf16 only): the two CTAs of a (2,1,1) cluster compute one 256 x BLOCK_N output tile with
+// tcgen05.mma.cta_group::2.  Each CTA loads its own 128-row A patch and HALF of the B tile (BLOCK_N/2 weight rows), the
+// leader CTA's MMA thread issues for both, and every CTA drains the 128 accumulator rows that live in its own TMEM.
+// Per SM and K block that is 16 KB + BLOCK_N/2*128 B from L2 instead of 16 KB + BLOCK_N*128 B: the single-CTA kernel
+// is pinned at the ~11 TB/s L2->SM limit (48 KB per 128x256x64 MACs), the pair needs a third less.
+//   full_bar      lives in the leader; both CTAs' TMA loads complete_tx on it (leader expects the bytes of both)
+//   empty_bar     one per CTA, signalled by the leader's multicast tcgen05.commit
+//   tmem_full     one per CTA, multicast commit
+//   tmem_empty    lives in the leader; the epilogue warps of both CTAs arrive on it (remote arrive from the peer)
+template <int BLOCK_N, bool TF32X3, bool CG2>
+__device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   using Cfg = ConvGemmCfg<BLOCK_N, TF32X3>;
+  static_assert(!(CG2 && TF32X3), "CTA-pair mode is bf16 only");
   const int kStages = TF32X3 ? Cfg::kStages : p.n_stages;
   const int kCSlots = TF32X3 ? kMinCSlots : p.n_cslots;
+  constexpr int kBRows = CG2 ? BLOCK_N / 2 : BLOCK_N;       // weight rows this CTA stages per K block
+  constexpr int kBBytes = kBRows * 128;
+  constexpr int kStageBytes = (Cfg::kABytes + kBBytes) * (TF32X3 ? 2 : 1);
+  const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;   // 0 = leader
+  // tile walk: a "unit" is one CTA (one M tile) or one CTA pair (two adjacent M tiles)
+  const int unit = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_units = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                  // [stage][128 rows][128 B]
-  uint8_t* sB = sA + kStages * Cfg::kABytes;           // [stage][BLOCK_N rows][128 B]
-  uint8_t* sA_lo = sB + kStages * Cfg::kBBytes;        // TF32X3 only
+  uint8_t* sB = sA + kStages * Cfg::kABytes;           // [stage][kBRows rows][128 B]
+  uint8_t* sA_lo = sB + kStages * kBBytes;             // TF32X3 only
   uint8_t* sB_lo = sA_lo + kStages * Cfg::kABytes;     // TF32X3 only
-  uint8_t* sC = smem + kStages * Cfg::kStageBytes;     // bf16 only: [kCSlots][128 rows][128 B]
+  uint8_t* sC = smem + kStages * kStageBytes;          // bf16 only: [kCSlots][128 rows][128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBudget);
   uint64_t* full_bar = bars;                     // TMA -> (splitter | MMA)
   uint64_t* empty_bar = bars + kMaxStages;       // MMA -> TMA
@@ -171,6 +206,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail (launch.cuh)
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
     tma_prefetch_desc(&p.b_map);
@@ -187,7 +223,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], Cfg::kNumEpiWarps);
+      mbar_init(&tmem_empty[i], Cfg::kNumEpiWarps * (CG2 ? 2 : 1));
     }
     for (int i = 0; i < kCSlots; ++i) {
       mbar_init(&c_full[i], 1);
@@ -196,26 +232,37 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG2) {
+      tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync(); else __syncthreads();   // barrier inits visible to the peer before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // everything above touched only shared / tensor memory and kernel parameters
 
   const int num_kb = p.n_taps * p.cpt;
   // rows beyond *m_dev are never needed: only the M tiles that hold valid rows are computed
   const int m_tiles = p.m_dev ? (min(__ldg(p.m_dev), p.Wo) + kBlockM - 1) / kBlockM : p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = m_tiles * p.n_tiles;
+  // CG2: a unit tile is (pair of M tiles, N tile); the odd CTA of a last, half-empty pair works on an M tile past the
+  // end (its image coordinate is out of range: TMA zero-fills the loads and clips the stores)
+  const int total_tiles = (CG2 ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles;
+  auto m_of = [&](int tile) { return CG2 ? 2 * (tile / p.n_tiles) + static_cast<int>(cta_rank) : tile / p.n_tiles; };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (A/B stages)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
+      // CG2: the bytes of both CTAs land on the leader's full barrier
+      const uint32_t full0 = CG2 ? mapa_cluster(smem_u32(full_bar), 0) : smem_u32(full_bar);
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
+        const int m_blk = m_of(tile), n_blk = tile % p.n_tiles;
         const int iw = m_blk % p.tiles_w;
         const int ih = (m_blk / p.tiles_w) % p.tiles_h;
         const int in = m_blk / (p.tiles_w * p.tiles_h);
@@ -223,29 +270,31 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         int tap = 0, cb = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+          if (!CG2 || cta_rank == 0) mbar_expect_tx(&full_bar[stage], (p.a_bytes + p.b_bytes) * (CG2 ? 2u : 1u));
+          const uint32_t bar = full0 + stage * 8;
           const TapDesc t = p.taps[tap];
           const int map = (cb < p.tsm_split_cb) ? p.tsm_map : t.map;
           if (p.a_clip_T == 0)
-            tma_load_5d(sA + stage * Cfg::kABytes, &p.a_map[map], &full_bar[stage], cb * Cfg::kBlockK + t.c_off,
-                        w0 + t.dw, h0 + t.dh, t.plane, n0);
+            tma_load_5d<CG2>(sA + stage * Cfg::kABytes, &p.a_map[map], bar, cb * Cfg::kBlockK + t.c_off,
+                             w0 + t.dw, h0 + t.dh, t.plane, n0);
           else   // plane = temporal tap offset (frame t-1 / t / t+1 of the same clip; out of range -> zero fill)
-            tma_load_5d(sA + stage * Cfg::kABytes, &p.a_map[map], &full_bar[stage], cb * Cfg::kBlockK + t.c_off,
-                        w0 + t.dw, h0 + t.dh, n0 % p.a_clip_T + t.plane, n0 / p.a_clip_T);
-          tma_load_2d(sB + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * Cfg::kBlockK, n_blk * BLOCK_N);
+            tma_load_5d<CG2>(sA + stage * Cfg::kABytes, &p.a_map[map], bar, cb * Cfg::kBlockK + t.c_off,
+                             w0 + t.dw, h0 + t.dh, n0 % p.a_clip_T + t.plane, n0 / p.a_clip_T);
+          tma_load_2d<CG2>(sB + stage * kBBytes, &p.b_map, bar, kb * Cfg::kBlockK,
+                           n_blk * BLOCK_N + static_cast<int>(cta_rank) * kBRows);
           if (++cb == p.cpt) { cb = 0; ++tap; }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc(TF32X3 ? 2u : 1u, kBlockM, BLOCK_N);
+    // ------------------------------------------------------------ MMA issuer (CG2: the leader issues for the pair)
+    if ((!CG2 || cta_rank == 0) && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(TF32X3 ? 2u : 1u, CG2 ? 2 * kBlockM : kBlockM, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
         const int acc = TF32X3 ? 0 : (it & 1);
         mbar_wait(&tmem_empty[acc], (TF32X3 ? (it & 1) : ((it >> 1) & 1)) ^ 1);
         tc_fence_after();
@@ -254,27 +303,30 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           mbar_wait(TF32X3 ? &split_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
+          const uint32_t b_addr = smem_u32(sB + stage * kBBytes);
 #pragma unroll
           for (int k = 0; k < Cfg::kBlockK / Cfg::kUmmaK; ++k) {
             const uint64_t da = umma_desc_sw128(a_addr + k * 32);
             const uint64_t db = umma_desc_sw128(b_addr + k * 32);
             if constexpr (TF32X3) {
               const uint64_t da_lo = umma_desc_sw128(smem_u32(sA_lo + stage * Cfg::kABytes) + k * 32);
-              const uint64_t db_lo = umma_desc_sw128(smem_u32(sB_lo + stage * Cfg::kBBytes) + k * 32);
+              const uint64_t db_lo = umma_desc_sw128(smem_u32(sB_lo + stage * kBBytes) + k * 32);
               constexpr int kHiAcc = Cfg::kNumAcc - 1;
               const uint32_t d_hi = tmem_base + (1 + kb % kHiAcc) * BLOCK_N;
               umma_tf32(tmem_base, da_lo, db, idesc, (kb | k) != 0);      // accumulator 0: correction terms
               umma_tf32(tmem_base, da, db_lo, idesc, 1);
               umma_tf32(d_hi, da, db, idesc, (kb >= kHiAcc) || (k != 0));  // hi*hi partial sums
+            } else if constexpr (CG2) {
+              umma_bf16_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
             } else {
               umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
             }
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if constexpr (CG2) umma_commit_cg2(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        if constexpr (CG2) umma_commit_cg2(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
       }
     }
   } else if (!TF32X3 && warp == 3) {
@@ -282,8 +334,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     if (elect_one()) {
       const bool has_res = p.residual != nullptr;
       int c_it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
+        const int m_blk = m_of(tile), n_blk = tile % p.n_tiles;
         const int iw = m_blk % p.tiles_w;
         const int ih = (m_blk / p.tiles_w) % p.tiles_h;
         const int in = m_blk / (p.tiles_w * p.tiles_h);
@@ -317,8 +369,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const int HW = p.Ho * p.Wo;
     int it = 0;
     [[maybe_unused]] int c_it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
+    for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
+      const int m_blk = m_of(tile), n_blk = tile % p.n_tiles;
       const int iw = m_blk % p.tiles_w;
       const int ih = (m_blk / p.tiles_w) % p.tiles_h;
       const int in = m_blk / (p.tiles_w * p.tiles_h);
@@ -436,15 +488,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             uint32_t r[16];
             tmem_ld_32x16(taddr + my_sub * 64 + cs, r);
             tmem_ld_wait();
-            float v[16];
+            float2 v[8];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+            for (int e = 0; e < 8; ++e) v[e] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
             if (col0 < p.N) {
               if (p.bias) {
 #pragma unroll
-                for (int e = 0; e < 16; e += 4) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + e));   // N % 32 == 0 (host check)
-                  v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+                for (int e = 0; e < 8; e += 2) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 2 * e));   // N % 32 == 0 (host check)
+                  v[e] = __fadd2_rn(v[e], make_float2(b4.x, b4.y));
+                  v[e + 1] = __fadd2_rn(v[e + 1], make_float2(b4.z, b4.w));
                 }
               }
               if (has_res) {
@@ -453,20 +506,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                   const uint4 q = *reinterpret_cast<const uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4));
                   const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(h2[e]);
-                    v[c * 8 + 2 * e] += f.x; v[c * 8 + 2 * e + 1] += f.y;
-                  }
+                  for (int e = 0; e < 4; ++e) v[c * 4 + e] = __fadd2_rn(v[c * 4 + e], __bfloat1622float2(h2[e]));
                 }
               }
-              apply_act16(v, p.act);
+              apply_act8x2(v, p.act);
             }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               uint4 o;
               __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1]);
+              for (int e = 0; e < 4; ++e) h2[e] = __float22bfloat162_rn(v[c * 4 + e]);
               *reinterpret_cast<uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4)) = o;
             }
           }
@@ -513,7 +563,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (CG2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+      }
     }
     if constexpr (!TF32X3) {
       if (lane == 0) tma_store_wait_all();   // (storing warps) stores complete before the CTA exits
@@ -524,7 +576,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const int tid = threadIdx.x - 12 * 32;   // 0..127
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < total_tiles; tile += n_units) {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         float4* a_hi = reinterpret_cast<float4*>(sA + stage * Cfg::kABytes);
@@ -552,11 +604,24 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync(); else __syncthreads();   // the peer's barriers / smem stay valid until both are done
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CG2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+template <int BLOCK_N, bool TF32X3>
+__global__ void __launch_bounds__(ConvGemmCfg<BLOCK_N, TF32X3>::kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  conv_gemm_body<BLOCK_N, TF32X3, false>(p);
+}
+
+// CTA-pair variant: launch with an even grid; consecutive CTAs (2i, 2i+1) form the cluster.
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ConvGemmCfg<BLOCK_N, false>::kThreads, 1)
+conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
+  conv_gemm_body<BLOCK_N, false, true>(p);
 }
 
 }  // namespace vcg

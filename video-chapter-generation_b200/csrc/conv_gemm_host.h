@@ -11,12 +11,16 @@ struct ConvGemmLaunch {
   ConvGemmParams p;
   int block_n = 0;
   bool fp32 = false;
+  bool cg2 = false;   // CTA-pair kernel (cta_group::2): 256-row tiles, each CTA stages half of the B tile
   int grid = 0;
   double flops = 0;   // 2*M*N*K of useful work (for reporting)
   const char* name = "";
 };
 
-int sm_count();   // engine.cu
+int sm_count();   // conv_gemm.cu
+
+// CTA-pair policy: VCG_CG2=0 never, =1 whenever possible, unset -> per-layer heuristic (use_cg2)
+int cg2_policy();   // conv_gemm.cu
 
 inline int elem_size(bool fp32) { return fp32 ? 4 : 2; }
 inline int block_k(bool fp32) { return fp32 ? 32 : 64; }
@@ -49,6 +53,20 @@ inline void pick_patch(int Wo, int Ho, int Nimg, int& bw, int& bh, int& nf) {
   nf = 128 / (bw * bh);
 }
 
+// The pair kernel pays when the K loop is long enough to be limited by L2->SM operand traffic (the single-CTA kernel
+// saturates it at ~900 TFLOP/s with 128x256 tiles); short-K / residual layers are HBM-bound either way.
+inline bool use_cg2(int N, int num_kb, long m_tiles, bool fp32) {
+  if (fp32) return false;
+  const int pol = cg2_policy();
+  if (pol == 0) return false;
+  if (m_tiles < 2) return false;
+  if (pol == 1) return true;
+  // measured on B200 (tools/bench_layer.py, VCG_CG2=0 vs 1): +8..13 % for K loops of >= 16 blocks (3x3 convs of
+  // layer3/4, FFN-out, conv1 of layer3/4) and for the wide 12-block GEMMs (QKV, FFN-in); -5..-14 % for the short-K,
+  // HBM-bound layers (conv3, downsample, conv1 of layer1/2)
+  return num_kb >= 16 || (num_kb >= 12 && N >= 1024);
+}
+
 inline void finish_launch(ConvGemmLaunch& L, int Wo, int Ho, int Nimg, int N, bool fp32) {
   ConvGemmParams& p = L.p;
   p.Wo = Wo; p.Ho = Ho; p.Nimg = Nimg; p.N = N;
@@ -58,10 +76,16 @@ inline void finish_launch(ConvGemmLaunch& L, int Wo, int Ho, int Nimg, int N, bo
   L.block_n = pick_block_n(N, fp32);
   L.fp32 = fp32;
   p.n_tiles = (N + L.block_n - 1) / L.block_n;
+  const long m_tiles = static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n;
+  L.cg2 = use_cg2(N, p.n_taps * p.cpt, m_tiles, fp32);
   p.a_bytes = static_cast<uint32_t>(p.bw * p.bh * p.nf) * 128u;
-  p.b_bytes = static_cast<uint32_t>(L.block_n) * 128u;
-  const long total = static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n * p.n_tiles;
-  L.grid = static_cast<int>(std::min<long>(total, sm_count()));
+  p.b_bytes = static_cast<uint32_t>(L.cg2 ? L.block_n / 2 : L.block_n) * 128u;
+  if (L.cg2) {
+    const long pairs = (m_tiles + 1) / 2 * p.n_tiles;
+    L.grid = 2 * static_cast<int>(std::min<long>(pairs, sm_count() / 2));
+  } else {
+    L.grid = static_cast<int>(std::min<long>(m_tiles * p.n_tiles, sm_count()));
+  }
   VCG_REQUIRE(N % 8 == 0, "output channels must be a multiple of 8");
   VCG_REQUIRE(p.bw * p.bh * p.nf <= 128, "patch larger than the M tile");
 }
@@ -109,7 +133,7 @@ inline void set_epilogue(ConvGemmLaunch& L, void* out, int ld_out, const Epilogu
   if (e.tsm_out) VCG_REQUIRE(e.tsm_fold % 32 == 0, "TSM fold must be a multiple of 32 channels");
   if (!L.fp32) {
     // smem split: residual layers are HBM-bound -> short K loops get few A/B stages and a deep residual-prefetch ring
-    const int stage_bytes = kBlockM * 128 + L.block_n * 128;
+    const int stage_bytes = kBlockM * 128 + static_cast<int>(p.b_bytes);
     const int budget = 224 * 1024;
     const int min_slots = std::max(kMinCSlots, L.block_n / 64 + 1);   // at least one C tile of prefetch beyond a tile
     const int max_stages = std::min(kMaxStages, (budget - min_slots * kCBytes) / stage_bytes);
@@ -159,7 +183,7 @@ inline ConvGemmLaunch build_gemm(const void* A, long lda, const void* W, void* o
   p.taps[0] = TapDesc{0, 0, 0, 0, 0};
   p.tsm_split_cb = 0; p.tsm_map = 0;
   finish_launch(L, /*Wo=*/M, /*Ho=*/1, /*Nimg=*/1, N, fp32);
-  p.b_map = weight_map(W, N, K, L.block_n, fp32);
+  p.b_map = weight_map(W, N, K, L.cg2 ? L.block_n / 2 : L.block_n, fp32);
   set_epilogue(L, out, ld_out, e);
   L.flops = 2.0 * M * N * K;
   return L;
@@ -233,7 +257,7 @@ inline ConvGemmLaunch build_conv(const void* in, int Nimg, int H, int W, int Cin
     p.tsm_split_cb = tsm_in_ch / bk;
   }
   finish_launch(L, Wo, Ho, Nimg, Cout, fp32);
-  p.b_map = weight_map(Wp, Cout, k * k * Cin, L.block_n, fp32);
+  p.b_map = weight_map(Wp, Cout, k * k * Cin, L.cg2 ? L.block_n / 2 : L.block_n, fp32);
   set_epilogue(L, out, Cout, e);
   L.flops = 2.0 * Nimg * Ho * Wo * static_cast<double>(Cout) * k * k * Cin;
   return L;
@@ -284,7 +308,7 @@ inline ConvGemmLaunch build_stem(const void* in_padded, int Nimg, int Hp, int Wp
   }
   for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
   finish_launch(L, Wo, Ho, Nimg, Cout, fp32);
-  p.b_map = weight_map(Wp_packed, Cout, fp32 ? 7 * 32 : 4 * 64, L.block_n, fp32);
+  p.b_map = weight_map(Wp_packed, Cout, fp32 ? 7 * 32 : 4 * 64, L.cg2 ? L.block_n / 2 : L.block_n, fp32);
   set_epilogue(L, out, Cout, e);
   L.flops = 2.0 * Nimg * Ho * Wo * static_cast<double>(Cout) * 147;
   return L;
@@ -315,7 +339,7 @@ inline ConvGemmLaunch build_conv1_shared(const void* x0u, int n_clips, int T, in
     p.taps[i] = t;
   }
   finish_launch(L, W, H, Nimg, Cout, false);
-  p.b_map = weight_map(Wp, Cout, 3 * Cin, L.block_n, false);
+  p.b_map = weight_map(Wp, Cout, 3 * Cin, L.cg2 ? L.block_n / 2 : L.block_n, false);
   set_epilogue(L, out, Cout, e);
   L.flops = 2.0 * Nimg * H * W * static_cast<double>(Cout) * Cin;
   return L;

@@ -2,6 +2,7 @@
 // BERT embedding + LayerNorm, LayerNorm, and weight packing.  All use 8/16-byte vector accesses with consecutive
 // threads on consecutive addresses; grids are sized from the element count (>= several waves at bench sizes).
 #include "kernels.cuh"
+#include "launch.cuh"
 #include "tensormap.h"
 #include <cuda_bf16.h>
 #include <type_traits>
@@ -74,6 +75,7 @@ template <bool FP32>
 __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ frame_index,
                                      const int32_t* __restrict__ clip_start, int T, long total,
                                      elem_t<FP32>* __restrict__ out) {
+  pdl_enter();
   const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   constexpr int W4 = kImg / 4;
@@ -109,6 +111,7 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ frames, const i
 // fp32 NCHW (already normalised, the reference's img_clip) -> padded NHWC4
 template <bool FP32>
 __global__ void nchw_to_stem_kernel(const float* __restrict__ img, long total, elem_t<FP32>* __restrict__ out) {
+  pdl_enter();
   const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   const int w = static_cast<int>(idx % kImg);
@@ -134,6 +137,7 @@ __global__ void nchw_to_stem_kernel(const float* __restrict__ img, long total, e
 template <bool FP32>
 __global__ void maxpool_tsm_kernel(const elem_t<FP32>* __restrict__ in, long total, elem_t<FP32>* __restrict__ out,
                                    elem_t<FP32>* __restrict__ shifted, int T, int fold) {
+  pdl_enter();
   constexpr int C = 64, HI = kStemOut, HO = kStemOut / 2;
   const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
@@ -176,6 +180,7 @@ __global__ void maxpool_tsm_kernel(const elem_t<FP32>* __restrict__ in, long tot
 template <bool FP32>
 __global__ void avgpool_kernel(const elem_t<FP32>* __restrict__ in, long total, int hw, int C,
                                float* __restrict__ out, elem_t<FP32>* __restrict__ out_act) {
+  pdl_enter();
   const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   const int c8 = static_cast<int>(idx % (C / 8));
@@ -237,6 +242,7 @@ template <bool FP32>
 __global__ void layernorm768_kernel(const elem_t<FP32>* __restrict__ x, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, elem_t<FP32>* __restrict__ y, int rows,
                                     const int32_t* __restrict__ rows_dev, float eps) {
+  pdl_enter();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (rows_dev) rows = min(rows, *rows_dev);     // token-packed BERT: only the packed rows exist
@@ -254,6 +260,7 @@ __global__ void bert_embed_ln_kernel(const int64_t* __restrict__ ids, int rows, 
                                      const elem_t<FP32>* __restrict__ word, const elem_t<FP32>* __restrict__ pos,
                                      const elem_t<FP32>* __restrict__ type, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, elem_t<FP32>* __restrict__ out) {
+  pdl_enter();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (rows_dev) rows = min(rows, *rows_dev);
@@ -283,6 +290,7 @@ __global__ void bert_embed_ln_kernel(const int64_t* __restrict__ ids, int rows, 
 __global__ void __launch_bounds__(1024) bert_pack_kernel(const int64_t* __restrict__ mask, int B, int L,
                                                           int32_t* __restrict__ cu, int32_t* __restrict__ tok_src,
                                                           uint8_t* __restrict__ key_ok, int32_t* __restrict__ total) {
+  pdl_enter();
   extern __shared__ int s_cnt[];   // [B + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int b = warp; b < B; b += nwarps) {
@@ -322,6 +330,7 @@ __global__ void __launch_bounds__(1024) bert_pack_kernel(const int64_t* __restri
 template <bool FP32>
 __global__ void gather_rows768_kernel(const elem_t<FP32>* __restrict__ x, const int32_t* __restrict__ row_of, int stride,
                                       int B, elem_t<FP32>* __restrict__ out) {
+  pdl_enter();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -395,12 +404,14 @@ __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __res
 
 template <bool FP32>
 __global__ void convert_kernel(const float* __restrict__ in, elem_t<FP32>* __restrict__ out, long n) {
+  pdl_enter();
   const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (idx >= n) return;
   if constexpr (FP32) out[idx] = in[idx]; else out[idx] = __float2bfloat16_rn(in[idx]);
 }
 template <bool FP32>
 __global__ void cast_to_f32_kernel(const elem_t<FP32>* __restrict__ in, float* __restrict__ out, long n) {
+  pdl_enter();
   const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (idx >= n) return;
   if constexpr (FP32) out[idx] = in[idx]; else out[idx] = __bfloat162float(in[idx]);
@@ -432,23 +443,20 @@ void launch_preprocess_u8(const uint8_t* frames, const int32_t* frame_index, int
                           cudaStream_t s) {
   const long total = static_cast<long>(n) * kImg * (kImg / 4);
   if (total == 0) return;
-  VCG_DISPATCH(fp32, (preprocess_u8_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(
-                         frames, frame_index, nullptr, 1, total, static_cast<elem_t<FP>*>(out))));
+  VCG_DISPATCH(fp32, (launch_pdl(preprocess_u8_kernel<FP>, blocks_for(total, 256), 256, 0, s, frames, frame_index, nullptr, 1, total, static_cast<elem_t<FP>*>(out))));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_preprocess_u8_clips(const uint8_t* frames, const int32_t* clip_start, int B, int T, void* out, bool fp32,
                                 cudaStream_t s) {
   const long total = static_cast<long>(B) * T * kImg * (kImg / 4);
   if (total == 0) return;
-  VCG_DISPATCH(fp32, (preprocess_u8_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(
-                         frames, nullptr, clip_start, T, total, static_cast<elem_t<FP>*>(out))));
+  VCG_DISPATCH(fp32, (launch_pdl(preprocess_u8_kernel<FP>, blocks_for(total, 256), 256, 0, s, frames, nullptr, clip_start, T, total, static_cast<elem_t<FP>*>(out))));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_nchw_to_stem(const float* img, int n, void* out, bool fp32, cudaStream_t s) {
   const long total = static_cast<long>(n) * kImg * kImg;
   if (total == 0) return;
-  VCG_DISPATCH(fp32, (nchw_to_stem_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(
-                         img, total, static_cast<elem_t<FP>*>(out))));
+  VCG_DISPATCH(fp32, (launch_pdl(nchw_to_stem_kernel<FP>, blocks_for(total, 256), 256, 0, s, img, total, static_cast<elem_t<FP>*>(out))));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_maxpool_tsm(const void* in, int n, void* out, void* out_shifted, int T, int fold, bool fp32,
@@ -456,36 +464,32 @@ void launch_maxpool_tsm(const void* in, int n, void* out, void* out_shifted, int
   VCG_REQUIRE(out_shifted == nullptr || (fold % 8 == 0 && fold > 0), "TSM fold of the stem output must be a multiple of 8");
   const long total = static_cast<long>(n) * 56 * 56 * 8;
   if (total == 0) return;
-  VCG_DISPATCH(fp32, (maxpool_tsm_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(
-                         static_cast<const elem_t<FP>*>(in), total, static_cast<elem_t<FP>*>(out),
+  VCG_DISPATCH(fp32, (launch_pdl(maxpool_tsm_kernel<FP>, blocks_for(total, 256), 256, 0, s, static_cast<const elem_t<FP>*>(in), total, static_cast<elem_t<FP>*>(out),
                          static_cast<elem_t<FP>*>(out_shifted), T, fold)));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_avgpool(const void* in, int n, int hw, int C, float* out, void* out_act, cudaStream_t s, bool fp32) {
   const long total = static_cast<long>(n) * (C / 8);
   if (total == 0) return;
-  VCG_DISPATCH(fp32, (avgpool_kernel<FP><<<blocks_for(total, 128), 128, 0, s>>>(
-                         static_cast<const elem_t<FP>*>(in), total, hw, C, out, static_cast<elem_t<FP>*>(out_act))));
+  VCG_DISPATCH(fp32, (launch_pdl(avgpool_kernel<FP>, blocks_for(total, 128), 128, 0, s, static_cast<const elem_t<FP>*>(in), total, hw, C, out, static_cast<elem_t<FP>*>(out_act))));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_bert_pack(const int64_t* mask, int B, int L, int32_t* cu, int32_t* tok_src, uint8_t* key_ok, int32_t* total,
                       cudaStream_t s) {
   if (B == 0) return;
-  bert_pack_kernel<<<1, 1024, (B + 1) * sizeof(int), s>>>(mask, B, L, cu, tok_src, key_ok, total);
+  launch_pdl(bert_pack_kernel, 1, 1024, (B + 1) * sizeof(int), s, mask, B, L, cu, tok_src, key_ok, total);
   VCG_CUDA(cudaGetLastError());
 }
 void launch_gather_rows768(const void* x, const int32_t* row_of, int stride, int B, void* out, bool fp32, cudaStream_t s) {
   if (B == 0) return;
-  VCG_DISPATCH(fp32, (gather_rows768_kernel<FP><<<blocks_for(B, 8), 256, 0, s>>>(
-                         static_cast<const elem_t<FP>*>(x), row_of, stride, B, static_cast<elem_t<FP>*>(out))));
+  VCG_DISPATCH(fp32, (launch_pdl(gather_rows768_kernel<FP>, blocks_for(B, 8), 256, 0, s, static_cast<const elem_t<FP>*>(x), row_of, stride, B, static_cast<elem_t<FP>*>(out))));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const int32_t* tok_src, const int32_t* rows_dev,
                           const void* word, const void* pos, const void* type, const float* gamma, const float* beta,
                           void* out, bool fp32, cudaStream_t s) {
   if (rows == 0) return;
-  VCG_DISPATCH(fp32, (bert_embed_ln_kernel<FP><<<blocks_for(rows, 8), 256, 0, s>>>(
-                         ids, rows, L, tok_src, rows_dev, static_cast<const elem_t<FP>*>(word), static_cast<const elem_t<FP>*>(pos),
+  VCG_DISPATCH(fp32, (launch_pdl(bert_embed_ln_kernel<FP>, blocks_for(rows, 8), 256, 0, s, ids, rows, L, tok_src, rows_dev, static_cast<const elem_t<FP>*>(word), static_cast<const elem_t<FP>*>(pos),
                          static_cast<const elem_t<FP>*>(type), gamma, beta, static_cast<elem_t<FP>*>(out))));
   VCG_CUDA(cudaGetLastError());
 }
@@ -493,8 +497,7 @@ void launch_layernorm(const void* x, const float* gamma, const float* beta, void
                       bool fp32, cudaStream_t s, const int32_t* rows_dev) {
   VCG_REQUIRE(cols == 768, "LayerNorm kernel is specialised for 768 columns");
   if (rows == 0) return;
-  VCG_DISPATCH(fp32, (layernorm768_kernel<FP><<<blocks_for(rows, 8), 256, 0, s>>>(
-                         static_cast<const elem_t<FP>*>(x), gamma, beta, static_cast<elem_t<FP>*>(y), rows, rows_dev, eps)));
+  VCG_DISPATCH(fp32, (launch_pdl(layernorm768_kernel<FP>, blocks_for(rows, 8), 256, 0, s, static_cast<const elem_t<FP>*>(x), gamma, beta, static_cast<elem_t<FP>*>(y), rows, rows_dev, eps)));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_pack_conv(const float* w, const float* bn_w, const float* bn_b, const float* bn_mean, const float* bn_var,
@@ -522,12 +525,12 @@ void launch_pack_stem(const float* w, const float* bn_w, const float* bn_b, cons
 }
 void launch_convert(const float* in, void* out, long n, bool fp32, cudaStream_t s) {
   if (n == 0) return;
-  VCG_DISPATCH(fp32, (convert_kernel<FP><<<blocks_for(n, 256), 256, 0, s>>>(in, static_cast<elem_t<FP>*>(out), n)));
+  VCG_DISPATCH(fp32, (launch_pdl(convert_kernel<FP>, blocks_for(n, 256), 256, 0, s, in, static_cast<elem_t<FP>*>(out), n)));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_cast_to_f32(const void* in, float* out, long n, bool fp32, cudaStream_t s) {
   if (n == 0) return;
-  VCG_DISPATCH(fp32, (cast_to_f32_kernel<FP><<<blocks_for(n, 256), 256, 0, s>>>(static_cast<const elem_t<FP>*>(in),
+  VCG_DISPATCH(fp32, (launch_pdl(cast_to_f32_kernel<FP>, blocks_for(n, 256), 256, 0, s, static_cast<const elem_t<FP>*>(in),
                                                                                  out, n)));
   VCG_CUDA(cudaGetLastError());
 }

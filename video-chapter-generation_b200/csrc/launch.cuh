@@ -1,0 +1,48 @@
+// Programmatic dependent launch (PDL) for the forward path.
+//
+// A scoring pass is a chain of ~100 short kernels on one stream.  Launched the ordinary way, kernel i+1 is only
+// scheduled after kernel i has drained, so every boundary costs launch latency plus the prologue of the next kernel
+// (barrier init, TMEM allocation, tensor-map prefetch).  With PDL every forward kernel
+//   * calls griddepcontrol.launch_dependents first thing, so its successor's CTAs become resident as soon as SMs free up,
+//   * and executes griddepcontrol.wait before its first access to global memory that a predecessor may still be
+//     reading or writing (the wait returns when ALL earlier grids of the chain have completed and flushed).
+// Both instructions are no-ops for a kernel launched without the attribute.  VCG_PDL=0 disables the attribute.
+#pragma once
+#include "tensormap.h"
+#include <cstdlib>
+
+namespace vcg {
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// for kernels without a prologue worth overlapping
+__device__ __forceinline__ void pdl_enter() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* v = getenv("VCG_PDL");
+    on = (v && atoi(v) == 0) ? 0 : 1;
+  }
+  return on != 0;
+}
+
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VCG_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
+}  // namespace vcg

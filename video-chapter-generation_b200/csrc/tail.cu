@@ -5,6 +5,7 @@
 //     head_type attn  4-head self-attention over the T+1 tokens, token 0 only   two_stream.py:31-48
 // The pooler (tanh) and the two bias-free projections (ReLU) run on the tcgen05 GEMM kernel (engine.cu).
 #include "kernels.cuh"
+#include "launch.cuh"
 #include "tensormap.h"
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -21,6 +22,7 @@ template <bool FP32>
 __global__ void __launch_bounds__(128) head_final_kernel(const TailParams p) {
   using in_t = typename std::conditional<FP32, float, __nv_bfloat16>::type;
   extern __shared__ float sm[];
+  pdl_enter();
   const int H = p.H, T = p.T, tid = threadIdx.x, b = blockIdx.x, ntok = T + 1;
   float* s_tok = sm;                       // [(T+1)][H]
   float* s_k = s_tok + ntok * H;           // attn only: [(T+1)][H]
@@ -124,8 +126,8 @@ void launch_head_final(const TailParams& p, int B, bool fp32, cudaStream_t s) {
     else VCG_CUDA(cudaFuncSetAttribute(head_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured[fp32] = smem;
   }
-  if (fp32) head_final_kernel<true><<<B, 128, smem, s>>>(p);
-  else head_final_kernel<false><<<B, 128, smem, s>>>(p);
+  if (fp32) launch_pdl(head_final_kernel<true>, B, 128, smem, s, p);
+  else launch_pdl(head_final_kernel<false>, B, 128, smem, s, p);
   VCG_CUDA(cudaGetLastError());
 }
 
