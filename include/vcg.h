@@ -158,6 +158,13 @@ VCG_API int vcg_op_maxpool_tsm(const void* in, int32_t n, void* out, void* out_s
 VCG_API int vcg_op_bert_attention(const void* qkv, const int64_t* attention_mask, void* ctx, int32_t B, int32_t L,
                           int32_t precision, void* stream);
 
+/* The same attention on the token-packed layout the engine uses (bf16 only): clip b owns rows cu[b] .. cu[b+1]-1 of
+ * qkv [rows, 2304] / ctx [rows, 768]; key_ok[row] != 0 marks keys that may be attended; max_len >= every clip length.
+ * `rows` = rows of the qkv allocation (>= cu[B] + 31, finite values everywhere).  max_len <= 128 runs the tcgen05
+ * kernel (one 128 x 128 score tile per clip and head), longer clips the mma.sync kernel with an online softmax. */
+VCG_API int vcg_op_bert_attention_packed(const void* qkv, const int32_t* cu, const uint8_t* key_ok, void* ctx, int32_t B,
+                                 int32_t max_len, int64_t rows, void* stream);
+
 /* y = LayerNorm(x) * gamma + beta over rows of 768, eps 1e-12 (modeling_bert.py BertSelfOutput/BertOutput). */
 VCG_API int vcg_op_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t cols,
                      float eps, int32_t precision, void* stream);

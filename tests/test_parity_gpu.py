@@ -193,3 +193,34 @@ def test_no_cpu_fallback():
     model, _ = build_model(8, "mlp", "bf16")
     with pytest.raises(RuntimeError):
         model(torch.zeros(1, 8, 3, 224, 224), torch.zeros(1, 16, dtype=torch.long), torch.ones(1, 16, dtype=torch.long))
+
+
+@pytest.mark.parametrize("max_len", [128, 200])   # <= 128: tcgen05 kernel; longer: mma.sync kernel with online softmax
+def test_packed_attention_matches_torch(max_len):
+    """Token-packed BERT attention (the layout the engine uses) against a plain torch fp32 softmax(QK^T/8 + mask)V,
+    clip by clip: ragged lengths including 1, 16/17, 64/65 and the maximum, masked keys inside a clip."""
+    from vcg_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    lens = [1, 16, 17, 33, 64, 65, 100, max_len, 5, 127 if max_len >= 127 else 31] + \
+        [int(x) for x in torch.randint(1, max_len + 1, (40,), generator=g)]
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32)
+    total = int(cu[-1])
+    rows = total + 160
+    qkv = torch.randn(rows, 2304, generator=g).to(torch.bfloat16)
+    key_ok = torch.ones(rows, dtype=torch.uint8)
+    for b, n in enumerate(lens):   # mask a few keys (never all of a clip)
+        if n >= 4:
+            key_ok[int(cu[b]) + 1 + b % (n - 2)] = 0
+    ctx = ops.bert_attention_packed(qkv.cuda(), cu.cuda(), key_ok.cuda(), max_len).float().cpu()
+    worst = 0.0
+    for b, n in enumerate(lens):
+        r0 = int(cu[b])
+        x = qkv[r0:r0 + n].float()
+        q, k, v = (x[:, i * 768:(i + 1) * 768].view(n, 12, 64).transpose(0, 1) for i in range(3))
+        s = q @ k.transpose(1, 2) / 8.0
+        s = s.masked_fill(key_ok[r0:r0 + n].view(1, 1, n) == 0, float("-inf"))
+        ref = (torch.softmax(s, -1) @ v).transpose(0, 1).reshape(n, 768)
+        worst = max(worst, float((ctx[r0:r0 + n] - ref).abs().max() / ref.abs().max()))
+    print("packed attention max rel err", worst)
+    assert worst <= 1.5e-2   # bf16 probabilities and outputs
+    assert torch.count_nonzero(ctx[total:]) == 0   # rows past the packed tokens are never written

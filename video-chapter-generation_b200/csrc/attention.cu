@@ -1,14 +1,17 @@
 // BERT self-attention  ctx = softmax(Q K^T / sqrt(64) + key_mask) V   (modeling_bert.py:115-140, 12 heads x 64).
 //
-// bf16 path: one CTA per (clip, head, 64-query block); K, V and the Q block are staged in shared memory (rows padded
-// to 144 B so ldmatrix is bank-conflict free), each warp owns 16 query rows and walks the keys in blocks of 64 with an
-// online softmax (fp32 statistics, quad shuffles for the row reductions); QK^T and PV run on mma.sync m16n8k16.
-// Attention is 2 % of the path's FLOPs at L=100 (10 % at L=512), so it stays on the legacy tensor path for now.
+// bf16 path: one CTA (8 warps) per (clip, head, 128-query block); K, V and the Q block are staged in shared memory by
+// cp.async in two groups (Q+K, then V, so QK^T starts while V is still in flight; rows padded to 144 B so ldmatrix is
+// bank-conflict free), each warp owns 16 query rows and walks the keys in blocks of 64 with an online softmax (fp32
+// statistics, quad shuffles for the row reductions); QK^T and PV run on mma.sync m16n8k16.  At L <= 128 one CTA sees
+// all queries of its (clip, head), so K and V are read exactly once.  Attention is 2 % of the path's FLOPs at L=100
+// (10 % at L=512) and latency/L2-bound at these sizes, so it stays on the legacy tensor path.
 // fp32 path (verification mode): straightforward SIMT kernel, one warp per query row.
 #include "kernels.cuh"
 #include "launch.cuh"
 #include "tensormap.h"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace vcg {
 
@@ -16,7 +19,7 @@ namespace {
 
 constexpr int kHeadDim = 64;
 constexpr int kRowPad = 72;   // bf16 elements per padded smem row (144 B)
-constexpr int kQBlock = 64;    // queries per CTA (4 warps x 16 rows)
+constexpr int kQBlock = 128;   // queries per CTA (8 warps x 16 rows)
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
   const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -34,6 +37,13 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -41,7 +51,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 // Packed (variable-length) mode: cu[b] .. cu[b+1] are the rows of clip b in the token-packed activation matrices and
 // key_ok[row] says whether that token may be attended to; cu == nullptr: rows b*L .. b*L+L-1 and the int64 mask.
-__global__ void __launch_bounds__(128) bert_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(256, 3) bert_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                   const int64_t* __restrict__ mask,
                                                                   const int32_t* __restrict__ cu,
                                                                   const uint8_t* __restrict__ key_ok,
@@ -59,40 +69,39 @@ __global__ void __launch_bounds__(128) bert_attention_bf16_kernel(const __nv_bfl
   __nv_bfloat16* sQ = sV + Lp_max * kRowPad;
   float* sMask = reinterpret_cast<float*>(sQ + kQBlock * kRowPad);
   const int ld = 3 * kBertHidden;
+  const int Lk = (L + 15) / 16 * 16;                // keys in steps of 16: tiles beyond Lk are skipped (p = 0 exactly)
+  const int nq = min(kQBlock, L - q0);              // query rows of this block
+  const int nqp = (nq + 15) / 16 * 16;
 
-  // stage K, V (all keys) and the Q block; rows beyond L are zero (their probabilities are exactly 0)
+  // group 0: Q block + K; group 1: V.  Rows beyond L are zero (their probabilities are exactly 0).
+  const __nv_bfloat16* src0 = qkv + row_base * ld + head * kHeadDim;
+  for (int i = tid; i < nqp * 8; i += blockDim.x) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    if (r < nq) cp_async16(sQ + r * kRowPad + c, src0 + static_cast<long>(q0 + r) * ld + c);
+    else *reinterpret_cast<uint4*>(sQ + r * kRowPad + c) = make_uint4(0, 0, 0, 0);
+  }
   for (int i = tid; i < Lp * 8; i += blockDim.x) {
     const int r = i >> 3, c = (i & 7) * 8;
-    uint4 k4 = make_uint4(0, 0, 0, 0), v4 = make_uint4(0, 0, 0, 0);
-    if (r < L) {
-      const __nv_bfloat16* src = qkv + (row_base + r) * ld + head * kHeadDim + c;
-      k4 = *reinterpret_cast<const uint4*>(src + kBertHidden);
-      v4 = *reinterpret_cast<const uint4*>(src + 2 * kBertHidden);
-    }
-    *reinterpret_cast<uint4*>(sK + r * kRowPad + c) = k4;
-    *reinterpret_cast<uint4*>(sV + r * kRowPad + c) = v4;
+    if (r < L) cp_async16(sK + r * kRowPad + c, src0 + static_cast<long>(r) * ld + kBertHidden + c);
+    else *reinterpret_cast<uint4*>(sK + r * kRowPad + c) = make_uint4(0, 0, 0, 0);
   }
-  for (int i = tid; i < kQBlock * 8; i += blockDim.x) {
+  cp_async_commit();
+  for (int i = tid; i < Lp * 8; i += blockDim.x) {
     const int r = i >> 3, c = (i & 7) * 8;
-    uint4 q4 = make_uint4(0, 0, 0, 0);
-    if (q0 + r < L) q4 = *reinterpret_cast<const uint4*>(qkv + (row_base + q0 + r) * ld + head * kHeadDim + c);
-    *reinterpret_cast<uint4*>(sQ + r * kRowPad + c) = q4;
+    if (r < L) cp_async16(sV + r * kRowPad + c, src0 + static_cast<long>(r) * ld + 2 * kBertHidden + c);
+    else *reinterpret_cast<uint4*>(sV + r * kRowPad + c) = make_uint4(0, 0, 0, 0);
   }
+  cp_async_commit();
   for (int j = tid; j < Lp; j += blockDim.x) {
     bool ok = j < L;
     if (ok) ok = cu ? (key_ok[row_base + j] != 0) : (mask[row_base + j] != 0);
     sMask[j] = ok ? 0.f : -INFINITY;
   }
-  __syncthreads();
+  cp_async_wait<1>();
+  __syncthreads();          // Q, K and the mask are in shared memory
 
   const int qrow = warp * 16;                 // this warp's 16 query rows within the block
-  if (q0 + qrow >= L) return;                 // whole warp out of range (no further block-wide syncs below)
-
-  // Q fragments: 4 k-steps of 16
-  uint32_t qf[4][4];
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-    ldmatrix_x4(qf[ks], sQ + (qrow + (lane & 7) + ((lane >> 3) & 1) * 8) * kRowPad + ks * 16 + (lane >> 4) * 8);
+  const bool active = q0 + qrow < L;          // (warp-uniform) idle warps only take part in the barrier below
 
   const float sl2 = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
   float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
@@ -101,74 +110,88 @@ __global__ void __launch_bounds__(128) bert_attention_bf16_kernel(const __nv_bfl
   for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
 
   for (int kb = 0; kb < Lp; kb += 64) {
-    float s[8][4];
+    uint32_t pf[4][4];   // P as A fragments: 4 k-steps of 16 keys
+    float corr[2] = {1.f, 1.f};
+    if (active) {
+      float s[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t qf[4];    // Q fragment of this k-step (re-read per key block: cheaper than 16 live registers)
+        ldmatrix_x4(qf, sQ + (qrow + (lane & 7) + ((lane >> 3) & 1) * 8) * kRowPad + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {   // pairs of 8-key tiles
-        uint32_t kf[4];
-        ldmatrix_x4(kf, sK + (kb + np * 16 + (lane & 7) + (lane >> 4) * 8) * kRowPad + ks * 16 + ((lane >> 3) & 1) * 8);
-        mma_bf16_16816(s[2 * np], qf[ks], kf[0], kf[1]);
-        mma_bf16_16816(s[2 * np + 1], qf[ks], kf[2], kf[3]);
+        for (int np = 0; np < 4; ++np) {   // pairs of 8-key tiles
+          if (kb + np * 16 >= Lk) break;   // (uniform) nothing but padding from here on
+          uint32_t kf[4];
+          ldmatrix_x4(kf, sK + (kb + np * 16 + (lane & 7) + (lane >> 4) * 8) * kRowPad + ks * 16 + ((lane >> 3) & 1) * 8);
+          mma_bf16_16816(s[2 * np], qf, kf[0], kf[1]);
+          mma_bf16_16816(s[2 * np + 1], qf, kf[2], kf[3]);
+        }
+      }
+      // scale, mask, block row-max
+      float bm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int key = kb + nt * 8 + (lane & 3) * 2;
+        const float mk0 = sMask[key], mk1 = sMask[key + 1];
+        s[nt][0] = s[nt][0] * sl2 + mk0; s[nt][1] = s[nt][1] * sl2 + mk1;
+        s[nt][2] = s[nt][2] * sl2 + mk0; s[nt][3] = s[nt][3] * sl2 + mk1;
+        bm[0] = fmaxf(bm[0], fmaxf(s[nt][0], s[nt][1]));
+        bm[1] = fmaxf(bm[1], fmaxf(s[nt][2], s[nt][3]));
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 1));
+        bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 2));
+      }
+      float mnew[2], msub[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mnew[r] = fmaxf(m[r], bm[r]);
+        msub[r] = (mnew[r] == -INFINITY) ? 0.f : mnew[r];
+        corr[r] = exp2f(m[r] - msub[r]);   // m = -inf -> 0
+        m[r] = mnew[r];
+      }
+      float rs[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float p0 = exp2f(s[nt][0] - msub[0]), p1 = exp2f(s[nt][1] - msub[0]);
+        const float p2 = exp2f(s[nt][2] - msub[1]), p3 = exp2f(s[nt][3] - msub[1]);
+        rs[0] += p0 + p1; rs[1] += p2 + p3;
+        pf[nt >> 1][(nt & 1) * 2] = pack2(p0, p1);
+        pf[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2, p3);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+        rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+        l[r] = l[r] * corr[r] + rs[r];
       }
     }
-    // scale, mask, block row-max
-    float bm[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int key = kb + nt * 8 + (lane & 3) * 2;
-      const float mk0 = sMask[key], mk1 = sMask[key + 1];
-      s[nt][0] = s[nt][0] * sl2 + mk0; s[nt][1] = s[nt][1] * sl2 + mk1;
-      s[nt][2] = s[nt][2] * sl2 + mk0; s[nt][3] = s[nt][3] * sl2 + mk1;
-      bm[0] = fmaxf(bm[0], fmaxf(s[nt][0], s[nt][1]));
-      bm[1] = fmaxf(bm[1], fmaxf(s[nt][2], s[nt][3]));
+    if (kb == 0) {            // (CTA-uniform) V has landed
+      cp_async_wait<0>();
+      __syncthreads();
     }
+    if (active) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 1));
-      bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 2));
-    }
-    float mnew[2], corr[2], msub[2];
+      for (int dt = 0; dt < 8; ++dt) {
+        o[dt][0] *= corr[0]; o[dt][1] *= corr[0]; o[dt][2] *= corr[1]; o[dt][3] *= corr[1];
+      }
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      mnew[r] = fmaxf(m[r], bm[r]);
-      msub[r] = (mnew[r] == -INFINITY) ? 0.f : mnew[r];
-      corr[r] = exp2f(m[r] - msub[r]);   // m = -inf -> 0
-      m[r] = mnew[r];
-    }
-    float rs[2] = {0.f, 0.f};
-    uint32_t pf[4][4];   // P as A fragments: 4 k-steps of 16 keys
+      for (int ks = 0; ks < 4; ++ks) {       // 16 keys per step
+        if (kb + ks * 16 >= Lk) break;       // (uniform) padding keys: p = 0
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = exp2f(s[nt][0] - msub[0]), p1 = exp2f(s[nt][1] - msub[0]);
-      const float p2 = exp2f(s[nt][2] - msub[1]), p3 = exp2f(s[nt][3] - msub[1]);
-      rs[0] += p0 + p1; rs[1] += p2 + p3;
-      pf[nt >> 1][(nt & 1) * 2] = pack2(p0, p1);
-      pf[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2, p3);
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
-      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
-      l[r] = l[r] * corr[r] + rs[r];
-    }
-#pragma unroll
-    for (int dt = 0; dt < 8; ++dt) {
-      o[dt][0] *= corr[0]; o[dt][1] *= corr[0]; o[dt][2] *= corr[1]; o[dt][3] *= corr[1];
-    }
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {       // 16 keys per step
-#pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {     // pairs of 8-wide d tiles
-        uint32_t vf[4];
-        ldmatrix_x4_trans(vf, sV + (kb + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kRowPad + dp * 16 + (lane >> 4) * 8);
-        mma_bf16_16816(o[2 * dp], pf[ks], vf[0], vf[1]);
-        mma_bf16_16816(o[2 * dp + 1], pf[ks], vf[2], vf[3]);
+        for (int dp = 0; dp < 4; ++dp) {     // pairs of 8-wide d tiles
+          uint32_t vf[4];
+          ldmatrix_x4_trans(vf, sV + (kb + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kRowPad + dp * 16 + (lane >> 4) * 8);
+          mma_bf16_16816(o[2 * dp], pf[ks], vf[0], vf[1]);
+          mma_bf16_16816(o[2 * dp + 1], pf[ks], vf[2], vf[3]);
+        }
       }
     }
   }
+  if (!active) return;
 
   // normalise and write: row g -> regs 0,1 ; row g+8 -> regs 2,3
   const int g = lane >> 2, t2 = (lane & 3) * 2;
@@ -245,9 +268,18 @@ __global__ void __launch_bounds__(128) bert_attention_fp32_kernel(const float* _
 }  // namespace
 
 void launch_bert_attention(const void* qkv, const int64_t* mask, const int32_t* cu, const uint8_t* key_ok, void* ctx, int B,
-                           int L, bool fp32, cudaStream_t s) {
+                           int L, bool fp32, cudaStream_t s, long qkv_rows) {
   if (B == 0) return;
   VCG_REQUIRE(L >= 1 && L <= 512, "BERT sequence length must be in [1, 512]");
+  static int tc_policy = -1;   // VCG_ATTN_TC=0 keeps the mma.sync kernel everywhere
+  if (tc_policy < 0) {
+    const char* v = getenv("VCG_ATTN_TC");
+    tc_policy = (v && atoi(v) == 0) ? 0 : 1;
+  }
+  if (!fp32 && cu && key_ok && L <= 128 && qkv_rows > 0 && tc_policy) {   // packed bf16, one score tile per (clip, head)
+    launch_bert_attention_tc(qkv, cu, key_ok, ctx, B, qkv_rows, s);
+    return;
+  }
   if (!fp32) {
     const int Lp = (L + 63) / 64 * 64;
     const size_t smem = static_cast<size_t>(2 * Lp + kQBlock) * kRowPad * sizeof(__nv_bfloat16) + Lp * sizeof(float);
@@ -258,7 +290,7 @@ void launch_bert_attention(const void* qkv, const int64_t* mask, const int32_t* 
       configured = smem;
     }
     dim3 grid(kBertHeads, B, (L + kQBlock - 1) / kQBlock);
-    launch_pdl(bert_attention_bf16_kernel, grid, 128, smem, s, static_cast<const __nv_bfloat16*>(qkv), mask, cu, key_ok,
+    launch_pdl(bert_attention_bf16_kernel, grid, 256, smem, s, static_cast<const __nv_bfloat16*>(qkv), mask, cu, key_ok,
                static_cast<__nv_bfloat16*>(ctx), L, Lp);
   } else {
     const size_t smem = static_cast<size_t>(4) * (kHeadDim + L) * sizeof(float);

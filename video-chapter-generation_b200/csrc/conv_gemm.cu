@@ -23,33 +23,40 @@ int cg2_policy() {
   return pol;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool LNF = false>
 static void launch_pair_t(const ConvGemmLaunch& L, cudaStream_t stream) {
   using Cfg = ConvGemmCfg<BLOCK_N, false>;
   static bool configured = false;
   if (!configured) {
-    VCG_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VCG_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BLOCK_N, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     configured = true;
   }
-  launch_pdl(conv_gemm_pair_kernel<BLOCK_N>, L.grid, Cfg::kThreads, Cfg::kSmemBytes, stream, L.p);   // __cluster_dims__(2,1,1)
+  launch_pdl(conv_gemm_pair_kernel<BLOCK_N, LNF>, L.grid, Cfg::kThreads, Cfg::kSmemBytes, stream, L.p);   // __cluster_dims__(2,1,1)
 }
 
-template <int BLOCK_N, bool TF32X3>
+template <int BLOCK_N, bool TF32X3, bool LNF = false>
 static void launch_t(const ConvGemmLaunch& L, cudaStream_t stream) {
   using Cfg = ConvGemmCfg<BLOCK_N, TF32X3>;
   static bool configured = false;
   if (!configured) {
-    VCG_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VCG_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, TF32X3, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     configured = true;
   }
-  launch_pdl(conv_gemm_kernel<BLOCK_N, TF32X3>, L.grid, Cfg::kThreads, Cfg::kSmemBytes, stream, L.p);
+  launch_pdl(conv_gemm_kernel<BLOCK_N, TF32X3, LNF>, L.grid, Cfg::kThreads, Cfg::kSmemBytes, stream, L.p);
 }
 
 void launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
   if (L.grid <= 0) return;
-  if (L.cg2) {
+  if (L.lnf) {   // BERT GEMMs with the LayerNorm terms: N = 768 (192-wide tiles), 2304 / 3072 (256-wide)
+    VCG_REQUIRE(!L.fp32 && (L.block_n == 192 || L.block_n == 256), "LayerNorm-fused epilogue: unsupported tile");
+    if (L.cg2) {
+      if (L.block_n == 192) launch_pair_t<192, true>(L, stream); else launch_pair_t<256, true>(L, stream);
+    } else {
+      if (L.block_n == 192) launch_t<192, false, true>(L, stream); else launch_t<256, false, true>(L, stream);
+    }
+  } else if (L.cg2) {
     VCG_REQUIRE(!L.fp32 && L.grid % 2 == 0, "CTA-pair launch needs bf16 and an even grid");
     switch (L.block_n) {
       case 64: launch_pair_t<64>(L, stream); break;

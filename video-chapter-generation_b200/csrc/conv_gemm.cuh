@@ -63,6 +63,15 @@ struct ConvGemmParams {
   int act;
   void* tsm_out;               // [Nimg*Ho*Wo, tsm_ld] shifted copy of channels [0, 2*tsm_fold), or nullptr
   int tsm_ld, tsm_fold, T;
+  // ---- LayerNorm folded into the GEMMs around it (bf16 plain GEMMs, LNF instantiations; see "LayerNorm" in DESIGN.md)
+  // row statistics are (sum, sum of squares) over the ln_dim columns of a pre-LayerNorm matrix
+  const float2* a_stats;       // A is a raw pre-LN matrix, W was packed as W*gamma: D = rstd*(acc - mean*ln_c1) + bias'
+  const float* ln_c1;          // [N] sum_k W'[n,k]  (bias' = bias + sum_k beta_k W[n,k] arrives through `bias`)
+  const float2* res_stats;     // the residual is a raw pre-LN matrix: residual = (t - mean)*rstd*res_gamma + res_beta
+  const float* res_gamma;      // [N]
+  const float* res_beta;       // [N]
+  float2* out_stats;           // accumulate (sum, sum of squares) of the bf16-rounded outputs per row (atomics)
+  float ln_inv_dim, ln_eps;
 };
 
 constexpr int kBlockM = 128;
@@ -172,7 +181,7 @@ __device__ __forceinline__ void apply_act8x2(float2 (&v)[8], int act) {
 //   empty_bar     one per CTA, signalled by the leader's multicast tcgen05.commit
 //   tmem_full     one per CTA, multicast commit
 //   tmem_empty    lives in the leader; the epilogue warps of both CTAs arrive on it (remote arrive from the peer)
-template <int BLOCK_N, bool TF32X3, bool CG2>
+template <int BLOCK_N, bool TF32X3, bool CG2, bool LNF = false>
 __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   using Cfg = ConvGemmCfg<BLOCK_N, TF32X3>;
   static_assert(!(CG2 && TF32X3), "CTA-pair mode is bf16 only");
@@ -475,6 +484,22 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
           }
         }
         const int n_sub = min(kSub, (p.N - n_blk * BLOCK_N + 63) / 64);
+        [[maybe_unused]] float mean_a = 0.f, rstd_a = 1.f, mean_r = 0.f, rstd_r = 1.f;
+        [[maybe_unused]] float2 st_sum = make_float2(0.f, 0.f), st_sq = make_float2(0.f, 0.f);
+        if constexpr (LNF) {
+          if (my_sub < n_sub && row_ok) {
+            if (p.a_stats) {
+              const float2 st = __ldg(p.a_stats + grow);
+              mean_a = st.x * p.ln_inv_dim;
+              rstd_a = rsqrtf(fmaxf(st.y * p.ln_inv_dim - mean_a * mean_a, 0.f) + p.ln_eps);
+            }
+            if (p.res_stats) {
+              const float2 st = __ldg(p.res_stats + grow);
+              mean_r = st.x * p.ln_inv_dim;
+              rstd_r = rsqrtf(fmaxf(st.y * p.ln_inv_dim - mean_r * mean_r, 0.f) + p.ln_eps);
+            }
+          }
+        }
         if (my_sub < n_sub) {
           const int my_it = c_it + my_sub;
           const int slot = my_it % kCSlots;
@@ -492,6 +517,17 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
             if (col0 < p.N) {
+              if constexpr (LNF) {
+                if (p.a_stats) {     // LayerNorm of the A rows, applied after the contraction
+                  const float2 nm = make_float2(-mean_a, -mean_a), rs = make_float2(rstd_a, rstd_a);
+#pragma unroll
+                  for (int e = 0; e < 8; e += 2) {
+                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + col0 + 2 * e));
+                    v[e] = __fmul2_rn(__ffma2_rn(nm, make_float2(c4.x, c4.y), v[e]), rs);
+                    v[e + 1] = __fmul2_rn(__ffma2_rn(nm, make_float2(c4.z, c4.w), v[e + 1]), rs);
+                  }
+                }
+              }
               if (p.bias) {
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
@@ -501,15 +537,49 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                 }
               }
               if (has_res) {
+                bool ln_res = false;
+                if constexpr (LNF) ln_res = p.res_stats != nullptr;
+                if (ln_res) {        // residual = LayerNorm(raw tile) recomputed from the row statistics
+                  const float2 nm = make_float2(-mean_r, -mean_r), rs = make_float2(rstd_r, rstd_r);
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {      // logical 16-byte chunk cs/8 + c, XOR-swizzled with row % 8
-                  const uint4 q = *reinterpret_cast<const uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4));
-                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+                  for (int c = 0; c < 2; ++c) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4));
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.res_gamma + col0 + c * 8));
+                    const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.res_gamma + col0 + c * 8 + 4));
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.res_beta + col0 + c * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.res_beta + col0 + c * 8 + 4));
+                    const float2 gg[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y),
+                                          make_float2(g1.z, g1.w)};
+                    const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                          make_float2(b1.z, b1.w)};
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) v[c * 4 + e] = __fadd2_rn(v[c * 4 + e], __bfloat1622float2(h2[e]));
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 xn = __fmul2_rn(__fadd2_rn(__bfloat1622float2(h2[e]), nm), rs);
+                      v[c * 4 + e] = __fadd2_rn(v[c * 4 + e], __ffma2_rn(xn, gg[e], bb[e]));
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int c = 0; c < 2; ++c) {      // logical 16-byte chunk cs/8 + c, XOR-swizzled with row % 8
+                    const uint4 q = *reinterpret_cast<const uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4));
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[c * 4 + e] = __fadd2_rn(v[c * 4 + e], __bfloat1622float2(h2[e]));
+                  }
                 }
               }
               apply_act8x2(v, p.act);
+              if constexpr (LNF) {
+                if (p.out_stats) {   // statistics of what the consumers will read: the bf16-rounded values
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float2 r2 = __bfloat1622float2(__float22bfloat162_rn(v[e]));
+                    st_sum = __fadd2_rn(st_sum, r2);
+                    st_sq = __ffma2_rn(r2, r2, st_sq);
+                  }
+                }
+              }
             }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -548,6 +618,12 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                   }
                 }
               }
+            }
+          }
+          if constexpr (LNF) {
+            if (p.out_stats && row_ok) {
+              atomicAdd(&p.out_stats[grow].x, st_sum.x + st_sum.y);
+              atomicAdd(&p.out_stats[grow].y, st_sq.x + st_sq.y);
             }
           }
           // release the slot; the storing warp first waits until its bulk store has finished READING the tile (the
@@ -611,17 +687,18 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   }
 }
 
-template <int BLOCK_N, bool TF32X3>
+// LNF: epilogue with the LayerNorm terms (BERT GEMMs of the bf16 path)
+template <int BLOCK_N, bool TF32X3, bool LNF = false>
 __global__ void __launch_bounds__(ConvGemmCfg<BLOCK_N, TF32X3>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, TF32X3, false>(p);
+  conv_gemm_body<BLOCK_N, TF32X3, false, LNF>(p);
 }
 
 // CTA-pair variant: launch with an even grid; consecutive CTAs (2i, 2i+1) form the cluster.
-template <int BLOCK_N>
+template <int BLOCK_N, bool LNF = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ConvGemmCfg<BLOCK_N, false>::kThreads, 1)
 conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, false, true>(p);
+  conv_gemm_body<BLOCK_N, false, true, LNF>(p);
 }
 
 }  // namespace vcg

@@ -12,6 +12,7 @@ struct ConvGemmLaunch {
   int block_n = 0;
   bool fp32 = false;
   bool cg2 = false;   // CTA-pair kernel (cta_group::2): 256-row tiles, each CTA stages half of the B tile
+  bool lnf = false;   // epilogue with the LayerNorm terms
   int grid = 0;
   double flops = 0;   // 2*M*N*K of useful work (for reporting)
   const char* name = "";
@@ -99,6 +100,16 @@ struct Epilogue {
   int tsm_ld = 0, tsm_fold = 0, T = 1;
   // residual given per UNIQUE frame and shared by overlapping clips: image (clip b, frame t) reads frame b*stride + t
   int res_clip_T = 0, res_clip_stride = 0;
+  // LayerNorm folded into the GEMM (bf16 plain GEMMs; ConvGemmParams)
+  const float2* a_stats = nullptr;
+  const float* ln_c1 = nullptr;
+  const float2* res_stats = nullptr;
+  const float* res_gamma = nullptr;
+  const float* res_beta = nullptr;
+  float2* out_stats = nullptr;
+  int ln_dim = 768;
+  float ln_eps = 1e-12f;
+  bool ln_fused() const { return a_stats || res_stats || out_stats; }
 };
 
 // (C, W, H, T, clip) view of a per-unique-frame NHWC tensor: clip b, frame t -> unique frame b*clip_stride + t
@@ -131,6 +142,14 @@ inline void set_epilogue(ConvGemmLaunch& L, void* out, int ld_out, const Epilogu
   p.bias = e.bias; p.residual = e.residual; p.ld_res = e.ld_res; p.act = e.act;
   p.tsm_out = e.tsm_out; p.tsm_ld = e.tsm_ld; p.tsm_fold = e.tsm_fold; p.T = e.T > 0 ? e.T : 1;
   if (e.tsm_out) VCG_REQUIRE(e.tsm_fold % 32 == 0, "TSM fold must be a multiple of 32 channels");
+  L.lnf = e.ln_fused();
+  if (L.lnf) {
+    VCG_REQUIRE(!L.fp32 && p.Ho == 1 && p.Nimg == 1, "LayerNorm-fused epilogue: bf16 plain GEMMs only");
+    VCG_REQUIRE((e.a_stats == nullptr) == (e.ln_c1 == nullptr), "a_stats and ln_c1 go together");
+    VCG_REQUIRE(e.res_stats == nullptr || (e.residual && e.res_gamma && e.res_beta), "res_stats needs residual, gamma, beta");
+    p.a_stats = e.a_stats; p.ln_c1 = e.ln_c1; p.res_stats = e.res_stats; p.res_gamma = e.res_gamma; p.res_beta = e.res_beta;
+    p.out_stats = e.out_stats; p.ln_inv_dim = 1.0f / static_cast<float>(e.ln_dim); p.ln_eps = e.ln_eps;
+  }
   if (!L.fp32) {
     // smem split: residual layers are HBM-bound -> short K loops get few A/B stages and a deep residual-prefetch ring
     const int stage_bytes = kBlockM * 128 + static_cast<int>(p.b_bytes);

@@ -8,6 +8,7 @@
 #include "kernels.cuh"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -79,11 +80,15 @@ struct LinearW {
 struct BertLayerW {
   LinearW qkv, out, ffn1, ffn2;
   DevBuf ln1_g, ln1_b, ln2_g, ln2_b;
+  // bf16 path, LayerNorm folded into the consuming GEMMs (kernels.cu fold_ln_linear_kernel): the bias slot of the
+  // LinearW holds c2b, `c1` the column sums.  qkv_f folds the PREVIOUS layer's output LayerNorm (absent in layer 0).
+  LinearW qkv_f, ffn1_f;
+  DevBuf qkv_c1, ffn1_c1;
 };
 
 // One step of a plan.
 struct Step {
-  enum Kind { CONV_GEMM, MAXPOOL, AVGPOOL, EMBED, LAYERNORM, ATTENTION } kind;
+  enum Kind { CONV_GEMM, MAXPOOL, AVGPOOL, EMBED, LAYERNORM, ATTENTION, ZERO_STATS } kind;
   ConvGemmLaunch gemm;
   // generic arguments for the small kernels
   const void* in = nullptr;
@@ -110,6 +115,8 @@ struct VisionPlan {
 struct BertPlan {
   int B = 0, L = 0;
   std::vector<Step> steps;   // everything after the embedding (whose ids pointer varies)
+  const void* final_hidden = nullptr;   // last layer's output
+  bool final_is_raw = false;            // ... is a raw pre-LayerNorm matrix (LayerNorm folded into the GEMMs)
 };
 
 }  // namespace
@@ -141,6 +148,10 @@ struct vcg_engine {
   DevBuf hid, hid2, qkv, ctx, tmp, ffn, cls;
   // token packing (variable-length BERT): cu [Bt+1], tok_src / key_ok [Bt*Lmax], m_total [1]
   DevBuf pk_cu, pk_src, pk_ok, pk_total;
+  // LayerNorm folded into the GEMMs (bf16): per layer two (sum, sum of squares) row-statistics arrays
+  bool ln_fused = false;
+  DevBuf ln_stats;
+  size_t ln_stats_rows = 0;
   int last_bert_rows = 0;   // bt*L of the most recent BERT pass (profile scaling)
   // host-call staging
   DevBuf st_frames, st_ids, st_mask, st_start, st_logits, st_probs;
@@ -358,12 +369,46 @@ void finalize_text(vcg_engine* e, cudaStream_t s) {
     copy_f32(lw.ln2_g, need(e, pre + "output.LayerNorm.weight", {kBertHidden}), s);
     copy_f32(lw.ln2_b, need(e, pre + "output.LayerNorm.bias", {kBertHidden}), s);
   }
+  {
+    // opt-in (VCG_LN_FUSED=1): measured on B200 the LayerNorm terms lengthen the latency-bound GEMM epilogues by more
+    // (0.48 ms per 256-clip pass) than the 24 stand-alone LayerNorm launches cost (0.34 ms); see DESIGN.md
+    const char* v = getenv("VCG_LN_FUSED");
+    e->ln_fused = !e->fp32 && v && atoi(v) == 1;
+  }
+  if (e->ln_fused) {
+    for (int i = 0; i < n_layers; ++i) {
+      BertLayerW& lw = e->layers[i];
+      const std::string pre = lm + "encoder.layer." + std::to_string(i) + ".";
+      // FFN-in consumes LayerNorm1 of this layer
+      lw.ffn1_f.N = kBertFfn; lw.ffn1_f.K = kBertHidden;
+      lw.ffn1_f.w.alloc(static_cast<size_t>(kBertFfn) * kBertHidden * 2);
+      lw.ffn1_f.bias.alloc(kBertFfn * sizeof(float));
+      lw.ffn1_c1.alloc(kBertFfn * sizeof(float));
+      launch_fold_ln_linear(fptr(need(e, pre + "intermediate.dense.weight")), lw.ln1_g.as<float>(), lw.ln1_b.as<float>(),
+                            fptr(need(e, pre + "intermediate.dense.bias")), kBertFfn, kBertHidden, lw.ffn1_f.w.p,
+                            lw.ffn1_c1.as<float>(), lw.ffn1_f.bias.as<float>(), s);
+      if (i == 0) continue;
+      // QKV consumes LayerNorm2 of the previous layer
+      const BertLayerW& prev = e->layers[i - 1];
+      lw.qkv_f.N = 3 * kBertHidden; lw.qkv_f.K = kBertHidden;
+      lw.qkv_f.w.alloc(static_cast<size_t>(3) * kBertHidden * kBertHidden * 2);
+      lw.qkv_f.bias.alloc(3 * kBertHidden * sizeof(float));
+      lw.qkv_c1.alloc(3 * kBertHidden * sizeof(float));
+      const char* names[3] = {"query", "key", "value"};
+      for (int j = 0; j < 3; ++j)
+        launch_fold_ln_linear(fptr(need(e, pre + "attention.self." + names[j] + ".weight")), prev.ln2_g.as<float>(),
+                              prev.ln2_b.as<float>(), fptr(need(e, pre + "attention.self." + names[j] + ".bias")),
+                              kBertHidden, kBertHidden,
+                              static_cast<uint8_t*>(lw.qkv_f.w.p) + static_cast<size_t>(j) * kBertHidden * kBertHidden * 2,
+                              lw.qkv_c1.as<float>() + j * kBertHidden, lw.qkv_f.bias.as<float>() + j * kBertHidden, s);
+    }
+  }
   pack_linear(e, e->pooler, lm + "pooler.dense", kBertHidden, kBertHidden, s);
   // workspace: +128 rows of slack so that a TMA box starting at the last valid row never leaves the allocation
   const size_t rows = static_cast<size_t>(e->Bt) * e->Lmax + 128, es = e->es();
   e->hid.alloc(rows * kBertHidden * es);
   e->hid2.alloc(rows * kBertHidden * es);
-  e->qkv.alloc(rows * 3 * kBertHidden * es);
+  e->qkv.alloc(rows * 3 * kBertHidden * es, /*zero=*/true);   // rows past the packed tokens are read (and multiplied by 0)
   e->ctx.alloc(rows * kBertHidden * es);
   e->tmp.alloc(rows * kBertHidden * es);
   e->ffn.alloc(rows * kBertFfn * es);
@@ -372,6 +417,10 @@ void finalize_text(vcg_engine* e, cudaStream_t s) {
   e->pk_src.alloc(rows * sizeof(int32_t));
   e->pk_ok.alloc(rows);
   e->pk_total.alloc(sizeof(int32_t), /*zero=*/true);
+  if (e->ln_fused) {
+    e->ln_stats_rows = rows;
+    e->ln_stats.alloc(static_cast<size_t>(2) * n_layers * rows * sizeof(float2), /*zero=*/true);
+  }
 }
 
 void finalize_head(vcg_engine* e, cudaStream_t s) {
@@ -510,27 +559,74 @@ BertPlan& bert_plan(vcg_engine* e, int B, int L) {
   plan.B = B; plan.L = L;
   const int M = B * L;
   const bool fp = e->fp32;
-  auto gemm_step = [&](const void* A, const LinearW& w, void* out, int act, const void* res, const char* name) {
+  auto gemm_step = [&](const void* A, const LinearW& w, void* out, int act, const Epilogue& ep0, const char* name) {
     Step st{}; st.kind = Step::CONV_GEMM;
-    Epilogue ep; ep.bias = w.bias.as<float>(); ep.act = act; ep.residual = res; ep.ld_res = w.N;
+    Epilogue ep = ep0; ep.bias = w.bias.as<float>(); ep.act = act; ep.ld_res = w.N;
     st.gemm = build_gemm(A, w.K, w.w.p, out, w.N, M, w.N, w.K, fp, ep, name);
     st.gemm.p.m_dev = e->pk_total.as<int32_t>();   // only the packed rows are computed
     plan.steps.push_back(st);
   };
-  auto ln_step = [&](const void* x, const DevBuf& g, const DevBuf& b, void* y) {
-    Step st{}; st.kind = Step::LAYERNORM;
-    st.in = x; st.out = y; st.g = g.as<float>(); st.b = b.as<float>(); st.n = M;
-    plan.steps.push_back(st);
-  };
-  for (size_t i = 0; i < e->layers.size(); ++i) {
-    const BertLayerW& lw = e->layers[i];
-    gemm_step(e->hid.p, lw.qkv, e->qkv.p, ACT_NONE, nullptr, "bert.qkv");
-    { Step st{}; st.kind = Step::ATTENTION; st.in = e->qkv.p; st.out = e->ctx.p; st.n = B; st.a = L; plan.steps.push_back(st); }
-    gemm_step(e->ctx.p, lw.out, e->tmp.p, ACT_NONE, e->hid.p, "bert.attn_out");
-    ln_step(e->tmp.p, lw.ln1_g, lw.ln1_b, e->hid2.p);
-    gemm_step(e->hid2.p, lw.ffn1, e->ffn.p, ACT_GELU, nullptr, "bert.ffn_in");
-    gemm_step(e->ffn.p, lw.ffn2, e->tmp.p, ACT_NONE, e->hid2.p, "bert.ffn_out");
-    ln_step(e->tmp.p, lw.ln2_g, lw.ln2_b, e->hid.p);
+  auto res_ep = [](const void* res) { Epilogue ep; ep.residual = res; return ep; };
+  if (!e->ln_fused) {
+    auto ln_step = [&](const void* x, const DevBuf& g, const DevBuf& b, void* y) {
+      Step st{}; st.kind = Step::LAYERNORM;
+      st.in = x; st.out = y; st.g = g.as<float>(); st.b = b.as<float>(); st.n = M;
+      plan.steps.push_back(st);
+    };
+    for (size_t i = 0; i < e->layers.size(); ++i) {
+      const BertLayerW& lw = e->layers[i];
+      gemm_step(e->hid.p, lw.qkv, e->qkv.p, ACT_NONE, Epilogue{}, "bert.qkv");
+      { Step st{}; st.kind = Step::ATTENTION; st.in = e->qkv.p; st.out = e->ctx.p; st.n = B; st.a = L; plan.steps.push_back(st); }
+      gemm_step(e->ctx.p, lw.out, e->tmp.p, ACT_NONE, res_ep(e->hid.p), "bert.attn_out");
+      ln_step(e->tmp.p, lw.ln1_g, lw.ln1_b, e->hid2.p);
+      gemm_step(e->hid2.p, lw.ffn1, e->ffn.p, ACT_GELU, Epilogue{}, "bert.ffn_in");
+      gemm_step(e->ffn.p, lw.ffn2, e->tmp.p, ACT_NONE, res_ep(e->hid2.p), "bert.ffn_out");
+      ln_step(e->tmp.p, lw.ln2_g, lw.ln2_b, e->hid.p);
+    }
+    plan.final_hidden = e->hid.p;
+  } else {
+    // LayerNorm folded into the GEMMs: t1 = attn_out + x (raw, in tmp) and t2 = ffn_out + LN1(t1) (raw, in hid2) are
+    // stored un-normalised together with their row statistics (accumulated by the producing epilogue); the consumers
+    // apply the LayerNorm algebraically (A side) or recompute it on the residual tile.  No LayerNorm kernel runs.
+    { Step st{}; st.kind = Step::ZERO_STATS; plan.steps.push_back(st); }
+    auto stats = [&](size_t layer, int which) {
+      return e->ln_stats.as<float2>() + (2 * layer + which) * e->ln_stats_rows;
+    };
+    for (size_t i = 0; i < e->layers.size(); ++i) {
+      const BertLayerW& lw = e->layers[i];
+      if (i == 0) {
+        gemm_step(e->hid.p, lw.qkv, e->qkv.p, ACT_NONE, Epilogue{}, "bert.qkv");
+      } else {
+        Epilogue ep; ep.a_stats = stats(i - 1, 1); ep.ln_c1 = lw.qkv_c1.as<float>();
+        gemm_step(e->hid2.p, lw.qkv_f, e->qkv.p, ACT_NONE, ep, "bert.qkv");
+      }
+      { Step st{}; st.kind = Step::ATTENTION; st.in = e->qkv.p; st.out = e->ctx.p; st.n = B; st.a = L; plan.steps.push_back(st); }
+      {
+        Epilogue ep;
+        if (i == 0) {
+          ep.residual = e->hid.p;
+        } else {
+          const BertLayerW& prev = e->layers[i - 1];
+          ep.residual = e->hid2.p; ep.res_stats = stats(i - 1, 1);
+          ep.res_gamma = prev.ln2_g.as<float>(); ep.res_beta = prev.ln2_b.as<float>();
+        }
+        ep.out_stats = stats(i, 0);
+        gemm_step(e->ctx.p, lw.out, e->tmp.p, ACT_NONE, ep, "bert.attn_out");
+      }
+      {
+        Epilogue ep; ep.a_stats = stats(i, 0); ep.ln_c1 = lw.ffn1_c1.as<float>();
+        gemm_step(e->tmp.p, lw.ffn1_f, e->ffn.p, ACT_GELU, ep, "bert.ffn_in");
+      }
+      {
+        Epilogue ep;
+        ep.residual = e->tmp.p; ep.res_stats = stats(i, 0);
+        ep.res_gamma = lw.ln1_g.as<float>(); ep.res_beta = lw.ln1_b.as<float>();
+        ep.out_stats = stats(i, 1);
+        gemm_step(e->ffn.p, lw.ffn2, e->hid2.p, ACT_NONE, ep, "bert.ffn_out");
+      }
+    }
+    plan.final_hidden = e->hid2.p;
+    plan.final_is_raw = true;
   }
   return e->bplans.emplace(key, std::move(plan)).first->second;
 }
@@ -581,7 +677,13 @@ void run_steps(vcg_engine* e, const std::vector<Step>& steps, const int64_t* mas
       }
       case Step::ATTENTION: {
         ProfScope ps(e, s, "bert_attention|bert.attn", 4.0 * st.n * kBertHeads * static_cast<double>(st.a) * st.a * 64, 0, true);
-        launch_bert_attention(st.in, mask, e->pk_cu.as<int32_t>(), e->pk_ok.as<uint8_t>(), st.out, st.n, st.a, e->fp32, s);
+        launch_bert_attention(st.in, mask, e->pk_cu.as<int32_t>(), e->pk_ok.as<uint8_t>(), st.out, st.n, st.a, e->fp32, s,
+                              static_cast<long>(e->Bt) * e->Lmax + 128);
+        break;
+      }
+      case Step::ZERO_STATS: {
+        ProfScope ps(e, s, "memset|bert.ln_stats", 0, static_cast<double>(e->ln_stats.bytes));
+        VCG_CUDA(cudaMemsetAsync(e->ln_stats.p, 0, e->ln_stats.bytes, s));
         break;
       }
       default: throw Error("vcg: unknown plan step");
@@ -642,7 +744,8 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
       launch_bert_embed_ln(ids + static_cast<long>(b0) * L, bt * L, L, e->pk_src.as<int32_t>(), e->pk_total.as<int32_t>(),
                            e->word.p, e->pos.p, e->type.p, e->emb_g.as<float>(), e->emb_b.as<float>(), e->hid.p, e->fp32, s);
     }
-    run_steps(e, bert_plan(e, bt, L).steps, mask + static_cast<long>(b0) * L, s);
+    BertPlan& bp = bert_plan(e, bt, L);
+    run_steps(e, bp.steps, mask + static_cast<long>(b0) * L, s);
     // ---- BertPooler (tanh) + lang projection (ReLU) for the bt clips: two small tcgen05 GEMMs over the [CLS] rows
     {
       auto key = std::make_pair(bt, L);
@@ -659,7 +762,13 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
       }
       {
         ProfScope ps(e, s, "gather_rows768|head.cls", 0, static_cast<double>(bt) * kBertHidden * 2 * e->es());
-        launch_gather_rows768(e->hid.p, e->pk_cu.as<int32_t>(), L, bt, e->cls.p, e->fp32, s);
+        if (bp.final_is_raw) {   // the last LayerNorm, for the pooled rows only
+          const BertLayerW& last = e->layers.back();
+          launch_gather_ln_rows768(bp.final_hidden, e->pk_cu.as<int32_t>(), L, bt, last.ln2_g.as<float>(),
+                                   last.ln2_b.as<float>(), 1e-12f, e->cls.p, s);
+        } else {
+          launch_gather_rows768(bp.final_hidden, e->pk_cu.as<int32_t>(), L, bt, e->cls.p, e->fp32, s);
+        }
       }
       for (const ConvGemmLaunch& g : it->second) {
         ProfScope ps(e, s, gemm_kernel_name(g), g.flops, 0);
@@ -1086,6 +1195,13 @@ int vcg_op_maxpool_tsm(const void* in, int32_t n, void* out, void* out_shifted, 
 int vcg_op_bert_attention(const void* qkv, const int64_t* attention_mask, void* ctx, int32_t B, int32_t L,
                           int32_t precision, void* stream) {
   return guarded([&] { launch_bert_attention(qkv, attention_mask, nullptr, nullptr, ctx, B, L, precision == VCG_PREC_FP32, static_cast<cudaStream_t>(stream)); });
+}
+int vcg_op_bert_attention_packed(const void* qkv, const int32_t* cu, const uint8_t* key_ok, void* ctx, int32_t B,
+                                 int32_t max_len, int64_t rows, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(qkv && cu && key_ok && ctx, "null argument");
+    launch_bert_attention(qkv, nullptr, cu, key_ok, ctx, B, max_len, false, static_cast<cudaStream_t>(stream), rows);
+  });
 }
 int vcg_op_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t cols,
                      float eps, int32_t precision, void* stream) {

@@ -327,6 +327,48 @@ __global__ void __launch_bounds__(1024) bert_pack_kernel(const int64_t* __restri
 }
 
 // [CLS] rows of the packed hidden states -> dense [B, 768] (the pooler GEMM's A operand)
+// CLS rows of a RAW pre-LayerNorm matrix -> LayerNorm -> out (bf16 path with LayerNorm folded into the GEMMs: the final
+// LayerNorm is only ever needed for the B pooled rows).  One warp per clip, exact two-pass statistics.
+__global__ void gather_ln_rows768_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ row_of, int stride,
+                                         int B, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                         __nv_bfloat16* __restrict__ out) {
+  pdl_enter();
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const long row = row_of ? row_of[b] : static_cast<long>(b) * stride;
+  float v[3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) load8<false>(x + row * 768L + c * 256 + lane * 8, v[c]);
+  ln_row_768<false>(v, gamma, beta, eps, out + b * 768L, lane);
+}
+
+// Linear layer that consumes LayerNorm(x) re-expressed on the raw x (conv_gemm.cuh, LNF epilogue):
+//   LN(x) W^T + b = rstd * (x (W*gamma)^T - mean * c1) + c2b,   c1[n] = sum_k W'[n,k],  c2b[n] = b[n] + sum_k beta[k] W[n,k]
+// W' = bf16(W * gamma) is what the tensor core multiplies, so c1 is summed over the ROUNDED values (the mean term then
+// cancels exactly).  One warp per output row n.
+__global__ void fold_ln_linear_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ bias, int N, int K,
+                                      __nv_bfloat16* __restrict__ w_out, float* __restrict__ c1, float* __restrict__ c2b) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = w[static_cast<long>(n) * K + k];
+    const __nv_bfloat16 wb = __float2bfloat16_rn(wv * gamma[k]);
+    w_out[static_cast<long>(n) * K + k] = wb;
+    s1 += __bfloat162float(wb);
+    s2 = fmaf(beta[k], wv, s2);
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    c1[n] = s1;
+    c2b[n] = s2 + bias[n];
+  }
+}
+
 template <bool FP32>
 __global__ void gather_rows768_kernel(const elem_t<FP32>* __restrict__ x, const int32_t* __restrict__ row_of, int stride,
                                       int B, elem_t<FP32>* __restrict__ out) {
@@ -498,6 +540,17 @@ void launch_layernorm(const void* x, const float* gamma, const float* beta, void
   VCG_REQUIRE(cols == 768, "LayerNorm kernel is specialised for 768 columns");
   if (rows == 0) return;
   VCG_DISPATCH(fp32, (launch_pdl(layernorm768_kernel<FP>, blocks_for(rows, 8), 256, 0, s, static_cast<const elem_t<FP>*>(x), gamma, beta, static_cast<elem_t<FP>*>(y), rows, rows_dev, eps)));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_gather_ln_rows768(const void* x, const int32_t* row_of, int stride, int B, const float* gamma, const float* beta,
+                              float eps, void* out, cudaStream_t s) {
+  if (B == 0) return;
+  launch_pdl(gather_ln_rows768_kernel, blocks_for(B, 8), 256, 0, s, static_cast<const __nv_bfloat16*>(x), row_of, stride, B,
+             gamma, beta, eps, static_cast<__nv_bfloat16*>(out));
+}
+void launch_fold_ln_linear(const float* w, const float* gamma, const float* beta, const float* bias, int N, int K, void* w_out,
+                           float* c1, float* c2b, cudaStream_t s) {
+  fold_ln_linear_kernel<<<blocks_for(N, 8), 256, 0, s>>>(w, gamma, beta, bias, N, K, static_cast<__nv_bfloat16*>(w_out), c1, c2b);
   VCG_CUDA(cudaGetLastError());
 }
 void launch_pack_conv(const float* w, const float* bn_w, const float* bn_b, const float* bn_mean, const float* bn_var,

@@ -36,11 +36,20 @@ void launch_gather_rows768(const void* x, const int32_t* row_of, int stride, int
 void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const int32_t* tok_src, const int32_t* rows_dev,
                           const void* word, const void* pos, const void* type, const float* gamma, const float* beta,
                           void* out, bool fp32, cudaStream_t s);
+// bf16 path, LayerNorm folded into the GEMMs: out[b] = LayerNorm(x[row_of[b]]) for the B pooled rows
+void launch_gather_ln_rows768(const void* x, const int32_t* row_of, int stride, int B, const float* gamma, const float* beta,
+                              float eps, void* out, cudaStream_t s);
+// W' = bf16(W * gamma) [N][K], c1[n] = sum_k W'[n,k], c2b[n] = bias[n] + sum_k beta[k] W[n,k]
+void launch_fold_ln_linear(const float* w, const float* gamma, const float* beta, const float* bias, int N, int K, void* w_out,
+                           float* c1, float* c2b, cudaStream_t s);
 void launch_layernorm(const void* x, const float* gamma, const float* beta, void* y, int rows, int cols, float eps,
                       bool fp32, cudaStream_t s, const int32_t* rows_dev = nullptr);
 // cu / key_ok: packed layout (nullptr: rows b*L.., int64 mask)
+// qkv_rows: rows of the qkv allocation that may be read (> 0 enables the tcgen05 kernel for packed bf16, L <= 128)
 void launch_bert_attention(const void* qkv, const int64_t* mask, const int32_t* cu, const uint8_t* key_ok, void* ctx, int B,
-                           int L, bool fp32, cudaStream_t s);
+                           int L, bool fp32, cudaStream_t s, long qkv_rows = 0);
+void launch_bert_attention_tc(const void* qkv, const int32_t* cu, const uint8_t* key_ok, void* ctx, int B, long rows,
+                              cudaStream_t s);   // attention_tc.cu
 
 struct TailParams {
   // inputs

@@ -117,6 +117,18 @@ def bert_attention(qkv, attention_mask, B, L):
     return ctx
 
 
+def bert_attention_packed(qkv, cu, key_ok, max_len):
+    """Token-packed layout: qkv [rows, 2304] bf16, cu int32 [B+1], key_ok uint8 [rows] -> ctx [rows, 768] (rows past
+    cu[B] are left untouched)."""
+    _need_cuda(qkv, cu, key_ok)
+    assert qkv.dtype == torch.bfloat16 and cu.dtype == torch.int32 and key_ok.dtype == torch.uint8
+    ctx = torch.zeros(qkv.shape[0], 768, dtype=qkv.dtype, device=qkv.device)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_bert_attention_packed(qkv.data_ptr(), cu.data_ptr(), key_ok.data_ptr(), ctx.data_ptr(),
+                                              cu.shape[0] - 1, max_len, qkv.shape[0], _stream()))
+    return ctx
+
+
 def layernorm(x, gamma, beta, eps=1e-12):
     _need_cuda(x, gamma, beta)
     y = torch.empty_like(x)
