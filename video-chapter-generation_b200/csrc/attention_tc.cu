@@ -3,17 +3,17 @@
 //   ctx = softmax(Q K^T / 8 + key_mask) V        per (clip, head); modeling_bert.py:115-140 (12 heads x 64)
 //
 // A work item is one (clip, head): at L <= 128 all its queries and keys fit one 128 x 128 score tile, so there is no
-// online-softmax loop.  The kernel is persistent (one CTA per SM walks items blockIdx.x, +gridDim.x, ...) and
-// warp-specialised, so the latencies that bound the mma.sync kernel (global -> shared staging, ldmatrix chains,
-// 3 CTAs per SM) are hidden by a pipeline instead of by occupancy:
+// online-softmax loop.  An item is tiny (~2 MFLOP); what bounds the kernel is the chain of hand-offs
+//   TMA -> S = Q K^T -> softmax -> O = P V -> output        (about 3 k cycles of barrier / MMA-completion latency)
+// so the kernel is persistent (one CTA per SM walks items blockIdx.x, +gridDim.x, ...), warp-specialised and keeps
+// THREE items in compute plus one in flight from memory:
 //   warp 0      TMA producer: Q, K, V rows of the item (32-row boxes of the packed [rows, 2304] QKV matrix, only
-//               ceil(L/32) of them) into a 3-stage ring; publishes (first row, L) next to the stage
-//   warp 1      MMA issuer: S = Q K^T (tcgen05.mma 128 x Nk x 64, Nk = L rounded up to 16) into one of two TMEM score
-//               buffers, and, once the softmax warps have written P, O = P V (128 x 64 x Nk) with V consumed in place
-//               as an MN-major operand (rows of 128 B, exactly what TMA delivered); S of item i+1 is issued before
-//               P V of item i
-//   warp 2      TMEM allocator
-//   warps 4-7 / 8-11   two softmax groups (even / odd items), one thread per query row: tcgen05.ld the score row twice
+//               ceil(L/32) of them) into one of four 48 KB slots; its lanes also gather the item's key-mask bits
+//   warp 1      S issuer: tcgen05.mma 128 x Nk x 64 (Nk = L rounded up to 16) into the slot's 128 TMEM columns
+//   warp 2      TMEM allocator, then O issuer: once the softmax warps have written P, O = P V (128 x 64 x Nk) with V
+//               consumed in place as an MN-major operand (rows of 128 B, exactly what TMA delivered).  O re-uses the
+//               first 64 TMEM columns of S, and P re-uses the shared memory of Q and K (both dead by then)
+//   warps 4-15  three softmax groups (items i = g, g+3, ...), one thread per query row: tcgen05.ld the score row twice
 //               (row max, then exp2 / row sum / bf16 P into the swizzled K-major A-operand layout), later tcgen05.ld the
 //               O row, scale by 1/sum and store 128 contiguous bytes of ctx.  A thread owns its row: no shuffles.
 // Keys beyond L and masked keys are excluded by SELECT (not by adding -inf), so stale shared-memory rows can never
@@ -30,17 +30,19 @@ namespace vcg {
 
 namespace {
 
-constexpr int kStages = 3;
+constexpr int kSlots = 4;                         // items resident in shared / tensor memory
+constexpr int kGroups = 3;                        // softmax groups = items in compute
 constexpr int kTileBytes = 128 * 128;             // 128 rows x 64 bf16
-constexpr int kStageBytes = 3 * kTileBytes;       // Q, K, V
-constexpr int kPBytes = 2 * kTileBytes;           // P: 128 rows x 128 keys bf16 = two 64-key K blocks
-constexpr int kSmemTiles = kStages * kStageBytes + 2 * kPBytes;
-constexpr int kSmemBytes = kSmemTiles + 1024 /*align*/ + 2 * 128 * 4 /*masks*/ + 256 /*barriers, info*/;
-constexpr int kThreads = 12 * 32;
-constexpr uint32_t kTmemCols = 512;               // S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
+constexpr int kSlotBytes = 3 * kTileBytes;        // Q | K | V; P (128 rows x 128 keys = two 64-key K blocks) overwrites Q | K
+constexpr int kSmemTiles = kSlots * kSlotBytes;
+constexpr int kSmemBytes = kSmemTiles + 1024 /*align*/ + 512 /*barriers, item info*/;
+constexpr int kThreads = (4 + 4 * kGroups) * 32;
+constexpr uint32_t kTmemCols = 512;               // slot s: S in columns [128 s, +Nk), later O in [128 s, +64)
 
 struct ItemInfo {
   int row_base, L;
+  uint32_t key_bits[4];   // bit j: key j of the clip may be attended (j < L and key_ok)
+  int pad[2];
 };
 
 struct AttnParams {
@@ -54,26 +56,24 @@ struct AttnParams {
 __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sStage = smem;                                   // [stage][Q | K | V][128 rows][128 B]
-  uint8_t* sP = smem + kStages * kStageBytes;               // [buf][2 K blocks][128 rows][128 B]
-  float* sMask = reinterpret_cast<float*>(smem + kSmemTiles);   // per softmax group: 128 key bits (1 = may be attended)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 2 * 128);
-  uint64_t* full = bars;                 // [kStages] TMA -> MMA / softmax
-  uint64_t* empty = full + kStages;      // [kStages] MMA -> TMA
-  uint64_t* s_full = empty + kStages;    // [2] MMA -> softmax
-  uint64_t* p_full = s_full + 2;         // [2] softmax -> MMA
-  uint64_t* o_full = p_full + 2;         // [2] MMA -> softmax
-  uint64_t* t_empty = o_full + 2;        // [2] softmax -> MMA (S and O buffers drained)
-  ItemInfo* info = reinterpret_cast<ItemInfo*>(t_empty + 2);   // [kStages]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(info + kStages);
+  uint8_t* sSlot = smem;                                    // [slot][Q | K | V][128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemTiles);
+  uint64_t* full = bars;                 // [kSlots] TMA -> S issuer / softmax
+  uint64_t* empty = full + kSlots;       // [kSlots] O MMAs retired -> TMA (the slot's shared memory is free)
+  uint64_t* s_full = empty + kSlots;     // [kSlots] S MMAs retired -> softmax
+  uint64_t* p_full = s_full + kSlots;    // [kSlots] softmax -> O issuer (P written, S consumed)
+  uint64_t* o_full = p_full + kSlots;    // [kSlots] O MMAs retired -> softmax
+  uint64_t* t_empty = o_full + kSlots;   // [kSlots] softmax -> S issuer (O read: the slot's TMEM columns are free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + kSlots);
+  ItemInfo* info = reinterpret_cast<ItemInfo*>(bars + 32);     // [kSlots], 32 bytes each, 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) tma_prefetch_desc(&p.qkv_map);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&t_empty[i], 4);
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&t_empty[i], 4);
     }
     fence_mbar_init();
   }
@@ -90,91 +90,126 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
   const int n_my = (p.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (elect_one()) {
-      for (int i = 0; i < n_my; ++i) {
-        const int item = blockIdx.x + i * gridDim.x;
-        const int b = item / kBertHeads, h = item - b * kBertHeads;
-        const int stage = i % kStages;
-        const int row_base = __ldg(p.cu + b);
-        const int L = min(__ldg(p.cu + b + 1) - row_base, 128);
-        mbar_wait(&empty[stage], ((i / kStages) & 1) ^ 1);
-        info[stage] = ItemInfo{row_base, L};
-        const int nch = (L + 31) >> 5;
-        mbar_expect_tx(&full[stage], static_cast<uint32_t>(3 * nch) * 4096u);
-        uint8_t* dst = sStage + stage * kStageBytes;
-        for (int c = 0; c < nch; ++c) {
+    // ------------------------------------------------------------ TMA producer (whole warp: the lanes gather the key bits)
+    // Everything the producer reads from global memory is fetched ahead of use: a dependent cu -> key_ok chain per item
+    // (two L2 round trips, ~1.5 k cycles) would otherwise bound the whole kernel at ~20 items per CTA.
+    auto item_rows = [&](int i, int& row_base, int& L) {     // lane-parallel: lane j holds item (i0 + j)
+      const int b = (blockIdx.x + i * gridDim.x) / kBertHeads;
+      row_base = __ldg(p.cu + b);
+      L = min(__ldg(p.cu + b + 1) - row_base, 128);
+    };
+    int my_rb = 0, my_L = 0;                                  // lane j: rows of item (batch * 32 + j)
+    if (lane < n_my) item_rows(lane, my_rb, my_L);
+    auto load_keys = [&](int rb, int L, uint8_t (&k)[4]) {
 #pragma unroll
-          for (int op = 0; op < 3; ++op)
-            tma_load_2d(dst + op * kTileBytes + c * 4096, &p.qkv_map, &full[stage], op * kBertHidden + h * 64, row_base + c * 32);
+      for (int q = 0; q < 4; ++q) {
+        const int j = q * 32 + lane;
+        k[q] = j < L ? __ldg(p.key_ok + rb + j) : uint8_t(0);
+      }
+    };
+    uint8_t keys[4] = {0, 0, 0, 0};
+    int rb_cur = __shfl_sync(0xffffffffu, my_rb, 0), L_cur = __shfl_sync(0xffffffffu, my_L, 0);
+    if (n_my > 0) load_keys(rb_cur, L_cur, keys);
+    for (int i = 0; i < n_my; ++i) {
+      const int item = blockIdx.x + i * gridDim.x;
+      const int h = item % kBertHeads;
+      const int slot = i % kSlots;
+      const int row_base = rb_cur, L = L_cur;
+      uint32_t bits[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bits[q] = __ballot_sync(0xffffffffu, keys[q] != 0);
+      // prefetch the next item's rows (new batch of 32 items every 32 iterations) and key bytes
+      if (i + 1 < n_my) {
+        if (((i + 1) & 31) == 0 && i + 1 + lane < n_my) item_rows(i + 1 + lane, my_rb, my_L);
+        rb_cur = __shfl_sync(0xffffffffu, my_rb, (i + 1) & 31);
+        L_cur = __shfl_sync(0xffffffffu, my_L, (i + 1) & 31);
+        load_keys(rb_cur, L_cur, keys);
+      }
+      mbar_wait(&empty[slot], ((i / kSlots) & 1) ^ 1);
+      if (lane == 0) {
+        ItemInfo inf;
+        inf.row_base = row_base; inf.L = L;
+        inf.key_bits[0] = bits[0]; inf.key_bits[1] = bits[1]; inf.key_bits[2] = bits[2]; inf.key_bits[3] = bits[3];
+        inf.pad[0] = inf.pad[1] = 0;
+        info[slot] = inf;
+        const int nch = (L + 31) >> 5;
+        mbar_expect_tx(&full[slot], static_cast<uint32_t>(3 * nch) * 4096u);
+        uint8_t* dst = sSlot + slot * kSlotBytes;
+        // Q chunk c lands in 32-row block (c + i) % 4 of the tile: TMEM lanes [32 w, +32) can only be read by warps with
+        // warp % 4 == w, which all sit on scheduler w, and most clips are short -- without the rotation scheduler 0
+        // would run the softmax of (almost) every item while schedulers 2 and 3 idle
+        for (int c = 0; c < nch; ++c) {
+          tma_load_2d(dst + ((c + i) & 3) * 4096, &p.qkv_map, &full[slot], h * 64, row_base + c * 32);
+#pragma unroll
+          for (int op = 1; op < 3; ++op)
+            tma_load_2d(dst + op * kTileBytes + c * 4096, &p.qkv_map, &full[slot], op * kBertHidden + h * 64, row_base + c * 32);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------ S issuer
     if (elect_one()) {
       constexpr uint32_t idesc_base = umma_idesc(1u, 128, 0);
-      auto issue_s = [&](int i) {
-        const int stage = i % kStages, buf = i & 1;
-        mbar_wait(&full[stage], (i / kStages) & 1);
-        mbar_wait(&t_empty[buf], ((i >> 1) & 1) ^ 1);
+      for (int i = 0; i < n_my; ++i) {
+        const int slot = i % kSlots;
+        const uint32_t ph = (i / kSlots) & 1;
+        mbar_wait(&full[slot], ph);
+        mbar_wait(&t_empty[slot], ph ^ 1);      // the previous item of this slot has read its O
         tc_fence_after();
-        const int Nk = (info[stage].L + 15) & ~15;
+        const int Nk = (info[slot].L + 15) & ~15;
         const uint32_t idesc = idesc_base | (static_cast<uint32_t>(Nk >> 3) << 17);
-        const uint32_t q_addr = smem_u32(sStage + stage * kStageBytes);
+        const uint32_t q_addr = smem_u32(sSlot + slot * kSlotBytes);
         const uint32_t k_addr = q_addr + kTileBytes;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + buf * 128, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc, k != 0);
-        umma_commit(&s_full[buf]);
-      };
-      if (n_my > 0) issue_s(0);
+          umma_bf16(tmem_base + slot * 128, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc, k != 0);
+        umma_commit(&s_full[slot]);
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ O issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_pv = umma_idesc(1u, 128, 64) | (1u << 16);   // B (= V) is MN-major
       for (int i = 0; i < n_my; ++i) {
-        if (i + 1 < n_my) issue_s(i + 1);
-        const int stage = i % kStages, buf = i & 1;
-        const int Nk = (info[stage].L + 15) & ~15;
-        mbar_wait(&p_full[buf], (i >> 1) & 1);
+        const int slot = i % kSlots;
+        mbar_wait(&p_full[slot], (i / kSlots) & 1);
         tc_fence_after();
-        // O = P V: A = P (K-major, 64-key K blocks), B = V in place, MN-major (d contiguous), 8-key atoms 1024 B apart
-        constexpr uint32_t idesc_pv = umma_idesc(1u, 128, 64) | (1u << 16);
-        const uint32_t p_addr = smem_u32(sP + buf * kPBytes);
-        const uint32_t v_addr = smem_u32(sStage + stage * kStageBytes + 2 * kTileBytes);
+        const int Nk = (info[slot].L + 15) & ~15;
+        // O = P V: A = P (K-major, 64-key K blocks, where Q | K were), B = V in place (8-key atoms 1024 B apart)
+        const uint32_t p_addr = smem_u32(sSlot + slot * kSlotBytes);
+        const uint32_t v_addr = p_addr + 2 * kTileBytes;
         for (int j = 0; j < Nk / 16; ++j)
-          umma_bf16(tmem_base + 256 + buf * 64, umma_desc_sw128(p_addr + (j >> 2) * kTileBytes + (j & 3) * 32),
+          umma_bf16(tmem_base + slot * 128, umma_desc_sw128(p_addr + (j >> 2) * kTileBytes + (j & 3) * 32),
                     umma_desc_sw128(v_addr + j * 2048), idesc_pv, j != 0);
-        umma_commit(&empty[stage]);     // Q, K, V of this stage are free once these MMAs retire
-        umma_commit(&o_full[buf]);
+        umma_commit(&empty[slot]);     // the slot's shared memory is free once these MMAs retire
+        umma_commit(&o_full[slot]);
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax + output, one thread per query row
-    const int group = (warp - 4) >> 2;            // even / odd items
+    const int group = (warp - 4) >> 2;
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
     const int row = quarter * 32 + lane;
     const float sl2 = 0.125f * 1.4426950408889634f;        // 1/sqrt(64) * log2(e)
-    uint32_t* mbits = reinterpret_cast<uint32_t*>(sMask) + group * 4;   // 128 key bits of the group's current item
-    for (int i = group; i < n_my; i += 2) {
+    for (int i = group; i < n_my; i += kGroups) {
       const int item = blockIdx.x + i * gridDim.x;
       const int h = item % kBertHeads;
-      const int stage = i % kStages, buf = i & 1;           // buf == group
-      mbar_wait(&full[stage], (i / kStages) & 1);            // (row_base, L) published by the producer
-      const ItemInfo it = info[stage];
-      const int Nk = (it.L + 15) & ~15;
-      {   // key bits: warp `quarter` of the group covers keys [32*quarter, +32)
-        const int j = quarter * 32 + lane;
-        const uint32_t bits = __ballot_sync(0xffffffffu, j < it.L && p.key_ok[it.row_base + j] != 0);
-        if (lane == 0) mbits[quarter] = bits;
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
-      const uint4 kb4 = *reinterpret_cast<const uint4*>(mbits);
+      const int slot = i % kSlots;
+      const uint32_t ph = (i / kSlots) & 1;
+      mbar_wait(&full[slot], ph);                            // item info published by the producer
+      const int row_base = info[slot].row_base, L = info[slot].L;
+      const uint4 kb4 = *reinterpret_cast<const uint4*>(info[slot].key_bits);
       const uint32_t kbits[4] = {kb4.x, kb4.y, kb4.z, kb4.w};
-      mbar_wait(&s_full[buf], (i >> 1) & 1);
+      const int Nk = (L + 15) & ~15;
+      mbar_wait(&s_full[slot], ph);
       tc_fence_after();
-      const bool warp_active = quarter * 32 < it.L;          // (warp-uniform) at least one valid row
+      const int qrow = (((quarter - i) & 3) << 5) + lane;      // query handled by this thread (Q blocks are rotated by i)
+      const bool warp_active = (qrow - lane) < L;              // (warp-uniform) at least one valid row
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * 128;
       float l = 0.f;
       if (warp_active) {
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 128;
-        uint8_t* prow = sP + buf * kPBytes + row * 128;
+        uint8_t* prow = sSlot + slot * kSlotBytes + row * 128;      // P overwrites Q | K (S has retired)
         // 64 score columns per TMEM round trip (four tcgen05.ld, one wait); columns >= Nk are never touched
         auto load64 = [&](int c0, uint32_t (&r)[4][16]) {
 #pragma unroll
@@ -187,13 +222,15 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
           for (int q = 0; q < 4; ++q) {
             if (c0 + q * 16 < Nk) {
               const uint32_t w = kbits[(c0 + q * 16) >> 5] >> ((c0 + q * 16) & 31);   // 16 key bits of this chunk
+              float m4[4] = {m, -INFINITY, -INFINITY, -INFINITY};
               if ((w & 0xffffu) == 0xffffu) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) m = fmaxf(m, __uint_as_float(r[q][e]));
+                for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(r[q][e]));
               } else {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) m = fmaxf(m, (w >> e) & 1u ? __uint_as_float(r[q][e]) : -INFINITY);
+                for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], (w >> e) & 1u ? __uint_as_float(r[q][e]) : -INFINITY);
               }
+              m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             }
           }
           return m;
@@ -206,12 +243,14 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
               const uint32_t w = kbits[c >> 5] >> (c & 31);
               float pv[16];
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                float x;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(fmaf(__uint_as_float(r[q][e]), sl2, -msub)));
-                pv[e] = (w >> e) & 1u ? x : 0.f;      // select, not add: stale rows beyond L may hold anything
-                l += pv[e];
+              for (int e = 0; e < 16; ++e)
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv[e]) : "f"(fmaf(__uint_as_float(r[q][e]), sl2, -msub)));
+              if ((w & 0xffffu) != 0xffffu) {           // select, not add: stale rows beyond L may hold anything
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pv[e] = (w >> e) & 1u ? pv[e] : 0.f;
               }
+              l += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7])) +
+                   (((pv[8] + pv[9]) + (pv[10] + pv[11])) + ((pv[12] + pv[13]) + (pv[14] + pv[15])));
 #pragma unroll
               for (int t = 0; t < 2; ++t) {
                 uint4 o;
@@ -241,19 +280,18 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[buf]);
+      if (lane == 0) mbar_arrive(&p_full[slot]);
       // ---- output
-      mbar_wait(&o_full[buf], (i >> 1) & 1);
+      mbar_wait(&o_full[slot], ph);
       tc_fence_after();
       if (warp_active) {
-        const uint32_t oaddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256 + buf * 64;
         const float inv = 1.0f / l;
-        __nv_bfloat16* dst = p.ctx + static_cast<long>(it.row_base + row) * kBertHidden + h * 64;
+        __nv_bfloat16* dst = p.ctx + static_cast<long>(row_base + qrow) * kBertHidden + h * 64;
         uint32_t r[4][16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) tmem_ld_32x16(oaddr + q * 16, r[q]);
+        for (int q = 0; q < 4; ++q) tmem_ld_32x16(taddr + q * 16, r[q]);
         tmem_ld_wait();
-        if (row < it.L) {
+        if (qrow < L) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
 #pragma unroll
@@ -270,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[buf]);
+      if (lane == 0) mbar_arrive(&t_empty[slot]);
     }
   }
 
