@@ -32,6 +32,10 @@ enum { VCG_HEAD_MLP = 0, VCG_HEAD_ATTN = 1 };       /* two_stream.py:63-68 head_
 enum { VCG_PREC_BF16 = 0, VCG_PREC_FP32 = 1 };      /* bf16 tensor-core mode / 3xTF32 fp32-accurate mode       */
 enum { VCG_VISION_R50TSM = 0, VCG_VISION_NONE = 1 };/* resnet50_tsm.py:15-19 / precomputed vision embeddings   */
 enum { VCG_DTYPE_F32 = 0, VCG_DTYPE_I64 = 1 };
+/* which reference model the engine is: TwoStream (two_stream.py), or one of the single-modality scorers of
+ * --data_mode image / text: Resnet50TSM / Resnet50 (resnet50_tsm.py:68-77, resnet50.py:64-73), BertHugface
+ * (bert_hugface.py:98-132, pretrain_stage=False).  The single-modality state dicts use base_model.* / head.* keys. */
+enum { VCG_MODALITY_TWO_STREAM = 0, VCG_MODALITY_VISION = 1, VCG_MODALITY_TEXT = 2 };
 enum { VCG_ACT_NONE = 0, VCG_ACT_RELU = 1, VCG_ACT_GELU = 2, VCG_ACT_TANH = 3 };
 
 typedef struct vcg_config {
@@ -42,7 +46,8 @@ typedef struct vcg_config {
   int32_t precision;     /* VCG_PREC_*                                                                          */
   int32_t vision;        /* VCG_VISION_*                                                                        */
   int32_t max_batch;     /* clips scored per internal pass (workspace is sized for this)                        */
-  int32_t shift_div;     /* TSM fold divisor, 8 in the reference (resnet50_tsm.py:16)                           */
+  int32_t shift_div;     /* TSM fold divisor, 8 in the reference (resnet50_tsm.py:16); 0 = plain ResNet-50      */
+  int32_t modality;      /* VCG_MODALITY_*                                                                      */
 } vcg_config;
 
 /* Lifetime ------------------------------------------------------------------------------------------------- */
@@ -70,6 +75,17 @@ VCG_API int vcg_finalize(vcg_engine* e, void* stream);
 VCG_API int vcg_forward(vcg_engine* e, const float* img_clip, const float* vision_emb, const int64_t* text_ids,
                 const int64_t* attention_mask, int32_t B, int32_t L, float* logits, float* probs,
                 float* vision_emb_out, float* lang_emb_out, void* stream);
+
+/* Single-modality scorers (engine created with VCG_MODALITY_VISION / VCG_MODALITY_TEXT).
+ *   vcg_forward_vision = Resnet50TSM.forward / Resnet50.forward (resnet50_tsm.py:68-77, resnet50.py:64-73):
+ *       img_clip [B,T,3,224,224] fp32 -> backbone -> [B, T*2048] -> head Linear(T*2048, 2) -> softmax
+ *   vcg_forward_text   = BertHugface.forward with pretrain_stage=False (bert_hugface.py:98-132):
+ *       pooler_output [B,768] -> head Linear(768, 2) -> softmax
+ * logits, probs [B,2] fp32 out; vision_emb_out [B,T,2048] / lang_emb_out [B,768] fp32 out or NULL. */
+VCG_API int vcg_forward_vision(vcg_engine* e, const float* img_clip, int32_t B, float* logits, float* probs,
+                       float* vision_emb_out, void* stream);
+VCG_API int vcg_forward_text(vcg_engine* e, const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L,
+                     float* logits, float* probs, float* lang_emb_out, void* stream);
 
 /* Sliding-window scoring of one video straight from decoded frames (replaces ToTensor+Normalize at
  * test_video_segment_point.py:142-145, the clip gather of infer_youtube_video_dataset.py:117 and the forward).

@@ -159,6 +159,24 @@ def two_stream_forward(sd, img_clip, text_ids, attention_mask, segment_size, hid
     return logits, F.softmax(logits, dim=1), vision_emb, lang_emb
 
 
+# ----------------------------------------------------------------------------------------------- single modality
+def vision_only_forward(sd, img_clip, segment_size, shift_div=8):
+    """Resnet50TSM.forward / Resnet50.forward (model/vision/resnet50_tsm.py:68-77, resnet50.py:64-73):
+    backbone -> view [B, T*2048] -> head Linear -> softmax.  shift_div = 0 (or plain conv1 keys): no temporal shift."""
+    B = img_clip.shape[0]
+    x = img_clip.reshape(B * segment_size, *img_clip.shape[2:]).contiguous()
+    emb = resnet50_tsm_forward(sd, x, segment_size, shift_div, prefix="base_model.").view(B, -1)
+    logits = F.linear(emb, sd["head.weight"], sd["head.bias"])
+    return logits, F.softmax(logits, dim=1), emb.view(B, segment_size, -1)
+
+
+def text_only_forward(sd, text_ids, attention_mask):
+    """BertHugface.forward with pretrain_stage=False (model/lang/bert_hugface.py:98-132): pooler output -> head."""
+    pooled = bert_forward(sd, text_ids, attention_mask, prefix="base_model.")
+    logits = F.linear(pooled, sd["head.weight"], sd["head.bias"])
+    return logits, F.softmax(logits, dim=1), pooled
+
+
 # ----------------------------------------------------------------------------------------------- post-processing
 def predict_labels(logits):
     """pred_label = logits.topk(1) index (test_video_segment_point.py:201-203)."""

@@ -123,6 +123,33 @@ def make_state_dict(clip_frames=16, head_type="mlp", hidden_size=128, seed=123, 
     return sd
 
 
+def make_unimodal_state_dict(kind, clip_frames=16, seed=123):
+    """State dict of a single-modality reference model (--data_mode image / text), keyed like the reference modules:
+      kind "r50tsm": Resnet50TSM (base_model.* with '.conv1.net.' keys, head Linear(T*2048, 2))
+      kind "r50":    Resnet50    (base_model.*, plain conv1 keys, same head)
+      kind "bert":   BertHugface (base_model.* = BertModel keys, head Linear(768, 2))
+    The backbone values are those of make_state_dict (same seed), so the backbones agree with the two-stream cases."""
+    full = make_state_dict(clip_frames, "mlp", seed=seed, tsm=(kind != "r50"), include_vision=(kind != "bert"))
+    g = _gen(seed + 77)
+    sd = {}
+    if kind in ("r50tsm", "r50"):
+        for k, v in full.items():
+            if k.startswith("vision_model."):
+                sd["base_model." + k[len("vision_model."):]] = v
+        d = clip_frames * 2048
+    elif kind == "bert":
+        for k, v in full.items():
+            if k.startswith("lang_model."):
+                sd["base_model." + k[len("lang_model."):]] = v
+        d = 768
+    else:
+        raise ValueError(kind)
+    bound = 1.0 / d ** 0.5                       # nn.Linear default init range
+    sd["head.weight"] = (torch.rand(2, d, generator=g) * 2 - 1) * bound * 4   # x4: keeps the two logits well apart
+    sd["head.bias"] = (torch.rand(2, generator=g) * 2 - 1) * bound
+    return sd
+
+
 def make_text(batch, max_len, seed=123):
     """Synthetic token ids / attention mask: [CLS]=101 first, len ~ U{10..L}, pad id 0."""
     g = _gen(seed + 1)

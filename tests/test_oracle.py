@@ -71,3 +71,44 @@ def test_preprocess_matches_totensor_normalize():
     f = frames[1, 10, 20].float() / 255.0
     exp = (f - torch.tensor(orc.IMAGENET_MEAN)) / torch.tensor(orc.IMAGENET_STD)
     assert torch.allclose(x[1, :, 10, 20], exp, atol=1e-6)
+
+
+@pytest.mark.parametrize("case,kind", [("r50tsm_T8_B2", "r50tsm"), ("r50_T8_B2", "r50"), ("bert_L48_B3", "bert")])
+def test_unimodal_oracle_matches_reference_golden(golden_dir, case, kind):
+    """Single-modality scorers (--data_mode image / text): restatement vs the reference's own outputs."""
+    import numpy as np
+    import torch
+    from oracle import two_stream_oracle as orc
+    from oracle import weights as W
+    g = np.load(f"{golden_dir}/unimodal_{case}.npz")
+    T, L, B, seed = [int(x) for x in g["meta"]]
+    sd = W.make_unimodal_state_dict(kind, clip_frames=max(T, 1), seed=123)
+    with torch.no_grad():
+        if kind == "bert":
+            ids, mask = W.make_text(B, L, seed=seed)
+            assert np.array_equal(ids.numpy(), g["text_ids"])
+            logits, probs, _ = orc.text_only_forward(sd, ids, mask)
+        else:
+            frames = W.make_frames_u8(4 * (B - 1) + T, seed=seed)
+            img = orc.gather_clips(orc.preprocess_u8(frames), [int(s) for s in g["clip_starts"]], T)
+            logits, probs, _ = orc.vision_only_forward(sd, img, T, 8 if kind == "r50tsm" else 0)
+    assert np.abs(logits.numpy() - g["logits"]).max() <= 1e-5 * np.abs(g["logits"]).max()
+    assert np.abs(probs.numpy() - g["probs"]).max() <= 1e-5
+    assert orc.predict_labels(logits) == g["labels"].tolist()
+
+
+def test_vision_emb_io_roundtrip(tmp_path):
+    """convert2vision_emb.py's file layout: vision_emb_{start}_{end}.npy, fp32 [T,2048] per clip."""
+    import os
+    import sys
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "video-chapter-generation_b200"))
+    from vcg_b200 import vision_emb_io as vio
+    emb = torch.randn(3, 16, 2048)
+    infos = [{"vid": "abc", "clip_start_end": (4 * i, 4 * i + 16)} for i in range(3)]
+    paths = vio.save_vision_embs(str(tmp_path), infos, emb)
+    assert [os.path.basename(p) for p in paths] == ["vision_emb_0_16.npy", "vision_emb_4_20.npy", "vision_emb_8_24.npy"]
+    assert np.load(paths[1]).shape == (16, 2048) and np.load(paths[1]).dtype == np.float32
+    back = vio.load_vision_embs(str(tmp_path), "abc", [0, 4, 8], 16)
+    assert back.shape == (3, 16, 2048, 1, 1) and torch.equal(back.view(3, 16, 2048), emb)

@@ -142,7 +142,7 @@ struct vcg_engine {
   DevBuf head_w, head_b, q_w_t, q_b, k_w_t, k_b, v_w_t, v_b, proj_w, proj_b;   // head, fp32
 
   // vision workspace (sized for Bv clips)
-  DevBuf stem_in, stem_out, x0, xa, xb, dsbuf, mid1, mid2, vis_emb, vis_emb_act, vis_out, lang_out, pooled;
+  DevBuf stem_in, stem_out, x0, xa, xb, dsbuf, mid1, mid2, vis_emb, vis_emb_act, vis_out, lang_out, pooled, pooled32;
   std::vector<std::unique_ptr<DevBuf>> shifted;   // one per bottleneck: its temporally shifted input channels
   // text workspace (sized for Bt clips x Lmax tokens)
   DevBuf hid, hid2, qkv, ctx, tmp, ffn, cls;
@@ -198,6 +198,10 @@ struct vcg_engine {
   }
 
   int es() const { return fp32 ? 4 : 2; }
+  // state-dict prefixes: TwoStream keeps the backbones as vision_model.* / lang_model.*, the single-modality
+  // models (Resnet50TSM, Resnet50, BertHugface) as base_model.*
+  std::string vis_prefix() const { return cfg.modality == VCG_MODALITY_VISION ? "base_model." : "vision_model."; }
+  std::string lang_prefix() const { return cfg.modality == VCG_MODALITY_TEXT ? "base_model." : "lang_model."; }
 };
 
 namespace {
@@ -261,7 +265,7 @@ void pack_linear(vcg_engine* e, LinearW& lw, const std::string& prefix, int N, i
 }
 
 void finalize_vision(vcg_engine* e, cudaStream_t s) {
-  const std::string vm = "vision_model.";
+  const std::string vm = e->vis_prefix();
   {
     const RawTensor& w = need(e, vm + "conv1.weight", {64, 3, 7, 7});
     const RawTensor& g = need(e, vm + "bn1.weight", {64});
@@ -328,7 +332,7 @@ void finalize_vision(vcg_engine* e, cudaStream_t s) {
 }
 
 void finalize_text(vcg_engine* e, cudaStream_t s) {
-  const std::string lm = "lang_model.";
+  const std::string lm = e->lang_prefix();
   const RawTensor& word = need(e, lm + "embeddings.word_embeddings.weight");
   VCG_REQUIRE(word.shape.size() == 2 && word.shape[1] == kBertHidden, "word embedding must be [vocab,768]");
   const RawTensor& pos = need(e, lm + "embeddings.position_embeddings.weight");
@@ -426,6 +430,20 @@ void finalize_text(vcg_engine* e, cudaStream_t s) {
 void finalize_head(vcg_engine* e, cudaStream_t s) {
   const std::string fh = "fusion_head.";
   const int H = e->H, T = e->T;
+  if (e->cfg.modality != VCG_MODALITY_TWO_STREAM) {   // nn.Linear(D, 2) on the backbone embedding
+    const int64_t D = e->cfg.modality == VCG_MODALITY_VISION ? static_cast<int64_t>(T) * kVisionDim : kBertHidden;
+    copy_f32(e->head_w, need(e, "head.weight", {2, D}), s);
+    copy_f32(e->head_b, need(e, "head.bias", {2}), s);
+    if (e->cfg.modality == VCG_MODALITY_VISION) {
+      const size_t max_frames = static_cast<size_t>(e->Bv) * T;
+      e->vis_emb.alloc(max_frames * kVisionDim * sizeof(float));
+      if (!e->fp32) e->vis_emb_act.alloc(max_frames * kVisionDim * e->es());
+    } else {
+      e->pooled.alloc((static_cast<size_t>(e->Bt) + 128) * kBertHidden * e->es());
+      e->pooled32.alloc(static_cast<size_t>(e->Bt) * kBertHidden * sizeof(float));
+    }
+    return;
+  }
   convert_to(e->lang_w, need(e, fh + "lang_proj_head.weight", {H, kBertHidden}), e->fp32, s);
   convert_to(e->vis_w, need(e, fh + "vision_proj_head.weight", {H, kVisionDim}), e->fp32, s);
   if (e->cfg.head_type == VCG_HEAD_MLP) {
@@ -721,10 +739,97 @@ struct HostFeed {
 };
 
 // Scores B clips; any of the sources may be used for the vision stream (or precomputed embeddings).
+// Text stream for clips [b0, b0 + bt): token packing, embeddings, the encoder, BertPooler (tanh) into e->pooled and,
+// for the two-stream model, the language projection (ReLU) into e->lang_out.
+void run_text(vcg_engine* e, const int64_t* ids, const int64_t* mask, int b0, int bt, int L, float* lang_emb_out,
+              cudaStream_t s) {
+  {
+    ProfScope ps(e, s, "bert_pack|bert.pack", 0, static_cast<double>(bt) * L * 13);
+    launch_bert_pack(mask + static_cast<long>(b0) * L, bt, L, e->pk_cu.as<int32_t>(), e->pk_src.as<int32_t>(),
+                     e->pk_ok.as<uint8_t>(), e->pk_total.as<int32_t>(), s);
+  }
+  e->last_bert_rows = bt * L;
+  {
+    ProfScope ps(e, s, "bert_embed_ln|bert.embed", 0, static_cast<double>(bt) * L * 768 * 4 * e->es(), true);
+    launch_bert_embed_ln(ids + static_cast<long>(b0) * L, bt * L, L, e->pk_src.as<int32_t>(), e->pk_total.as<int32_t>(),
+                         e->word.p, e->pos.p, e->type.p, e->emb_g.as<float>(), e->emb_b.as<float>(), e->hid.p, e->fp32, s);
+  }
+  BertPlan& bp = bert_plan(e, bt, L);
+  run_steps(e, bp.steps, mask + static_cast<long>(b0) * L, s);
+  // ---- BertPooler (tanh) + lang projection (ReLU) for the bt clips: two small tcgen05 GEMMs over the [CLS] rows
+  const bool with_proj = e->cfg.modality == VCG_MODALITY_TWO_STREAM;
+  auto key = std::make_pair(bt, L);
+  auto it = e->lang_tail_plans.find(key);
+  if (it == e->lang_tail_plans.end()) {
+    std::vector<ConvGemmLaunch> v;
+    Epilogue ep1; ep1.bias = e->pooler.bias.as<float>(); ep1.act = ACT_TANH;
+    v.push_back(build_gemm(e->cls.p, kBertHidden, e->pooler.w.p, e->pooled.p, kBertHidden, bt, kBertHidden, kBertHidden,
+                           e->fp32, ep1, "head.pooler"));
+    if (with_proj) {
+      Epilogue ep2; ep2.act = ACT_RELU;
+      v.push_back(build_gemm(e->pooled.p, kBertHidden, e->lang_w.p, e->lang_out.p, e->H, bt, e->H, kBertHidden, e->fp32, ep2,
+                             "head.lang_proj"));
+    }
+    it = e->lang_tail_plans.emplace(key, std::move(v)).first;
+  }
+  {
+    ProfScope ps(e, s, "gather_rows768|head.cls", 0, static_cast<double>(bt) * kBertHidden * 2 * e->es());
+    if (bp.final_is_raw) {   // the last LayerNorm, for the pooled rows only
+      const BertLayerW& last = e->layers.back();
+      launch_gather_ln_rows768(bp.final_hidden, e->pk_cu.as<int32_t>(), L, bt, last.ln2_g.as<float>(),
+                               last.ln2_b.as<float>(), 1e-12f, e->cls.p, s);
+    } else {
+      launch_gather_rows768(bp.final_hidden, e->pk_cu.as<int32_t>(), L, bt, e->cls.p, e->fp32, s);
+    }
+  }
+  for (const ConvGemmLaunch& g : it->second) {
+    ProfScope ps(e, s, gemm_kernel_name(g), g.flops, 0);
+    launch_conv_gemm(g, s);
+  }
+  if (lang_emb_out) {
+    ProfScope ps(e, s, "cast_to_f32|head.lang_emb", 0, static_cast<double>(bt) * kBertHidden * (4 + e->es()));
+    launch_cast_to_f32(e->pooled.p, lang_emb_out, static_cast<long>(bt) * kBertHidden, e->fp32, s);
+  }
+}
+
+// Vision stream for clips [g0, g0 + bv) of the caller's numbering: pre-processing, ResNet-50(-TSM), average pool.
+// Returns the fp32 embeddings [bv*T, 2048] (in the caller's buffer when vision_emb_out is given) and leaves the same
+// values in the activation type at the fixed GEMM-operand address (e->vis_emb / e->vis_emb_act).
+const float* run_vision(vcg_engine* e, const FrameSource& src, int g0, int bv, float* vision_emb_out, cudaStream_t s) {
+  const int T = e->T;
+  if (src.img_clip) {
+    ProfScope ps(e, s, "nchw_to_stem|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (4 + e->es()));
+    launch_nchw_to_stem(src.img_clip + static_cast<long>(g0) * T * 3 * kImg * kImg, bv * T, e->stem_in.p, e->fp32, s);
+  } else if (shared_stem_ok(e, src.grid_stride)) {
+    // overlapping clips: every unique frame of this pass is pre-processed (and run through the stem) once
+    const int U = src.grid_stride * (bv - 1) + T;
+    const long f0 = src.grid_start + static_cast<long>(src.grid_stride) * g0;
+    ProfScope ps(e, s, "preprocess_u8|preprocess", 0, static_cast<double>(U) * kImg * kImg * 3 * (1 + e->es()));
+    launch_preprocess_u8(src.frames_u8 + f0 * kImg * kImg * 3, nullptr, U, e->stem_in.p, e->fp32, s);
+  } else {
+    ProfScope ps(e, s, "preprocess_u8|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (1 + e->es()));
+    launch_preprocess_u8_clips(src.frames_u8, src.clip_start + g0, bv, T, e->stem_in.p, e->fp32, s);
+  }
+  VisionPlan& vp = vision_plan(e, bv, (src.frames_u8 && shared_stem_ok(e, src.grid_stride)) ? src.grid_stride : 0);
+  run_steps(e, vp.steps, nullptr, s);
+  // fp32 embeddings go to the caller's buffer when asked for; in fp32 mode they are also the GEMM operand
+  float* dst = vision_emb_out ? vision_emb_out + static_cast<long>(g0) * T * kVisionDim : e->vis_emb.as<float>();
+  {
+    ProfScope ps(e, s, "avgpool|avgpool", 0, static_cast<double>(bv) * T * kVisionDim * (49 * e->es() + 4));
+    launch_avgpool(vp.final_act, bv * T, 49, kVisionDim, dst, e->fp32 ? nullptr : e->vis_emb_act.p, s, e->fp32);
+  }
+  if (e->fp32 && vision_emb_out)   // keep the GEMM operand at a fixed address (cached tensor maps)
+    VCG_CUDA(cudaMemcpyAsync(e->vis_emb.p, dst, static_cast<size_t>(bv) * T * kVisionDim * sizeof(float),
+                             cudaMemcpyDeviceToDevice, s));
+  return dst;
+}
+
+// Scores B clips; any of the sources may be used for the vision stream (or precomputed embeddings).
 void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, const int64_t* ids, const int64_t* mask,
            int B, int L, float* logits, float* probs, float* vision_emb_out, float* lang_emb_out, cudaStream_t s,
            const HostFeed* feed = nullptr) {
   VCG_REQUIRE(e->finalized, "vcg_finalize has not been called");
+  VCG_REQUIRE(e->cfg.modality == VCG_MODALITY_TWO_STREAM, "engine was created for a single modality");
   VCG_REQUIRE(B >= 0 && L >= 1 && L <= e->Lmax, "token count exceeds max_tokens of the engine");
   const bool have_frames = src.img_clip || src.frames_u8;
   VCG_REQUIRE(have_frames || vision_emb_in, "no vision input given");
@@ -732,54 +837,7 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
   const int T = e->T;
   for (int b0 = 0; b0 < B; b0 += e->Bt) {
     const int bt = std::min(e->Bt, B - b0);
-    // ---- text stream for bt clips
-    {
-      ProfScope ps(e, s, "bert_pack|bert.pack", 0, static_cast<double>(bt) * L * 13);
-      launch_bert_pack(mask + static_cast<long>(b0) * L, bt, L, e->pk_cu.as<int32_t>(), e->pk_src.as<int32_t>(),
-                       e->pk_ok.as<uint8_t>(), e->pk_total.as<int32_t>(), s);
-    }
-    e->last_bert_rows = bt * L;
-    {
-      ProfScope ps(e, s, "bert_embed_ln|bert.embed", 0, static_cast<double>(bt) * L * 768 * 4 * e->es(), true);
-      launch_bert_embed_ln(ids + static_cast<long>(b0) * L, bt * L, L, e->pk_src.as<int32_t>(), e->pk_total.as<int32_t>(),
-                           e->word.p, e->pos.p, e->type.p, e->emb_g.as<float>(), e->emb_b.as<float>(), e->hid.p, e->fp32, s);
-    }
-    BertPlan& bp = bert_plan(e, bt, L);
-    run_steps(e, bp.steps, mask + static_cast<long>(b0) * L, s);
-    // ---- BertPooler (tanh) + lang projection (ReLU) for the bt clips: two small tcgen05 GEMMs over the [CLS] rows
-    {
-      auto key = std::make_pair(bt, L);
-      auto it = e->lang_tail_plans.find(key);
-      if (it == e->lang_tail_plans.end()) {
-        std::vector<ConvGemmLaunch> v;
-        Epilogue ep1; ep1.bias = e->pooler.bias.as<float>(); ep1.act = ACT_TANH;
-        v.push_back(build_gemm(e->cls.p, kBertHidden, e->pooler.w.p, e->pooled.p, kBertHidden, bt, kBertHidden, kBertHidden,
-                               e->fp32, ep1, "head.pooler"));
-        Epilogue ep2; ep2.act = ACT_RELU;
-        v.push_back(build_gemm(e->pooled.p, kBertHidden, e->lang_w.p, e->lang_out.p, e->H, bt, e->H, kBertHidden, e->fp32, ep2,
-                               "head.lang_proj"));
-        it = e->lang_tail_plans.emplace(key, std::move(v)).first;
-      }
-      {
-        ProfScope ps(e, s, "gather_rows768|head.cls", 0, static_cast<double>(bt) * kBertHidden * 2 * e->es());
-        if (bp.final_is_raw) {   // the last LayerNorm, for the pooled rows only
-          const BertLayerW& last = e->layers.back();
-          launch_gather_ln_rows768(bp.final_hidden, e->pk_cu.as<int32_t>(), L, bt, last.ln2_g.as<float>(),
-                                   last.ln2_b.as<float>(), 1e-12f, e->cls.p, s);
-        } else {
-          launch_gather_rows768(bp.final_hidden, e->pk_cu.as<int32_t>(), L, bt, e->cls.p, e->fp32, s);
-        }
-      }
-      for (const ConvGemmLaunch& g : it->second) {
-        ProfScope ps(e, s, gemm_kernel_name(g), g.flops, 0);
-        launch_conv_gemm(g, s);
-      }
-      if (lang_emb_out) {
-        ProfScope ps(e, s, "cast_to_f32|head.lang_emb", 0, static_cast<double>(bt) * kBertHidden * (4 + e->es()));
-        launch_cast_to_f32(e->pooled.p, lang_emb_out + static_cast<long>(b0) * kBertHidden, static_cast<long>(bt) * kBertHidden,
-                           e->fp32, s);
-      }
-    }
+    run_text(e, ids, mask, b0, bt, L, lang_emb_out ? lang_emb_out + static_cast<long>(b0) * kBertHidden : nullptr, s);
     TailParams tp{};
     tp.T = T; tp.H = e->H; tp.head_type = e->cfg.head_type;
     tp.head_w = e->head_w.as<float>(); tp.head_b = e->head_b.as<float>();
@@ -792,36 +850,9 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
     for (int c0 = 0; c0 < bt; c0 += step) {
       const int bv = std::min(step, bt - c0);
       const int g0 = b0 + c0;   // first clip of this sub-chunk in the caller's numbering
-      const void* vis_act = nullptr;   // [bv*T, 2048] in the activation type
       if (feed) feed->wait_for(s, g0, g0 + bv);
       if (have_frames) {
-        if (src.img_clip) {
-          ProfScope ps(e, s, "nchw_to_stem|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (4 + e->es()));
-          launch_nchw_to_stem(src.img_clip + static_cast<long>(g0) * T * 3 * kImg * kImg, bv * T, e->stem_in.p, e->fp32, s);
-        } else if (shared_stem_ok(e, src.grid_stride)) {
-          // overlapping clips: every unique frame of this pass is pre-processed (and run through the stem) once
-          const int U = src.grid_stride * (bv - 1) + T;
-          const long f0 = src.grid_start + static_cast<long>(src.grid_stride) * g0;
-          ProfScope ps(e, s, "preprocess_u8|preprocess", 0, static_cast<double>(U) * kImg * kImg * 3 * (1 + e->es()));
-          launch_preprocess_u8(src.frames_u8 + f0 * kImg * kImg * 3, nullptr, U, e->stem_in.p, e->fp32, s);
-        } else {
-          ProfScope ps(e, s, "preprocess_u8|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (1 + e->es()));
-          launch_preprocess_u8_clips(src.frames_u8, src.clip_start + g0, bv, T, e->stem_in.p, e->fp32, s);
-        }
-        VisionPlan& vp = vision_plan(e, bv, (src.frames_u8 && shared_stem_ok(e, src.grid_stride)) ? src.grid_stride : 0);
-        run_steps(e, vp.steps, nullptr, s);
-        // fp32 embeddings go to the caller's buffer when asked for; in fp32 mode they are also the GEMM operand
-        float* dst = vision_emb_out ? vision_emb_out + static_cast<long>(g0) * T * kVisionDim : e->vis_emb.as<float>();
-        {
-          ProfScope ps(e, s, "avgpool|avgpool", 0, static_cast<double>(bv) * T * kVisionDim * (49 * e->es() + 4));
-          launch_avgpool(vp.final_act, bv * T, 49, kVisionDim, dst, e->fp32 ? nullptr : e->vis_emb_act.p, s, e->fp32);
-        }
-        vis_act = e->fp32 ? static_cast<const void*>(dst) : e->vis_emb_act.p;
-        if (e->fp32 && vision_emb_out) {   // keep the GEMM operand at a fixed address (cached tensor maps)
-          VCG_CUDA(cudaMemcpyAsync(e->vis_emb.p, dst, static_cast<size_t>(bv) * T * kVisionDim * sizeof(float),
-                                   cudaMemcpyDeviceToDevice, s));
-          vis_act = e->vis_emb.p;
-        }
+        run_vision(e, src, g0, bv, vision_emb_out, s);
       } else {
         const float* vis = vision_emb_in + static_cast<long>(g0) * T * kVisionDim;
         if (vision_emb_out)
@@ -829,14 +860,11 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
                                    static_cast<size_t>(bv) * T * kVisionDim * sizeof(float), cudaMemcpyDeviceToDevice, s));
         // caller's fp32 embeddings -> activation type at the fixed operand address
         ProfScope ps(e, s, "convert|head.vision_emb_in", 0, static_cast<double>(bv) * T * kVisionDim * (4 + e->es()));
-        if (e->fp32) {
+        if (e->fp32)
           VCG_CUDA(cudaMemcpyAsync(e->vis_emb.p, vis, static_cast<size_t>(bv) * T * kVisionDim * sizeof(float),
                                    cudaMemcpyDeviceToDevice, s));
-          vis_act = e->vis_emb.p;
-        } else {
+        else
           launch_convert(vis, e->vis_emb_act.p, static_cast<long>(bv) * T * kVisionDim, false, s);
-          vis_act = e->vis_emb_act.p;
-        }
       }
       {
         auto it = e->vis_proj_plans.find(bv * T);
@@ -846,7 +874,6 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
           it = e->vis_proj_plans.emplace(bv * T, build_gemm(a, kVisionDim, e->vis_w.p, e->vis_out.p, e->H, bv * T, e->H,
                                                             kVisionDim, e->fp32, ep, "head.vision_proj")).first;
         }
-        (void)vis_act;
         ProfScope ps(e, s, gemm_kernel_name(it->second), it->second.flops, 0);
         launch_conv_gemm(it->second, s);
       }
@@ -860,6 +887,37 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
         launch_head_final(hp, bv, e->fp32, s);
       }
     }
+  }
+}
+
+// Single-modality models of the reference (--data_mode image / text): backbone embedding -> nn.Linear(D, 2) -> softmax.
+//   Resnet50TSM.forward / Resnet50.forward (model/vision/resnet50_tsm.py:68-77, resnet50.py:64-73): D = T*2048
+//   BertHugface.forward, pretrain_stage=False (model/lang/bert_hugface.py:98-132): D = 768 on the pooler output
+void score_vision_only(vcg_engine* e, const FrameSource& src, int B, float* logits, float* probs, float* vision_emb_out,
+                       cudaStream_t s) {
+  VCG_REQUIRE(e->finalized, "vcg_finalize has not been called");
+  VCG_REQUIRE(e->cfg.modality == VCG_MODALITY_VISION, "engine was not created for the image-only model");
+  for (int g0 = 0; g0 < B; g0 += e->Bv) {
+    const int bv = std::min(e->Bv, B - g0);
+    const float* emb = run_vision(e, src, g0, bv, vision_emb_out, s);
+    ProfScope ps(e, s, "linear_head2|head.final", 2.0 * bv * e->T * kVisionDim * 2, 0);
+    launch_linear_head2(emb, e->head_w.as<float>(), e->head_b.as<float>(), bv, e->T * kVisionDim, logits + g0 * 2L,
+                        probs + g0 * 2L, s);
+  }
+}
+
+void score_text_only(vcg_engine* e, const int64_t* ids, const int64_t* mask, int B, int L, float* logits, float* probs,
+                     float* lang_emb_out, cudaStream_t s) {
+  VCG_REQUIRE(e->finalized, "vcg_finalize has not been called");
+  VCG_REQUIRE(e->cfg.modality == VCG_MODALITY_TEXT, "engine was not created for the text-only model");
+  VCG_REQUIRE(B >= 0 && L >= 1 && L <= e->Lmax, "token count exceeds max_tokens of the engine");
+  for (int b0 = 0; b0 < B; b0 += e->Bt) {
+    const int bt = std::min(e->Bt, B - b0);
+    float* pooled32 = lang_emb_out ? lang_emb_out + static_cast<long>(b0) * kBertHidden : e->pooled32.as<float>();
+    run_text(e, ids, mask, b0, bt, L, pooled32, s);
+    ProfScope ps(e, s, "linear_head2|head.final", 2.0 * bt * kBertHidden * 2, 0);
+    launch_linear_head2(pooled32, e->head_w.as<float>(), e->head_b.as<float>(), bt, kBertHidden, logits + b0 * 2L,
+                        probs + b0 * 2L, s);
   }
 }
 
@@ -895,6 +953,8 @@ int vcg_create(const vcg_config* cfg, vcg_engine** out) {
     if (cfg->head_type != VCG_HEAD_MLP && cfg->head_type != VCG_HEAD_ATTN)
       throw Error("Unknown head_type " + std::to_string(cfg->head_type));   // two_stream.py:68
     VCG_REQUIRE(cfg->precision == VCG_PREC_BF16 || cfg->precision == VCG_PREC_FP32, "unknown precision");
+    VCG_REQUIRE(cfg->modality >= VCG_MODALITY_TWO_STREAM && cfg->modality <= VCG_MODALITY_TEXT, "unknown modality");
+    if (cfg->modality == VCG_MODALITY_VISION) VCG_REQUIRE(cfg->vision == VCG_VISION_R50TSM, "the image-only model needs a vision backbone");
     VCG_REQUIRE(cfg->max_batch >= 1, "max_batch must be positive");
     VCG_REQUIRE(cfg->shift_div == 8 || cfg->shift_div == 4 || cfg->shift_div == 0, "shift_div must be 8, 4 or 0 (no shift)");
     int dev = 0, major = 0, minor = 0;
@@ -940,8 +1000,8 @@ int vcg_finalize(vcg_engine* e, void* stream) {
     e->bplans.clear();
     e->lang_tail_plans.clear();
     e->vis_proj_plans.clear();
-    if (e->cfg.vision == VCG_VISION_R50TSM) finalize_vision(e, s);
-    finalize_text(e, s);
+    if (e->cfg.vision == VCG_VISION_R50TSM && e->cfg.modality != VCG_MODALITY_TEXT) finalize_vision(e, s);
+    if (e->cfg.modality != VCG_MODALITY_VISION) finalize_text(e, s);
     finalize_head(e, s);
     VCG_CUDA(cudaStreamSynchronize(s));
     e->raw.clear();   // packed copies are all the kernels read
@@ -958,6 +1018,24 @@ int vcg_forward(vcg_engine* e, const float* img_clip, const float* vision_emb, c
     src.img_clip = img_clip;
     score(e, src, vision_emb, text_ids, attention_mask, B, L, logits, probs, vision_emb_out, lang_emb_out,
           static_cast<cudaStream_t>(stream));
+  });
+}
+
+int vcg_forward_vision(vcg_engine* e, const float* img_clip, int32_t B, float* logits, float* probs, float* vision_emb_out,
+                       void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e && img_clip && logits && probs, "null argument");
+    FrameSource src;
+    src.img_clip = img_clip;
+    score_vision_only(e, src, B, logits, probs, vision_emb_out, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int vcg_forward_text(vcg_engine* e, const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L,
+                     float* logits, float* probs, float* lang_emb_out, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e && text_ids && attention_mask && logits && probs, "null argument");
+    score_text_only(e, text_ids, attention_mask, B, L, logits, probs, lang_emb_out, static_cast<cudaStream_t>(stream));
   });
 }
 

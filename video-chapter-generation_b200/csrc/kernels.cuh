@@ -69,6 +69,9 @@ struct TailParams {
   float* probs;            // [B,2]
 };
 void launch_head_final(const TailParams& p, int B, bool fp32, cudaStream_t s);     // head + softmax
+// single-modality heads: logits = x[B,D] w[2,D]^T + b, probs = softmax (all fp32)
+void launch_linear_head2(const float* x, const float* w, const float* b, int B, int D, float* logits, float* probs,
+                         cudaStream_t s);
 
 // weight packing (fp32 state-dict tensors -> kernel layouts)
 void launch_pack_conv(const float* w /*[Cout,Cin,k,k]*/, const float* bn_w, const float* bn_b, const float* bn_mean,

@@ -114,6 +114,44 @@ __global__ void __launch_bounds__(128) head_final_kernel(const TailParams p) {
 
 }  // namespace
 
+// nn.Linear(D, 2) + 2-way softmax on fp32 embeddings (single-modality heads): one CTA per clip.
+__global__ void __launch_bounds__(256) linear_head2_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ b, int D, float* __restrict__ logits,
+                                                           float* __restrict__ probs) {
+  pdl_enter();
+  const float* xr = x + static_cast<long>(blockIdx.x) * D;
+  float a0 = 0.f, a1 = 0.f;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {   // D % 4 == 0 (768, T*2048)
+    const float4 v = *reinterpret_cast<const float4*>(xr + i);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + i));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + D + i));
+    a0 += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
+    a1 += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
+  }
+  __shared__ float red[2][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a0; red[1][threadIdx.x >> 5] = a1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l0 = b[0], l1 = b[1];
+    for (int i = 0; i < 8; ++i) { l0 += red[0][i]; l1 += red[1][i]; }
+    const float m = fmaxf(l0, l1), e0 = expf(l0 - m), e1 = expf(l1 - m), inv = 1.f / (e0 + e1);
+    logits[blockIdx.x * 2] = l0; logits[blockIdx.x * 2 + 1] = l1;
+    probs[blockIdx.x * 2] = e0 * inv; probs[blockIdx.x * 2 + 1] = e1 * inv;
+  }
+}
+
+void launch_linear_head2(const float* x, const float* w, const float* b, int B, int D, float* logits, float* probs,
+                         cudaStream_t s) {
+  if (B == 0) return;
+  VCG_REQUIRE(D % 4 == 0, "linear head: feature size must be a multiple of 4");
+  launch_pdl(linear_head2_kernel, B, 256, 0, s, x, w, b, D, logits, probs);
+}
+
 void launch_head_final(const TailParams& p, int B, bool fp32, cudaStream_t s) {
   if (B == 0) return;
   VCG_REQUIRE(p.H == 128, "ChapterHead hidden size must be 128");

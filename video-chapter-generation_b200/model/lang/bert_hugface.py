@@ -122,5 +122,29 @@ class BertHugface(nn.Module):
             p.requires_grad = False
 
     def forward(self, text_ids, attention_mask, get_attention=False):
-        raise NotImplementedError("text-only scoring (--data_mode text) is a 'next' row of SURVEY.md 8f; "
-                                  "the supported path is TwoStream.forward")
+        """(logits [B,2], prob [B,2]) = softmax(head(pooler_output)) — the clip classifier of --data_mode text
+        (reference :98-132 with pretrain_stage=False).  BERT, pooler and head run inside libvcg_b200.so
+        (VCG_MODALITY_TEXT engine); the MLM pre-training branch (pretrain_stage=True) is training code, out of scope."""
+        import os
+        if self.pretrain_stage:
+            raise NotImplementedError("masked-LM pre-training (pretrain_stage=True) is out of scope (SURVEY.md section 2)")
+        if not text_ids.is_cuda:
+            raise RuntimeError("text-only scoring needs CUDA inputs: the B200 implementation has no CPU fallback")
+        if self.training:
+            raise RuntimeError("inference-only: call .eval() first")
+        from vcg_b200.engine import Engine
+        precision = getattr(self, "precision", os.environ.get("VCG_PRECISION", "bf16"))
+        max_tokens = max(128, text_ids.shape[1])
+        v = 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            v += t._version + (t.data_ptr() % 1000003)
+        key = (str(text_ids.device), precision, max_tokens, v)
+        if getattr(self, "_engine", None) is None or self._engine_key != key:
+            if getattr(self, "_engine", None) is not None:
+                self._engine.close()
+            eng = Engine(1, "mlp", precision, False, max_tokens, 256, 128, 8, device=text_ids.device, modality="text")
+            eng.load_state_dict(self.state_dict())
+            object.__setattr__(self, "_engine", eng)
+            object.__setattr__(self, "_engine_key", key)
+        with torch.no_grad():
+            return self._engine.forward_text(text_ids, attention_mask)

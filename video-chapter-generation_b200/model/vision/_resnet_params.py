@@ -82,3 +82,37 @@ class ResNet50Params(nn.Module):
 
     def forward(self, x):
         raise RuntimeError("the ResNet-50 backbone runs inside libvcg_b200.so; call TwoStream.forward")
+
+
+def _weights_version(module):
+    v = 0
+    for t in list(module.parameters()) + list(module.buffers()):
+        v += t._version + (t.data_ptr() % 1000003)
+    return v
+
+
+def _unimodal_vision_forward(module, x, shift_div):
+    """Shared body of Resnet50TSM.forward / Resnet50.forward (--data_mode image): the backbone and the
+    nn.Linear(T*2048, 2) head run inside libvcg_b200.so (VCG_MODALITY_VISION engine).  No CPU / eager fallback."""
+    import os
+    import torch
+    if module.head is None:
+        raise RuntimeError("call build_chapter_head() first")
+    if not x.is_cuda:
+        raise RuntimeError("image-only scoring needs CUDA inputs: the B200 implementation has no CPU fallback")
+    if module.training:
+        raise RuntimeError("inference-only: call .eval() first")
+    from vcg_b200.engine import Engine
+    precision = getattr(module, "precision", os.environ.get("VCG_PRECISION", "bf16"))
+    chunk = getattr(module, "vision_chunk", int(os.environ.get("VCG_VISION_CHUNK", "32")))
+    key = (str(x.device), precision, chunk, _weights_version(module))
+    if getattr(module, "_engine", None) is None or module._engine_key != key:
+        if getattr(module, "_engine", None) is not None:
+            module._engine.close()
+        eng = Engine(module.segments_size, "mlp", precision, True, 128, chunk, 128, shift_div, device=x.device,
+                     modality="vision")
+        eng.load_state_dict(module.state_dict())
+        object.__setattr__(module, "_engine", eng)
+        object.__setattr__(module, "_engine_key", key)
+    with torch.no_grad():
+        return module._engine.forward_vision(x)

@@ -5,7 +5,7 @@ import torch.nn as nn
 
 from ops.basic_ops import Identity
 
-from ._resnet_params import ResNet50Params
+from ._resnet_params import ResNet50Params, _unimodal_vision_forward
 
 
 class Resnet50(torch.nn.Module):
@@ -22,5 +22,5 @@ class Resnet50(torch.nn.Module):
         self.head = nn.Linear(self.segments_size * self.feature_dim, 2)
 
     def forward(self, x):
-        raise NotImplementedError("image-only scoring (--data_mode image) is a 'next' row of SURVEY.md 8f; "
-                                  "the supported path is TwoStream.forward")
+        """x [B,T,3,224,224] -> (logits [B,2], prob [B,2]) (reference :64-73), plain ResNet-50 (no temporal shift)."""
+        return _unimodal_vision_forward(self, x, 0)

@@ -11,7 +11,7 @@ import torch.nn as nn
 from ops.basic_ops import Identity
 from ops.temporal_shift import make_temporal_shift
 
-from ._resnet_params import ResNet50Params
+from ._resnet_params import ResNet50Params, _unimodal_vision_forward
 
 
 class Resnet50TSM(torch.nn.Module):
@@ -21,6 +21,7 @@ class Resnet50TSM(torch.nn.Module):
         self.base_model = ResNet50Params()
         make_temporal_shift(self.base_model, n_segment=segments_size, n_div=shift_div)
         self.segments_size = segments_size
+        self.shift_div = shift_div
         self.feature_dim = self.base_model.fc.in_features
         self.base_model.fc = Identity()   # discard the classifier
         self.head = None
@@ -29,5 +30,5 @@ class Resnet50TSM(torch.nn.Module):
         self.head = nn.Linear(self.segments_size * self.feature_dim, 2)
 
     def forward(self, x):
-        raise NotImplementedError("image-only scoring (--data_mode image) is a 'next' row of SURVEY.md 8f; "
-                                  "the supported path is TwoStream.forward")
+        """x [B,T,3,224,224] -> (logits [B,2], prob [B,2]) (reference :68-77).  Runs inside libvcg_b200.so."""
+        return _unimodal_vision_forward(self, x, self.shift_div)

@@ -15,6 +15,7 @@ CSRC_DIR = os.path.join(PKG_ROOT, "csrc")
 HEAD_MLP, HEAD_ATTN = 0, 1
 PREC_BF16, PREC_FP32 = 0, 1
 VISION_R50TSM, VISION_NONE = 0, 1
+MODALITY_TWO_STREAM, MODALITY_VISION, MODALITY_TEXT = 0, 1, 2
 DTYPE_F32, DTYPE_I64 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
 
@@ -29,6 +30,7 @@ class VcgConfig(ctypes.Structure):
         ("vision", ctypes.c_int32),
         ("max_batch", ctypes.c_int32),
         ("shift_div", ctypes.c_int32),
+        ("modality", ctypes.c_int32),
     ]
 
 
@@ -48,6 +50,8 @@ PROTOTYPES = {
     "vcg_load_tensor": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(_i64), _i32, _i32, _vp]),
     "vcg_finalize": (ctypes.c_int, [_vp, _vp]),
     "vcg_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "vcg_forward_vision": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "vcg_forward_text": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "vcg_score_clips_u8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vcg_score_video_u8": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vcg_score_clips_u8_host": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),

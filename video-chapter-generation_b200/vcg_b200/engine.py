@@ -12,6 +12,7 @@ from . import binding as _b
 
 _HEADS = {"mlp": _b.HEAD_MLP, "attn": _b.HEAD_ATTN}
 _PRECS = {"bf16": _b.PREC_BF16, "fp32": _b.PREC_FP32}
+_MODALITIES = {"two_stream": _b.MODALITY_TWO_STREAM, "vision": _b.MODALITY_VISION, "text": _b.MODALITY_TEXT}
 
 
 def _stream():
@@ -20,11 +21,14 @@ def _stream():
 
 class Engine:
     def __init__(self, clip_frames, head_type="mlp", precision="bf16", vision=True, max_tokens=128, max_batch=32,
-                 hidden_size=128, shift_div=8, device=None):
+                 hidden_size=128, shift_div=8, device=None, modality="two_stream"):
         if head_type not in _HEADS:
             raise RuntimeError(f"Unknown head_type {head_type}")
         if precision not in _PRECS:
             raise RuntimeError(f"Unknown precision {precision}")
+        if modality not in _MODALITIES:
+            raise RuntimeError(f"Unknown modality {modality}")
+        self.modality = modality
         if not torch.cuda.is_available():
             raise RuntimeError("vcg_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -32,7 +36,7 @@ class Engine:
         self.vision, self.max_tokens, self.max_batch = vision, max_tokens, max_batch
         self._lib = _b.load_library()
         cfg = _b.VcgConfig(clip_frames, max_tokens, hidden_size, _HEADS[head_type], _PRECS[precision],
-                           _b.VISION_R50TSM if vision else _b.VISION_NONE, max_batch, shift_div)
+                           _b.VISION_R50TSM if vision else _b.VISION_NONE, max_batch, shift_div, _MODALITIES[modality])
         handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _b.check(self._lib.vcg_create(ctypes.byref(cfg), ctypes.byref(handle)))
@@ -55,8 +59,12 @@ class Engine:
         """state_dict: reference key schema; CPU tensors are moved to the GPU one at a time."""
         with torch.cuda.device(self.device):
             for key, t in state_dict.items():
-                if not (key.startswith("lang_model.") or key.startswith("fusion_head.") or
-                        (self.vision and key.startswith("vision_model."))):
+                if self.modality == "two_stream":
+                    wanted = (key.startswith("lang_model.") or key.startswith("fusion_head.") or
+                              (self.vision and key.startswith("vision_model.")))
+                else:   # Resnet50TSM / Resnet50 / BertHugface state dicts: base_model.* + head.*
+                    wanted = key.startswith("base_model.") or key in ("head.weight", "head.bias")
+                if not wanted:
                     continue
                 if key.endswith("num_batches_tracked"):
                     continue
@@ -109,6 +117,34 @@ class Engine:
         if return_emb:
             return logits, probs, ve, le
         return logits, probs
+
+    def forward_vision(self, img_clip, return_emb=False):
+        """Resnet50TSM.forward / Resnet50.forward: img_clip [B,T,3,224,224] fp32 -> (logits, probs)."""
+        if not img_clip.is_cuda:
+            raise RuntimeError("vcg_b200: inputs must be CUDA tensors (no CPU fallback)")
+        img_clip = img_clip.float().contiguous()
+        if tuple(img_clip.shape[1:]) != (self.clip_frames, 3, 224, 224):
+            raise RuntimeError(f"vcg_b200: img_clip must be [B,{self.clip_frames},3,224,224], got {tuple(img_clip.shape)}")
+        B, dev = img_clip.shape[0], img_clip.device
+        logits = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        probs = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        ve = torch.empty(B, self.clip_frames, 2048, dtype=torch.float32, device=dev) if return_emb else None
+        with torch.cuda.device(dev):
+            _b.check(self._lib.vcg_forward_vision(self._h, img_clip.data_ptr(), B, logits.data_ptr(), probs.data_ptr(),
+                                                  0 if ve is None else ve.data_ptr(), _stream()))
+        return (logits, probs, ve) if return_emb else (logits, probs)
+
+    def forward_text(self, text_ids, attention_mask, return_emb=False):
+        """BertHugface.forward (pretrain_stage=False): pooler output -> Linear(768, 2) -> softmax."""
+        ids, mask, B, L = self._text(text_ids, attention_mask)
+        dev = ids.device
+        logits = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        probs = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        le = torch.empty(B, 768, dtype=torch.float32, device=dev) if return_emb else None
+        with torch.cuda.device(dev):
+            _b.check(self._lib.vcg_forward_text(self._h, ids.data_ptr(), mask.data_ptr(), B, L, logits.data_ptr(),
+                                                probs.data_ptr(), 0 if le is None else le.data_ptr(), _stream()))
+        return (logits, probs, le) if return_emb else (logits, probs)
 
     def score_clips_u8(self, frames_u8, clip_start, text_ids, attention_mask, out=None):
         """Device-resident uint8 HWC frames [n,224,224,3] + int32 clip starts [B] -> (logits, probs)."""
