@@ -238,19 +238,75 @@ __device__ __forceinline__ void ln_row_768(float (&x)[3][8], const float* __rest
   }
 }
 
+// Two rows per warp: both rows' loads are in flight together and the two dependent shuffle reductions of each row
+// interleave (the kernel is latency-bound: 3 KB per row, everything L2-resident right after the producing GEMM);
+// gamma / beta are fetched once for both rows.
 template <bool FP32>
 __global__ void layernorm768_kernel(const elem_t<FP32>* __restrict__ x, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, elem_t<FP32>* __restrict__ y, int rows,
                                     const int32_t* __restrict__ rows_dev, float eps) {
   pdl_enter();
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int row0 = 2 * (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
   if (rows_dev) rows = min(rows, *rows_dev);     // token-packed BERT: only the packed rows exist
-  if (row >= rows) return;
-  float v[3][8];
+  if (row0 >= rows) return;
+  const bool two = row0 + 1 < rows;
+  float v[2][3][8];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) load8<FP32>(x + row * 768L + c * 256 + lane * 8, v[c]);
-  ln_row_768<FP32>(v, gamma, beta, eps, y + row * 768L, lane);
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (r == 0 || two) load8<FP32>(x + (row0 + r) * 768L + c * 256 + lane * 8, v[r][c]);
+      else
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[r][c][e] = 0.f;
+    }
+  float s[2] = {0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[r] += v[r][c][e];
+  float mean[2], q[2] = {0.f, 0.f}, rstd[2];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+    s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mean[r] = s[r] * (1.0f / 768.0f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[r][c][e] - mean[r]; q[r] += d * d; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    q[0] += __shfl_xor_sync(0xffffffffu, q[0], o);
+    q[1] += __shfl_xor_sync(0xffffffffu, q[1], o);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) rstd[r] = 1.0f / sqrtf(q[r] * (1.0f / 768.0f) + eps);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int col = c * 256 + lane * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (r == 1 && !two) break;
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[r][c][e] - mean[r]) * rstd[r] * g[e] + b[e];
+      store8<FP32>(y + (row0 + r) * 768L + col, o);
+    }
+  }
 }
 
 // BertEmbeddings (modeling_bert.py:72-113): word[id] + position[pos] + token_type[0], LayerNorm(eps 1e-12)
@@ -539,7 +595,7 @@ void launch_layernorm(const void* x, const float* gamma, const float* beta, void
                       bool fp32, cudaStream_t s, const int32_t* rows_dev) {
   VCG_REQUIRE(cols == 768, "LayerNorm kernel is specialised for 768 columns");
   if (rows == 0) return;
-  VCG_DISPATCH(fp32, (launch_pdl(layernorm768_kernel<FP>, blocks_for(rows, 8), 256, 0, s, static_cast<const elem_t<FP>*>(x), gamma, beta, static_cast<elem_t<FP>*>(y), rows, rows_dev, eps)));
+  VCG_DISPATCH(fp32, (launch_pdl(layernorm768_kernel<FP>, blocks_for(rows, 16), 256, 0, s, static_cast<const elem_t<FP>*>(x), gamma, beta, static_cast<elem_t<FP>*>(y), rows, rows_dev, eps)));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_gather_ln_rows768(const void* x, const int32_t* row_of, int stride, int B, const float* gamma, const float* beta,
