@@ -181,6 +181,19 @@ VCG_API int vcg_op_bert_attention(const void* qkv, const int64_t* attention_mask
 VCG_API int vcg_op_bert_attention_packed(const void* qkv, const int32_t* cu, const uint8_t* key_ok, void* ctx, int32_t B,
                                  int32_t max_len, int64_t rows, void* stream);
 
+/* Post-processing on the device, bit-identical to the reference's Python (all buffers device memory).
+ * vcg_op_cut_points: video v owns clips [video_offsets[v], video_offsets[v+1]) of logits [N,2];
+ *   labels_out [N] (or NULL) = argmax as logits.topk(1) (test_video_segment_point.py:201-203);
+ *   cut_points [n_videos, cap], counts [n_videos] = convert_clip_label2cut_point(labels, clip_frames, max_offset)
+ *   (eval_utils/eval_utils.py:3-18: half-to-even rounding, trailing run dropped).  counts[v] > cap: buffer too small.
+ * vcg_op_pr_hits: per video the six hit counts of calculate_pr (eval_utils.py:21-92):
+ *   hits [n_videos, 6] = {gt->pred exact, <=3 s, <=5 s, pred->gt exact, <=3 s, <=5 s}. */
+VCG_API int vcg_op_cut_points(const float* logits, const int32_t* video_offsets, int32_t n_videos, int32_t clip_frames,
+                      int32_t max_offset, int32_t cap, int32_t* labels_out, int32_t* cut_points, int32_t* counts,
+                      void* stream);
+VCG_API int vcg_op_pr_hits(const int32_t* gt, const int32_t* gt_offsets, const int32_t* pred, const int32_t* pred_offsets,
+                   int32_t n_videos, int32_t* hits, void* stream);
+
 /* y = LayerNorm(x) * gamma + beta over rows of 768, eps 1e-12 (modeling_bert.py BertSelfOutput/BertOutput). */
 VCG_API int vcg_op_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t cols,
                      float eps, int32_t precision, void* stream);

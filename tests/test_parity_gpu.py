@@ -264,3 +264,31 @@ def test_unimodal_models_match_reference_golden(golden_dir, case, kind, precisio
     tol = 4e-2 if (precision == "bf16" and kind != "bert") else TOL[precision]
     assert errs["logits"] <= tol and errs["probs"] <= tol, errs
     assert logits.topk(1, 1, True, True)[1].view(-1).tolist() == g["labels"].tolist()
+
+
+def test_device_postprocessing_matches_reference_vectors(golden_dir):
+    """argmax -> run-length cut points (half-to-even rounding, trailing run dropped) and the precision/recall hit
+    counts on the device: bit-identical to the reference functions (golden vectors + random label strings)."""
+    from oracle import two_stream_oracle as orc
+    from vcg_b200 import postprocess as pp
+    g = np.load(f"{golden_dir}/cut_points.npz", allow_pickle=True)
+    rng = np.random.RandomState(7)
+    for T in (8, 16, 32):
+        lab_lists = [list(map(int, l)) for l, t in zip(g["labels"], g["T"]) if int(t) == T]
+        lab_lists += [rng.randint(0, 2, size=n).tolist() for n in (0, 1, 3, 146, 896, 2500)]
+        lab_lists += [(rng.rand(n) < 0.08).astype(int).tolist() for n in (146, 896)]
+        off = np.concatenate([[0], np.cumsum([len(l) for l in lab_lists])]).astype(np.int32)
+        flat = np.array([x for l in lab_lists for x in l], dtype=np.int64)
+        logits = torch.randn(len(flat), 2)
+        lo, hi = logits.min(1).values, logits.max(1).values
+        f = torch.from_numpy(flat)
+        logits = torch.stack([torch.where(f == 1, lo, hi), torch.where(f == 1, hi, lo)], 1)   # argmax == label
+        logits[f == 0, 1] = logits[f == 0, 0]                                                  # ties -> label 0
+        labels, cuts = pp.cut_points_device(logits.cuda(), torch.from_numpy(off), T, 2)
+        assert labels.cpu().tolist() == flat.tolist()
+        want = [orc.convert_clip_label2cut_point(l, T, 2) for l in lab_lists]
+        assert cuts == want
+        gt = [sorted(set(rng.randint(0, 4 * max(len(l), 1) + T, size=rng.randint(1, 12)).tolist())) for l in lab_lists]
+        got = pp.pr_hits_device(gt, want)
+        for v in range(len(lab_lists)):
+            assert got[v] == orc.calculate_pr(gt[v], want[v]), v

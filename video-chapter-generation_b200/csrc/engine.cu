@@ -1281,6 +1281,23 @@ int vcg_op_bert_attention_packed(const void* qkv, const int32_t* cu, const uint8
     launch_bert_attention(qkv, nullptr, cu, key_ok, ctx, B, max_len, false, static_cast<cudaStream_t>(stream), rows);
   });
 }
+int vcg_op_cut_points(const float* logits, const int32_t* video_offsets, int32_t n_videos, int32_t clip_frames,
+                      int32_t max_offset, int32_t cap, int32_t* labels_out, int32_t* cut_points, int32_t* counts,
+                      void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(logits && video_offsets && cut_points && counts && cap >= 1 && clip_frames >= 1 && max_offset >= 1,
+                "bad argument");
+    launch_cut_points(logits, video_offsets, n_videos, clip_frames, max_offset, cap, labels_out, cut_points, counts,
+                      static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_pr_hits(const int32_t* gt, const int32_t* gt_offsets, const int32_t* pred, const int32_t* pred_offsets,
+                   int32_t n_videos, int32_t* hits, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(gt && gt_offsets && pred && pred_offsets && hits, "null argument");
+    launch_pr_hits(gt, gt_offsets, pred, pred_offsets, n_videos, hits, static_cast<cudaStream_t>(stream));
+  });
+}
 int vcg_op_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t cols,
                      float eps, int32_t precision, void* stream) {
   return guarded([&] { launch_layernorm(x, gamma, beta, y, rows, cols, eps, precision == VCG_PREC_FP32, static_cast<cudaStream_t>(stream)); });

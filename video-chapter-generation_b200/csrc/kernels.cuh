@@ -73,6 +73,12 @@ void launch_head_final(const TailParams& p, int B, bool fp32, cudaStream_t s);  
 void launch_linear_head2(const float* x, const float* w, const float* b, int B, int D, float* logits, float* probs,
                          cudaStream_t s);
 
+// post-processing (postprocess.cu): labels / run-length cut points per video, precision-recall hit counts
+void launch_cut_points(const float* logits, const int32_t* offsets, int n_videos, int clip_frames, int max_offset, int cap,
+                       int32_t* labels_out, int32_t* cuts, int32_t* counts, cudaStream_t s);
+void launch_pr_hits(const int32_t* gt, const int32_t* gt_off, const int32_t* pred, const int32_t* pred_off, int n_videos,
+                    int32_t* hits, cudaStream_t s);
+
 // weight packing (fp32 state-dict tensors -> kernel layouts)
 void launch_pack_conv(const float* w /*[Cout,Cin,k,k]*/, const float* bn_w, const float* bn_b, const float* bn_mean,
                       const float* bn_var, float eps, int Cout, int Cin, int k, void* w_out /*[Cout][k][k][Cin]*/,

@@ -68,6 +68,8 @@ PROTOTYPES = {
     "vcg_op_maxpool_tsm": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
     "vcg_op_bert_attention": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "vcg_op_bert_attention_packed": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, ctypes.c_int64, _vp]),
+    "vcg_op_cut_points": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "vcg_op_pr_hits": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "vcg_op_layernorm": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _vp]),
 }
 
