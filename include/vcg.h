@@ -35,7 +35,8 @@ enum { VCG_DTYPE_F32 = 0, VCG_DTYPE_I64 = 1 };
 /* which reference model the engine is: TwoStream (two_stream.py), or one of the single-modality scorers of
  * --data_mode image / text: Resnet50TSM / Resnet50 (resnet50_tsm.py:68-77, resnet50.py:64-73), BertHugface
  * (bert_hugface.py:98-132, pretrain_stage=False).  The single-modality state dicts use base_model.* / head.* keys. */
-enum { VCG_MODALITY_TWO_STREAM = 0, VCG_MODALITY_VISION = 1, VCG_MODALITY_TEXT = 2 };
+enum { VCG_MODALITY_TWO_STREAM = 0, VCG_MODALITY_VISION = 1, VCG_MODALITY_TEXT = 2,
+       VCG_MODALITY_EMBED = 3 /* both backbones, no head: vcg_embed (window model, two_stream_window.py:404-428) */ };
 enum { VCG_ACT_NONE = 0, VCG_ACT_RELU = 1, VCG_ACT_GELU = 2, VCG_ACT_TANH = 3 };
 
 typedef struct vcg_config {
@@ -86,6 +87,12 @@ VCG_API int vcg_forward_vision(vcg_engine* e, const float* img_clip, int32_t B, 
                        float* vision_emb_out, void* stream);
 VCG_API int vcg_forward_text(vcg_engine* e, const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L,
                      float* logits, float* probs, float* lang_emb_out, void* stream);
+
+/* Backbone embeddings only (engine created with VCG_MODALITY_EMBED; state-dict keys lang_model.* / vision_model.*):
+ * what the window model computes per clip before its own heads (two_stream_window.py:404-428).
+ *   vision_emb_out [B,T,2048], lang_emb_out [B,768] (BertPooler output), both fp32. */
+VCG_API int vcg_embed(vcg_engine* e, const float* img_clip, const int64_t* text_ids, const int64_t* attention_mask, int32_t B,
+              int32_t L, float* vision_emb_out, float* lang_emb_out, void* stream);
 
 /* Sliding-window scoring of one video straight from decoded frames (replaces ToTensor+Normalize at
  * test_video_segment_point.py:142-145, the clip gather of infer_youtube_video_dataset.py:117 and the forward).
@@ -193,6 +200,53 @@ VCG_API int vcg_op_cut_points(const float* logits, const int32_t* video_offsets,
                       void* stream);
 VCG_API int vcg_op_pr_hits(const int32_t* gt, const int32_t* gt_offsets, const int32_t* pred, const int32_t* pred_offsets,
                    int32_t n_videos, int32_t* hits, void* stream);
+
+/* ---- window ("update") model, post-backbone part (two_stream_window.py, stacked_window_self_attention.py) --------
+ * All tensors fp32 device memory; weights are the reference's nn.Linear / nn.LayerNorm parameters as they are
+ * (Linear weight [out, in] row-major).  The host mirror (model/fusion/two_stream_window.py) strings these together. */
+enum { VCG_MLP_LINEAR = 0, VCG_MLP_LAYERNORM = 1, VCG_MLP_RELU = 2, VCG_MLP_GELU = 3 };
+typedef struct vcg_mlp_op {
+  int32_t type;          /* VCG_MLP_*                                                    */
+  int32_t in_dim;        /* LINEAR: input features                                       */
+  int32_t out_dim;       /* LINEAR: output features                                      */
+  float eps;             /* LAYERNORM: epsilon (nn.LayerNorm default 1e-5)               */
+  const void* w;         /* LINEAR: weight [out, in]; LAYERNORM: weight [dim]            */
+  const void* b;         /* LINEAR: bias [out] or NULL; LAYERNORM: bias [dim]            */
+} vcg_mlp_op;
+/* One row per CTA through an nn.Sequential of Linear / LayerNorm / ReLU / GELU (Dropout is the identity in eval):
+ * the per-position lang / vision projection heads and the "mlp" fusion head of ChapterHead
+ * (two_stream_window.py:146-185, 252-268).  The input row is the concatenation of x0[r] (dim0) and x1[r] (dim1). */
+VCG_API int vcg_op_mlp_chain(const float* x0, int32_t dim0, int64_t stride0, const float* x1, int32_t dim1, int64_t stride1,
+                     int32_t rows, const vcg_mlp_op* ops, int32_t n_ops, float* out, int64_t out_stride, void* stream);
+
+typedef struct vcg_cross_attn_params {   /* CrossAttention (two_stream_window.py:11-88), hidden size 128 */
+  int32_t num_heads;
+  const float *lang_norm_w, *lang_norm_b, *vision_norm_w, *vision_norm_b;
+  const float *pos_w, *pos_b;            /* frame_pos_encoding = Linear(1, 128): weight [128,1], bias [128] */
+  const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b;
+} vcg_cross_attn_params;
+/* lang [B,128], vision [B,T,128] -> out [B,128] */
+VCG_API int vcg_op_cross_attention(const vcg_cross_attn_params* p, const float* lang, const float* vision, int32_t B,
+                           int32_t T, float* out, void* stream);
+
+typedef struct vcg_window_layer {        /* VideoChapterBlock (stacked_window_self_attention.py:99-148) */
+  const float *attn_norm_w, *attn_norm_b, *ffn_norm_w, *ffn_norm_b;
+  const float *pos_w, *pos_b;            /* position_encoding = Linear(1, 128) */
+  const float *pos_bias;                 /* window_pos_bias [1, 16, 1, 2w+1] */
+  const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b;
+  const float *f0_w, *f0_b, *f1_w, *f1_b, *f2_w, *f2_b, *f3_w, *f3_b;   /* ffn: 128->256->512->256->128 */
+} vcg_window_layer;
+typedef struct vcg_window_stack_params { /* StackedVideoChapterAttention (:151-223) */
+  int32_t num_layers;                    /* 6 in the reference */
+  int32_t pos_bias_stride;               /* 2w+1 */
+  vcg_window_layer layers[8];
+  const float *final_norm_w, *final_norm_b;
+  const float *cls_w[5], *cls_b[5];      /* classifier Linears: 128->128->128->64->32->2 */
+  const float *cls_norm_w[4], *cls_norm_b[4];
+} vcg_window_stack_params;
+/* x [B, W, 128] (W = 2w+1 fused clip embeddings) -> logits, probs [B,2] of the middle clip */
+VCG_API int vcg_op_window_stack(const vcg_window_stack_params* p, const float* x, int32_t B, int32_t W, float* logits,
+                        float* probs, void* stream);
 
 /* y = LayerNorm(x) * gamma + beta over rows of 768, eps 1e-12 (modeling_bert.py BertSelfOutput/BertOutput). */
 VCG_API int vcg_op_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t cols,

@@ -150,6 +150,61 @@ def make_unimodal_state_dict(kind, clip_frames=16, seed=123):
     return sd
 
 
+def make_window_state_dict(clip_frames=8, window_size=1, head_type="cross_attn", hidden_size=128, seed=123):
+    """State dict of the reference's window model (model/fusion/two_stream_window.py TwoStream + build_chapter_head):
+    backbones as in make_state_dict (same seed) plus window_mlp.*, fusion_head.* (per-position heads) and window_attn.*.
+    Linear weights ~ U(+-1.5/sqrt(in)), biases ~ U(+-0.1), LayerNorm weight ~ U(0.5, 1.5), bias ~ U(+-0.1)."""
+    full = make_state_dict(clip_frames, "mlp", hidden_size, seed=seed)
+    sd = {k: v for k, v in full.items() if not k.startswith("fusion_head.")}
+    g = _gen(seed + 501)
+    h, W = hidden_size, 2 * window_size + 1
+
+    def u(shape, a):
+        return (torch.rand(shape, generator=g) * 2 - 1) * a
+
+    def linear(prefix, d_in, d_out):
+        sd[prefix + ".weight"] = u((d_out, d_in), 1.5 / d_in ** 0.5)
+        sd[prefix + ".bias"] = u((d_out,), 0.1)
+
+    def norm(prefix, d):
+        sd[prefix + ".weight"] = torch.rand(d, generator=g) + 0.5
+        sd[prefix + ".bias"] = u((d,), 0.1)
+
+    def seq(prefix, dims, norm_last=False):
+        """nn.Sequential(Linear, LayerNorm, act, Dropout, ...): module index 4*j for Linear j, 4*j+1 for its LayerNorm"""
+        for j in range(len(dims) - 1):
+            linear(f"{prefix}.{4 * j}", dims[j], dims[j + 1])
+            if j < len(dims) - 2 or norm_last:
+                norm(f"{prefix}.{4 * j + 1}", dims[j + 1])
+
+    seq("window_mlp", [h * W, h, h // 2, h // 4, h // 8, h // 16, 2])
+    for i in range(W):
+        seq(f"fusion_head.lang_proj_heads.{i}", [768, 384, h])
+        seq(f"fusion_head.vision_proj_heads.{i}", [2048, 8 * h, 4 * h, h])
+        if head_type == "mlp":
+            seq(f"fusion_head.head.{i}", [(clip_frames + 1) * h, 8 * h, 4 * h, h])
+    if head_type == "cross_attn":
+        for n in ("query_proj", "key_proj", "value_proj", "out_proj"):
+            linear(f"fusion_head.head.{n}", h, h)
+        norm("fusion_head.head.lang_norm", h)
+        norm("fusion_head.head.vision_norm", h)
+        linear("fusion_head.head.frame_pos_encoding", 1, h)
+        linear("fusion_head.output_proj", h, 2)
+    for l in range(6):
+        p = f"window_attn.layers.{l}"
+        norm(p + ".attention_norm", h)
+        norm(p + ".ffn_norm", h)
+        for n in ("query", "key", "value", "out_proj"):
+            linear(f"{p}.attention.{n}", h, h)
+        linear(p + ".attention.position_encoding", 1, h)
+        sd[p + ".attention.window_pos_bias"] = u((1, 16, 1, W), 0.5)
+        for j, (a, b) in enumerate(((h, 2 * h), (2 * h, 4 * h), (4 * h, 2 * h), (2 * h, h))):
+            linear(f"{p}.ffn.{3 * j}", a, b)      # Sequential(Linear, GELU, Dropout, ...): Linear j at index 3*j
+    norm("window_attn.final_layer_norm", h)
+    seq("window_attn.classifier", [h, h, h, h // 2, h // 4, 2])
+    return sd
+
+
 def make_text(batch, max_len, seed=123):
     """Synthetic token ids / attention mask: [CLS]=101 first, len ~ U{10..L}, pad id 0."""
     g = _gen(seed + 1)

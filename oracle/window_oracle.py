@@ -1,0 +1,94 @@
+"""TEST INFRASTRUCTURE — CPU restatement (plain PyTorch fp32, functional) of the reference's window model:
+model/fusion/two_stream_window.py (ChapterHead :134-290, CrossAttention :11-88, TwoStream.forward :392-445) and
+model/fusion/stacked_window_self_attention.py (:6-224).  Pinned against the unmodified reference by
+oracle/make_golden_window.py.  Only tests may import this."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from oracle import two_stream_oracle as orc
+
+
+def _lin(sd, p, x):
+    return F.linear(x, sd[p + ".weight"], sd[p + ".bias"])
+
+
+def _ln(sd, p, x):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
+
+
+def _mlp(sd, prefix, x, n_linear, act=F.relu, step=4):
+    """nn.Sequential(Linear, LayerNorm, act, Dropout) x (n-1) + Linear (two_stream_window.py:146-185)."""
+    for j in range(n_linear):
+        x = _lin(sd, f"{prefix}.{step * j}", x)
+        if j < n_linear - 1:
+            x = act(_ln(sd, f"{prefix}.{step * j + 1}", x))
+    return x
+
+
+def cross_attention(sd, p, lang, vision, num_heads=16):
+    """CrossAttention.forward, two_stream_window.py:53-88: lang [B,H] queries vision [B,T,H]."""
+    B, T, H = vision.shape
+    hd = H // num_heads
+    lang = _ln(sd, p + ".lang_norm", lang)
+    vision = _ln(sd, p + ".vision_norm", vision)
+    pos = (torch.arange(T).float() / (T - 1)).unsqueeze(-1)
+    vision = vision + _lin(sd, p + ".frame_pos_encoding", pos)
+    q = _lin(sd, p + ".query_proj", lang).view(B, 1, num_heads, hd).transpose(1, 2)
+    k = _lin(sd, p + ".key_proj", vision).view(B, T, num_heads, hd).transpose(1, 2)
+    v = _lin(sd, p + ".value_proj", vision).view(B, T, num_heads, hd).transpose(1, 2)
+    att = F.softmax(q @ k.transpose(-2, -1) / math.sqrt(hd), dim=-1)
+    ctx = (att @ v).transpose(1, 2).contiguous().view(B, 1, H)
+    return _lin(sd, p + ".out_proj", ctx).squeeze(1)
+
+
+def chapter_head(sd, lang_emb, vision_emb, i, T, head_type, H=128):
+    """ChapterHead.forward for window position i, two_stream_window.py:252-290 -> fusion_emb [B,H]."""
+    B = lang_emb.shape[0]
+    lang_out = F.relu(_mlp(sd, f"fusion_head.lang_proj_heads.{i}", lang_emb, 2))
+    vis_out = F.relu(_mlp(sd, f"fusion_head.vision_proj_heads.{i}", vision_emb.reshape(-1, vision_emb.shape[-1]), 3))
+    vis_out = vis_out.view(B, T, H)
+    if head_type == "mlp":
+        x = torch.cat([vis_out, lang_out.unsqueeze(1)], dim=1).view(B, -1)
+        return _mlp(sd, f"fusion_head.head.{i}", x, 3)
+    if head_type == "cross_attn":
+        return cross_attention(sd, "fusion_head.head", lang_out, vis_out)
+    raise RuntimeError(f"Unknown head_type {head_type}")
+
+
+def window_stack(sd, x, num_layers=6, num_heads=16):
+    """StackedVideoChapterAttention.forward (stacked_window_self_attention.py:203-223): x [B,W,H] -> logits, probs."""
+    B, W, H = x.shape
+    hd, mid = H // num_heads, W // 2
+    for l in range(num_layers):
+        p = f"window_attn.layers.{l}"
+        n = _ln(sd, p + ".attention_norm", x)
+        pos = ((torch.arange(W) - mid).float() / (mid + 1e-6)).unsqueeze(-1)
+        n = n + _lin(sd, p + ".attention.position_encoding", pos)
+        q, k, v = (_lin(sd, f"{p}.attention.{nm}", n).view(B, W, num_heads, hd).permute(0, 2, 1, 3)
+                   for nm in ("query", "key", "value"))
+        s = q @ k.transpose(-1, -2) / math.sqrt(hd) + sd[p + ".attention.window_pos_bias"][:, :, :, :W]
+        ctx = (F.softmax(s, dim=-1) @ v).permute(0, 2, 1, 3).contiguous().view(B, W, H)
+        x = x + _lin(sd, p + ".attention.out_proj", ctx)
+        n = _ln(sd, p + ".ffn_norm", x)
+        for j in range(4):
+            n = _lin(sd, f"{p}.ffn.{3 * j}", n)
+            if j < 3:
+                n = F.gelu(n)
+        x = x + n
+    x = _ln(sd, "window_attn.final_layer_norm", x)[:, mid]
+    logits = _mlp(sd, "window_attn.classifier", x, 5, act=F.gelu)
+    return logits, F.softmax(logits, dim=-1)
+
+
+def window_forward(sd, img_clips, text_ids, attention_masks, T, head_type="cross_attn", shift_div=8):
+    """two_stream_window.TwoStream.forward, :392-445."""
+    B, W, L = text_ids.shape
+    fused = []
+    for i in range(W):
+        lang_emb = orc.bert_forward(sd, text_ids[:, i], attention_masks[:, i])
+        x = img_clips[:, i].reshape(B * T, *img_clips.shape[3:]).contiguous()
+        vis = orc.resnet50_tsm_forward(sd, x, T, shift_div).view(B, T, -1)
+        fused.append(chapter_head(sd, lang_emb, vis, i, T, head_type))
+    return window_stack(sd, torch.stack(fused, dim=1))

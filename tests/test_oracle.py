@@ -112,3 +112,22 @@ def test_vision_emb_io_roundtrip(tmp_path):
     assert np.load(paths[1]).shape == (16, 2048) and np.load(paths[1]).dtype == np.float32
     back = vio.load_vision_embs(str(tmp_path), "abc", [0, 4, 8], 16)
     assert back.shape == (3, 16, 2048, 1, 1) and torch.equal(back.view(3, 16, 2048), emb)
+
+
+@pytest.mark.parametrize("case,head", [("cross_attn_T8_w1_L24_B2", "cross_attn"), ("mlp_T8_w1_L24_B2", "mlp")])
+def test_window_oracle_matches_reference_golden(golden_dir, case, head):
+    """Window ("update") model: restatement vs the reference's own outputs (oracle/make_golden_window.py)."""
+    import numpy as np
+    import torch
+    from oracle import weights as W
+    from oracle import window_oracle as worc
+    from oracle.make_golden_window import make_inputs
+    g = np.load(f"{golden_dir}/window_{case}.npz")
+    T, window, L, B, seed = [int(x) for x in g["meta"]]
+    sd = W.make_window_state_dict(T, window, head, seed=123)
+    img, ids, mask = make_inputs(T, window, L, B, seed)
+    assert np.array_equal(ids.numpy(), g["text_ids"])
+    with torch.no_grad():
+        logits, probs = worc.window_forward(sd, img, ids, mask, T, head)
+    assert np.abs(logits.numpy() - g["logits"]).max() <= 1e-5 * np.abs(g["logits"]).max()
+    assert np.abs(probs.numpy() - g["probs"]).max() <= 1e-5

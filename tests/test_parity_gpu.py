@@ -292,3 +292,34 @@ def test_device_postprocessing_matches_reference_vectors(golden_dir):
         got = pp.pr_hits_device(gt, want)
         for v in range(len(lab_lists)):
             assert got[v] == orc.calculate_pr(gt[v], want[v]), v
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case,head", [("cross_attn_T8_w1_L24_B2", "cross_attn"), ("mlp_T8_w1_L24_B2", "mlp")])
+def test_window_model_matches_reference_golden(golden_dir, case, head, precision):
+    """two_stream_window.TwoStream (test_video_segment_update.py:99-107) through the mirrored module API against the
+    reference's own outputs: backbones of all window clips in one engine pass, per-position heads, six window-attention
+    blocks, classifier."""
+    from model.fusion import two_stream_window
+    from model.lang import bert_hugface
+    from model.vision import resnet50_tsm
+    from oracle import weights as W
+    from oracle.make_golden_window import make_inputs
+    g = np.load(f"{golden_dir}/window_{case}.npz")
+    T, window, L, B, seed = [int(x) for x in g["meta"]]
+    sd = W.make_window_state_dict(T, window, head, seed=123)
+    lang = bert_hugface.BertHugface(pretrain_stage=False)
+    vis = resnet50_tsm.Resnet50TSM(segments_size=T, shift_div=8, pretrain_stage=False)
+    model = two_stream_window.TwoStream(lang.base_model, vis.base_model, lang.embed_size, vis.feature_dim, T, 128, window)
+    model.build_chapter_head(output_size=2, head_type=head)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(0).eval()
+    model.precision = precision
+    img, ids, mask = make_inputs(T, window, L, B, seed)
+    logits, probs = model(img.cuda(), ids.cuda(), mask.cuda(), clip_info=None)
+    torch.cuda.synchronize()
+    errs = {"logits": rel(logits, torch.from_numpy(g["logits"])), "probs": rel(probs, torch.from_numpy(g["probs"]))}
+    print(case, precision, errs, logits.tolist())
+    assert errs["logits"] <= TOL[precision] and errs["probs"] <= TOL[precision], errs
+    if precision == "fp32":
+        assert logits.topk(1, 1, True, True)[1].view(-1).tolist() == g["labels"].tolist()

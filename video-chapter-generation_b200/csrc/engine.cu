@@ -430,6 +430,15 @@ void finalize_text(vcg_engine* e, cudaStream_t s) {
 void finalize_head(vcg_engine* e, cudaStream_t s) {
   const std::string fh = "fusion_head.";
   const int H = e->H, T = e->T;
+  if (e->cfg.modality == VCG_MODALITY_EMBED) {        // backbones only
+    const size_t max_frames = static_cast<size_t>(e->Bv) * T;
+    if (e->cfg.vision == VCG_VISION_R50TSM) {
+      e->vis_emb.alloc(max_frames * kVisionDim * sizeof(float));
+      if (!e->fp32) e->vis_emb_act.alloc(max_frames * kVisionDim * e->es());
+    }
+    e->pooled.alloc((static_cast<size_t>(e->Bt) + 128) * kBertHidden * e->es());
+    return;
+  }
   if (e->cfg.modality != VCG_MODALITY_TWO_STREAM) {   // nn.Linear(D, 2) on the backbone embedding
     const int64_t D = e->cfg.modality == VCG_MODALITY_VISION ? static_cast<int64_t>(T) * kVisionDim : kBertHidden;
     copy_f32(e->head_w, need(e, "head.weight", {2, D}), s);
@@ -953,7 +962,7 @@ int vcg_create(const vcg_config* cfg, vcg_engine** out) {
     if (cfg->head_type != VCG_HEAD_MLP && cfg->head_type != VCG_HEAD_ATTN)
       throw Error("Unknown head_type " + std::to_string(cfg->head_type));   // two_stream.py:68
     VCG_REQUIRE(cfg->precision == VCG_PREC_BF16 || cfg->precision == VCG_PREC_FP32, "unknown precision");
-    VCG_REQUIRE(cfg->modality >= VCG_MODALITY_TWO_STREAM && cfg->modality <= VCG_MODALITY_TEXT, "unknown modality");
+    VCG_REQUIRE(cfg->modality >= VCG_MODALITY_TWO_STREAM && cfg->modality <= VCG_MODALITY_EMBED, "unknown modality");
     if (cfg->modality == VCG_MODALITY_VISION) VCG_REQUIRE(cfg->vision == VCG_VISION_R50TSM, "the image-only model needs a vision backbone");
     VCG_REQUIRE(cfg->max_batch >= 1, "max_batch must be positive");
     VCG_REQUIRE(cfg->shift_div == 8 || cfg->shift_div == 4 || cfg->shift_div == 0, "shift_div must be 8, 4 or 0 (no shift)");
@@ -1036,6 +1045,22 @@ int vcg_forward_text(vcg_engine* e, const int64_t* text_ids, const int64_t* atte
   return guarded([&] {
     VCG_REQUIRE(e && text_ids && attention_mask && logits && probs, "null argument");
     score_text_only(e, text_ids, attention_mask, B, L, logits, probs, lang_emb_out, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int vcg_embed(vcg_engine* e, const float* img_clip, const int64_t* text_ids, const int64_t* attention_mask, int32_t B,
+              int32_t L, float* vision_emb_out, float* lang_emb_out, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e && img_clip && text_ids && attention_mask && vision_emb_out && lang_emb_out, "null argument");
+    VCG_REQUIRE(e->finalized, "vcg_finalize has not been called");
+    VCG_REQUIRE(e->cfg.modality == VCG_MODALITY_EMBED && e->cfg.vision == VCG_VISION_R50TSM, "engine was not created for embeddings");
+    VCG_REQUIRE(B >= 0 && L >= 1 && L <= e->Lmax, "token count exceeds max_tokens of the engine");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (int b0 = 0; b0 < B; b0 += e->Bt)
+      run_text(e, text_ids, attention_mask, b0, std::min(e->Bt, B - b0), L, lang_emb_out + static_cast<long>(b0) * kBertHidden, s);
+    FrameSource src;
+    src.img_clip = img_clip;
+    for (int g0 = 0; g0 < B; g0 += e->Bv) run_vision(e, src, g0, std::min(e->Bv, B - g0), vision_emb_out, s);
   });
 }
 
@@ -1296,6 +1321,27 @@ int vcg_op_pr_hits(const int32_t* gt, const int32_t* gt_offsets, const int32_t* 
   return guarded([&] {
     VCG_REQUIRE(gt && gt_offsets && pred && pred_offsets && hits, "null argument");
     launch_pr_hits(gt, gt_offsets, pred, pred_offsets, n_videos, hits, static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_mlp_chain(const float* x0, int32_t dim0, int64_t stride0, const float* x1, int32_t dim1, int64_t stride1,
+                     int32_t rows, const vcg_mlp_op* ops, int32_t n_ops, float* out, int64_t out_stride, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(x0 && ops && out && (dim1 == 0 || x1), "null argument");
+    launch_mlp_chain(x0, dim0, stride0, x1, dim1, stride1, rows, ops, n_ops, out, out_stride, static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_cross_attention(const vcg_cross_attn_params* p, const float* lang, const float* vision, int32_t B, int32_t T,
+                           float* out, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(p && lang && vision && out, "null argument");
+    launch_cross_attention(*p, lang, vision, B, T, out, static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_window_stack(const vcg_window_stack_params* p, const float* x, int32_t B, int32_t W, float* logits, float* probs,
+                        void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(p && x && logits && probs, "null argument");
+    launch_window_stack(*p, x, B, W, logits, probs, static_cast<cudaStream_t>(stream));
   });
 }
 int vcg_op_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t cols,

@@ -1,6 +1,7 @@
 // Launchers of the memory-bound / small kernels around the tcgen05 GEMMs (definitions in kernels.cu, attention.cu,
 // tail.cu, pack.cu).  `fp32` selects the element type of activations: false = bf16, true = fp32.
 #pragma once
+#include "../../include/vcg.h"
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -78,6 +79,14 @@ void launch_cut_points(const float* logits, const int32_t* offsets, int n_videos
                        int32_t* labels_out, int32_t* cuts, int32_t* counts, cudaStream_t s);
 void launch_pr_hits(const int32_t* gt, const int32_t* gt_off, const int32_t* pred, const int32_t* pred_off, int n_videos,
                     int32_t* hits, cudaStream_t s);
+
+// window model, post-backbone part (window.cu); parameter structs are those of include/vcg.h
+void launch_mlp_chain(const float* x0, int dim0, long stride0, const float* x1, int dim1, long stride1, int rows,
+                      const vcg_mlp_op* ops, int n_ops, float* out, long out_stride, cudaStream_t s);
+void launch_cross_attention(const vcg_cross_attn_params& p, const float* lang, const float* vision, int B, int T, float* out,
+                            cudaStream_t s);
+void launch_window_stack(const vcg_window_stack_params& p, const float* x, int B, int W, float* logits, float* probs,
+                         cudaStream_t s);
 
 // weight packing (fp32 state-dict tensors -> kernel layouts)
 void launch_pack_conv(const float* w /*[Cout,Cin,k,k]*/, const float* bn_w, const float* bn_b, const float* bn_mean,

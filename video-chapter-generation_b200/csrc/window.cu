@@ -1,0 +1,300 @@
+// Post-backbone part of the reference's WINDOW ("update") model, model/fusion/two_stream_window.py +
+// model/fusion/stacked_window_self_attention.py.  Everything here is a few MFLOP per clip on
+// [rows, <= 2176] fp32 vectors (the backbones are > 99.9 % of the work and run in the tcgen05 kernels), so the kernels are
+// plain fp32 SIMT, one CTA per row / batch item, weights read through L2:
+//   mlp_chain_kernel        a short program of Linear / LayerNorm / ReLU / GELU steps over one row (the per-position
+//                           projection heads, the "mlp" fusion head): ChapterHead.forward, two_stream_window.py:252-290
+//   cross_attention_kernel  CrossAttention.forward, two_stream_window.py:53-88 (head_type "cross_attn", the default of
+//                           test_video_segment_update.py:43)
+//   window_stack_kernel     StackedVideoChapterAttention.forward, stacked_window_self_attention.py:203-223: six pre-LN
+//                           blocks over the 2w+1 clip tokens, final LayerNorm, middle token, classifier, softmax
+#include "../../include/vcg.h"
+#include "kernels.cuh"
+#include "launch.cuh"
+
+namespace vcg {
+
+namespace {
+
+constexpr int kMaxDim = 2304;   // widest row of any step ((T+1)*128 with T <= 17, 2048, 1024 ...)
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();                      // red may still be read from a previous call
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < static_cast<int>(blockDim.x >> 5); ++i) t += red[i];
+  return t;
+}
+
+// y[n] = sum_k x[k] W[n,k] + b[n]; x, y in shared memory, one warp per output neuron (coalesced weight rows)
+__device__ __forceinline__ void row_linear(const float* x, int K, const float* __restrict__ W, const float* __restrict__ b,
+                                           float* y, int N) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int n = warp; n < N; n += nw) {
+    const float* w = W + static_cast<long>(n) * K;
+    float acc = 0.f;
+    if ((K & 3) == 0) {
+      for (int k = lane * 4; k < K; k += 128) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
+        acc = fmaf(x[k], wv.x, acc); acc = fmaf(x[k + 1], wv.y, acc);
+        acc = fmaf(x[k + 2], wv.z, acc); acc = fmaf(x[k + 3], wv.w, acc);
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) acc = fmaf(x[k], __ldg(w + k), acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[n] = acc + (b ? b[n] : 0.f);
+  }
+  __syncthreads();
+}
+
+// nn.LayerNorm over a row in shared memory (two-pass statistics, in place)
+__device__ __forceinline__ void row_layernorm(float* x, int N, const float* __restrict__ g, const float* __restrict__ b,
+                                              float eps, float* red) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += x[i];
+  const float mean = block_sum(s, red) / N;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { const float d = x[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(block_sum(q, red) / N + eps);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) x[i] = (x[i] - mean) * rstd * g[i] + b[i];
+  __syncthreads();
+}
+
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+
+struct MlpProgram {
+  vcg_mlp_op ops[16];
+  int n_ops;
+};
+
+__global__ void __launch_bounds__(256) mlp_chain_kernel(const float* __restrict__ x0, int dim0, long stride0,
+                                                        const float* __restrict__ x1, int dim1, long stride1,
+                                                        const __grid_constant__ MlpProgram prog, float* __restrict__ out,
+                                                        long out_stride) {
+  pdl_enter();
+  __shared__ float buf[2][kMaxDim];
+  __shared__ float red[8];
+  const long r = blockIdx.x;
+  for (int i = threadIdx.x; i < dim0; i += blockDim.x) buf[0][i] = x0[r * stride0 + i];
+  for (int i = threadIdx.x; i < dim1; i += blockDim.x) buf[0][dim0 + i] = x1[r * stride1 + i];
+  __syncthreads();
+  int cur = 0, dim = dim0 + dim1;
+  for (int s = 0; s < prog.n_ops; ++s) {
+    const vcg_mlp_op op = prog.ops[s];
+    if (op.type == VCG_MLP_LINEAR) {
+      row_linear(buf[cur], op.in_dim, static_cast<const float*>(op.w), static_cast<const float*>(op.b), buf[cur ^ 1], op.out_dim);
+      cur ^= 1;
+      dim = op.out_dim;
+    } else if (op.type == VCG_MLP_LAYERNORM) {
+      row_layernorm(buf[cur], dim, static_cast<const float*>(op.w), static_cast<const float*>(op.b), op.eps, red);
+    } else {
+      for (int i = threadIdx.x; i < dim; i += blockDim.x)
+        buf[cur][i] = op.type == VCG_MLP_RELU ? fmaxf(buf[cur][i], 0.f) : gelu_erf(buf[cur][i]);
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) out[r * out_stride + i] = buf[cur][i];
+}
+
+// CrossAttention.forward (two_stream_window.py:53-88), hidden size H = 128, nh heads: the language vector queries the T
+// frame vectors of its clip.  One CTA per clip.
+__global__ void __launch_bounds__(128) cross_attention_kernel(const __grid_constant__ vcg_cross_attn_params p,
+                                                              const float* __restrict__ lang, const float* __restrict__ vision,
+                                                              int T, float* __restrict__ out) {
+  pdl_enter();
+  constexpr int H = 128, kMaxT = 40;
+  extern __shared__ float dyn[];                      // sv | sk | sval, T rows of H each
+  float (*sv)[H] = reinterpret_cast<float (*)[H]>(dyn);
+  float (*sk)[H] = sv + T;
+  float (*sval)[H] = sk + T;
+  __shared__ float sl[H], sq[H], sctx[H], sp[16][kMaxT], red[8];
+  const long b = blockIdx.x;
+  const int nh = p.num_heads, hd = H / nh;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) sl[i] = lang[b * H + i];
+  for (int i = threadIdx.x; i < T * H; i += blockDim.x) sv[i / H][i % H] = vision[b * T * H + i];
+  __syncthreads();
+  row_layernorm(sl, H, p.lang_norm_w, p.lang_norm_b, 1e-5f, red);
+  for (int t = 0; t < T; ++t) {
+    row_layernorm(sv[t], H, p.vision_norm_w, p.vision_norm_b, 1e-5f, red);
+    const float pos = static_cast<float>(t) / static_cast<float>(T - 1);   // get_relative_positions: t / (T - 1)
+    for (int i = threadIdx.x; i < H; i += blockDim.x) sv[t][i] += pos * p.pos_w[i] + p.pos_b[i];   // Linear(1, H)
+    __syncthreads();
+  }
+  row_linear(sl, H, p.q_w, p.q_b, sq, H);
+  for (int t = 0; t < T; ++t) {
+    row_linear(sv[t], H, p.k_w, p.k_b, sk[t], H);
+    row_linear(sv[t], H, p.v_w, p.v_b, sval[t], H);
+  }
+  const float scale = rsqrtf(static_cast<float>(hd));
+  for (int i = threadIdx.x; i < nh * T; i += blockDim.x) {
+    const int h = i / T, t = i % T;
+    float s = 0.f;
+    for (int d = 0; d < hd; ++d) s = fmaf(sq[h * hd + d], sk[t][h * hd + d], s);
+    sp[h][t] = s * scale;
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < nh) {
+    const int h = threadIdx.x;
+    float m = -INFINITY, sum = 0.f;
+    for (int t = 0; t < T; ++t) m = fmaxf(m, sp[h][t]);
+    for (int t = 0; t < T; ++t) { sp[h][t] = expf(sp[h][t] - m); sum += sp[h][t]; }
+    for (int t = 0; t < T; ++t) sp[h][t] /= sum;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const int h = i / hd;
+    float c = 0.f;
+    for (int t = 0; t < T; ++t) c = fmaf(sp[h][t], sval[t][i], c);
+    sctx[i] = c;
+  }
+  __syncthreads();
+  row_linear(sctx, H, p.o_w, p.o_b, sq, H);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) out[b * H + i] = sq[i];
+}
+
+// StackedVideoChapterAttention.forward: x [B, W, 128] -> logits, probs [B, 2].  One CTA per batch item.
+__global__ void __launch_bounds__(256) window_stack_kernel(const __grid_constant__ vcg_window_stack_params p,
+                                                           const float* __restrict__ x, int W, float* __restrict__ logits,
+                                                           float* __restrict__ probs) {
+  pdl_enter();
+  constexpr int H = 128, kMaxW = 9, NH = 16, HD = 8;
+  __shared__ float h[kMaxW][H], n[kMaxW][H], q[kMaxW][H], k[kMaxW][H], v[kMaxW][H], f1[4 * H], f2[4 * H];
+  __shared__ float sc[NH][kMaxW][kMaxW], red[8];
+  const long b = blockIdx.x;
+  for (int i = threadIdx.x; i < W * H; i += blockDim.x) h[i / H][i % H] = x[b * W * H + i];
+  __syncthreads();
+  const int mid = W / 2;
+  for (int l = 0; l < p.num_layers; ++l) {
+    const vcg_window_layer& L = p.layers[l];
+    // ---- attention: pre-LN, + Linear(1,H)((t - mid) / (mid + 1e-6)), 16 heads x 8, + window_pos_bias[head, key]
+    for (int t = 0; t < W; ++t) {
+      for (int i = threadIdx.x; i < H; i += blockDim.x) n[t][i] = h[t][i];
+      __syncthreads();
+      row_layernorm(n[t], H, L.attn_norm_w, L.attn_norm_b, 1e-5f, red);
+      const float pos = static_cast<float>(t - mid) / (static_cast<float>(mid) + 1e-6f);
+      for (int i = threadIdx.x; i < H; i += blockDim.x) n[t][i] += pos * L.pos_w[i] + L.pos_b[i];
+      __syncthreads();
+      row_linear(n[t], H, L.q_w, L.q_b, q[t], H);
+      row_linear(n[t], H, L.k_w, L.k_b, k[t], H);
+      row_linear(n[t], H, L.v_w, L.v_b, v[t], H);
+    }
+    for (int i = threadIdx.x; i < NH * W * W; i += blockDim.x) {
+      const int hh = i / (W * W), tq = (i / W) % W, tk = i % W;
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) s = fmaf(q[tq][hh * HD + d], k[tk][hh * HD + d], s);
+      sc[hh][tq][tk] = s * 0.35355339059327373f + L.pos_bias[hh * p.pos_bias_stride + tk];   // / sqrt(8)
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NH * W; i += blockDim.x) {
+      float* row = sc[i / W][i % W];
+      float m = -INFINITY, sum = 0.f;
+      for (int t = 0; t < W; ++t) m = fmaxf(m, row[t]);
+      for (int t = 0; t < W; ++t) { row[t] = expf(row[t] - m); sum += row[t]; }
+      for (int t = 0; t < W; ++t) row[t] /= sum;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < W * H; i += blockDim.x) {     // context, written over n
+      const int t = i / H, c = i % H, hh = c / HD;
+      float a = 0.f;
+      for (int tk = 0; tk < W; ++tk) a = fmaf(sc[hh][t][tk], v[tk][c], a);
+      n[t][c] = a;
+    }
+    __syncthreads();
+    for (int t = 0; t < W; ++t) {
+      row_linear(n[t], H, L.o_w, L.o_b, q[t], H);
+      for (int i = threadIdx.x; i < H; i += blockDim.x) h[t][i] += q[t][i];     // residual
+      __syncthreads();
+    }
+    // ---- FFN: pre-LN, 128 -> 256 -> 512 -> 256 -> 128 with GELU between, residual
+    for (int t = 0; t < W; ++t) {
+      for (int i = threadIdx.x; i < H; i += blockDim.x) n[t][i] = h[t][i];
+      __syncthreads();
+      row_layernorm(n[t], H, L.ffn_norm_w, L.ffn_norm_b, 1e-5f, red);
+      row_linear(n[t], H, L.f0_w, L.f0_b, f1, 2 * H);
+      for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) f1[i] = gelu_erf(f1[i]);
+      __syncthreads();
+      row_linear(f1, 2 * H, L.f1_w, L.f1_b, f2, 4 * H);
+      for (int i = threadIdx.x; i < 4 * H; i += blockDim.x) f2[i] = gelu_erf(f2[i]);
+      __syncthreads();
+      row_linear(f2, 4 * H, L.f2_w, L.f2_b, f1, 2 * H);
+      for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) f1[i] = gelu_erf(f1[i]);
+      __syncthreads();
+      row_linear(f1, 2 * H, L.f3_w, L.f3_b, f2, H);
+      for (int i = threadIdx.x; i < H; i += blockDim.x) h[t][i] += f2[i];
+      __syncthreads();
+    }
+  }
+  // ---- final LayerNorm, middle (target) clip, classifier: 4 x (Linear, LayerNorm, GELU), Linear(32, 2), softmax
+  float* t0 = h[mid];
+  row_layernorm(t0, H, p.final_norm_w, p.final_norm_b, 1e-5f, red);
+  const int dims[5] = {H, H, H, H / 2, H / 4};
+  float* a = t0;
+  float* o = f1;
+  for (int i = 0; i < 4; ++i) {
+    row_linear(a, dims[i], p.cls_w[i], p.cls_b[i], o, dims[i + 1]);
+    row_layernorm(o, dims[i + 1], p.cls_norm_w[i], p.cls_norm_b[i], 1e-5f, red);
+    for (int j = threadIdx.x; j < dims[i + 1]; j += blockDim.x) o[j] = gelu_erf(o[j]);
+    __syncthreads();
+    float* tmp = a; a = o; o = (tmp == t0) ? f2 : tmp;
+  }
+  row_linear(a, H / 4, p.cls_w[4], p.cls_b[4], o, 2);
+  if (threadIdx.x == 0) {
+    const float l0 = o[0], l1 = o[1], m = fmaxf(l0, l1), e0 = expf(l0 - m), e1 = expf(l1 - m);
+    logits[b * 2] = l0; logits[b * 2 + 1] = l1;
+    probs[b * 2] = e0 / (e0 + e1); probs[b * 2 + 1] = e1 / (e0 + e1);
+  }
+}
+
+}  // namespace
+
+void launch_mlp_chain(const float* x0, int dim0, long stride0, const float* x1, int dim1, long stride1, int rows,
+                      const vcg_mlp_op* ops, int n_ops, float* out, long out_stride, cudaStream_t s) {
+  if (rows == 0) return;
+  VCG_REQUIRE(n_ops >= 1 && n_ops <= 16, "mlp chain: 1..16 steps");
+  VCG_REQUIRE(dim0 + dim1 <= kMaxDim, "mlp chain: input row too wide");
+  MlpProgram prog{};
+  prog.n_ops = n_ops;
+  int dim = dim0 + dim1;
+  for (int i = 0; i < n_ops; ++i) {
+    prog.ops[i] = ops[i];
+    if (ops[i].type == VCG_MLP_LINEAR) {
+      VCG_REQUIRE(ops[i].in_dim == dim && ops[i].out_dim >= 1 && ops[i].out_dim <= kMaxDim && ops[i].w, "mlp chain: bad linear step");
+      dim = ops[i].out_dim;
+    } else if (ops[i].type == VCG_MLP_LAYERNORM) {
+      VCG_REQUIRE(ops[i].w && ops[i].b, "mlp chain: LayerNorm needs weight and bias");
+    } else {
+      VCG_REQUIRE(ops[i].type == VCG_MLP_RELU || ops[i].type == VCG_MLP_GELU, "mlp chain: unknown step");
+    }
+  }
+  launch_pdl(mlp_chain_kernel, rows, 256, 0, s, x0, dim0, stride0, x1, dim1, stride1, prog, out, out_stride);
+}
+
+void launch_cross_attention(const vcg_cross_attn_params& p, const float* lang, const float* vision, int B, int T, float* out,
+                            cudaStream_t s) {
+  if (B == 0) return;
+  VCG_REQUIRE(T >= 2 && T <= 40, "cross attention: 2..40 frames per clip");
+  VCG_REQUIRE(p.num_heads >= 1 && p.num_heads <= 16 && 128 % p.num_heads == 0, "cross attention: bad head count");
+  const size_t smem = static_cast<size_t>(3) * T * 128 * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    VCG_CUDA(cudaFuncSetAttribute(cross_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  launch_pdl(cross_attention_kernel, B, 128, smem, s, p, lang, vision, T, out);
+}
+
+void launch_window_stack(const vcg_window_stack_params& p, const float* x, int B, int W, float* logits, float* probs,
+                         cudaStream_t s) {
+  if (B == 0) return;
+  VCG_REQUIRE(W >= 1 && W <= 9 && (W & 1), "window stack: odd window of at most 9 clips");
+  VCG_REQUIRE(p.num_layers >= 0 && p.num_layers <= 8 && p.pos_bias_stride >= W, "window stack: bad parameters");
+  launch_pdl(window_stack_kernel, B, 256, 0, s, p, x, W, logits, probs);
+}
+
+}  // namespace vcg

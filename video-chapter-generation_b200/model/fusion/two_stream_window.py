@@ -1,0 +1,248 @@
+"""Mirror of the reference's model/fusion/two_stream_window.py — the WINDOW ("update") chapter-boundary model that
+test_video_segment_update.py:99-107 builds: every sample is a window of 2w+1 neighbouring clips; each clip goes through
+BERT + ResNet-50-TSM and a per-position fusion head (ChapterHead), the 2w+1 fused vectors through six window-attention
+blocks (StackedVideoChapterAttention) and the middle clip's vector through a classifier.
+
+Same classes, constructor arguments and state-dict keys as the reference (:11-445); the modules only hold parameters.
+``TwoStream.forward(img_clips, text_ids, attention_masks, clip_info)`` runs
+  * the backbones of all B*(2w+1) clips in ONE pass of the tcgen05 engine (vcg_embed; the reference loops over the window
+    positions, :404-434),
+  * the per-position heads and the window stack through the fp32 operators of include/vcg.h (vcg_op_mlp_chain,
+    vcg_op_cross_attention, vcg_op_window_stack).
+Supported head types: "cross_attn" (the caller's default, test_video_segment_update.py:43) and "mlp"; the reference's
+experimental "bilinear" / "multiplication" / "self_attn" variants are not built.  No CPU / eager fallback.
+"""
+import ctypes
+import math
+import os
+
+import torch
+from torch import nn
+
+from model.fusion.stacked_window_self_attention import StackedVideoChapterAttention, _no_forward
+from ops.temporal_shift import TemporalShift
+
+
+class CrossAttention(nn.Module):
+    def __init__(self, hidden_size, num_heads, dropout=0.1):
+        super().__init__()
+        if hidden_size % num_heads != 0:
+            raise ValueError(f"The hidden size {hidden_size} is not a multiple of the number of attention "
+                             f"heads {num_heads}.")
+        self.hidden_size, self.num_heads, self.head_dim = hidden_size, num_heads, hidden_size // num_heads
+        self.query_proj = nn.Linear(hidden_size, hidden_size)
+        self.key_proj = nn.Linear(hidden_size, hidden_size)
+        self.value_proj = nn.Linear(hidden_size, hidden_size)
+        self.out_proj = nn.Linear(hidden_size, hidden_size)
+        self.lang_norm = nn.LayerNorm(hidden_size)
+        self.vision_norm = nn.LayerNorm(hidden_size)
+        self.attention_dropout = nn.Dropout(dropout)
+        self.output_dropout = nn.Dropout(dropout)
+        self.frame_pos_encoding = nn.Linear(1, hidden_size)
+        scale = 1.0 / math.sqrt(self.head_dim)
+        for proj in (self.query_proj, self.key_proj, self.value_proj, self.out_proj):
+            nn.init.xavier_uniform_(proj.weight, gain=scale)
+            nn.init.zeros_(proj.bias)
+        nn.init.xavier_uniform_(self.frame_pos_encoding.weight)
+        nn.init.zeros_(self.frame_pos_encoding.bias)
+
+    forward = _no_forward
+
+
+def _mlp3(d_in, d1, d2, d_out):
+    return nn.Sequential(nn.Linear(d_in, d1), nn.LayerNorm(d1), nn.ReLU(), nn.Dropout(0.1),
+                         nn.Linear(d1, d2), nn.LayerNorm(d2), nn.ReLU(), nn.Dropout(0.1), nn.Linear(d2, d_out))
+
+
+class ChapterHead(nn.Module):
+    def __init__(self, lang_emb_size, vision_emb_size, segment_size, hidden_size, window_size, output_size,
+                 head_type="mlp"):
+        super().__init__()
+        self.lang_emb_size, self.vision_emb_size = lang_emb_size, vision_emb_size
+        self.segment_size, self.hidden_size = segment_size, hidden_size
+        self.head_type, self.window_size = head_type, window_size
+        self.num_clips = 2 * window_size + 1
+        self.lang_proj_heads = nn.ModuleList([
+            nn.Sequential(nn.Linear(lang_emb_size, lang_emb_size // 2), nn.LayerNorm(lang_emb_size // 2), nn.ReLU(),
+                          nn.Dropout(0.1), nn.Linear(lang_emb_size // 2, hidden_size)) for _ in range(self.num_clips)])
+        self.vision_proj_heads = nn.ModuleList([
+            _mlp3(vision_emb_size, 8 * hidden_size, 4 * hidden_size, hidden_size) for _ in range(self.num_clips)])
+        if head_type == "mlp":
+            self.head = nn.ModuleList([
+                _mlp3((segment_size + 1) * hidden_size, 8 * hidden_size, 4 * hidden_size, hidden_size)
+                for _ in range(self.num_clips)])
+        elif head_type == "cross_attn":
+            self.head = CrossAttention(hidden_size, num_heads=16)
+            self.output_proj = nn.Linear(hidden_size, output_size)
+        elif head_type in ("bilinear", "multiplication", "self_attn"):
+            raise NotImplementedError(f"window head_type {head_type!r} is an experimental variant of the reference "
+                                      "that this build does not cover (supported: cross_attn, mlp)")
+        else:
+            raise RuntimeError(f"Unknown head_type {head_type}")
+
+    forward = _no_forward
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class TwoStream(nn.Module):
+    def __init__(self, lang_model, vision_model, lang_embed_size, vision_embed_size, segment_size, hidden_size,
+                 window_size):
+        super().__init__()
+        self.lang_model, self.vision_model = lang_model, vision_model
+        self.segment_size, self.hidden_size, self.window_size = segment_size, hidden_size, window_size
+        self.lang_embed_size, self.vision_embed_size = lang_embed_size, vision_embed_size
+        if hidden_size != 128:
+            raise RuntimeError("the window kernels are built for hidden_size 128 (every reference caller)")
+        h = hidden_size
+        self.window_mlp = nn.Sequential(        # present in the reference's state dict, unused by its forward (:436-441)
+            nn.Linear(h * (2 * window_size + 1), h), nn.LayerNorm(h), nn.ReLU(), nn.Dropout(0.1),
+            nn.Linear(h, h // 2), nn.LayerNorm(h // 2), nn.ReLU(), nn.Dropout(0.1),
+            nn.Linear(h // 2, h // 4), nn.LayerNorm(h // 4), nn.ReLU(), nn.Dropout(0.1),
+            nn.Linear(h // 4, h // 8), nn.LayerNorm(h // 8), nn.ReLU(), nn.Dropout(0.1),
+            nn.Linear(h // 8, h // 16), nn.LayerNorm(h // 16), nn.ReLU(), nn.Dropout(0.1),
+            nn.Linear(h // 16, 2))
+        self.precision = os.environ.get("VCG_PRECISION", "bf16")
+        self.vision_chunk = int(os.environ.get("VCG_VISION_CHUNK", "32"))
+        self.max_tokens = 128
+        self._engine = None
+        self._engine_key = None
+
+    def build_chapter_head(self, output_size, head_type="mlp"):
+        self.fusion_head = ChapterHead(self.lang_embed_size, self.vision_embed_size, self.segment_size,
+                                       self.hidden_size, self.window_size, output_size, head_type)
+        cfg = type("Config", (), {"hidden_size": self.hidden_size, "num_attention_heads": 16,
+                                  "attention_probs_dropout_prob": 0.1, "window_size": self.window_size})
+        self.window_attn = StackedVideoChapterAttention(cfg)
+
+    def configure_optimizers(self, train_config):
+        raise NotImplementedError("training is out of scope (SURVEY.md section 2); this package is inference-only")
+
+    # ------------------------------------------------------------------ plumbing
+    def _weights_version(self):
+        v = 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            v += t._version + (t.data_ptr() % 1000003)
+        return v
+
+    def _get_engine(self, device, n_tokens):
+        from vcg_b200.engine import Engine
+        shift_div = 0
+        for m in self.vision_model.modules():
+            if isinstance(m, TemporalShift):
+                shift_div = m.fold_div
+                break
+        max_tokens = max(self.max_tokens, n_tokens)
+        key = (str(device), self.precision, self.vision_chunk, max_tokens, shift_div, self._weights_version())
+        if self._engine is None or key != self._engine_key:
+            if self._engine is not None:
+                self._engine.close()
+            self.max_tokens = max_tokens
+            eng = Engine(self.segment_size, "mlp", self.precision, True, max_tokens, self.vision_chunk,
+                         self.hidden_size, shift_div, device=device, modality="embed")
+            eng.load_state_dict(self.state_dict())
+            self._engine, self._engine_key = eng, key
+        return self._engine
+
+    @staticmethod
+    def _program(seq, final_relu):
+        """nn.Sequential of Linear / LayerNorm / ReLU / GELU / Dropout -> array of vcg_mlp_op."""
+        from vcg_b200 import binding as B
+        ops = []
+        for m in seq:
+            if isinstance(m, nn.Linear):
+                ops.append(B.VcgMlpOp(B.MLP_LINEAR, m.in_features, m.out_features, 0.0, m.weight.data_ptr(),
+                                      m.bias.data_ptr() if m.bias is not None else None))
+            elif isinstance(m, nn.LayerNorm):
+                ops.append(B.VcgMlpOp(B.MLP_LAYERNORM, 0, 0, m.eps, m.weight.data_ptr(), m.bias.data_ptr()))
+            elif isinstance(m, nn.ReLU):
+                ops.append(B.VcgMlpOp(B.MLP_RELU, 0, 0, 0.0, None, None))
+            elif isinstance(m, nn.GELU):
+                ops.append(B.VcgMlpOp(B.MLP_GELU, 0, 0, 0.0, None, None))
+            elif not isinstance(m, nn.Dropout):
+                raise RuntimeError(f"unsupported module in an MLP chain: {type(m).__name__}")
+        if final_relu:
+            ops.append(B.VcgMlpOp(B.MLP_RELU, 0, 0, 0.0, None, None))
+        return (B.VcgMlpOp * len(ops))(*ops), len(ops)
+
+    def _run_chain(self, seq, final_relu, x0, x1=None):
+        from vcg_b200 import binding as B
+        lib = B.load_library()
+        ops, n = self._program(seq, final_relu)
+        out_dim = [m for m in seq if isinstance(m, nn.Linear)][-1].out_features
+        rows = x0.shape[0]
+        out = torch.empty(rows, out_dim, dtype=torch.float32, device=x0.device)
+        s = torch.cuda.current_stream().cuda_stream
+        B.check(lib.vcg_op_mlp_chain(x0.data_ptr(), x0.shape[1], x0.stride(0), 0 if x1 is None else x1.data_ptr(),
+                                     0 if x1 is None else x1.shape[1], 0 if x1 is None else x1.stride(0), rows, ops, n,
+                                     out.data_ptr(), out.stride(0), s))
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, img_clips, text_ids, attention_masks, clip_info=None):
+        """img_clips [B,W,T,3,224,224], text_ids / attention_masks [B,W,L] -> (binary_logits, binary_prob) [B,2]
+        (reference :392-445; clip_info is accepted and, as in the reference, not used by the arithmetic)."""
+        from vcg_b200 import binding as B
+        if not text_ids.is_cuda:
+            raise RuntimeError("TwoStream.forward needs CUDA inputs: the B200 implementation has no CPU fallback")
+        if self.training:
+            raise RuntimeError("inference-only: call .eval() first")
+        lib = B.load_library()
+        bs, W, L = text_ids.shape
+        T, H = self.segment_size, self.hidden_size
+        if W != 2 * self.window_size + 1:
+            raise RuntimeError(f"expected {2 * self.window_size + 1} clips per window, got {W}")
+        eng = self._get_engine(text_ids.device, L)
+        fh = self.fusion_head
+        s = torch.cuda.current_stream().cuda_stream
+        with torch.no_grad():
+            # backbones of every clip of every window, window position major: row = i * bs + b
+            img = img_clips.float().transpose(0, 1).reshape(W * bs, T, 3, 224, 224)
+            ids = text_ids.transpose(0, 1).reshape(W * bs, L)
+            mask = attention_masks.transpose(0, 1).reshape(W * bs, L)
+            vis_emb, lang_emb = eng.embed(img, ids, mask)                      # [W*bs,T,2048], [W*bs,768]
+            fused = torch.empty(bs, W, H, dtype=torch.float32, device=ids.device)
+            for i in range(W):
+                le = lang_emb[i * bs:(i + 1) * bs]
+                ve = vis_emb[i * bs:(i + 1) * bs].reshape(bs * T, self.vision_embed_size)
+                lang_out = self._run_chain(fh.lang_proj_heads[i], True, le)                 # relu(proj(lang)) [bs,H]
+                vis_out = self._run_chain(fh.vision_proj_heads[i], True, ve)                # [bs*T,H]
+                if fh.head_type == "mlp":      # cat([vision_out, lang_out]) -> head[i]
+                    f = self._run_chain(fh.head[i], False, vis_out.view(bs, T * H), lang_out)
+                else:                           # cross_attn: lang queries the T frame vectors
+                    ca = fh.head
+                    p = B.VcgCrossAttnParams(ca.num_heads, *[t.data_ptr() for t in (
+                        ca.lang_norm.weight, ca.lang_norm.bias, ca.vision_norm.weight, ca.vision_norm.bias,
+                        ca.frame_pos_encoding.weight, ca.frame_pos_encoding.bias,
+                        ca.query_proj.weight, ca.query_proj.bias, ca.key_proj.weight, ca.key_proj.bias,
+                        ca.value_proj.weight, ca.value_proj.bias, ca.out_proj.weight, ca.out_proj.bias)])
+                    f = torch.empty(bs, H, dtype=torch.float32, device=ids.device)
+                    B.check(lib.vcg_op_cross_attention(ctypes.byref(p), lang_out.data_ptr(), vis_out.data_ptr(), bs, T,
+                                                       f.data_ptr(), s))
+                fused[:, i] = f
+            # six window-attention blocks + classifier on the middle clip
+            wa = self.window_attn
+            sp = B.VcgWindowStackParams()
+            sp.num_layers, sp.pos_bias_stride = wa.num_layers, 2 * self.window_size + 1
+            for li, blk in enumerate(wa.layers):
+                a, lins = blk.attention, [m for m in blk.ffn if isinstance(m, nn.Linear)]
+                vals = [blk.attention_norm.weight, blk.attention_norm.bias, blk.ffn_norm.weight, blk.ffn_norm.bias,
+                        a.position_encoding.weight, a.position_encoding.bias, a.window_pos_bias,
+                        a.query.weight, a.query.bias, a.key.weight, a.key.bias, a.value.weight, a.value.bias,
+                        a.out_proj.weight, a.out_proj.bias]
+                for lin in lins:
+                    vals += [lin.weight, lin.bias]
+                sp.layers[li] = B.VcgWindowLayer(*[t.data_ptr() for t in vals])
+            sp.final_norm_w, sp.final_norm_b = wa.final_layer_norm.weight.data_ptr(), wa.final_layer_norm.bias.data_ptr()
+            lins = [m for m in wa.classifier if isinstance(m, nn.Linear)]
+            lns = [m for m in wa.classifier if isinstance(m, nn.LayerNorm)]
+            for j, lin in enumerate(lins):
+                sp.cls_w[j], sp.cls_b[j] = lin.weight.data_ptr(), lin.bias.data_ptr()
+            for j, ln in enumerate(lns):
+                sp.cls_norm_w[j], sp.cls_norm_b[j] = ln.weight.data_ptr(), ln.bias.data_ptr()
+            logits = torch.empty(bs, 2, dtype=torch.float32, device=ids.device)
+            probs = torch.empty(bs, 2, dtype=torch.float32, device=ids.device)
+            B.check(lib.vcg_op_window_stack(ctypes.byref(sp), fused.data_ptr(), bs, W, logits.data_ptr(), probs.data_ptr(), s))
+        return logits, probs

@@ -15,7 +15,7 @@ CSRC_DIR = os.path.join(PKG_ROOT, "csrc")
 HEAD_MLP, HEAD_ATTN = 0, 1
 PREC_BF16, PREC_FP32 = 0, 1
 VISION_R50TSM, VISION_NONE = 0, 1
-MODALITY_TWO_STREAM, MODALITY_VISION, MODALITY_TEXT = 0, 1, 2
+MODALITY_TWO_STREAM, MODALITY_VISION, MODALITY_TEXT, MODALITY_EMBED = 0, 1, 2, 3
 DTYPE_F32, DTYPE_I64 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
 
@@ -32,6 +32,36 @@ class VcgConfig(ctypes.Structure):
         ("shift_div", ctypes.c_int32),
         ("modality", ctypes.c_int32),
     ]
+
+
+class VcgMlpOp(ctypes.Structure):
+    _fields_ = [("type", ctypes.c_int32), ("in_dim", ctypes.c_int32), ("out_dim", ctypes.c_int32),
+                ("eps", ctypes.c_float), ("w", ctypes.c_void_p), ("b", ctypes.c_void_p)]
+
+
+_fp = ctypes.c_void_p
+
+
+class VcgCrossAttnParams(ctypes.Structure):
+    _fields_ = [("num_heads", ctypes.c_int32)] + [(n, _fp) for n in (
+        "lang_norm_w", "lang_norm_b", "vision_norm_w", "vision_norm_b", "pos_w", "pos_b",
+        "q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "o_w", "o_b")]
+
+
+class VcgWindowLayer(ctypes.Structure):
+    _fields_ = [(n, _fp) for n in (
+        "attn_norm_w", "attn_norm_b", "ffn_norm_w", "ffn_norm_b", "pos_w", "pos_b", "pos_bias",
+        "q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "o_w", "o_b",
+        "f0_w", "f0_b", "f1_w", "f1_b", "f2_w", "f2_b", "f3_w", "f3_b")]
+
+
+class VcgWindowStackParams(ctypes.Structure):
+    _fields_ = [("num_layers", ctypes.c_int32), ("pos_bias_stride", ctypes.c_int32), ("layers", VcgWindowLayer * 8),
+                ("final_norm_w", _fp), ("final_norm_b", _fp), ("cls_w", _fp * 5), ("cls_b", _fp * 5),
+                ("cls_norm_w", _fp * 4), ("cls_norm_b", _fp * 4)]
+
+
+MLP_LINEAR, MLP_LAYERNORM, MLP_RELU, MLP_GELU = 0, 1, 2, 3
 
 
 class VcgProfileEntry(ctypes.Structure):
@@ -70,6 +100,10 @@ PROTOTYPES = {
     "vcg_op_bert_attention_packed": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, ctypes.c_int64, _vp]),
     "vcg_op_cut_points": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "vcg_op_pr_hits": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "vcg_embed": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "vcg_op_mlp_chain": (ctypes.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, ctypes.POINTER(VcgMlpOp), _i32, _vp, _i64, _vp]),
+    "vcg_op_cross_attention": (ctypes.c_int, [ctypes.POINTER(VcgCrossAttnParams), _vp, _vp, _i32, _i32, _vp, _vp]),
+    "vcg_op_window_stack": (ctypes.c_int, [ctypes.POINTER(VcgWindowStackParams), _vp, _i32, _i32, _vp, _vp, _vp]),
     "vcg_op_layernorm": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _vp]),
 }
 

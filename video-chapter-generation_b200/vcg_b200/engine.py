@@ -12,7 +12,8 @@ from . import binding as _b
 
 _HEADS = {"mlp": _b.HEAD_MLP, "attn": _b.HEAD_ATTN}
 _PRECS = {"bf16": _b.PREC_BF16, "fp32": _b.PREC_FP32}
-_MODALITIES = {"two_stream": _b.MODALITY_TWO_STREAM, "vision": _b.MODALITY_VISION, "text": _b.MODALITY_TEXT}
+_MODALITIES = {"two_stream": _b.MODALITY_TWO_STREAM, "vision": _b.MODALITY_VISION, "text": _b.MODALITY_TEXT,
+               "embed": _b.MODALITY_EMBED}
 
 
 def _stream():
@@ -62,6 +63,8 @@ class Engine:
                 if self.modality == "two_stream":
                     wanted = (key.startswith("lang_model.") or key.startswith("fusion_head.") or
                               (self.vision and key.startswith("vision_model.")))
+                elif self.modality == "embed":   # backbones only (window model)
+                    wanted = key.startswith("lang_model.") or key.startswith("vision_model.")
                 else:   # Resnet50TSM / Resnet50 / BertHugface state dicts: base_model.* + head.*
                     wanted = key.startswith("base_model.") or key in ("head.weight", "head.bias")
                 if not wanted:
@@ -117,6 +120,20 @@ class Engine:
         if return_emb:
             return logits, probs, ve, le
         return logits, probs
+
+    def embed(self, img_clip, text_ids, attention_mask):
+        """Backbone embeddings of B clips: (vision_emb [B,T,2048], lang_emb [B,768]) fp32 (modality "embed")."""
+        ids, mask, B, L = self._text(text_ids, attention_mask)
+        img_clip = img_clip.float().contiguous()
+        if not img_clip.is_cuda or tuple(img_clip.shape) != (B, self.clip_frames, 3, 224, 224):
+            raise RuntimeError(f"vcg_b200: img_clip must be a CUDA tensor [B,{self.clip_frames},3,224,224], got {tuple(img_clip.shape)}")
+        dev = ids.device
+        ve = torch.empty(B, self.clip_frames, 2048, dtype=torch.float32, device=dev)
+        le = torch.empty(B, 768, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _b.check(self._lib.vcg_embed(self._h, img_clip.data_ptr(), ids.data_ptr(), mask.data_ptr(), B, L,
+                                         ve.data_ptr(), le.data_ptr(), _stream()))
+        return ve, le
 
     def forward_vision(self, img_clip, return_emb=False):
         """Resnet50TSM.forward / Resnet50.forward: img_clip [B,T,3,224,224] fp32 -> (logits, probs)."""
