@@ -323,3 +323,20 @@ def test_window_model_matches_reference_golden(golden_dir, case, head, precision
     assert errs["logits"] <= TOL[precision] and errs["probs"] <= TOL[precision], errs
     if precision == "fp32":
         assert logits.topk(1, 1, True, True)[1].view(-1).tolist() == g["labels"].tolist()
+
+
+def test_window_chain_routes_wide_layers_to_the_gemm():
+    """The per-position vision projection (2048 -> 1024 -> 512 -> 128 with LayerNorm + ReLU) over >= 128 rows takes the
+    tcgen05 GEMM (3xTF32) for its wide Linear layers and vcg_op_mlp_chain for the rest; both routes against torch fp32."""
+    from model.fusion import two_stream_window as tsw
+    torch.manual_seed(0)
+    seq = tsw._mlp3(2048, 1024, 512, 128).cuda().eval()
+    model = tsw.TwoStream.__new__(tsw.TwoStream)          # only _run_chain / _mlp_op are used
+    for rows in (16, 256):                                 # 16: one chain program; 256: GEMM + chain stretches
+        x = torch.randn(rows, 2048, device="cuda")
+        with torch.no_grad():
+            ref = torch.relu(seq(x))
+            got = tsw.TwoStream._run_chain(model, seq, True, x)
+        err = rel(got, ref)
+        print("rows", rows, "rel err", err)
+        assert err <= 2e-5

@@ -147,38 +147,53 @@ class TwoStream(nn.Module):
         return self._engine
 
     @staticmethod
-    def _program(seq, final_relu):
-        """nn.Sequential of Linear / LayerNorm / ReLU / GELU / Dropout -> array of vcg_mlp_op."""
+    def _mlp_op(m):
         from vcg_b200 import binding as B
-        ops = []
-        for m in seq:
-            if isinstance(m, nn.Linear):
-                ops.append(B.VcgMlpOp(B.MLP_LINEAR, m.in_features, m.out_features, 0.0, m.weight.data_ptr(),
-                                      m.bias.data_ptr() if m.bias is not None else None))
-            elif isinstance(m, nn.LayerNorm):
-                ops.append(B.VcgMlpOp(B.MLP_LAYERNORM, 0, 0, m.eps, m.weight.data_ptr(), m.bias.data_ptr()))
-            elif isinstance(m, nn.ReLU):
-                ops.append(B.VcgMlpOp(B.MLP_RELU, 0, 0, 0.0, None, None))
-            elif isinstance(m, nn.GELU):
-                ops.append(B.VcgMlpOp(B.MLP_GELU, 0, 0, 0.0, None, None))
-            elif not isinstance(m, nn.Dropout):
-                raise RuntimeError(f"unsupported module in an MLP chain: {type(m).__name__}")
-        if final_relu:
-            ops.append(B.VcgMlpOp(B.MLP_RELU, 0, 0, 0.0, None, None))
-        return (B.VcgMlpOp * len(ops))(*ops), len(ops)
+        if isinstance(m, nn.Linear):
+            return B.VcgMlpOp(B.MLP_LINEAR, m.in_features, m.out_features, 0.0, m.weight.data_ptr(),
+                              m.bias.data_ptr() if m.bias is not None else None)
+        if isinstance(m, nn.LayerNorm):
+            return B.VcgMlpOp(B.MLP_LAYERNORM, 0, 0, m.eps, m.weight.data_ptr(), m.bias.data_ptr())
+        if isinstance(m, nn.ReLU):
+            return B.VcgMlpOp(B.MLP_RELU, 0, 0, 0.0, None, None)
+        if isinstance(m, nn.GELU):
+            return B.VcgMlpOp(B.MLP_GELU, 0, 0, 0.0, None, None)
+        raise RuntimeError(f"unsupported module in an MLP chain: {type(m).__name__}")
 
     def _run_chain(self, seq, final_relu, x0, x1=None):
+        """nn.Sequential of Linear / LayerNorm / ReLU / GELU / Dropout over the rows of x0 (| x1).  Wide Linear layers
+        over many rows (the 2048->1024->512 vision projections, B*T rows) go to the tcgen05 GEMM in its fp32 (3xTF32)
+        mode; everything else runs as one vcg_op_mlp_chain program per stretch."""
         from vcg_b200 import binding as B
+        from vcg_b200 import ops
         lib = B.load_library()
-        ops, n = self._program(seq, final_relu)
-        out_dim = [m for m in seq if isinstance(m, nn.Linear)][-1].out_features
-        rows = x0.shape[0]
-        out = torch.empty(rows, out_dim, dtype=torch.float32, device=x0.device)
         s = torch.cuda.current_stream().cuda_stream
-        B.check(lib.vcg_op_mlp_chain(x0.data_ptr(), x0.shape[1], x0.stride(0), 0 if x1 is None else x1.data_ptr(),
-                                     0 if x1 is None else x1.shape[1], 0 if x1 is None else x1.stride(0), rows, ops, n,
-                                     out.data_ptr(), out.stride(0), s))
-        return out
+        mods = [m for m in seq if not isinstance(m, nn.Dropout)] + ([nn.ReLU()] if final_relu else [])
+        pending, cur, cur1 = [], x0, x1
+
+        def flush():
+            nonlocal pending, cur, cur1
+            if not pending:
+                return
+            lins = [m for m in pending if isinstance(m, nn.Linear)]
+            out_dim = lins[-1].out_features if lins else cur.shape[1] + (0 if cur1 is None else cur1.shape[1])
+            ops_arr = (B.VcgMlpOp * len(pending))(*[self._mlp_op(m) for m in pending])
+            out = torch.empty(cur.shape[0], out_dim, dtype=torch.float32, device=cur.device)
+            B.check(lib.vcg_op_mlp_chain(cur.data_ptr(), cur.shape[1], cur.stride(0), 0 if cur1 is None else cur1.data_ptr(),
+                                         0 if cur1 is None else cur1.shape[1], 0 if cur1 is None else cur1.stride(0),
+                                         cur.shape[0], ops_arr, len(pending), out.data_ptr(), out.stride(0), s))
+            pending, cur, cur1 = [], out, None
+
+        for m in mods:
+            big = (isinstance(m, nn.Linear) and cur1 is None and x0.shape[0] >= 128 and m.in_features >= 512
+                   and m.out_features >= 512 and m.in_features % 32 == 0 and m.out_features % 64 == 0)
+            if big:
+                flush()
+                cur = ops.gemm(cur.contiguous(), m.weight.detach(), m.bias.detach(), None, B.ACT_NONE)
+            else:
+                pending.append(m)
+        flush()
+        return cur
 
     # ------------------------------------------------------------------ forward
     def forward(self, img_clips, text_ids, attention_masks, clip_info=None):
