@@ -344,11 +344,12 @@ def main():
                      "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                      "share_of_step": dom["ms"] / tot_ms, "launches_per_step": dom["launches"] // args.steps,
                      "how": "executed 2*M*N*K FLOPs of every launch of this kernel (M = packed token rows) / its CUDA-event time"},
-        # algorithmic = SURVEY.md 8d (full padded length L); executed = what the kernels really did (the text stream
-        # drops masked tokens, which is exact: synthetic lengths are U{10..L})
-        "whole_path": {"tflops": value / n_gpus * fl / 1e12, "frac_of_sustained_bf16_peak": value / n_gpus * fl / 1e12 / peaks["tf_sustained"],
-                       "flops_per_clip": fl,
-                       "tflops_executed": sum(k["flops"] for k in kern.values()) / args.steps / (sec / args.steps) / 1e12},
+        # executed = the FLOPs the kernels really did (the text stream drops masked tokens, which is exact: synthetic
+        # lengths are U{10..L}); padded = SURVEY.md 8d's per-clip figure at the full length L, for reference only
+        "whole_path": {"tflops_executed": sum(k["flops"] for k in kern.values()) / args.steps / (sec / args.steps) / 1e12,
+                       "frac_of_sustained_bf16_peak": sum(k["flops"] for k in kern.values()) / args.steps / (sec / args.steps) / 1e12 / peaks["tf_sustained"],
+                       "flops_per_clip_padded": fl, "tflops_at_padded_flops": value / n_gpus * fl / 1e12,
+                       "note": "frac uses executed FLOPs; token packing skips masked tokens exactly, so clips/s x padded FLOPs would overstate the tensor work"},
         "kernels": {n: {"share": round(k["ms"] / tot_ms, 4), "tflops": round(k["flops"] / k["ms"] / 1e9, 1) if k["flops"] else None,
                         "launches_per_step": k["launches"] // args.steps} for n, k in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
     }
