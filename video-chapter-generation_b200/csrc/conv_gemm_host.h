@@ -3,6 +3,7 @@
 #include "conv_gemm.cuh"
 #include "tensormap.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace vcg {
@@ -154,10 +155,17 @@ inline void set_epilogue(ConvGemmLaunch& L, void* out, int ld_out, const Epilogu
     // smem split: residual layers are HBM-bound -> short K loops get few A/B stages and a deep residual-prefetch ring
     const int stage_bytes = kBlockM * 128 + static_cast<int>(p.b_bytes);
     const int budget = 224 * 1024;
-    const int min_slots = std::max(kMinCSlots, L.block_n / 64 + 1);   // at least one C tile of prefetch beyond a tile
+    // C ring: one slot per concurrently draining 64-column sub-tile; layers with a residual keep one more so that the
+    // next tile's residual prefetch can start early.  Everything else goes to A/B stages: deeper rings are what the
+    // long-K GEMMs need (measured at 14 k rows: 3 / 4 / 5 stages -> FFN-out 69 / 62 / 57 us)
+    const int min_slots = std::max(kMinCSlots, L.block_n / 64 + (e.residual ? 1 : 0));
     const int max_stages = std::min(kMaxStages, (budget - min_slots * kCBytes) / stage_bytes);
     const int num_kb = p.n_taps * p.cpt;
     p.n_stages = e.residual ? std::max(2, std::min(max_stages, num_kb + 1)) : max_stages;
+    if (const char* v = getenv("VCG_STAGES")) {   // tuning knob (tools/bench_layer.py)
+      const int forced = atoi(v);
+      if (forced >= 2 && (budget - forced * stage_bytes) / kCBytes >= kMinCSlots) p.n_stages = std::min(forced, kMaxStages);
+    }
     p.n_cslots = std::min(kMaxCSlots, (budget - p.n_stages * stage_bytes) / kCBytes);
     VCG_REQUIRE(p.n_stages >= 2 && p.n_cslots >= min_slots, "shared-memory split failed");
     VCG_REQUIRE(p.N % 32 == 0, "bf16 path: output channels must be a multiple of 32");
