@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(128) bert_attention_fp32_kernel(const float* _
 }  // namespace
 
 void launch_bert_attention(const void* qkv, const int64_t* mask, const int32_t* cu, const uint8_t* key_ok, void* ctx, int B,
-                           int L, bool fp32, cudaStream_t s, long qkv_rows) {
+                           int L, bool fp32, cudaStream_t s, long qkv_rows, const void* items, const int32_t* n_items) {
   if (B == 0) return;
   VCG_REQUIRE(L >= 1 && L <= 512, "BERT sequence length must be in [1, 512]");
   static int tc_policy = -1;   // VCG_ATTN_TC=0 keeps the mma.sync kernel everywhere
@@ -277,7 +277,7 @@ void launch_bert_attention(const void* qkv, const int64_t* mask, const int32_t* 
     tc_policy = (v && atoi(v) == 0) ? 0 : 1;
   }
   if (!fp32 && cu && key_ok && L <= 128 && qkv_rows > 0 && tc_policy) {   // packed bf16, one score tile per (clip, head)
-    launch_bert_attention_tc(qkv, cu, key_ok, ctx, B, qkv_rows, s);
+    launch_bert_attention_tc(qkv, cu, key_ok, ctx, B, qkv_rows, s, items, n_items);
     return;
   }
   if (!fp32) {

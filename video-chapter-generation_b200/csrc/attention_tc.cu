@@ -2,8 +2,8 @@
 //
 //   ctx = softmax(Q K^T / 8 + key_mask) V        per (clip, head); modeling_bert.py:115-140 (12 heads x 64)
 //
-// A work item is one (clip, head): at L <= 128 all its queries and keys fit one 128 x 128 score tile, so there is no
-// online-softmax loop.  An item is tiny (~2 MFLOP); what bounds the kernel is the chain of hand-offs
+// A work item is one clip and 1, 2 or 4 of its heads (attn_items_kernel): at L <= 128 all queries and keys of a head
+// fit one 128 x 128 score tile, so there is no online-softmax loop, and short clips stack several heads in one tile.  An item is tiny (~2 MFLOP); what bounds the kernel is the chain of hand-offs
 //   TMA -> S = Q K^T -> softmax -> O = P V -> output        (about 3 k cycles of barrier / MMA-completion latency)
 // so the kernel is persistent (one CTA per SM walks items blockIdx.x, +gridDim.x, ...), warp-specialised and keeps
 // THREE items in compute plus one in flight from memory:
@@ -42,7 +42,7 @@ constexpr uint32_t kTmemCols = 512;               // slot s: S in columns [128 s
 struct ItemInfo {
   int row_base, L;
   uint32_t key_bits[4];   // bit j: key j of the clip may be attended (j < L and key_ok)
-  int pad[2];
+  int head0, G;           // the item covers heads head0 .. head0 + G - 1 of the clip (G = 1, 2 or 4)
 };
 
 struct AttnParams {
@@ -50,8 +50,42 @@ struct AttnParams {
   const int32_t* cu;          // [B + 1]
   const uint8_t* key_ok;      // [rows]
   __nv_bfloat16* ctx;         // [rows, 768]
-  int n_items;                // B * 12
+  const int2* items;          // work list: x = clip, y = head0 | G << 8
+  const int32_t* n_items;     // its length (device)
 };
+
+// Work list: a clip of L <= 32 tokens packs FOUR heads into one 128-row tile (rows / keys [32 g, 32 g + L) belong to head
+// head0 + g), 32 < L <= 64 packs TWO, longer clips one.  S = Q K^T of the stacked tile has the wanted per-head score
+// blocks on its diagonal (the cross-head blocks are never read), P is written block-diagonal (zeros elsewhere) and
+// O = P V then yields every head's output in its own rows: G heads for the barrier / MMA latency chain of one.
+// The list is sorted by clip length, longest first (counting sort), and CTA k takes items k, k + gridDim.x, ...: every
+// CTA gets the same mix of expensive and cheap items.  (In clip order the static split left the slowest of 148 CTAs
+// with ~1.5x the mean work at the U{10..100} length mix.)  One CTA.
+__global__ void __launch_bounds__(256) attn_items_kernel(const int32_t* __restrict__ cu, int B, int2* __restrict__ items,
+                                                         int32_t* __restrict__ n_items) {
+  pdl_enter();
+  __shared__ int s_off[130];       // s_off[l]: next free item slot for clips of length l (clamped to 128)
+  for (int i = threadIdx.x; i < 130; i += blockDim.x) s_off[i] = 0;
+  __syncthreads();
+  auto heads_per_item = [](int L) { return L <= 32 ? 4 : L <= 64 ? 2 : 1; };
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int L = min(cu[b + 1] - cu[b], 128);
+    atomicAdd(&s_off[L], kBertHeads / heads_per_item(L));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {          // exclusive prefix over descending length
+    int acc = 0;
+    for (int l = 128; l >= 0; --l) { const int c = s_off[l]; s_off[l] = acc; acc += c; }
+    *n_items = acc;
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int L = min(cu[b + 1] - cu[b], 128);
+    const int G = heads_per_item(L), cnt = kBertHeads / G;
+    const int base = atomicAdd(&s_off[L], cnt);
+    for (int i = 0; i < cnt; ++i) items[base + i] = make_int2(b, (i * G) | (G << 8));
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -81,25 +115,33 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  // V tiles start out as zeros: with several heads per tile the O MMA also walks V rows that no TMA box of the item
+  // covered; they meet p = 0 exactly, which is only harmless while they hold finite values (later: older V rows)
+  for (int i = threadIdx.x; i < kSlots * (kTileBytes / 16); i += blockDim.x)
+    reinterpret_cast<uint4*>(sSlot + (i / (kTileBytes / 16)) * kSlotBytes + 2 * kTileBytes)[i % (kTileBytes / 16)] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
-  const int n_my = (p.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int n_items = __ldg(p.n_items);
+  const int n_my = n_items > static_cast<int>(blockIdx.x)
+                       ? (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp: the lanes gather the key bits)
-    // Everything the producer reads from global memory is fetched ahead of use: a dependent cu -> key_ok chain per item
-    // (two L2 round trips, ~1.5 k cycles) would otherwise bound the whole kernel at ~20 items per CTA.
-    auto item_rows = [&](int i, int& row_base, int& L) {     // lane-parallel: lane j holds item (i0 + j)
-      const int b = (blockIdx.x + i * gridDim.x) / kBertHeads;
-      row_base = __ldg(p.cu + b);
-      L = min(__ldg(p.cu + b + 1) - row_base, 128);
+    // Everything the producer reads from global memory is fetched ahead of use: a dependent items -> cu -> key_ok chain per
+    // item (three L2 round trips) would otherwise bound the whole kernel.
+    auto fetch_item = [&](int i, int& row_base, int& L, int& hg) {     // lane-parallel: lane j holds item (i0 + j)
+      const int2 it = __ldg(p.items + blockIdx.x + static_cast<long>(i) * gridDim.x);
+      row_base = __ldg(p.cu + it.x);
+      L = min(__ldg(p.cu + it.x + 1) - row_base, 128);
+      hg = it.y;
     };
-    int my_rb = 0, my_L = 0;                                  // lane j: rows of item (batch * 32 + j)
-    if (lane < n_my) item_rows(lane, my_rb, my_L);
+    int my_rb = 0, my_L = 0, my_hg = 0;
+    if (lane < n_my) fetch_item(lane, my_rb, my_L, my_hg);
     auto load_keys = [&](int rb, int L, uint8_t (&k)[4]) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -109,20 +151,19 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
     };
     uint8_t keys[4] = {0, 0, 0, 0};
     int rb_cur = __shfl_sync(0xffffffffu, my_rb, 0), L_cur = __shfl_sync(0xffffffffu, my_L, 0);
+    int hg_cur = __shfl_sync(0xffffffffu, my_hg, 0);
     if (n_my > 0) load_keys(rb_cur, L_cur, keys);
     for (int i = 0; i < n_my; ++i) {
-      const int item = blockIdx.x + i * gridDim.x;
-      const int h = item % kBertHeads;
       const int slot = i % kSlots;
-      const int row_base = rb_cur, L = L_cur;
+      const int row_base = rb_cur, L = L_cur, head0 = hg_cur & 0xff, G = hg_cur >> 8;
       uint32_t bits[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) bits[q] = __ballot_sync(0xffffffffu, keys[q] != 0);
-      // prefetch the next item's rows (new batch of 32 items every 32 iterations) and key bytes
-      if (i + 1 < n_my) {
-        if (((i + 1) & 31) == 0 && i + 1 + lane < n_my) item_rows(i + 1 + lane, my_rb, my_L);
+      if (i + 1 < n_my) {     // prefetch the next item (a new batch of 32 items every 32 iterations) and its key bytes
+        if (((i + 1) & 31) == 0 && i + 1 + lane < n_my) fetch_item(i + 1 + lane, my_rb, my_L, my_hg);
         rb_cur = __shfl_sync(0xffffffffu, my_rb, (i + 1) & 31);
         L_cur = __shfl_sync(0xffffffffu, my_L, (i + 1) & 31);
+        hg_cur = __shfl_sync(0xffffffffu, my_hg, (i + 1) & 31);
         load_keys(rb_cur, L_cur, keys);
       }
       mbar_wait(&empty[slot], ((i / kSlots) & 1) ^ 1);
@@ -130,19 +171,24 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
         ItemInfo inf;
         inf.row_base = row_base; inf.L = L;
         inf.key_bits[0] = bits[0]; inf.key_bits[1] = bits[1]; inf.key_bits[2] = bits[2]; inf.key_bits[3] = bits[3];
-        inf.pad[0] = inf.pad[1] = 0;
+        inf.head0 = head0; inf.G = G;
         info[slot] = inf;
-        const int nch = (L + 31) >> 5;
-        mbar_expect_tx(&full[slot], static_cast<uint32_t>(3 * nch) * 4096u);
+        const int nch = (L + 31) >> 5;                 // 32-row chunks per head (<= 4 / G)
+        const int cpb = 4 / G;                         // chunks per head block of the tile
+        mbar_expect_tx(&full[slot], static_cast<uint32_t>(3 * G * nch) * 4096u);
         uint8_t* dst = sSlot + slot * kSlotBytes;
-        // Q chunk c lands in 32-row block (c + i) % 4 of the tile: TMEM lanes [32 w, +32) can only be read by warps with
-        // warp % 4 == w, which all sit on scheduler w, and most clips are short -- without the rotation scheduler 0
-        // would run the softmax of (almost) every item while schedulers 2 and 3 idle
-        for (int c = 0; c < nch; ++c) {
-          tma_load_2d(dst + ((c + i) & 3) * 4096, &p.qkv_map, &full[slot], h * 64, row_base + c * 32);
-#pragma unroll
-          for (int op = 1; op < 3; ++op)
-            tma_load_2d(dst + op * kTileBytes + c * 4096, &p.qkv_map, &full[slot], op * kBertHidden + h * 64, row_base + c * 32);
+        for (int g = 0; g < G; ++g) {
+          const int col = (head0 + g) * 64;
+          for (int c = 0; c < nch; ++c) {
+            const int blk = g * cpb + c;
+            // one head per tile: Q chunk c lands in 32-row block (c + i) % 4, because TMEM lanes [32 w, +32) can only be
+            // read by warps with warp % 4 == w, which all sit on scheduler w -- without the rotation scheduler 0 would run
+            // the softmax of every item.  Several heads per tile spread the rows by themselves.
+            const int qblk = G == 1 ? ((c + i) & 3) : blk;
+            tma_load_2d(dst + qblk * 4096, &p.qkv_map, &full[slot], col, row_base + c * 32);
+            tma_load_2d(dst + kTileBytes + blk * 4096, &p.qkv_map, &full[slot], kBertHidden + col, row_base + c * 32);
+            tma_load_2d(dst + 2 * kTileBytes + blk * 4096, &p.qkv_map, &full[slot], 2 * kBertHidden + col, row_base + c * 32);
+          }
         }
       }
       __syncwarp();
@@ -157,7 +203,8 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
         mbar_wait(&full[slot], ph);
         mbar_wait(&t_empty[slot], ph ^ 1);      // the previous item of this slot has read its O
         tc_fence_after();
-        const int Nk = (info[slot].L + 15) & ~15;
+        const int G = info[slot].G;
+        const int Nk = (G - 1) * (128 / G) + ((info[slot].L + 15) & ~15);   // keys up to the last head's last one
         const uint32_t idesc = idesc_base | (static_cast<uint32_t>(Nk >> 3) << 17);
         const uint32_t q_addr = smem_u32(sSlot + slot * kSlotBytes);
         const uint32_t k_addr = q_addr + kTileBytes;
@@ -175,7 +222,8 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
         const int slot = i % kSlots;
         mbar_wait(&p_full[slot], (i / kSlots) & 1);
         tc_fence_after();
-        const int Nk = (info[slot].L + 15) & ~15;
+        const int G = info[slot].G;
+        const int Nk = (G - 1) * (128 / G) + ((info[slot].L + 15) & ~15);
         // O = P V: A = P (K-major, 64-key K blocks, where Q | K were), B = V in place (8-key atoms 1024 B apart)
         const uint32_t p_addr = smem_u32(sSlot + slot * kSlotBytes);
         const uint32_t v_addr = p_addr + 2 * kTileBytes;
@@ -187,95 +235,106 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ softmax + output, one thread per query row
+    // ------------------------------------------------------------ softmax + output, one thread per tile row
     const int group = (warp - 4) >> 2;
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
     const int row = quarter * 32 + lane;
     const float sl2 = 0.125f * 1.4426950408889634f;        // 1/sqrt(64) * log2(e)
     for (int i = group; i < n_my; i += kGroups) {
-      const int item = blockIdx.x + i * gridDim.x;
-      const int h = item % kBertHeads;
       const int slot = i % kSlots;
       const uint32_t ph = (i / kSlots) & 1;
       mbar_wait(&full[slot], ph);                            // item info published by the producer
-      const int row_base = info[slot].row_base, L = info[slot].L;
+      const int row_base = info[slot].row_base, L = info[slot].L, G = info[slot].G, head0 = info[slot].head0;
       const uint4 kb4 = *reinterpret_cast<const uint4*>(info[slot].key_bits);
       const uint32_t kbits[4] = {kb4.x, kb4.y, kb4.z, kb4.w};
-      const int Nk = (L + 15) & ~15;
+      const int bs = 128 / G;                                // rows (= keys) per head block
+      const int Nh = (L + 15) & ~15;                         // score columns of one head
+      const int Nk = (G - 1) * bs + Nh;                      // columns the O MMA walks
+      // tile row -> (head block g, query q).  One head per tile: Q blocks are rotated by i (see the producer)
+      const int g = G == 1 ? 0 : row / bs;
+      const int q = G == 1 ? ((((quarter - i) & 3) << 5) + lane) : row % bs;
+      const int c_base = g * bs;                             // first score column of this row's head
       mbar_wait(&s_full[slot], ph);
       tc_fence_after();
-      const int qrow = (((quarter - i) & 3) << 5) + lane;      // query handled by this thread (Q blocks are rotated by i)
-      const bool warp_active = (qrow - lane) < L;              // (warp-uniform) at least one valid row
+      const bool warp_active = (q - lane) < L;               // (warp-uniform) at least one valid row
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * 128;
       float l = 0.f;
       if (warp_active) {
         uint8_t* prow = sSlot + slot * kSlotBytes + row * 128;      // P overwrites Q | K (S has retired)
-        // 64 score columns per TMEM round trip (four tcgen05.ld, one wait); columns >= Nk are never touched
+        // 64 score columns per TMEM round trip (four tcgen05.ld, one wait); c0 is relative to the head's first column
         auto load64 = [&](int c0, uint32_t (&r)[4][16]) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (c0 + q * 16 < Nk) tmem_ld_32x16(taddr + c0 + q * 16, r[q]);
+          for (int t = 0; t < 4; ++t)
+            if (c0 + t * 16 < Nh) tmem_ld_32x16(taddr + c_base + c0 + t * 16, r[t]);
           tmem_ld_wait();
         };
         auto row_max = [&](int c0, const uint32_t (&r)[4][16], float m) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (c0 + q * 16 < Nk) {
-              const uint32_t w = kbits[(c0 + q * 16) >> 5] >> ((c0 + q * 16) & 31);   // 16 key bits of this chunk
+          for (int t = 0; t < 4; ++t) {
+            if (c0 + t * 16 < Nh) {
+              const uint32_t w = kbits[(c0 + t * 16) >> 5] >> ((c0 + t * 16) & 31);   // 16 key bits of this chunk
               float m4[4] = {m, -INFINITY, -INFINITY, -INFINITY};
               if ((w & 0xffffu) == 0xffffu) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(r[q][e]));
+                for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(r[t][e]));
               } else {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], (w >> e) & 1u ? __uint_as_float(r[q][e]) : -INFINITY);
+                for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], (w >> e) & 1u ? __uint_as_float(r[t][e]) : -INFINITY);
               }
               m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             }
           }
           return m;
         };
+        auto store16 = [&](int c, const float (&pv)[16]) {          // c: absolute P column (multiple of 16)
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            uint4 o;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(pv[t * 8 + 2 * e], pv[t * 8 + 2 * e + 1]);
+            const int chunk = ((c & 63) >> 3) + t;     // 16-byte chunk inside the 128-byte row of the K block
+            *reinterpret_cast<uint4*>(prow + (c >> 6) * kTileBytes + ((chunk ^ (row & 7)) << 4)) = o;
+          }
+        };
         auto exp_store = [&](int c0, const uint32_t (&r)[4][16], float msub) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c = c0 + q * 16;
-            if (c < Nk) {
+          for (int t = 0; t < 4; ++t) {
+            const int c = c0 + t * 16;
+            if (c < Nh) {
               const uint32_t w = kbits[c >> 5] >> (c & 31);
               float pv[16];
 #pragma unroll
               for (int e = 0; e < 16; ++e)
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv[e]) : "f"(fmaf(__uint_as_float(r[q][e]), sl2, -msub)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv[e]) : "f"(fmaf(__uint_as_float(r[t][e]), sl2, -msub)));
               if ((w & 0xffffu) != 0xffffu) {           // select, not add: stale rows beyond L may hold anything
 #pragma unroll
                 for (int e = 0; e < 16; ++e) pv[e] = (w >> e) & 1u ? pv[e] : 0.f;
               }
               l += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7])) +
                    (((pv[8] + pv[9]) + (pv[10] + pv[11])) + ((pv[12] + pv[13]) + (pv[14] + pv[15])));
-#pragma unroll
-              for (int t = 0; t < 2; ++t) {
-                uint4 o;
-                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(pv[t * 8 + 2 * e], pv[t * 8 + 2 * e + 1]);
-                const int chunk = ((c & 63) >> 3) + t;     // 16-byte chunk inside the 128-byte row of the K block
-                *reinterpret_cast<uint4*>(prow + (c >> 6) * kTileBytes + ((chunk ^ (row & 7)) << 4)) = o;
-              }
+              store16(c_base + c, pv);
             }
           }
         };
         uint32_t r[4][16];
         load64(0, r);
         float m = row_max(0, r, -INFINITY);
-        if (Nk > 64) {
+        if (Nh > 64) {
           load64(64, r);
           m = row_max(64, r, m);
         }
         const float msub = (m == -INFINITY) ? 0.f : m * sl2;
-        if (Nk > 64) {
+        if (Nh > 64) {
           exp_store(64, r, msub);       // the upper half is still in registers
           load64(0, r);
         }
         exp_store(0, r, msub);
+        if (G > 1) {                    // block-diagonal P: zeros in the other heads' key columns
+          const float z[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int c = 0; c < Nk; c += 16)
+            if (c < c_base || c >= c_base + Nh) store16(c, z);
+        }
         fence_proxy_async_smem();
       }
       tc_fence_before();
@@ -286,22 +345,22 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
       tc_fence_after();
       if (warp_active) {
         const float inv = 1.0f / l;
-        __nv_bfloat16* dst = p.ctx + static_cast<long>(row_base + qrow) * kBertHidden + h * 64;
+        __nv_bfloat16* dst = p.ctx + static_cast<long>(row_base + q) * kBertHidden + (head0 + g) * 64;
         uint32_t r[4][16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) tmem_ld_32x16(taddr + q * 16, r[q]);
+        for (int t = 0; t < 4; ++t) tmem_ld_32x16(taddr + t * 16, r[t]);
         tmem_ld_wait();
-        if (qrow < L) {
+        if (q < L) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int t = 0; t < 4; ++t) {
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
+            for (int u = 0; u < 2; ++u) {
               uint4 o;
               __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                h2[e] = __floats2bfloat162_rn(__uint_as_float(r[q][t * 8 + 2 * e]) * inv, __uint_as_float(r[q][t * 8 + 2 * e + 1]) * inv);
-              *reinterpret_cast<uint4*>(dst + q * 16 + t * 8) = o;
+                h2[e] = __floats2bfloat162_rn(__uint_as_float(r[t][u * 8 + 2 * e]) * inv, __uint_as_float(r[t][u * 8 + 2 * e + 1]) * inv);
+              *reinterpret_cast<uint4*>(dst + t * 16 + u * 8) = o;
             }
           }
         }
@@ -322,10 +381,17 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
 
 }  // namespace
 
+// Work list of the kernel above for B clips: items [12 * B] (int2), n_items [1]; depends only on cu.
+void launch_attention_items(const int32_t* cu, int B, void* items, int32_t* n_items, cudaStream_t s) {
+  if (B == 0) return;
+  launch_pdl(attn_items_kernel, 1, 256, 0, s, cu, B, static_cast<int2*>(items), n_items);
+}
+
 // Packed layout only (cu, key_ok), bf16, every clip at most 128 tokens.  `rows` = rows of the qkv allocation that may be
-// read (at least cu[B] + 31; rows beyond the packed ones must hold finite values).
+// read (at least cu[B] + 31; rows beyond the packed ones must hold finite values).  items / n_items: work list from
+// launch_attention_items (nullptr: built here into a cached scratch buffer).
 void launch_bert_attention_tc(const void* qkv, const int32_t* cu, const uint8_t* key_ok, void* ctx, int B, long rows,
-                              cudaStream_t s) {
+                              cudaStream_t s, const void* items, const int32_t* n_items) {
   if (B == 0) return;
   static bool configured = false;
   if (!configured) {
@@ -341,14 +407,27 @@ void launch_bert_attention_tc(const void* qkv, const int32_t* cu, const uint8_t*
     const uint32_t box[2] = {64, 32};
     it = maps.emplace(key, make_tensor_map(qkv, false, 2, dims, str, box)).first;
   }
+  if (!items) {   // stand-alone operator: scratch work list (grown on demand, per device; not thread-safe like the engine)
+    static void* scratch = nullptr;
+    static int scratch_B = 0;
+    if (B > scratch_B) {
+      if (scratch) VCG_CUDA(cudaFree(scratch));
+      VCG_CUDA(cudaMalloc(&scratch, static_cast<size_t>(B) * kBertHeads * sizeof(int2) + 16));
+      scratch_B = B;
+    }
+    int32_t* cnt = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(scratch) + static_cast<size_t>(scratch_B) * kBertHeads * sizeof(int2));
+    launch_attention_items(cu, B, scratch, cnt, s);
+    items = scratch;
+    n_items = cnt;
+  }
   AttnParams p;
   p.qkv_map = it->second;
   p.cu = cu; p.key_ok = key_ok; p.ctx = static_cast<__nv_bfloat16*>(ctx);
-  p.n_items = B * kBertHeads;
+  p.items = static_cast<const int2*>(items); p.n_items = n_items;
   int dev = 0, sms = 0;
   VCG_CUDA(cudaGetDevice(&dev));
   VCG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = std::min(p.n_items, sms);
+  const int grid = std::min(B * kBertHeads, sms);
   launch_pdl(bert_attention_tc_kernel, grid, kThreads, kSmemBytes, s, p);
 }
 

@@ -147,7 +147,7 @@ struct vcg_engine {
   // text workspace (sized for Bt clips x Lmax tokens)
   DevBuf hid, hid2, qkv, ctx, tmp, ffn, cls;
   // token packing (variable-length BERT): cu [Bt+1], tok_src / key_ok [Bt*Lmax], m_total [1]
-  DevBuf pk_cu, pk_src, pk_ok, pk_total;
+  DevBuf pk_cu, pk_src, pk_ok, pk_total, pk_items, pk_nitems;   // + work list of the tcgen05 attention kernel
   // LayerNorm folded into the GEMMs (bf16): per layer two (sum, sum of squares) row-statistics arrays
   bool ln_fused = false;
   DevBuf ln_stats;
@@ -421,6 +421,8 @@ void finalize_text(vcg_engine* e, cudaStream_t s) {
   e->pk_src.alloc(rows * sizeof(int32_t));
   e->pk_ok.alloc(rows);
   e->pk_total.alloc(sizeof(int32_t), /*zero=*/true);
+  e->pk_items.alloc(static_cast<size_t>(e->Bt) * kBertHeads * 8);
+  e->pk_nitems.alloc(sizeof(int32_t), /*zero=*/true);
   if (e->ln_fused) {
     e->ln_stats_rows = rows;
     e->ln_stats.alloc(static_cast<size_t>(2) * n_layers * rows * sizeof(float2), /*zero=*/true);
@@ -705,7 +707,7 @@ void run_steps(vcg_engine* e, const std::vector<Step>& steps, const int64_t* mas
       case Step::ATTENTION: {
         ProfScope ps(e, s, "bert_attention|bert.attn", 4.0 * st.n * kBertHeads * static_cast<double>(st.a) * st.a * 64, 0, true);
         launch_bert_attention(st.in, mask, e->pk_cu.as<int32_t>(), e->pk_ok.as<uint8_t>(), st.out, st.n, st.a, e->fp32, s,
-                              static_cast<long>(e->Bt) * e->Lmax + 128);
+                              static_cast<long>(e->Bt) * e->Lmax + 128, e->pk_items.p, e->pk_nitems.as<int32_t>());
         break;
       }
       case Step::ZERO_STATS: {
@@ -758,6 +760,10 @@ void run_text(vcg_engine* e, const int64_t* ids, const int64_t* mask, int b0, in
                      e->pk_ok.as<uint8_t>(), e->pk_total.as<int32_t>(), s);
   }
   e->last_bert_rows = bt * L;
+  if (!e->fp32 && L <= 128) {
+    ProfScope ps(e, s, "attn_items|bert.pack", 0, static_cast<double>(bt) * 12 * 8);
+    launch_attention_items(e->pk_cu.as<int32_t>(), bt, e->pk_items.p, e->pk_nitems.as<int32_t>(), s);
+  }
   {
     ProfScope ps(e, s, "bert_embed_ln|bert.embed", 0, static_cast<double>(bt) * L * 768 * 4 * e->es(), true);
     launch_bert_embed_ln(ids + static_cast<long>(b0) * L, bt * L, L, e->pk_src.as<int32_t>(), e->pk_total.as<int32_t>(),

@@ -349,35 +349,60 @@ __global__ void __launch_bounds__(1024) bert_pack_kernel(const int64_t* __restri
   pdl_enter();
   extern __shared__ int s_cnt[];   // [B + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // (the kernel is one CTA and purely latency-bound: the four 32-token groups of a step are loaded together)
   for (int b = warp; b < B; b += nwarps) {
     int c = 0;
-    for (int j0 = 0; j0 < L; j0 += 32) {
-      const int j = j0 + lane;
-      const bool v = j < L && (mask[static_cast<long>(b) * L + j] != 0 || j == 0);
-      c += __popc(__ballot_sync(0xffffffffu, v));
+    for (int j0 = 0; j0 < L; j0 += 128) {
+      bool v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * 32 + lane;
+        v[u] = j < L && (mask[static_cast<long>(b) * L + j] != 0 || j == 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) c += __popc(__ballot_sync(0xffffffffu, v[u]));
     }
     if (lane == 0) s_cnt[b] = c;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {          // B <= a few hundred: a serial scan is negligible
-    int acc = 0;
-    for (int b = 0; b < B; ++b) { const int c = s_cnt[b]; s_cnt[b] = acc; cu[b] = acc; acc += c; }
-    s_cnt[B] = acc; cu[B] = acc; *total = acc;
+  if (warp == 0) {                 // exclusive scan of the per-clip counts: 32 clips per step, carry in a register
+    int carry = 0;
+    for (int b0 = 0; b0 < B; b0 += 32) {
+      const int b = b0 + lane;
+      const int c = b < B ? s_cnt[b] : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (b < B) { s_cnt[b] = carry + incl - c; cu[b] = carry + incl - c; }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) { s_cnt[B] = carry; cu[B] = carry; *total = carry; }
   }
   __syncthreads();
   for (int b = warp; b < B; b += nwarps) {
     int base = s_cnt[b];
-    for (int j0 = 0; j0 < L; j0 += 32) {
-      const int j = j0 + lane;
-      const bool m = j < L && mask[static_cast<long>(b) * L + j] != 0;
-      const bool v = m || j == 0;
-      const unsigned bal = __ballot_sync(0xffffffffu, v);
-      if (v) {
-        const int dst = base + __popc(bal & ((1u << lane) - 1));
-        tok_src[dst] = b * L + j;
-        key_ok[dst] = m ? 1 : 0;
+    for (int j0 = 0; j0 < L; j0 += 128) {
+      bool m[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * 32 + lane;
+        m[u] = j < L && mask[static_cast<long>(b) * L + j] != 0;
       }
-      base += __popc(bal);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * 32 + lane;
+        const bool v = m[u] || j == 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, v);
+        if (v) {
+          const int dst = base + __popc(bal & ((1u << lane) - 1));
+          tok_src[dst] = b * L + j;
+          key_ok[dst] = m[u] ? 1 : 0;
+        }
+        base += __popc(bal);
+      }
     }
   }
 }
@@ -503,9 +528,19 @@ __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __res
 template <bool FP32>
 __global__ void convert_kernel(const float* __restrict__ in, elem_t<FP32>* __restrict__ out, long n) {
   pdl_enter();
-  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
-  if (idx >= n) return;
-  if constexpr (FP32) out[idx] = in[idx]; else out[idx] = __float2bfloat16_rn(in[idx]);
+  // eight elements per thread (two 16-byte loads, one 16-byte store in the bf16 case); scalar tail / unaligned fallback
+  const long i8 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) * 8;
+  if (i8 >= n) return;
+  const bool vec = i8 + 8 <= n && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (vec) {
+    float v[8];
+    load8<true>(in + i8, v);
+    store8<FP32>(out + i8, v);
+  } else {
+    for (long i = i8; i < min(i8 + 8, n); ++i) {
+      if constexpr (FP32) out[i] = in[i]; else out[i] = __float2bfloat16_rn(in[i]);
+    }
+  }
 }
 template <bool FP32>
 __global__ void cast_to_f32_kernel(const elem_t<FP32>* __restrict__ in, float* __restrict__ out, long n) {
@@ -634,7 +669,7 @@ void launch_pack_stem(const float* w, const float* bn_w, const float* bn_b, cons
 }
 void launch_convert(const float* in, void* out, long n, bool fp32, cudaStream_t s) {
   if (n == 0) return;
-  VCG_DISPATCH(fp32, (launch_pdl(convert_kernel<FP>, blocks_for(n, 256), 256, 0, s, in, static_cast<elem_t<FP>*>(out), n)));
+  VCG_DISPATCH(fp32, (launch_pdl(convert_kernel<FP>, blocks_for((n + 7) / 8, 256), 256, 0, s, in, static_cast<elem_t<FP>*>(out), n)));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_cast_to_f32(const void* in, float* out, long n, bool fp32, cudaStream_t s) {

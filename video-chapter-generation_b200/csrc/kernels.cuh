@@ -48,9 +48,11 @@ void launch_layernorm(const void* x, const float* gamma, const float* beta, void
 // cu / key_ok: packed layout (nullptr: rows b*L.., int64 mask)
 // qkv_rows: rows of the qkv allocation that may be read (> 0 enables the tcgen05 kernel for packed bf16, L <= 128)
 void launch_bert_attention(const void* qkv, const int64_t* mask, const int32_t* cu, const uint8_t* key_ok, void* ctx, int B,
-                           int L, bool fp32, cudaStream_t s, long qkv_rows = 0);
+                           int L, bool fp32, cudaStream_t s, long qkv_rows = 0, const void* items = nullptr,
+                           const int32_t* n_items = nullptr);
 void launch_bert_attention_tc(const void* qkv, const int32_t* cu, const uint8_t* key_ok, void* ctx, int B, long rows,
-                              cudaStream_t s);   // attention_tc.cu
+                              cudaStream_t s, const void* items = nullptr, const int32_t* n_items = nullptr);   // attention_tc.cu
+void launch_attention_items(const int32_t* cu, int B, void* items, int32_t* n_items, cudaStream_t s);
 
 struct TailParams {
   // inputs
