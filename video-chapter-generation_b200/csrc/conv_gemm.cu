@@ -23,6 +23,27 @@ int cg2_policy() {
   return pol;
 }
 
+int fuse23_policy() {
+  static int pol = -2;
+  if (pol == -2) {
+    const char* v = getenv("VCG_FUSE23");
+    pol = v ? atoi(v) : -1;
+  }
+  return pol;
+}
+
+void launch_conv23(const Conv23Launch& L, cudaStream_t stream) {
+  if (L.grid <= 0) return;
+  static bool configured = false;
+  if (!configured) {
+    VCG_CUDA(cudaFuncSetAttribute(conv23_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC23SmemBytes));
+    VCG_CUDA(cudaFuncSetAttribute(conv23_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC23SmemBytes));
+    configured = true;
+  }
+  if (L.q.P == 64) launch_pdl(conv23_kernel<64>, L.grid, kC23Threads, kC23SmemBytes, stream, L.q);
+  else launch_pdl(conv23_kernel<128>, L.grid, kC23Threads, kC23SmemBytes, stream, L.q);
+}
+
 template <int BLOCK_N, bool LNF = false>
 static void launch_pair_t(const ConvGemmLaunch& L, cudaStream_t stream) {
   using Cfg = ConvGemmCfg<BLOCK_N, false>;

@@ -1,6 +1,7 @@
 // Host-side builders for conv_gemm_kernel launches: tensor maps, patch geometry, tap tables.
 #pragma once
 #include "conv_gemm.cuh"
+#include "conv23.cuh"
 #include "tensormap.h"
 #include <algorithm>
 #include <cstdlib>
@@ -373,5 +374,70 @@ inline ConvGemmLaunch build_conv1_shared(const void* x0u, int n_clips, int T, in
 }
 
 void launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream);   // conv_gemm.cu
+
+// ---- fused conv2 (3x3) + conv3 (1x1 + residual) of a bottleneck, planes P = 64 / 128 (conv23.cuh) -------------------
+struct Conv23Launch {
+  Conv23Params q;
+  int grid = 0;
+  double flops = 0;
+  const char* name = "";
+};
+
+// VCG_FUSE23=0 keeps the two separate kernels
+int fuse23_policy();   // conv_gemm.cu
+
+inline bool conv23_ok(int P, bool fp32) { return !fp32 && (P == 64 || P == 128) && fuse23_policy() != 0; }
+
+// in: conv2's input [Nimg, H, W, P]; W2 [P][3][3][P], bias2; W3 [4P][P]; e3 = conv3's epilogue (bias, residual, act, TSM)
+inline Conv23Launch build_conv23(const void* in, int Nimg, int H, int W, int P, int stride, const void* W2, const float* bias2,
+                                 const void* W3, void* out, const Epilogue& e3, const char* name) {
+  VCG_REQUIRE(P == 64 || P == 128, "fused conv2+conv3: planes must be 64 or 128");
+  Epilogue none;
+  ConvGemmLaunch g2 = build_conv(in, Nimg, H, W, P, W2, P, 3, stride, out, false, none, nullptr, 0, name);   // conv2 geometry
+  Conv23Launch L;
+  memset(&L.q, 0, sizeof L.q);
+  L.name = name;
+  ConvGemmParams& p = L.q.g;
+  p = g2.p;
+  const int Cout = 4 * P;
+  p.N = Cout;
+  p.n_tiles = Cout / 256;
+  p.b_map = weight_map(W2, P, 9 * P, P, false);
+  p.b_bytes = static_cast<uint32_t>(P) * 128u;
+  p.out = out; p.ld_out = Cout;
+  p.bias = e3.bias; p.residual = e3.residual; p.ld_res = Cout; p.act = e3.act;
+  p.tsm_out = e3.tsm_out; p.tsm_ld = e3.tsm_ld; p.tsm_fold = e3.tsm_fold; p.T = e3.T > 0 ? e3.T : 1;
+  if (e3.tsm_out) VCG_REQUIRE(e3.tsm_fold % 32 == 0, "TSM fold must be a multiple of 32 channels");
+  p.out_map = c_tile_map(out, Cout, p);
+  p.res_map = e3.residual ? c_tile_map(e3.residual, Cout, p) : p.out_map;
+  p.res_clip_T = 0;
+  if (e3.residual && e3.res_clip_T > 0) {
+    VCG_REQUIRE(e3.res_clip_T % p.nf == 0 && p.Nimg % e3.res_clip_T == 0, "clip-view residual: tile frames must stay inside a clip");
+    p.res_map = clip_view_map(e3.residual, Cout, p.Wo, p.Ho, e3.res_clip_T, p.Nimg / e3.res_clip_T, e3.res_clip_stride, 64, p.bw,
+                              p.bh, p.nf, false);
+    p.res_clip_T = e3.res_clip_T;
+  }
+  L.q.w3_map = weight_map(W3, Cout, P, 256, false);
+  L.q.bias2 = bias2;
+  L.q.P = P;
+  L.q.n2 = Cout / 256;
+  // shared memory: 32 KB stages | A2 double buffer (2 x P/64 x 16 KB) | C ring (16 KB slots, >= 4)
+  const int a2 = 2 * (P / 64) * kCBytes;
+  int stages = P == 64 ? 4 : 3;   // P = 64: 4 stages + 4 C slots; P = 128: 3 stages + 4 C slots (224 KB)
+  int cslots = (kC23Budget - a2 - stages * kC23StageBytes) / kCBytes;
+  if (const char* v = getenv("VCG_STAGES23")) {
+    const int f = atoi(v);
+    if (f >= 2 && (kC23Budget - a2 - f * kC23StageBytes) / kCBytes >= 4) { stages = f; cslots = (kC23Budget - a2 - f * kC23StageBytes) / kCBytes; }
+  }
+  L.q.n_stages = std::min(stages, kMaxStages);
+  L.q.n_cslots = std::min(cslots, kMaxCSlots);
+  VCG_REQUIRE(L.q.n_stages >= 2 && L.q.n_cslots >= 4, "fused conv2+conv3: shared-memory split failed");
+  const long m_tiles = static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n;
+  L.grid = static_cast<int>(std::min<long>(m_tiles, sm_count()));
+  L.flops = 2.0 * Nimg * p.Ho * p.Wo * (static_cast<double>(P) * 9 * P + static_cast<double>(Cout) * P);
+  return L;
+}
+
+void launch_conv23(const Conv23Launch& L, cudaStream_t stream);   // conv_gemm.cu
 
 }  // namespace vcg

@@ -88,8 +88,9 @@ struct BertLayerW {
 
 // One step of a plan.
 struct Step {
-  enum Kind { CONV_GEMM, MAXPOOL, AVGPOOL, EMBED, LAYERNORM, ATTENTION, ZERO_STATS } kind;
+  enum Kind { CONV_GEMM, CONV23, MAXPOOL, AVGPOOL, EMBED, LAYERNORM, ATTENTION, ZERO_STATS } kind;
   ConvGemmLaunch gemm;
+  Conv23Launch c23;   // CONV23: fused conv2 + conv3 of a bottleneck
   // generic arguments for the small kernels
   const void* in = nullptr;
   void* out = nullptr;
@@ -544,7 +545,8 @@ VisionPlan& vision_plan(vcg_engine* e, int B, int clip_stride = 0) {
       }
       plan.steps.push_back(st);
     }
-    {   // conv2 3x3 (stride) + BN + ReLU
+    const bool fuse23 = conv23_ok(bk.planes, fp);   // layer1 / layer2: conv2 + conv3 in one kernel (conv23.cuh)
+    if (!fuse23) {   // conv2 3x3 (stride) + BN + ReLU
       Step st{}; st.kind = Step::CONV_GEMM;
       Epilogue ep; ep.bias = bk.c2.bias.as<float>(); ep.act = ACT_RELU;
       st.gemm = build_conv(e->mid1.p, N, H, H, bk.planes, bk.c2.w.p, bk.planes, 3, bk.stride, e->mid2.p, fp, ep, nullptr, 0, kNames[stage][1]);
@@ -570,7 +572,13 @@ VisionPlan& vision_plan(vcg_engine* e, int B, int clip_stride = 0) {
         ep.tsm_ld = 2 * ep.tsm_fold;
         ep.T = e->T;
       }
-      st.gemm = build_conv(e->mid2.p, N, Ho, Ho, bk.planes, bk.c3.w.p, Cout, 1, 1, xnext, fp, ep, nullptr, 0, kNames[stage][2]);
+      if (fuse23) {
+        st.kind = Step::CONV23;
+        st.c23 = build_conv23(e->mid1.p, N, H, H, bk.planes, bk.stride, bk.c2.w.p, bk.c2.bias.as<float>(), bk.c3.w.p, xnext, ep,
+                              kNames[stage][2]);
+      } else {
+        st.gemm = build_conv(e->mid2.p, N, Ho, Ho, bk.planes, bk.c3.w.p, Cout, 1, 1, xnext, fp, ep, nullptr, 0, kNames[stage][2]);
+      }
       plan.steps.push_back(st);
     }
     x = xnext;
@@ -692,6 +700,11 @@ void run_steps(vcg_engine* e, const std::vector<Step>& steps, const int64_t* mas
       case Step::CONV_GEMM: {
         ProfScope ps(e, s, gemm_kernel_name(st.gemm), st.gemm.flops, 0, st.gemm.p.m_dev != nullptr);
         launch_conv_gemm(st.gemm, s);
+        break;
+      }
+      case Step::CONV23: {
+        ProfScope ps(e, s, std::string("conv23_bf16|") + st.c23.name, st.c23.flops, 0);
+        launch_conv23(st.c23, s);
         break;
       }
       case Step::MAXPOOL: {
