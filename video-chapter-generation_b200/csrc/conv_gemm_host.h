@@ -116,14 +116,14 @@ struct Epilogue {
 
 // (C, W, H, T, clip) view of a per-unique-frame NHWC tensor: clip b, frame t -> unique frame b*clip_stride + t
 inline CUtensorMap clip_view_map(const void* ptr, int C, int W, int H, int T, int n_clips, int clip_stride, int box_c,
-                                 int bw, int bh, int nf, bool fp32) {
+                                 int bw, int bh, int nf, bool fp32, int nf_clips = 1) {
   const uint64_t es = elem_size(fp32);
   const uint64_t img = static_cast<uint64_t>(H) * W * C * es;
   const uint64_t dims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                             static_cast<uint64_t>(T), static_cast<uint64_t>(n_clips)};
   const uint64_t str[4] = {static_cast<uint64_t>(C) * es, static_cast<uint64_t>(W) * C * es, img, img * clip_stride};
   const uint32_t box[5] = {static_cast<uint32_t>(box_c), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh),
-                           static_cast<uint32_t>(nf), 1};
+                           static_cast<uint32_t>(nf), static_cast<uint32_t>(nf_clips)};
   return make_tensor_map(ptr, fp32, 5, dims, str, box);
 }
 
@@ -339,6 +339,45 @@ inline ConvGemmLaunch build_stem(const void* in_padded, int Nimg, int Hp, int Wp
   p.b_map = weight_map(Wp_packed, Cout, fp32 ? 7 * 32 : 4 * 64, L.cg2 ? L.block_n / 2 : L.block_n, fp32);
   set_epilogue(L, out, Cout, e);
   L.flops = 2.0 * Nimg * Ho * Wo * static_cast<double>(Cout) * 147;
+  return L;
+}
+
+// Can conv1 of a TSM bottleneck read its temporally shifted channels straight from the block input?  The two shifted
+// groups are `fold` = Cin / shift_div channels each and a K block is 64 channels, so fold must be a multiple of 64
+// (Cin >= 512 at shift_div 8), and a tile's frames must be whole clips or divide one.
+inline bool conv1_tsm_direct_ok(int W, int H, int Nimg, int Cin, int fold, int T, bool fp32) {
+  if (fp32 || fold <= 0 || fold % 64 != 0 || Cin % fold != 0 || Cin / fold > 16 || T <= 0 || Nimg % T != 0) return false;
+  int bw, bh, nf;
+  pick_patch(W, H, Nimg, bw, bh, nf);
+  return nf <= T ? (T % nf == 0) : (nf % T == 0);
+}
+
+// conv1 (1x1) of a TSM bottleneck with the temporal shift folded into the TMA coordinates: the input is addressed as
+// (C, W, H, t, clip); K blocks of channels [0, fold) come from frame t+1, [fold, 2 fold) from frame t-1, the rest from
+// frame t, and frames outside the clip are TMA zero fill — no shifted copy of the activations exists anywhere
+// (ops/temporal_shift.py:34-51).  One "tap" per `fold` channels.  bf16.
+inline ConvGemmLaunch build_conv1_tsm_direct(const void* x, int Nimg, int T, int H, int W, int Cin, int fold, const void* Wp,
+                                             int Cout, void* out, const Epilogue& e, const char* name) {
+  ConvGemmLaunch L;
+  memset(&L.p, 0, sizeof L.p);
+  L.name = name;
+  ConvGemmParams& p = L.p;
+  pick_patch(W, H, Nimg, p.bw, p.bh, p.nf);
+  const int nf_t = std::min(p.nf, T), nf_c = p.nf / nf_t;
+  p.a_map[0] = clip_view_map(x, Cin, W, H, T, Nimg / T, T, 64, p.bw, p.bh, nf_t, false, nf_c);
+  for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+  p.a_clip_T = T;
+  p.n_taps = Cin / fold; p.cpt = fold / 64;
+  for (int i = 0; i < p.n_taps; ++i) {
+    TapDesc t{};
+    t.c_off = static_cast<int16_t>(i * fold);
+    t.plane = static_cast<int8_t>(i == 0 ? 1 : i == 1 ? -1 : 0);
+    p.taps[i] = t;
+  }
+  finish_launch(L, W, H, Nimg, Cout, false);
+  p.b_map = weight_map(Wp, Cout, Cin, L.cg2 ? L.block_n / 2 : L.block_n, false);
+  set_epilogue(L, out, Cout, e);
+  L.flops = 2.0 * Nimg * H * W * static_cast<double>(Cout) * Cin;
   return L;
 }
 

@@ -521,6 +521,14 @@ VisionPlan& vision_plan(vcg_engine* e, int B, int clip_stride = 0) {
   const void* x = e->x0.p;
   void* pingpong[2] = {e->xa.p, e->xb.p};
   int pp = 0;
+  // blocks whose conv1 reads the temporally shifted channels straight from frames t+1 / t-1 of its input (Cin >= 512);
+  // the others (layer1, layer2.0) get a shifted copy scattered by the producing epilogue.  VCG_TSM_DIRECT=0: never.
+  static const bool direct_on = !(getenv("VCG_TSM_DIRECT") && atoi(getenv("VCG_TSM_DIRECT")) == 0);
+  auto tsm_direct = [&](int blk) {
+    const Bottleneck& b = e->blocks[blk];
+    return direct_on && e->tsm && blk > 0 &&
+           conv1_tsm_direct_ok(b.H, b.H, N, b.Cin, b.Cin / e->cfg.shift_div, e->T, fp);
+  };
   static const char* const kNames[4][4] = {{"l1.conv1", "l1.conv2", "l1.conv3", "l1.downsample"},
                                            {"l2.conv1", "l2.conv2", "l2.conv3", "l2.downsample"},
                                            {"l3.conv1", "l3.conv2", "l3.conv3", "l3.downsample"},
@@ -540,6 +548,9 @@ VisionPlan& vision_plan(vcg_engine* e, int B, int clip_stride = 0) {
         ep.bias = bk.c1_shared.bias.as<float>();
         st.gemm = build_conv1_shared(x, B, e->T, clip_stride, H, H, bk.Cin, bk.c1_shared.w.p, bk.planes, e->mid1.p, ep,
                                      kNames[stage][0]);
+      } else if (tsm_direct(i)) {   // shifted channel groups straight from frames t+1 / t-1 of the block input
+        st.gemm = build_conv1_tsm_direct(x, N, e->T, H, H, bk.Cin, bk.Cin / e->cfg.shift_div, bk.c1.w.p, bk.planes, e->mid1.p, ep,
+                                         kNames[stage][0]);
       } else {
         st.gemm = build_conv(x, N, H, H, bk.Cin, bk.c1.w.p, bk.planes, 1, 1, e->mid1.p, fp, ep, sh, sh_ch, kNames[stage][0]);
       }
@@ -566,7 +577,7 @@ VisionPlan& vision_plan(vcg_engine* e, int B, int clip_stride = 0) {
       Epilogue ep; ep.bias = bk.c3.bias.as<float>(); ep.act = ACT_RELU;
       ep.residual = identity; ep.ld_res = Cout;
       if (shared && i == 0) { ep.res_clip_T = e->T; ep.res_clip_stride = clip_stride; }
-      if (e->tsm && i + 1 < 16) {
+      if (e->tsm && i + 1 < 16 && !tsm_direct(i + 1)) {
         ep.tsm_out = e->shifted[i + 1]->p;
         ep.tsm_fold = Cout / e->cfg.shift_div;
         ep.tsm_ld = 2 * ep.tsm_fold;
