@@ -340,3 +340,19 @@ def test_window_chain_routes_wide_layers_to_the_gemm():
         err = rel(got, ref)
         print("rows", rows, "rel err", err)
         assert err <= 2e-5
+
+
+def test_empty_and_single_clip_batches(golden_dir):
+    """Edge cases of the batch dimension: B = 0 returns empty [0,2] tensors without touching the GPU work queue, B = 1
+    equals the first clip of the B = 2 golden case (clips are independent under eval-mode BatchNorm)."""
+    g = np.load(f"{golden_dir}/two_stream_mlp_T16_L100_B2.npz")
+    T, L, B, ids, mask, frames, starts, img = golden_inputs(g)
+    model, _ = build_model(T, "mlp", "bf16")
+    l0, p0 = model(img[:0].cuda(), ids[:0].cuda(), mask[:0].cuda())
+    assert tuple(l0.shape) == (0, 2) and tuple(p0.shape) == (0, 2)
+    l2, _ = model(img.cuda(), ids.cuda(), mask.cuda())
+    l1, p1 = model(img[:1].cuda(), ids[:1].cuda(), mask[:1].cuda())
+    torch.cuda.synchronize()
+    assert tuple(l1.shape) == (1, 2)
+    assert rel(l1, l2[:1]) <= 2e-3      # same clip, different batch: only the tile schedule differs
+    assert abs(float(p1.sum()) - 1.0) < 1e-5

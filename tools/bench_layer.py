@@ -56,6 +56,8 @@ CASES = {
     "attn_out": lambda: gemm_case(GEMM_M, 768, 768, B.ACT_NONE, True),
     "ffn_in": lambda: gemm_case(GEMM_M, 3072, 768, B.ACT_GELU, False),
     "ffn_out": lambda: gemm_case(GEMM_M, 768, 3072, B.ACT_NONE, True),
+    "ffn_in_noact": lambda: gemm_case(GEMM_M, 3072, 768, B.ACT_NONE, False),
+    "ffn_in_relu": lambda: gemm_case(GEMM_M, 3072, 768, B.ACT_RELU, False),
 }
 
 def main():

@@ -113,6 +113,8 @@ class Engine:
         if return_emb:
             ve = torch.empty(B, self.clip_frames, 2048, dtype=torch.float32, device=dev)
             le = torch.empty(B, 768, dtype=torch.float32, device=dev)
+        if B == 0:      # nothing to score (empty tensors have no device pointer to hand over)
+            return (logits, probs, ve, le) if return_emb else (logits, probs)
         with torch.cuda.device(dev):
             _b.check(self._lib.vcg_forward(self._h, img_ptr, emb_ptr, ids.data_ptr(), mask.data_ptr(), B, L,
                                            logits.data_ptr(), probs.data_ptr(), 0 if ve is None else ve.data_ptr(),
@@ -130,6 +132,8 @@ class Engine:
         dev = ids.device
         ve = torch.empty(B, self.clip_frames, 2048, dtype=torch.float32, device=dev)
         le = torch.empty(B, 768, dtype=torch.float32, device=dev)
+        if B == 0:
+            return ve, le
         with torch.cuda.device(dev):
             _b.check(self._lib.vcg_embed(self._h, img_clip.data_ptr(), ids.data_ptr(), mask.data_ptr(), B, L,
                                          ve.data_ptr(), le.data_ptr(), _stream()))
@@ -146,6 +150,8 @@ class Engine:
         logits = torch.empty(B, 2, dtype=torch.float32, device=dev)
         probs = torch.empty(B, 2, dtype=torch.float32, device=dev)
         ve = torch.empty(B, self.clip_frames, 2048, dtype=torch.float32, device=dev) if return_emb else None
+        if B == 0:
+            return (logits, probs, ve) if return_emb else (logits, probs)
         with torch.cuda.device(dev):
             _b.check(self._lib.vcg_forward_vision(self._h, img_clip.data_ptr(), B, logits.data_ptr(), probs.data_ptr(),
                                                   0 if ve is None else ve.data_ptr(), _stream()))
@@ -158,6 +164,8 @@ class Engine:
         logits = torch.empty(B, 2, dtype=torch.float32, device=dev)
         probs = torch.empty(B, 2, dtype=torch.float32, device=dev)
         le = torch.empty(B, 768, dtype=torch.float32, device=dev) if return_emb else None
+        if B == 0:
+            return (logits, probs, le) if return_emb else (logits, probs)
         with torch.cuda.device(dev):
             _b.check(self._lib.vcg_forward_text(self._h, ids.data_ptr(), mask.data_ptr(), B, L, logits.data_ptr(),
                                                 probs.data_ptr(), 0 if le is None else le.data_ptr(), _stream()))
