@@ -356,3 +356,67 @@ def test_empty_and_single_clip_batches(golden_dir):
     assert tuple(l1.shape) == (1, 2)
     assert rel(l1, l2[:1]) <= 2e-3      # same clip, different batch: only the tile schedule differs
     assert abs(float(p1.sum()) - 1.0) < 1e-5
+
+
+def test_full_size_properties_config1():
+    """BASELINE.json configs[1] at its full size (256 clips, T=16, L=100, precomputed vision embeddings, bf16), checked
+    through size-independent properties: run-to-run determinism (bit-identical), permutation equivariance over the
+    clips and independence of the batch composition (a clip scores the same alone, in a batch of 64 and of 256)."""
+    from oracle import weights as W
+    T, L, B = 16, 100, 256
+    model, _ = build_model(T, "mlp", "bf16", vision=False)
+    g = torch.Generator().manual_seed(31)
+    emb = (torch.rand(B, T, 2048, generator=g) * 2.0).cuda().view(B, T, 2048, 1, 1)
+    ids, mask = W.make_text(B, L, seed=31)
+    ids, mask = ids.cuda(), mask.cuda()
+    l1, p1 = model(emb, ids, mask)
+    l2, p2 = model(emb, ids, mask)
+    assert torch.equal(l1, l2) and torch.equal(p1, p2)                         # deterministic
+    assert torch.isfinite(l1).all() and torch.allclose(p1.sum(1), torch.ones(B, device="cuda"), atol=1e-5)
+    perm = torch.randperm(B, generator=g).cuda()
+    lp, _ = model(emb[perm], ids[perm], mask[perm])
+    # a different batch order only changes which tile a token lands in: same values up to bf16 accumulation order
+    assert rel(lp, l1[perm]) <= 5e-3
+    l64, _ = model(emb[:64], ids[:64], mask[:64])
+    lone, _ = model(emb[5:6], ids[5:6], mask[5:6])
+    assert rel(l64, l1[:64]) <= 5e-3 and rel(lone, l1[5:6]) <= 5e-3
+    lab = l1.topk(1, 1, True, True)[1].view(-1)
+    margin = (l1[:, 0] - l1[:, 1]).abs()
+    safe = margin > 0.05 * l1.abs().max()                                      # labels can only differ on near ties
+    assert torch.equal(lp.topk(1, 1, True, True)[1].view(-1)[safe[perm]], lab[perm][safe[perm]])
+
+
+def test_full_size_properties_video_pipeline():
+    """BASELINE.json configs[0]/[2] shape: a synthetic 10-minute video (600 frames -> 146 clips, T=16, L=100) from uint8
+    frames.  The per-clip path, the shared-stem grid path and the host-buffer entry point must agree; a run in several
+    internal passes (max_batch 32) must equal one in a single pass; cut points from the device post-processing must equal
+    the reference peak picker on the same labels."""
+    from oracle import two_stream_oracle as orc
+    from oracle import weights as W
+    from vcg_b200 import postprocess as pp
+    T, L, n_frames = 16, 100, 600
+    starts = W.clip_starts(n_frames, T)
+    B = len(starts)
+    assert B == 146
+    model, _ = build_model(T, "mlp", "bf16", chunk=32)
+    frames = W.make_frames_u8(n_frames, seed=41)
+    ids, mask = W.make_text(B, L, seed=41)
+    img1 = orc.gather_clips(orc.preprocess_u8(frames[:T]), [0], T)
+    model(img1.cuda(), ids[:1].cuda(), mask[:1].cuda())     # creates the engine
+    eng = model.engine
+    st = torch.tensor(starts, dtype=torch.int32)
+    fr, idc, mkc = frames.cuda(), ids.cuda(), mask.cuda()
+    grid, _ = eng.score_video_u8(fr, 0, 4, idc, mkc)
+    grid2, _ = eng.score_video_u8(fr, 0, 4, idc, mkc)
+    assert torch.equal(grid, grid2)                                            # deterministic
+    per_clip, _ = eng.score_clips_u8(fr, st.cuda(), idc, mkc)
+    host, _ = eng.score_clips_u8_host(frames.pin_memory(), st.pin_memory(), ids.pin_memory(), mask.pin_memory())
+    assert torch.equal(host, grid.cpu())
+    assert rel(per_clip, grid) <= 1e-2      # the grid path folds the shift of layer1.0.conv1 into three temporal taps (bf16)
+    big, _ = build_model(T, "mlp", "bf16", chunk=160)
+    big(img1.cuda(), ids[:1].cuda(), mask[:1].cuda())
+    one_pass, _ = big.engine.score_clips_u8(fr, st.cuda(), idc, mkc)
+    assert rel(one_pass, per_clip) <= 1e-2                                     # 5 passes of 32 == 1 pass of 146
+    labels, cuts = pp.cut_points_device(grid, torch.tensor([0, B], dtype=torch.int32), T, 2)
+    assert cuts[0] == orc.convert_clip_label2cut_point(labels.cpu().tolist(), T, 2)
+    assert labels.cpu().tolist() == orc.predict_labels(grid.cpu())
