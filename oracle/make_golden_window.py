@@ -31,7 +31,13 @@ def make_inputs(T, window, L, B, seed):
     # window b = clips starting at 4*(b + i), i = 0..2w  (neighbouring clips overlap, as in the dataset)
     img = torch.stack([orc.gather_clips(norm, [4 * (b + i) for i in range(Wn)], T) for b in range(B)])   # [B,W,T,3,224,224]
     ids, mask = W.make_text(B * Wn, L, seed=seed)
-    return img, ids.view(B, Wn, L), mask.view(B, Wn, L)
+    ids, mask = ids.view(B, Wn, L).clone(), mask.view(B, Wn, L).clone()
+    # window 0 sits at the start of its video: its first clip is the dataset's padding (zero frames, zero ids, ZERO mask;
+    # infer_youtube_video_dataset.py:488-499)
+    img[0, 0] = 0
+    ids[0, 0] = 0
+    mask[0, 0] = 0
+    return img, ids, mask
 
 
 def main():

@@ -47,7 +47,10 @@ def bert_forward(sd, ids, mask, prefix="lang_model.", taps=None):
     x = F.layer_norm(x, (768,), sd[p + "embeddings.LayerNorm.weight"], sd[p + "embeddings.LayerNorm.bias"], 1e-12)
     if taps is not None:
         taps["bert.embeddings"] = x
-    # additive key mask: 0 where attention_mask == 1, -inf-like elsewhere (modeling_bert.py:115-140 via sdpa)
+    # additive key mask: 0 where attention_mask == 1, -inf elsewhere (modeling_bert.py:115-140 via sdpa).  A row whose mask
+    # is ALL zero -- the window dataset's padding clips, infer_youtube_video_dataset.py:488-499 -- gets a ZERO attention
+    # context: torch's scaled_dot_product_attention (2.11, what the pinned oracle environment runs) uses a "safe softmax"
+    # that returns 0 for fully masked rows instead of NaN.  Verified against transformers 5.5 BertModel on CPU.
     add = torch.zeros(B, 1, 1, L, device=ids.device).masked_fill(mask[:, None, None, :] == 0, float("-inf"))
     n_layers = 0
     while f"{p}encoder.layer.{n_layers}.attention.self.query.weight" in sd:
@@ -61,6 +64,7 @@ def bert_forward(sd, ids, mask, prefix="lang_model.", taps=None):
         k = heads(F.linear(x, sd[q_ + "attention.self.key.weight"], sd[q_ + "attention.self.key.bias"]))
         v = heads(F.linear(x, sd[q_ + "attention.self.value.weight"], sd[q_ + "attention.self.value.bias"]))
         att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(64.0) + add, dim=-1)
+        att = torch.nan_to_num(att, nan=0.0)      # fully masked rows: safe softmax -> 0
         ctx = (att @ v).transpose(1, 2).reshape(B, L, 768)
         # BertSelfOutput, modeling_bert.py:294-298
         y = F.linear(ctx, sd[q_ + "attention.output.dense.weight"], sd[q_ + "attention.output.dense.bias"])

@@ -143,7 +143,8 @@ def test_shared_stem_for_overlapping_clips():
 
 def test_token_packing_irregular_masks():
     """The text stream drops masked tokens (exact: they are masked as keys everywhere and only h[:,0] is read).
-    Masks with holes, a masked [CLS] position and full-length rows must all match the dense oracle."""
+    Masks with holes, a masked [CLS] position, full-length rows and an ALL-ZERO mask (the window dataset's padding clips:
+    zero attention context, like torch's sdpa) must all match the dense oracle."""
     from oracle import two_stream_oracle as orc
     from oracle import weights as W
     T, L, B = 8, 48, 6
@@ -154,6 +155,7 @@ def test_token_packing_irregular_masks():
     mask[2] = 1                                                                     # full length
     mask[3] = (torch.rand(L, generator=g) > 0.5).long(); mask[3, 0] = 0; mask[3, 5] = 1   # [CLS] itself masked as a key
     mask[4] = 0; mask[4, 0] = 1                                                     # a single token
+    mask[5] = 0; ids[5] = 0                                                         # padding clip: nothing attendable
     emb = torch.rand(B, T, 2048, generator=g)
     ref_logits, _, _, ref_lang = orc.two_stream_forward(sd, None, ids, mask, T, vision_emb=emb)
     logits, probs, _, lang = model(emb.cuda().view(B, T, 2048, 1, 1), ids.cuda(), mask.cuda(), return_emb=True)

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256, 3) bert_attention_bf16_kernel(const __nv_
   for (int r = 0; r < 2; ++r) {
     const int q = q0 + qrow + g + r * 8;
     if (q < L) {
-      const float inv = 1.0f / l[r];
+      const float inv = l[r] > 0.f ? 1.0f / l[r] : 0.f;   // fully masked row: zero context (torch sdpa's safe softmax)
       __nv_bfloat16* dst = ctx + (row_base + q) * kBertHidden + head * kHeadDim + t2;
 #pragma unroll
       for (int dt = 0; dt < 8; ++dt)
@@ -259,8 +259,9 @@ __global__ void __launch_bounds__(128) bert_attention_fp32_kernel(const float* _
       a1 = fmaf(p, vp[lane + 32], a1);
     }
     float* dst = ctx + (row_base + q) * kBertHidden + head * kHeadDim;
-    dst[lane] = a0 / sum;
-    dst[lane + 32] = a1 / sum;
+    const float inv = sum > 0.f ? 1.0f / sum : 0.f;   // fully masked row: zero context (torch sdpa's safe softmax)
+    dst[lane] = a0 * inv;
+    dst[lane + 32] = a1 * inv;
     __syncwarp();
   }
 }

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
       mbar_wait(&o_full[slot], ph);
       tc_fence_after();
       if (warp_active) {
-        const float inv = 1.0f / l;
+        const float inv = l > 0.f ? 1.0f / l : 0.f;   // no attendable key (fully masked clip): zero context, as torch's sdpa
         __nv_bfloat16* dst = p.ctx + static_cast<long>(row_base + q) * kBertHidden + (head0 + g) * 64;
         uint32_t r[4][16];
 #pragma unroll
