@@ -422,3 +422,40 @@ def test_full_size_properties_video_pipeline():
     labels, cuts = pp.cut_points_device(grid, torch.tensor([0, B], dtype=torch.int32), T, 2)
     assert cuts[0] == orc.convert_clip_label2cut_point(labels.cpu().tolist(), T, 2)
     assert labels.cpu().tolist() == orc.predict_labels(grid.cpu())
+
+
+def test_window_score_video_equals_materialised_windows():
+    """score_video() computes every clip's backbone embedding once and gathers the 2w+1 neighbours (padding clip outside
+    the video); it must equal forward() on the windows materialised the way the reference's dataset does."""
+    from model.fusion import two_stream_window
+    from model.lang import bert_hugface
+    from model.vision import resnet50_tsm
+    from oracle import two_stream_oracle as orc
+    from oracle import weights as W
+    T, w, L, N = 8, 1, 24, 6
+    skip = T // 4
+    sd = W.make_window_state_dict(T, w, "cross_attn", seed=123)
+    lang = bert_hugface.BertHugface(pretrain_stage=False)
+    vis = resnet50_tsm.Resnet50TSM(segments_size=T, shift_div=8, pretrain_stage=False)
+    model = two_stream_window.TwoStream(lang.base_model, vis.base_model, 768, 2048, T, 128, w)
+    model.build_chapter_head(2, "cross_attn")
+    model.load_state_dict(sd, strict=True)
+    model = model.to(0).eval()
+    model.precision = "fp32"
+    frames = W.make_frames_u8(4 * (N - 1) + T, seed=5)
+    clips = orc.gather_clips(orc.preprocess_u8(frames), [4 * n for n in range(N)], T)          # [N,T,3,224,224]
+    ids, mask = W.make_text(N, L, seed=5)
+    Wn = 2 * w + 1
+    win_img = torch.zeros(N, Wn, T, 3, 224, 224)
+    win_ids = torch.zeros(N, Wn, L, dtype=torch.long)
+    win_mask = torch.zeros(N, Wn, L, dtype=torch.long)
+    for n in range(N):
+        for i in range(Wn):
+            src = n + (i - w) * skip
+            if 0 <= src < N:
+                win_img[n, i], win_ids[n, i], win_mask[n, i] = clips[src], ids[src], mask[src]
+    ref_logits, ref_probs = model(win_img.cuda(), win_ids.cuda(), win_mask.cuda(), None)
+    logits, probs = model.score_video(clips.cuda(), ids.cuda(), mask.cuda())
+    torch.cuda.synchronize()
+    print("score_video vs forward", rel(logits, ref_logits))
+    assert rel(logits, ref_logits) <= 1e-4 and rel(probs, ref_probs) <= 1e-4

@@ -33,5 +33,10 @@ ms = timed(lambda: model(img, ids, mask, None))
 eng = model.engine if hasattr(model, "engine") else model._engine
 flat = (img.transpose(0, 1).reshape(Wn * B, T, 3, 224, 224), ids.transpose(0, 1).reshape(Wn * B, L), mask.transpose(0, 1).reshape(Wn * B, L))
 ms_embed = timed(lambda: eng.embed(*flat))
+# per-video scoring with every clip embedded once (score_video): N = B * Wn clips of one video
+N = B * Wn
+clips = img.reshape(N, T, 3, 224, 224); cids = ids.reshape(N, L); cmask = mask.reshape(N, L)
+ms_video = timed(lambda: model.score_video(clips, cids, cmask))
+print(f"score_video: {N} clips of one video, each embedded once: {ms_video:.2f} ms -> {N/ms_video*1e3:.0f} windows/s")
 print(f"window model head={head} B={B} w={w} (clips per step {B*Wn}): {ms:.2f} ms/step -> {B/ms*1e3:.1f} windows/s, "
       f"{B*Wn/ms*1e3:.0f} clips/s; backbone pass {ms_embed:.2f} ms ({ms_embed/ms*100:.0f} %), heads + window stack {ms-ms_embed:.2f} ms")

@@ -196,68 +196,107 @@ class TwoStream(nn.Module):
         return cur
 
     # ------------------------------------------------------------------ forward
-    def forward(self, img_clips, text_ids, attention_masks, clip_info=None):
-        """img_clips [B,W,T,3,224,224], text_ids / attention_masks [B,W,L] -> (binary_logits, binary_prob) [B,2]
-        (reference :392-445; clip_info is accepted and, as in the reference, not used by the arithmetic)."""
+    def _fuse_and_classify(self, vis_by_pos, lang_by_pos):
+        """vis_by_pos[i] [bs,T,2048], lang_by_pos[i] [bs,768] (fp32 CUDA) for the 2w+1 window positions ->
+        (logits, probs) [bs,2]: per-position ChapterHead, six window-attention blocks, classifier."""
         from vcg_b200 import binding as B
+        lib = B.load_library()
+        fh = self.fusion_head
+        W, T, H = 2 * self.window_size + 1, self.segment_size, self.hidden_size
+        bs, dev = lang_by_pos[0].shape[0], lang_by_pos[0].device
+        s = torch.cuda.current_stream().cuda_stream
+        fused = torch.empty(bs, W, H, dtype=torch.float32, device=dev)
+        for i in range(W):
+            le = lang_by_pos[i].contiguous()
+            ve = vis_by_pos[i].reshape(bs * T, self.vision_embed_size).contiguous()
+            lang_out = self._run_chain(fh.lang_proj_heads[i], True, le)                 # relu(proj(lang)) [bs,H]
+            vis_out = self._run_chain(fh.vision_proj_heads[i], True, ve)                # [bs*T,H]
+            if fh.head_type == "mlp":      # cat([vision_out, lang_out]) -> head[i]
+                f = self._run_chain(fh.head[i], False, vis_out.view(bs, T * H), lang_out)
+            else:                           # cross_attn: lang queries the T frame vectors
+                ca = fh.head
+                p = B.VcgCrossAttnParams(ca.num_heads, *[t.data_ptr() for t in (
+                    ca.lang_norm.weight, ca.lang_norm.bias, ca.vision_norm.weight, ca.vision_norm.bias,
+                    ca.frame_pos_encoding.weight, ca.frame_pos_encoding.bias,
+                    ca.query_proj.weight, ca.query_proj.bias, ca.key_proj.weight, ca.key_proj.bias,
+                    ca.value_proj.weight, ca.value_proj.bias, ca.out_proj.weight, ca.out_proj.bias)])
+                f = torch.empty(bs, H, dtype=torch.float32, device=dev)
+                B.check(lib.vcg_op_cross_attention(ctypes.byref(p), lang_out.data_ptr(), vis_out.data_ptr(), bs, T,
+                                                   f.data_ptr(), s))
+            fused[:, i] = f
+        # six window-attention blocks + classifier on the middle clip
+        wa = self.window_attn
+        sp = B.VcgWindowStackParams()
+        sp.num_layers, sp.pos_bias_stride = wa.num_layers, W
+        for li, blk in enumerate(wa.layers):
+            a, lins = blk.attention, [m for m in blk.ffn if isinstance(m, nn.Linear)]
+            vals = [blk.attention_norm.weight, blk.attention_norm.bias, blk.ffn_norm.weight, blk.ffn_norm.bias,
+                    a.position_encoding.weight, a.position_encoding.bias, a.window_pos_bias,
+                    a.query.weight, a.query.bias, a.key.weight, a.key.bias, a.value.weight, a.value.bias,
+                    a.out_proj.weight, a.out_proj.bias]
+            for lin in lins:
+                vals += [lin.weight, lin.bias]
+            sp.layers[li] = B.VcgWindowLayer(*[t.data_ptr() for t in vals])
+        sp.final_norm_w, sp.final_norm_b = wa.final_layer_norm.weight.data_ptr(), wa.final_layer_norm.bias.data_ptr()
+        lins = [m for m in wa.classifier if isinstance(m, nn.Linear)]
+        lns = [m for m in wa.classifier if isinstance(m, nn.LayerNorm)]
+        for j, lin in enumerate(lins):
+            sp.cls_w[j], sp.cls_b[j] = lin.weight.data_ptr(), lin.bias.data_ptr()
+        for j, ln in enumerate(lns):
+            sp.cls_norm_w[j], sp.cls_norm_b[j] = ln.weight.data_ptr(), ln.bias.data_ptr()
+        logits = torch.empty(bs, 2, dtype=torch.float32, device=dev)
+        probs = torch.empty(bs, 2, dtype=torch.float32, device=dev)
+        B.check(lib.vcg_op_window_stack(ctypes.byref(sp), fused.data_ptr(), bs, W, logits.data_ptr(), probs.data_ptr(), s))
+        return logits, probs
+
+    def _check(self, text_ids):
         if not text_ids.is_cuda:
             raise RuntimeError("TwoStream.forward needs CUDA inputs: the B200 implementation has no CPU fallback")
         if self.training:
             raise RuntimeError("inference-only: call .eval() first")
-        lib = B.load_library()
+
+    def forward(self, img_clips, text_ids, attention_masks, clip_info=None):
+        """img_clips [B,W,T,3,224,224], text_ids / attention_masks [B,W,L] -> (binary_logits, binary_prob) [B,2]
+        (reference :392-445; clip_info is accepted and, as in the reference, not used by the arithmetic)."""
+        self._check(text_ids)
         bs, W, L = text_ids.shape
-        T, H = self.segment_size, self.hidden_size
+        T = self.segment_size
         if W != 2 * self.window_size + 1:
             raise RuntimeError(f"expected {2 * self.window_size + 1} clips per window, got {W}")
         eng = self._get_engine(text_ids.device, L)
-        fh = self.fusion_head
-        s = torch.cuda.current_stream().cuda_stream
         with torch.no_grad():
             # backbones of every clip of every window, window position major: row = i * bs + b
             img = img_clips.float().transpose(0, 1).reshape(W * bs, T, 3, 224, 224)
             ids = text_ids.transpose(0, 1).reshape(W * bs, L)
             mask = attention_masks.transpose(0, 1).reshape(W * bs, L)
             vis_emb, lang_emb = eng.embed(img, ids, mask)                      # [W*bs,T,2048], [W*bs,768]
-            fused = torch.empty(bs, W, H, dtype=torch.float32, device=ids.device)
-            for i in range(W):
-                le = lang_emb[i * bs:(i + 1) * bs]
-                ve = vis_emb[i * bs:(i + 1) * bs].reshape(bs * T, self.vision_embed_size)
-                lang_out = self._run_chain(fh.lang_proj_heads[i], True, le)                 # relu(proj(lang)) [bs,H]
-                vis_out = self._run_chain(fh.vision_proj_heads[i], True, ve)                # [bs*T,H]
-                if fh.head_type == "mlp":      # cat([vision_out, lang_out]) -> head[i]
-                    f = self._run_chain(fh.head[i], False, vis_out.view(bs, T * H), lang_out)
-                else:                           # cross_attn: lang queries the T frame vectors
-                    ca = fh.head
-                    p = B.VcgCrossAttnParams(ca.num_heads, *[t.data_ptr() for t in (
-                        ca.lang_norm.weight, ca.lang_norm.bias, ca.vision_norm.weight, ca.vision_norm.bias,
-                        ca.frame_pos_encoding.weight, ca.frame_pos_encoding.bias,
-                        ca.query_proj.weight, ca.query_proj.bias, ca.key_proj.weight, ca.key_proj.bias,
-                        ca.value_proj.weight, ca.value_proj.bias, ca.out_proj.weight, ca.out_proj.bias)])
-                    f = torch.empty(bs, H, dtype=torch.float32, device=ids.device)
-                    B.check(lib.vcg_op_cross_attention(ctypes.byref(p), lang_out.data_ptr(), vis_out.data_ptr(), bs, T,
-                                                       f.data_ptr(), s))
-                fused[:, i] = f
-            # six window-attention blocks + classifier on the middle clip
-            wa = self.window_attn
-            sp = B.VcgWindowStackParams()
-            sp.num_layers, sp.pos_bias_stride = wa.num_layers, 2 * self.window_size + 1
-            for li, blk in enumerate(wa.layers):
-                a, lins = blk.attention, [m for m in blk.ffn if isinstance(m, nn.Linear)]
-                vals = [blk.attention_norm.weight, blk.attention_norm.bias, blk.ffn_norm.weight, blk.ffn_norm.bias,
-                        a.position_encoding.weight, a.position_encoding.bias, a.window_pos_bias,
-                        a.query.weight, a.query.bias, a.key.weight, a.key.bias, a.value.weight, a.value.bias,
-                        a.out_proj.weight, a.out_proj.bias]
-                for lin in lins:
-                    vals += [lin.weight, lin.bias]
-                sp.layers[li] = B.VcgWindowLayer(*[t.data_ptr() for t in vals])
-            sp.final_norm_w, sp.final_norm_b = wa.final_layer_norm.weight.data_ptr(), wa.final_layer_norm.bias.data_ptr()
-            lins = [m for m in wa.classifier if isinstance(m, nn.Linear)]
-            lns = [m for m in wa.classifier if isinstance(m, nn.LayerNorm)]
-            for j, lin in enumerate(lins):
-                sp.cls_w[j], sp.cls_b[j] = lin.weight.data_ptr(), lin.bias.data_ptr()
-            for j, ln in enumerate(lns):
-                sp.cls_norm_w[j], sp.cls_norm_b[j] = ln.weight.data_ptr(), ln.bias.data_ptr()
-            logits = torch.empty(bs, 2, dtype=torch.float32, device=ids.device)
-            probs = torch.empty(bs, 2, dtype=torch.float32, device=ids.device)
-            B.check(lib.vcg_op_window_stack(ctypes.byref(sp), fused.data_ptr(), bs, W, logits.data_ptr(), probs.data_ptr(), s))
-        return logits, probs
+            return self._fuse_and_classify([vis_emb[i * bs:(i + 1) * bs] for i in range(W)],
+                                           [lang_emb[i * bs:(i + 1) * bs] for i in range(W)])
+
+    def score_video(self, img_clips, text_ids, attention_masks, skip=None):
+        """Every candidate clip of ONE video as a window target, with each clip's backbone embedding computed once.
+
+        img_clips [N,T,3,224,224], text_ids / attention_masks [N,L]: the video's clips in order.  Target n sees the
+        clips n + (i - w) * skip, i = 0..2w (skip = clip_frame_num // (2 * max_offset) = T // 4, the dataset's
+        get_clip_info, infer_youtube_video_dataset.py:459-478); positions outside the video are the dataset's padding
+        clip (zero frames, zero ids, zero mask, :488-499).  Equals forward() on the materialised windows; the reference
+        (and forward()) run the backbones 2w+1 times per clip, this runs them once.  -> (logits, probs) [N,2]."""
+        self._check(text_ids)
+        N, L = text_ids.shape
+        T, w = self.segment_size, self.window_size
+        skip = max(1, T // 4) if skip is None else skip
+        eng = self._get_engine(text_ids.device, L)
+        with torch.no_grad():
+            dev = text_ids.device
+            img = torch.cat([img_clips.float(), torch.zeros(1, T, 3, 224, 224, device=dev)])       # + padding clip
+            ids = torch.cat([text_ids.long(), torch.zeros(1, L, dtype=torch.long, device=dev)])
+            mask = torch.cat([attention_masks.long(), torch.zeros(1, L, dtype=torch.long, device=dev)])
+            vis_emb, lang_emb = eng.embed(img, ids, mask)                      # [N+1,T,2048], [N+1,768]
+            n = torch.arange(N, device=dev)
+            vis_by_pos, lang_by_pos = [], []
+            for i in range(2 * w + 1):
+                src = n + (i - w) * skip
+                src = torch.where((src >= 0) & (src < N), src, torch.full_like(src, N))     # N = the padding clip
+                vis_by_pos.append(vis_emb[src])
+                lang_by_pos.append(lang_emb[src])
+            return self._fuse_and_classify(vis_by_pos, lang_by_pos)
