@@ -248,19 +248,23 @@ __global__ void layernorm768_kernel(const elem_t<FP32>* __restrict__ x, const fl
   pdl_enter();
   const int row0 = 2 * (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
-  if (rows_dev) rows = min(rows, *rows_dev);     // token-packed BERT: only the packed rows exist
-  if (row0 >= rows) return;
-  const bool two = row0 + 1 < rows;
+  if (row0 >= rows) return;                      // `rows` = allocated rows: every load below stays inside the buffer
+  const bool two_alloc = row0 + 1 < rows;
   float v[2][3][8];
 #pragma unroll
   for (int r = 0; r < 2; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      if (r == 0 || two) load8<FP32>(x + (row0 + r) * 768L + c * 256 + lane * 8, v[r][c]);
+      if (r == 0 || two_alloc) load8<FP32>(x + (row0 + r) * 768L + c * 256 + lane * 8, v[r][c]);
       else
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[r][c][e] = 0.f;
     }
+  // token-packed BERT: only the packed rows exist.  Read the device-side count AFTER issuing the row loads (it is a
+  // dependent L2 round trip that would otherwise sit in front of them).
+  if (rows_dev) rows = min(rows, __ldg(rows_dev));
+  if (row0 >= rows) return;
+  const bool two = row0 + 1 < rows;
   float s[2] = {0.f, 0.f};
 #pragma unroll
   for (int r = 0; r < 2; ++r)
