@@ -28,6 +28,12 @@ def _worker(rank, world, port, n_clips, out_dir):
 
     got = vd.score_sharded(score, n_clips)
     ok = torch.equal(got, full)
+    # the overlapped form used by bench.py: several gathers in flight, waited for later
+    lo_, hi_ = vd.shard_range(n_clips, rank, world)
+    pend = [vd.allgather_scores_async(score(lo_, hi_) + k, n_clips) for k in range(3)]
+    for k, (res, work) in enumerate(pend):
+        work.wait()
+        ok = ok and torch.equal(res, full + k)
     lo, hi = vd.shard_range(n_clips, rank, world)
     torch.save({"ok": ok, "lo": lo, "hi": hi}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()

@@ -40,6 +40,26 @@ def allgather_scores(local_scores, n_total, group=None):
     return recv[:n_total]
 
 
+def allgather_scores_async(local_scores, n_total, group=None):
+    """Same exchange, not waited for: returns (result [n_total, C], work).  The collective runs on the backend's own
+    stream, so the next scoring pass can start underneath it; call ``work.wait()`` before reading the result (it makes
+    the current stream wait, it does not block the host on NCCL)."""
+    world = dist.get_world_size(group)
+    per = shard_size(n_total, world)
+    C = local_scores.shape[1]
+    send = local_scores
+    if local_scores.shape[0] != per:
+        send = torch.zeros(per, C, dtype=local_scores.dtype, device=local_scores.device)
+        send[:local_scores.shape[0]] = local_scores
+    recv = torch.empty(world * per, C, dtype=local_scores.dtype, device=local_scores.device)
+    if dist.get_backend(group) == "nccl":
+        work = dist.all_gather_into_tensor(recv, send.contiguous(), group=group, async_op=True)
+    else:
+        chunks = list(recv.view(world, per, C).unbind(0))
+        work = dist.all_gather(chunks, send.contiguous(), group=group, async_op=True)
+    return recv[:n_total], work
+
+
 def score_sharded(score_fn, n_clips, group=None):
     """score_fn(lo, hi) -> logits [hi-lo, 2] for this rank's shard; returns all logits [n_clips, 2] on every rank."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
