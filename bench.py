@@ -195,7 +195,7 @@ def pipeline_extra(args, peaks):
     starts = W.clip_starts(n_frames, T)
     B = len(starts)
     sd = W.make_state_dict(T, "mlp", seed=123)
-    eng = Engine(T, "mlp", "bf16", vision=True, max_tokens=128, max_batch=int(os.environ.get("VCG_VISION_CHUNK", "32")))
+    eng = Engine(T, "mlp", "bf16", vision=True, max_tokens=128, max_batch=int(os.environ.get("VCG_VISION_CHUNK", "64")))   # clips per vision pass (12 GB workspace)
     eng.load_state_dict(sd)
     del sd
     g = torch.Generator().manual_seed(5)
