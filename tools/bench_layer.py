@@ -46,6 +46,8 @@ CASES = {
     "conv1_l2": lambda: conv_case(28, 512, 128, 1, 1, False, False, True),
     "conv2_l2": lambda: conv_case(28, 128, 128, 3, 1, False, False, False),
     "conv3_l3": lambda: conv_case(14, 256, 1024, 1, 1, True, True, False),
+    "conv3_l3_nt": lambda: conv_case(14, 256, 1024, 1, 1, True, False, False),
+    "conv3_l4_nt": lambda: conv_case(7, 512, 2048, 1, 1, True, False, False),
     "conv1_l3": lambda: conv_case(14, 1024, 256, 1, 1, False, False, True),
     "conv2_l3": lambda: conv_case(14, 256, 256, 3, 1, False, False, False),
     "conv3_l4": lambda: conv_case(7, 512, 2048, 1, 1, True, True, False),
