@@ -89,3 +89,54 @@ def test_seed_helper():
     a = torch.rand(3)
     set_random_seed.use_fix_random_seed()
     assert torch.equal(a, torch.rand(3))
+
+
+def test_flat_clip_reader(tmp_path):
+    """Flat-clip JSON (flat_video2clip_for_quick_infer.py:112-119) -> frame table with every JPEG decoded once, per-clip
+    start indices and the reference's tokenisation ("[CLS] " + text, truncate, [PAD], mask 1/0)."""
+    import json
+    import os
+    import sys
+    import numpy as np
+    import torch
+    from PIL import Image
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "video-chapter-generation_b200"))
+    from vcg_b200 import flat_clips as fc
+
+    T, L, n_frames = 8, 12, 20
+    rng = np.random.RandomState(0)
+    vid_dir = tmp_path / "vidA"
+    vid_dir.mkdir()
+    pixels = {}
+    for i in range(n_frames):
+        arr = rng.randint(0, 256, size=(224, 224, 3), dtype=np.uint8)
+        p = str(vid_dir / f"{i + 1:05d}.png")            # PNG: lossless, so pixel equality can be asserted
+        Image.fromarray(arr).save(p)
+        pixels[p] = arr
+    paths = sorted(pixels)
+    clips = []
+    for s in range(0, n_frames - T, 4):
+        clips.append({"image_paths": paths[s:s + T], "text_clip": "hello world " * (s + 1), "clip_label": int(s == 4),
+                      "clip_start_end": [s, s + T], "cut_points": [6], "vid": "vidA"})
+    jf = tmp_path / "clips.json"
+    jf.write_text(json.dumps(clips))
+
+    class Tok:   # minimal stand-in for BertTokenizer
+        def tokenize(self, text):
+            return text.split()
+
+        def convert_tokens_to_ids(self, toks):
+            return [{"[CLS]": 101, "[PAD]": 0, "hello": 7592, "world": 2088}[t] for t in toks]
+
+    videos = list(fc.iter_videos(str(jf), Tok(), T, L, pin=False))
+    assert len(videos) == 1
+    v = videos[0]
+    assert v.vid == "vidA" and len(v) == len(clips) == 3
+    assert v.frames.shape == (16, 224, 224, 3) and v.frames.dtype == torch.uint8       # 3 clips x 8 frames, 16 distinct
+    assert v.clip_start.tolist() == [0, 4, 8]
+    for c, info in enumerate(clips):
+        for t, p in enumerate(info["image_paths"]):
+            assert np.array_equal(v.frames[v.clip_start[c] + t].numpy(), pixels[p])
+    assert v.text_ids[0].tolist() == [101, 7592, 2088] + [0] * 9 and v.attention_mask[0].tolist() == [1] * 3 + [0] * 9
+    assert v.attention_mask[2].sum() == L and v.text_ids[2, 0] == 101                    # truncated at max_text_len
+    assert v.labels.tolist() == [0, 1, 0] and v.cut_points == [6]

@@ -459,3 +459,57 @@ def test_window_score_video_equals_materialised_windows():
     torch.cuda.synchronize()
     print("score_video vs forward", rel(logits, ref_logits))
     assert rel(logits, ref_logits) <= 1e-4 and rel(probs, ref_probs) <= 1e-4
+
+
+def test_flat_clip_reader_end_to_end(tmp_path):
+    """Flat-clip JSON -> FlatClipVideo (every frame decoded once, uint8) -> engine host entry point, against the oracle
+    fed the reference's per-clip fp32 preprocessing of the same image files."""
+    import json
+    from PIL import Image
+    from oracle import two_stream_oracle as orc
+    from oracle import weights as W
+    from vcg_b200 import flat_clips as fc
+    T, L, B = 8, 24, 4
+    frames = W.make_frames_u8(4 * (B - 1) + T, seed=21)
+    paths = []
+    for i in range(frames.shape[0]):
+        p = str(tmp_path / f"{i + 1:05d}.png")
+        Image.fromarray(frames[i].numpy()).save(p)
+        paths.append(p)
+    ids, mask = W.make_text(B, L, seed=21)
+
+    class Tok:      # token "i" of clip b is the string "b:i"; ids come from the seeded text
+        def tokenize(self, text):
+            return text.split()
+
+        def convert_tokens_to_ids(self, toks):
+            out = []
+            for t in toks:
+                if t == "[PAD]":
+                    out.append(0)
+                elif t == "[CLS]":
+                    out.append(-1)
+                else:
+                    b, i = t.split(":")
+                    out.append(int(ids[int(b), int(i)]))
+            return out
+
+    clips = []
+    for b in range(B):
+        n = int(mask[b].sum())
+        clips.append({"image_paths": paths[4 * b:4 * b + T], "text_clip": " ".join(f"{b}:{i}" for i in range(1, n)),
+                      "clip_label": 0, "clip_start_end": [4 * b, 4 * b + T], "cut_points": [], "vid": "v"})
+    jf = tmp_path / "clips.json"
+    jf.write_text(json.dumps(clips))
+    video = next(fc.iter_videos(str(jf), Tok(), T, L))
+    video.text_ids[:, 0] = ids[:, 0]                                     # the [CLS] slot
+    assert torch.equal(video.text_ids * video.attention_mask, ids * mask) and torch.equal(video.attention_mask, mask)
+    assert torch.equal(video.frames, frames) and video.clip_start.tolist() == [0, 4, 8, 12]
+
+    model, sd = build_model(T, "mlp", "fp32")
+    img = orc.gather_clips(orc.preprocess_u8(frames), [4 * b for b in range(B)], T)
+    ref_logits, _, _, _ = orc.two_stream_forward(sd, img, ids, mask, T)
+    model(img[:1].cuda(), ids[:1].cuda(), mask[:1].cuda())
+    logits, probs = video.score(model.engine)
+    assert rel(logits, ref_logits) <= TOL["fp32"]
+    assert orc.predict_labels(logits) == orc.predict_labels(ref_logits)
