@@ -204,7 +204,8 @@ VCG_API int vcg_op_pr_hits(const int32_t* gt, const int32_t* gt_offsets, const i
 /* ---- window ("update") model, post-backbone part (two_stream_window.py, stacked_window_self_attention.py) --------
  * All tensors fp32 device memory; weights are the reference's nn.Linear / nn.LayerNorm parameters as they are
  * (Linear weight [out, in] row-major).  The host mirror (model/fusion/two_stream_window.py) strings these together. */
-enum { VCG_MLP_LINEAR = 0, VCG_MLP_LAYERNORM = 1, VCG_MLP_RELU = 2, VCG_MLP_GELU = 3 };
+enum { VCG_MLP_LINEAR = 0, VCG_MLP_LAYERNORM = 1, VCG_MLP_RELU = 2, VCG_MLP_GELU = 3,
+       VCG_MLP_MULHALVES = 4 /* row of 2n -> n: row[i] * row[n+i] ("multiplication" head, two_stream_window.py:277) */ };
 typedef struct vcg_mlp_op {
   int32_t type;          /* VCG_MLP_*                                                    */
   int32_t in_dim;        /* LINEAR: input features                                       */
@@ -228,6 +229,21 @@ typedef struct vcg_cross_attn_params {   /* CrossAttention (two_stream_window.py
 /* lang [B,128], vision [B,T,128] -> out [B,128] */
 VCG_API int vcg_op_cross_attention(const vcg_cross_attn_params* p, const float* lang, const float* vision, int32_t B,
                            int32_t T, float* out, void* stream);
+
+typedef struct vcg_self_attn_params {    /* SelfAttention (two_stream_window.py:91-131), n_embd 128 */
+  int32_t num_heads;                     /* 4 in the reference (:237) */
+  const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b;   /* query / key / value / proj */
+} vcg_self_attn_params;
+/* head_type "self_attn" (:281-283): tokens = the T frame vectors of vision [B,T,128] followed by lang [B,128]; unmasked
+ * attention, and only the FIRST token's context goes through proj (:129) -> out [B,128] */
+VCG_API int vcg_op_self_attention_first(const vcg_self_attn_params* p, const float* vision, const float* lang, int32_t B,
+                                int32_t T, float* out, void* stream);
+
+/* Contraction step of nn.Bilinear (head_type "bilinear", :189-191, 269-271): y [rows, out*in1] holds
+ * y[r, o*in1 + i] = sum_j W[o,i,j] x2[r,j] (one vcg_op_gemm over the weight viewed as [out*in1, in2]);
+ * out[r,o] = bias[o] + sum_i x1[r,i] * y[r, o*in1 + i]. */
+VCG_API int vcg_op_bilinear_contract(const float* y, const float* x1, const float* bias, int32_t rows, int32_t in1,
+                             int32_t out_features, float* out, void* stream);
 
 typedef struct vcg_window_layer {        /* VideoChapterBlock (stacked_window_self_attention.py:99-148) */
   const float *attn_norm_w, *attn_norm_b, *ffn_norm_w, *ffn_norm_b;

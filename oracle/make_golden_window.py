@@ -21,7 +21,10 @@ from oracle import window_oracle as worc  # noqa: E402
 from oracle.make_golden import GOLDEN, load_reference, rel  # noqa: E402
 
 # (name, head_type, T, window_size, L, B)
-CASES = [("cross_attn_T8_w1_L24_B2", "cross_attn", 8, 1, 24, 2), ("mlp_T8_w1_L24_B2", "mlp", 8, 1, 24, 2)]
+CASES = [("cross_attn_T8_w1_L24_B2", "cross_attn", 8, 1, 24, 2), ("mlp_T8_w1_L24_B2", "mlp", 8, 1, 24, 2),
+         # the reference's experimental fusion heads (two_stream_window.py:187-237)
+         ("bilinear_T8_w1_L24_B2", "bilinear", 8, 1, 24, 2), ("multiplication_T8_w1_L24_B2", "multiplication", 8, 1, 24, 2),
+         ("self_attn_T8_w1_L24_B2", "self_attn", 8, 1, 24, 2)]
 
 
 def make_inputs(T, window, L, B, seed):

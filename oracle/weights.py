@@ -183,6 +183,19 @@ def make_window_state_dict(clip_frames=8, window_size=1, head_type="cross_attn",
         seq(f"fusion_head.vision_proj_heads.{i}", [2048, 8 * h, 4 * h, h])
         if head_type == "mlp":
             seq(f"fusion_head.head.{i}", [(clip_frames + 1) * h, 8 * h, 4 * h, h])
+        elif head_type == "bilinear":       # nn.Bilinear(h, T*h, 2h) + Sequential(LN, ReLU, Drop, Linear, LN, ReLU, Drop, Linear)
+            sd[f"fusion_head.bilinear_layers.{i}.weight"] = u((2 * h, h, clip_frames * h), 1.5 / (h * clip_frames * h) ** 0.5)
+            sd[f"fusion_head.bilinear_layers.{i}.bias"] = u((2 * h,), 0.1)
+            norm(f"fusion_head.head.{i}.0", 2 * h)
+            linear(f"fusion_head.head.{i}.3", 2 * h, h)
+            norm(f"fusion_head.head.{i}.4", h)
+            linear(f"fusion_head.head.{i}.7", h, h)
+        elif head_type == "multiplication":
+            seq(f"fusion_head.lang_expand_layers.{i}", [h, 8 * h, clip_frames * h], norm_last=True)
+            seq(f"fusion_head.head.{i}", [clip_frames * h, 8 * h, 4 * h, h])
+    if head_type == "self_attn":
+        for n in ("key", "query", "value", "proj"):
+            linear(f"fusion_head.head.{n}", h, h)
     if head_type == "cross_attn":
         for n in ("query_proj", "key_proj", "value_proj", "out_proj"):
             linear(f"fusion_head.head.{n}", h, h)

@@ -43,6 +43,17 @@ def cross_attention(sd, p, lang, vision, num_heads=16):
     return _lin(sd, p + ".out_proj", ctx).squeeze(1)
 
 
+def self_attention_first(sd, p, x, num_heads=4):
+    """SelfAttention.forward, two_stream_window.py:114-131: unmasked attention over the tokens of x [B,N,C]; only the
+    first token's context goes through the output projection."""
+    B, N, C = x.shape
+    hd = C // num_heads
+    q, k, v = (_lin(sd, f"{p}.{nm}", x).view(B, N, num_heads, hd).transpose(1, 2) for nm in ("query", "key", "value"))
+    att = F.softmax(q @ k.transpose(-2, -1) * (1.0 / math.sqrt(hd)), dim=-1)
+    y = (att @ v).transpose(1, 2).contiguous().view(B, N, C)
+    return _lin(sd, p + ".proj", y[:, 0, :])
+
+
 def chapter_head(sd, lang_emb, vision_emb, i, T, head_type, H=128):
     """ChapterHead.forward for window position i, two_stream_window.py:252-290 -> fusion_emb [B,H]."""
     B = lang_emb.shape[0]
@@ -54,6 +65,19 @@ def chapter_head(sd, lang_emb, vision_emb, i, T, head_type, H=128):
         return _mlp(sd, f"fusion_head.head.{i}", x, 3)
     if head_type == "cross_attn":
         return cross_attention(sd, "fusion_head.head", lang_out, vis_out)
+    if head_type == "bilinear":           # :269-272
+        p = f"fusion_head.bilinear_layers.{i}"
+        x = F.bilinear(lang_out, vis_out.view(B, -1), sd[p + ".weight"], sd[p + ".bias"])
+        h = f"fusion_head.head.{i}"
+        x = _lin(sd, h + ".3", F.relu(_ln(sd, h + ".0", x)))
+        return _lin(sd, h + ".7", F.relu(_ln(sd, h + ".4", x)))
+    if head_type == "multiplication":     # :274-279
+        e = f"fusion_head.lang_expand_layers.{i}"
+        x = F.relu(_ln(sd, e + ".1", _lin(sd, e + ".0", lang_out)))
+        x = F.relu(_ln(sd, e + ".5", _lin(sd, e + ".4", x)))
+        return _mlp(sd, f"fusion_head.head.{i}", (vis_out * x.view(B, T, H)).view(B, -1), 3)
+    if head_type == "self_attn":          # :281-283 with SelfAttention.forward :114-131 (4 heads, first token out)
+        return self_attention_first(sd, "fusion_head.head", torch.cat([vis_out, lang_out.unsqueeze(1)], dim=1))
     raise RuntimeError(f"Unknown head_type {head_type}")
 
 

@@ -114,7 +114,10 @@ def test_vision_emb_io_roundtrip(tmp_path):
     assert back.shape == (3, 16, 2048, 1, 1) and torch.equal(back.view(3, 16, 2048), emb)
 
 
-@pytest.mark.parametrize("case,head", [("cross_attn_T8_w1_L24_B2", "cross_attn"), ("mlp_T8_w1_L24_B2", "mlp")])
+@pytest.mark.parametrize("case,head", [("cross_attn_T8_w1_L24_B2", "cross_attn"), ("mlp_T8_w1_L24_B2", "mlp"),
+                                       ("bilinear_T8_w1_L24_B2", "bilinear"),
+                                       ("multiplication_T8_w1_L24_B2", "multiplication"),
+                                       ("self_attn_T8_w1_L24_B2", "self_attn")])
 def test_window_oracle_matches_reference_golden(golden_dir, case, head):
     """Window ("update") model: restatement vs the reference's own outputs (oracle/make_golden_window.py)."""
     import numpy as np

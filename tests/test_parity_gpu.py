@@ -297,7 +297,10 @@ def test_device_postprocessing_matches_reference_vectors(golden_dir):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("case,head", [("cross_attn_T8_w1_L24_B2", "cross_attn"), ("mlp_T8_w1_L24_B2", "mlp")])
+@pytest.mark.parametrize("case,head", [("cross_attn_T8_w1_L24_B2", "cross_attn"), ("mlp_T8_w1_L24_B2", "mlp"),
+                                       ("bilinear_T8_w1_L24_B2", "bilinear"),
+                                       ("multiplication_T8_w1_L24_B2", "multiplication"),
+                                       ("self_attn_T8_w1_L24_B2", "self_attn")])
 def test_window_model_matches_reference_golden(golden_dir, case, head, precision):
     """two_stream_window.TwoStream (test_video_segment_update.py:99-107) through the mirrored module API against the
     reference's own outputs: backbones of all window clips in one engine pass, per-position heads, six window-attention
@@ -513,3 +516,45 @@ def test_flat_clip_reader_end_to_end(tmp_path):
     logits, probs = video.score(model.engine)
     assert rel(logits, ref_logits) <= TOL["fp32"]
     assert orc.predict_labels(logits) == orc.predict_labels(ref_logits)
+
+
+@pytest.mark.parametrize("head", ["bilinear", "multiplication", "self_attn"])
+@pytest.mark.parametrize("bs", [3, 160])
+def test_window_experimental_heads_vs_torch(head, bs):
+    """The reference's experimental fusion heads (two_stream_window.py:187-237, 269-283) at the batch sizes of both
+    routes (bs 3: chain programs; bs 160: wide Linear layers and the nn.Bilinear weight on the 3xTF32 tcgen05 GEMM),
+    against plain torch fp32 of the same modules."""
+    import math
+    import torch.nn.functional as F
+    from torch import nn
+    from model.fusion import two_stream_window as tsw
+    torch.manual_seed(1)
+    T, H = 8, 128
+    model = tsw.TwoStream(nn.Identity(), nn.Identity(), 768, 2048, T, H, 1)
+    model.build_chapter_head(2, head)
+    for m in model.modules():                      # non-trivial LayerNorm affine parameters
+        if isinstance(m, nn.LayerNorm):
+            nn.init.uniform_(m.weight, 0.5, 1.5)
+            nn.init.uniform_(m.bias, -0.1, 0.1)
+    model = model.cuda().eval()
+    fh = model.fusion_head
+    lang = torch.randn(bs, 768, device="cuda")
+    vis = torch.randn(bs, T, 2048, device="cuda").abs()
+    with torch.no_grad():
+        for i in (0, 2):
+            got = model._chapter_head(i, lang, vis)
+            lo = F.relu(fh.lang_proj_heads[i](lang))
+            vo = F.relu(fh.vision_proj_heads[i](vis.view(-1, 2048))).view(bs, T, H)
+            if head == "bilinear":
+                ref = fh.head[i](fh.bilinear_layers[i](lo, vo.view(bs, -1)))
+            elif head == "multiplication":
+                ref = fh.head[i]((vo * fh.lang_expand_layers[i](lo).view(bs, T, H)).view(bs, -1))
+            else:
+                x = torch.cat([vo, lo.unsqueeze(1)], dim=1)
+                sa = fh.head
+                q, k, v = (l(x).view(bs, T + 1, 4, 32).transpose(1, 2) for l in (sa.query, sa.key, sa.value))
+                y = (F.softmax(q @ k.transpose(-2, -1) / math.sqrt(32), dim=-1) @ v).transpose(1, 2).reshape(bs, T + 1, H)
+                ref = sa.proj(y[:, 0])
+            err = rel(got, ref)
+            print(head, bs, i, "rel err", err)
+            assert err <= 5e-5

@@ -1363,6 +1363,20 @@ int vcg_op_cross_attention(const vcg_cross_attn_params* p, const float* lang, co
     launch_cross_attention(*p, lang, vision, B, T, out, static_cast<cudaStream_t>(stream));
   });
 }
+int vcg_op_self_attention_first(const vcg_self_attn_params* p, const float* vision, const float* lang, int32_t B, int32_t T,
+                                float* out, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(p && lang && vision && out, "null argument");
+    launch_self_attention_first(*p, vision, lang, B, T, out, static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_bilinear_contract(const float* y, const float* x1, const float* bias, int32_t rows, int32_t in1,
+                             int32_t out_features, float* out, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(y && x1 && out, "null argument");
+    launch_bilinear_contract(y, x1, bias, rows, in1, out_features, out, static_cast<cudaStream_t>(stream));
+  });
+}
 int vcg_op_window_stack(const vcg_window_stack_params* p, const float* x, int32_t B, int32_t W, float* logits, float* probs,
                         void* stream) {
   return guarded([&] {

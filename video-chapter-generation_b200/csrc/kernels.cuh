@@ -87,6 +87,10 @@ void launch_mlp_chain(const float* x0, int dim0, long stride0, const float* x1, 
                       const vcg_mlp_op* ops, int n_ops, float* out, long out_stride, cudaStream_t s);
 void launch_cross_attention(const vcg_cross_attn_params& p, const float* lang, const float* vision, int B, int T, float* out,
                             cudaStream_t s);
+void launch_self_attention_first(const vcg_self_attn_params& p, const float* vision, const float* lang, int B, int T,
+                                 float* out, cudaStream_t s);
+void launch_bilinear_contract(const float* y, const float* x1, const float* bias, int rows, int in1, int out_features,
+                              float* out, cudaStream_t s);
 void launch_window_stack(const vcg_window_stack_params& p, const float* x, int B, int W, float* logits, float* probs,
                          cudaStream_t s);
 

@@ -16,7 +16,7 @@ namespace vcg {
 
 namespace {
 
-constexpr int kMaxDim = 2304;   // widest row of any step ((T+1)*128 with T <= 17, 2048, 1024 ...)
+constexpr int kMaxDim = 4352;   // widest row of any step (2 * T*128 with T <= 17 for the "multiplication" head)
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
 #pragma unroll
@@ -92,6 +92,10 @@ __global__ void __launch_bounds__(256) mlp_chain_kernel(const float* __restrict_
       dim = op.out_dim;
     } else if (op.type == VCG_MLP_LAYERNORM) {
       row_layernorm(buf[cur], dim, static_cast<const float*>(op.w), static_cast<const float*>(op.b), op.eps, red);
+    } else if (op.type == VCG_MLP_MULHALVES) {
+      dim >>= 1;
+      for (int i = threadIdx.x; i < dim; i += blockDim.x) buf[cur][i] *= buf[cur][dim + i];
+      __syncthreads();
     } else {
       for (int i = threadIdx.x; i < dim; i += blockDim.x)
         buf[cur][i] = op.type == VCG_MLP_RELU ? fmaxf(buf[cur][i], 0.f) : gelu_erf(buf[cur][i]);
@@ -155,6 +159,77 @@ __global__ void __launch_bounds__(128) cross_attention_kernel(const __grid_const
   __syncthreads();
   row_linear(sctx, H, p.o_w, p.o_b, sq, H);
   for (int i = threadIdx.x; i < H; i += blockDim.x) out[b * H + i] = sq[i];
+}
+
+// head_type "self_attn": SelfAttention.forward (two_stream_window.py:114-131) over the T frame vectors + the language
+// vector of one clip; only token 0's output row is used (:129), so only its query is formed.  One CTA per clip.
+__global__ void __launch_bounds__(128) self_attention_first_kernel(const __grid_constant__ vcg_self_attn_params p,
+                                                                   const float* __restrict__ vision,
+                                                                   const float* __restrict__ lang, int T,
+                                                                   float* __restrict__ out) {
+  pdl_enter();
+  constexpr int H = 128, kMaxN = 41;
+  extern __shared__ float dyn[];                      // sx | sk | sval, N = T + 1 rows of H each
+  const int N = T + 1;
+  float (*sx)[H] = reinterpret_cast<float (*)[H]>(dyn);
+  float (*sk)[H] = sx + N;
+  float (*sval)[H] = sk + N;
+  __shared__ float sq[H], sctx[H], sp[16][kMaxN];
+  const long b = blockIdx.x;
+  const int nh = p.num_heads, hd = H / nh;
+  for (int i = threadIdx.x; i < T * H; i += blockDim.x) sx[i / H][i % H] = vision[b * T * H + i];
+  for (int i = threadIdx.x; i < H; i += blockDim.x) sx[T][i] = lang[b * H + i];
+  __syncthreads();
+  row_linear(sx[0], H, p.q_w, p.q_b, sq, H);
+  for (int t = 0; t < N; ++t) {
+    row_linear(sx[t], H, p.k_w, p.k_b, sk[t], H);
+    row_linear(sx[t], H, p.v_w, p.v_b, sval[t], H);
+  }
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  for (int i = threadIdx.x; i < nh * N; i += blockDim.x) {
+    const int h = i / N, t = i % N;
+    float s = 0.f;
+    for (int d = 0; d < hd; ++d) s = fmaf(sq[h * hd + d], sk[t][h * hd + d], s);
+    sp[h][t] = s * scale;
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < nh) {
+    const int h = threadIdx.x;
+    float m = -INFINITY, sum = 0.f;
+    for (int t = 0; t < N; ++t) m = fmaxf(m, sp[h][t]);
+    for (int t = 0; t < N; ++t) { sp[h][t] = expf(sp[h][t] - m); sum += sp[h][t]; }
+    for (int t = 0; t < N; ++t) sp[h][t] /= sum;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const int h = i / hd;
+    float c = 0.f;
+    for (int t = 0; t < N; ++t) c = fmaf(sp[h][t], sval[t][i], c);
+    sctx[i] = c;
+  }
+  __syncthreads();
+  row_linear(sctx, H, p.o_w, p.o_b, sq, H);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) out[b * H + i] = sq[i];
+}
+
+// nn.Bilinear's contraction with x1 after the GEMM over x2: out[r,o] = bias[o] + sum_i x1[r,i] y[r, o*in1 + i].
+// One warp per (row, output): coalesced reads of y.
+__global__ void __launch_bounds__(256) bilinear_contract_kernel(const float* __restrict__ y, const float* __restrict__ x1,
+                                                                const float* __restrict__ bias, long n_out, int in1,
+                                                                int out_features, float* __restrict__ out) {
+  pdl_enter();
+  const long w = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_out) return;
+  const long r = w / out_features;
+  const int o = static_cast<int>(w % out_features);
+  const float* yr = y + (r * out_features + o) * in1;
+  const float* xr = x1 + r * in1;
+  float acc = 0.f;
+  for (int i = lane; i < in1; i += 32) acc = fmaf(xr[i], yr[i], acc);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if (lane == 0) out[w] = acc + (bias ? bias[o] : 0.f);
 }
 
 // StackedVideoChapterAttention.forward: x [B, W, 128] -> logits, probs [B, 2].  One CTA per batch item.
@@ -268,6 +343,9 @@ void launch_mlp_chain(const float* x0, int dim0, long stride0, const float* x1, 
       dim = ops[i].out_dim;
     } else if (ops[i].type == VCG_MLP_LAYERNORM) {
       VCG_REQUIRE(ops[i].w && ops[i].b, "mlp chain: LayerNorm needs weight and bias");
+    } else if (ops[i].type == VCG_MLP_MULHALVES) {
+      VCG_REQUIRE((dim & 1) == 0, "mlp chain: MULHALVES needs an even row");
+      dim >>= 1;
     } else {
       VCG_REQUIRE(ops[i].type == VCG_MLP_RELU || ops[i].type == VCG_MLP_GELU, "mlp chain: unknown step");
     }
@@ -287,6 +365,29 @@ void launch_cross_attention(const vcg_cross_attn_params& p, const float* lang, c
     configured = smem;
   }
   launch_pdl(cross_attention_kernel, B, 128, smem, s, p, lang, vision, T, out);
+}
+
+void launch_self_attention_first(const vcg_self_attn_params& p, const float* vision, const float* lang, int B, int T,
+                                 float* out, cudaStream_t s) {
+  if (B == 0) return;
+  VCG_REQUIRE(T >= 1 && T <= 40, "self attention: 1..40 frames per clip");
+  VCG_REQUIRE(p.num_heads >= 1 && p.num_heads <= 16 && 128 % p.num_heads == 0, "self attention: bad head count");
+  const size_t smem = static_cast<size_t>(3) * (T + 1) * 128 * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    VCG_CUDA(cudaFuncSetAttribute(self_attention_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  launch_pdl(self_attention_first_kernel, B, 128, smem, s, p, vision, lang, T, out);
+}
+
+void launch_bilinear_contract(const float* y, const float* x1, const float* bias, int rows, int in1, int out_features,
+                              float* out, cudaStream_t s) {
+  if (rows == 0) return;
+  VCG_REQUIRE(in1 >= 1 && out_features >= 1, "bilinear contract: bad sizes");
+  const long n_out = static_cast<long>(rows) * out_features;
+  const long blocks = (n_out * 32 + 255) / 256;
+  launch_pdl(bilinear_contract_kernel, static_cast<unsigned>(blocks), 256, 0, s, y, x1, bias, n_out, in1, out_features, out);
 }
 
 void launch_window_stack(const vcg_window_stack_params& p, const float* x, int B, int W, float* logits, float* probs,

@@ -9,8 +9,10 @@ Same classes, constructor arguments and state-dict keys as the reference (:11-44
     positions, :404-434),
   * the per-position heads and the window stack through the fp32 operators of include/vcg.h (vcg_op_mlp_chain,
     vcg_op_cross_attention, vcg_op_window_stack).
-Supported head types: "cross_attn" (the caller's default, test_video_segment_update.py:43) and "mlp"; the reference's
-experimental "bilinear" / "multiplication" / "self_attn" variants are not built.  No CPU / eager fallback.
+Head types: "cross_attn" (the caller's default, test_video_segment_update.py:43), "mlp", and the reference's experimental
+"bilinear" (one 3xTF32 tcgen05 GEMM over the [2h*h, T*h] view of nn.Bilinear's weight + vcg_op_bilinear_contract),
+"multiplication" (VCG_MLP_MULHALVES step of the chain program) and "self_attn" (vcg_op_self_attention_first).
+No CPU / eager fallback.
 """
 import ctypes
 import math
@@ -54,6 +56,28 @@ def _mlp3(d_in, d1, d2, d_out):
                          nn.Linear(d1, d2), nn.LayerNorm(d2), nn.ReLU(), nn.Dropout(0.1), nn.Linear(d2, d_out))
 
 
+class SelfAttention(nn.Module):
+    """Parameter holder of the reference's SelfAttention (:91-131): key / query / value / proj."""
+
+    def __init__(self, n_embd, n_head, output_size, attn_pdrop=0.1, resid_pdrop=0.1):
+        super().__init__()
+        assert n_embd % n_head == 0
+        self.n_head, self.n_embd = n_head, n_embd
+        self.key = nn.Linear(n_embd, n_embd)
+        self.query = nn.Linear(n_embd, n_embd)
+        self.value = nn.Linear(n_embd, n_embd)
+        self.attn_drop = nn.Dropout(attn_pdrop)
+        self.resid_drop = nn.Dropout(resid_pdrop)
+        self.proj = nn.Linear(n_embd, output_size)
+
+    forward = _no_forward
+
+
+class _MulHalves(nn.Module):
+    """Chain-program marker: a row of 2n values becomes row[:n] * row[n:] (VCG_MLP_MULHALVES)."""
+    forward = _no_forward
+
+
 class ChapterHead(nn.Module):
     def __init__(self, lang_emb_size, vision_emb_size, segment_size, hidden_size, window_size, output_size,
                  head_type="mlp"):
@@ -74,9 +98,21 @@ class ChapterHead(nn.Module):
         elif head_type == "cross_attn":
             self.head = CrossAttention(hidden_size, num_heads=16)
             self.output_proj = nn.Linear(hidden_size, output_size)
-        elif head_type in ("bilinear", "multiplication", "self_attn"):
-            raise NotImplementedError(f"window head_type {head_type!r} is an experimental variant of the reference "
-                                      "that this build does not cover (supported: cross_attn, mlp)")
+        elif head_type == "bilinear":
+            h = hidden_size
+            self.bilinear_layers = nn.ModuleList([nn.Bilinear(h, h * segment_size, 2 * h) for _ in range(self.num_clips)])
+            self.head = nn.ModuleList([
+                nn.Sequential(nn.LayerNorm(2 * h), nn.ReLU(), nn.Dropout(0.1), nn.Linear(2 * h, h), nn.LayerNorm(h),
+                              nn.ReLU(), nn.Dropout(0.1), nn.Linear(h, h)) for _ in range(self.num_clips)])
+        elif head_type == "multiplication":
+            h = hidden_size
+            self.lang_expand_layers = nn.ModuleList([
+                nn.Sequential(nn.Linear(h, 8 * h), nn.LayerNorm(8 * h), nn.ReLU(), nn.Dropout(0.1),
+                              nn.Linear(8 * h, h * segment_size), nn.LayerNorm(h * segment_size), nn.ReLU(),
+                              nn.Dropout(0.1)) for _ in range(self.num_clips)])
+            self.head = nn.ModuleList([_mlp3(h * segment_size, 8 * h, 4 * h, h) for _ in range(self.num_clips)])
+        elif head_type == "self_attn":
+            self.head = SelfAttention(hidden_size, 4, hidden_size)
         else:
             raise RuntimeError(f"Unknown head_type {head_type}")
 
@@ -158,6 +194,8 @@ class TwoStream(nn.Module):
             return B.VcgMlpOp(B.MLP_RELU, 0, 0, 0.0, None, None)
         if isinstance(m, nn.GELU):
             return B.VcgMlpOp(B.MLP_GELU, 0, 0, 0.0, None, None)
+        if isinstance(m, _MulHalves):
+            return B.VcgMlpOp(B.MLP_MULHALVES, 0, 0, 0.0, None, None)
         raise RuntimeError(f"unsupported module in an MLP chain: {type(m).__name__}")
 
     def _run_chain(self, seq, final_relu, x0, x1=None):
@@ -175,8 +213,9 @@ class TwoStream(nn.Module):
             nonlocal pending, cur, cur1
             if not pending:
                 return
-            lins = [m for m in pending if isinstance(m, nn.Linear)]
-            out_dim = lins[-1].out_features if lins else cur.shape[1] + (0 if cur1 is None else cur1.shape[1])
+            out_dim = cur.shape[1] + (0 if cur1 is None else cur1.shape[1])
+            for m in pending:
+                out_dim = m.out_features if isinstance(m, nn.Linear) else out_dim // 2 if isinstance(m, _MulHalves) else out_dim
             ops_arr = (B.VcgMlpOp * len(pending))(*[self._mlp_op(m) for m in pending])
             out = torch.empty(cur.shape[0], out_dim, dtype=torch.float32, device=cur.device)
             B.check(lib.vcg_op_mlp_chain(cur.data_ptr(), cur.shape[1], cur.stride(0), 0 if cur1 is None else cur1.data_ptr(),
@@ -185,6 +224,10 @@ class TwoStream(nn.Module):
             pending, cur, cur1 = [], out, None
 
         for m in mods:
+            if isinstance(m, _MulHalves):     # its own program, so that a wide Linear behind it can take the GEMM
+                pending.append(m)
+                flush()
+                continue
             big = (isinstance(m, nn.Linear) and cur1 is None and x0.shape[0] >= 128 and m.in_features >= 512
                    and m.out_features >= 512 and m.in_features % 32 == 0 and m.out_features % 64 == 0)
             if big:
@@ -196,34 +239,63 @@ class TwoStream(nn.Module):
         return cur
 
     # ------------------------------------------------------------------ forward
+    def _chapter_head(self, i, lang_emb, vis_emb):
+        """ChapterHead.forward for window position i (:248-289): lang_emb [bs,768], vis_emb [bs,T,2048] -> [bs,H]."""
+        from vcg_b200 import binding as B
+        lib = B.load_library()
+        fh = self.fusion_head
+        T, H = self.segment_size, self.hidden_size
+        bs, dev = lang_emb.shape[0], lang_emb.device
+        s = torch.cuda.current_stream().cuda_stream
+        le = lang_emb.contiguous()
+        ve = vis_emb.reshape(bs * T, self.vision_embed_size).contiguous()
+        lang_out = self._run_chain(fh.lang_proj_heads[i], True, le)                 # relu(proj(lang)) [bs,H]
+        vis_out = self._run_chain(fh.vision_proj_heads[i], True, ve)                # [bs*T,H]
+        if fh.head_type == "mlp":      # cat([vision_out, lang_out]) -> head[i]
+            f = self._run_chain(fh.head[i], False, vis_out.view(bs, T * H), lang_out)
+        elif fh.head_type == "multiplication":     # head[i](vision_out * lang_expand[i](lang_out))   (:274-279)
+            expanded = self._run_chain(fh.lang_expand_layers[i], False, lang_out)              # [bs, T*H]
+            f = self._run_chain([_MulHalves()] + list(fh.head[i]), False, vis_out.view(bs, T * H), expanded)
+        elif fh.head_type == "bilinear":           # head[i](Bilinear(lang_out, vision_flat))          (:269-272)
+            from vcg_b200 import ops
+            bl = fh.bilinear_layers[i]
+            w2 = bl.weight.detach().view(bl.out_features * bl.in1_features, bl.in2_features)   # [(o,i), j]
+            y = ops.gemm(vis_out.view(bs, T * H), w2, None, None, B.ACT_NONE)                   # [bs, (o,i)]
+            z = torch.empty(bs, bl.out_features, dtype=torch.float32, device=dev)
+            B.check(lib.vcg_op_bilinear_contract(y.data_ptr(), lang_out.data_ptr(), bl.bias.data_ptr(), bs,
+                                                 bl.in1_features, bl.out_features, z.data_ptr(), s))
+            f = self._run_chain(fh.head[i], False, z)
+        elif fh.head_type == "self_attn":          # SelfAttention over [frames..., lang], first token  (:281-283)
+            sa = fh.head
+            p = B.VcgSelfAttnParams(sa.n_head, *[t.data_ptr() for t in (
+                sa.query.weight, sa.query.bias, sa.key.weight, sa.key.bias, sa.value.weight, sa.value.bias,
+                sa.proj.weight, sa.proj.bias)])
+            f = torch.empty(bs, H, dtype=torch.float32, device=dev)
+            B.check(lib.vcg_op_self_attention_first(ctypes.byref(p), vis_out.data_ptr(), lang_out.data_ptr(), bs, T,
+                                                    f.data_ptr(), s))
+        else:                           # cross_attn: lang queries the T frame vectors
+            ca = fh.head
+            p = B.VcgCrossAttnParams(ca.num_heads, *[t.data_ptr() for t in (
+                ca.lang_norm.weight, ca.lang_norm.bias, ca.vision_norm.weight, ca.vision_norm.bias,
+                ca.frame_pos_encoding.weight, ca.frame_pos_encoding.bias,
+                ca.query_proj.weight, ca.query_proj.bias, ca.key_proj.weight, ca.key_proj.bias,
+                ca.value_proj.weight, ca.value_proj.bias, ca.out_proj.weight, ca.out_proj.bias)])
+            f = torch.empty(bs, H, dtype=torch.float32, device=dev)
+            B.check(lib.vcg_op_cross_attention(ctypes.byref(p), lang_out.data_ptr(), vis_out.data_ptr(), bs, T,
+                                               f.data_ptr(), s))
+        return f
+
     def _fuse_and_classify(self, vis_by_pos, lang_by_pos):
         """vis_by_pos[i] [bs,T,2048], lang_by_pos[i] [bs,768] (fp32 CUDA) for the 2w+1 window positions ->
         (logits, probs) [bs,2]: per-position ChapterHead, six window-attention blocks, classifier."""
         from vcg_b200 import binding as B
         lib = B.load_library()
-        fh = self.fusion_head
-        W, T, H = 2 * self.window_size + 1, self.segment_size, self.hidden_size
+        W, H = 2 * self.window_size + 1, self.hidden_size
         bs, dev = lang_by_pos[0].shape[0], lang_by_pos[0].device
         s = torch.cuda.current_stream().cuda_stream
         fused = torch.empty(bs, W, H, dtype=torch.float32, device=dev)
         for i in range(W):
-            le = lang_by_pos[i].contiguous()
-            ve = vis_by_pos[i].reshape(bs * T, self.vision_embed_size).contiguous()
-            lang_out = self._run_chain(fh.lang_proj_heads[i], True, le)                 # relu(proj(lang)) [bs,H]
-            vis_out = self._run_chain(fh.vision_proj_heads[i], True, ve)                # [bs*T,H]
-            if fh.head_type == "mlp":      # cat([vision_out, lang_out]) -> head[i]
-                f = self._run_chain(fh.head[i], False, vis_out.view(bs, T * H), lang_out)
-            else:                           # cross_attn: lang queries the T frame vectors
-                ca = fh.head
-                p = B.VcgCrossAttnParams(ca.num_heads, *[t.data_ptr() for t in (
-                    ca.lang_norm.weight, ca.lang_norm.bias, ca.vision_norm.weight, ca.vision_norm.bias,
-                    ca.frame_pos_encoding.weight, ca.frame_pos_encoding.bias,
-                    ca.query_proj.weight, ca.query_proj.bias, ca.key_proj.weight, ca.key_proj.bias,
-                    ca.value_proj.weight, ca.value_proj.bias, ca.out_proj.weight, ca.out_proj.bias)])
-                f = torch.empty(bs, H, dtype=torch.float32, device=dev)
-                B.check(lib.vcg_op_cross_attention(ctypes.byref(p), lang_out.data_ptr(), vis_out.data_ptr(), bs, T,
-                                                   f.data_ptr(), s))
-            fused[:, i] = f
+            fused[:, i] = self._chapter_head(i, lang_by_pos[i], vis_by_pos[i])
         # six window-attention blocks + classifier on the middle clip
         wa = self.window_attn
         sp = B.VcgWindowStackParams()
