@@ -195,6 +195,12 @@ VCG_API int vcg_op_bert_attention_packed(const void* qkv, const int32_t* cu, con
  *   (eval_utils/eval_utils.py:3-18: half-to-even rounding, trailing run dropped).  counts[v] > cap: buffer too small.
  * vcg_op_pr_hits: per video the six hit counts of calculate_pr (eval_utils.py:21-92):
  *   hits [n_videos, 6] = {gt->pred exact, <=3 s, <=5 s, pred->gt exact, <=3 s, <=5 s}. */
+/* vcg_op_auc_ap: per video, over its clips' scores (softmax prob of class 1) and 0/1 ground-truth labels:
+ *   auc[v] = sklearn.metrics.auc(*roc_curve(labels, scores, pos_label=1)[:2]) (nan when a video has one class only),
+ *   ap[v]  = sklearn.metrics.average_precision_score(labels, scores) (0 without positives)
+ *   (test_video_segment_point.py:253-257, 299-303; scikit-learn is an unpinned dependency, requirements.txt:16). */
+VCG_API int vcg_op_auc_ap(const float* scores, const int32_t* labels, const int32_t* video_offsets, int32_t n_videos,
+                  double* auc, double* ap, void* stream);
 VCG_API int vcg_op_cut_points(const float* logits, const int32_t* video_offsets, int32_t n_videos, int32_t clip_frames,
                       int32_t max_offset, int32_t cap, int32_t* labels_out, int32_t* cut_points, int32_t* counts,
                       void* stream);

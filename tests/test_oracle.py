@@ -134,3 +134,29 @@ def test_window_oracle_matches_reference_golden(golden_dir, case, head):
         logits, probs = worc.window_forward(sd, img, ids, mask, T, head)
     assert np.abs(logits.numpy() - g["logits"]).max() <= 1e-5 * np.abs(g["logits"]).max()
     assert np.abs(probs.numpy() - g["probs"]).max() <= 1e-5
+
+
+def test_metrics_oracle_matches_sklearn():
+    """roc_auc / average_precision restatement vs the scikit-learn of this image (the reference's own dependency), with
+    ties and the single-class cases; and the reference loop's clip grouping (first clip of each video twice)."""
+    import numpy as np
+    import warnings
+    sk = pytest.importorskip("sklearn.metrics")
+    from oracle import metrics_oracle as mo
+    rng = np.random.RandomState(0)
+    cases = [([0, 0, 0], [.1, .2, .3]), ([1, 1], [.3, .4]), ([0, 1, 1, 0], [.5, .5, .5, .5]), ([1], [0.2])]
+    for n in (2, 7, 50, 400):
+        for _ in range(6):
+            y = (rng.rand(n) < 0.2).astype(int)
+            s = rng.rand(n).astype(np.float32)
+            s = np.round(s, 1) if rng.rand() < 0.5 else s       # heavy ties half of the time
+            cases.append((y.tolist(), s.tolist()))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for y, s in cases:
+            fpr, tpr, _ = sk.roc_curve(y, s, pos_label=1)
+            want_auc, want_ap = sk.auc(fpr, tpr), sk.average_precision_score(y, s)
+            got_auc, got_ap = mo.roc_auc(y, s), mo.average_precision(y, s)
+            assert (np.isnan(want_auc) and np.isnan(got_auc)) or abs(got_auc - want_auc) <= 1e-12, (y, s)
+            assert abs(got_ap - want_ap) <= 1e-12, (y, s)
+    assert mo.reference_video_groups(["a", "a", "b", "b", "b", "c"]) == [[0, 0, 1], [2, 2, 3, 4], [5, 5]]

@@ -558,3 +558,37 @@ def test_window_experimental_heads_vs_torch(head, bs):
             err = rel(got, ref)
             print(head, bs, i, "rel err", err)
             assert err <= 5e-5
+
+
+def test_device_auc_ap_matches_metrics_oracle():
+    """vcg_op_auc_ap per video vs the sklearn restatement (oracle/metrics_oracle.py): ragged videos, tied scores, videos
+    with a single class (nan AUC, AP 0 / 1), one long video; the reference loop's grouping (first clip counted twice)."""
+    from oracle import metrics_oracle as mo
+    from vcg_b200 import postprocess as pp
+    rng = np.random.RandomState(3)
+    sizes = [1, 2, 5, 33, 257, 1000, 3, 4000, 64]
+    vids, scores, labels = [], [], []
+    for v, n in enumerate(sizes):
+        s = rng.rand(n).astype(np.float32)
+        if v % 2 == 0:
+            s = np.round(s, 1)                     # ties
+        y = (rng.rand(n) < 0.15).astype(np.int64)
+        if v == 2:
+            y[:] = 0
+        if v == 6:
+            y[:] = 1
+        vids += [f"v{v}"] * n
+        scores.append(s)
+        labels.append(y)
+    scores, labels = np.concatenate(scores), np.concatenate(labels)
+    idx, off = pp.reference_video_groups(vids)
+    assert [idx[off[v]:off[v + 1]].tolist() for v in range(len(sizes))] == mo.reference_video_groups(vids)
+    sc, lb = torch.from_numpy(scores).cuda()[idx.cuda()], torch.from_numpy(labels).cuda()[idx.cuda()]
+    auc, ap = pp.auc_ap_device(sc, lb, off)
+    auc2, ap2 = pp.auc_ap_device(sc, lb, off)
+    assert torch.equal(ap, ap2) and torch.equal(auc.nan_to_num(-1), auc2.nan_to_num(-1))      # fixed summation order
+    for v, g in enumerate(mo.reference_video_groups(vids)):
+        want_auc, want_ap = mo.roc_auc(labels[g], scores[g]), mo.average_precision(labels[g], scores[g])
+        assert (np.isnan(want_auc) and np.isnan(float(auc[v]))) or abs(float(auc[v]) - want_auc) <= 1e-12, v
+        assert abs(float(ap[v]) - want_ap) <= 1e-12, v
+    assert np.isnan(float(auc[2])) and float(ap[2]) == 0.0 and np.isnan(float(auc[6])) and float(ap[6]) == 1.0

@@ -1349,6 +1349,13 @@ int vcg_op_pr_hits(const int32_t* gt, const int32_t* gt_offsets, const int32_t* 
     launch_pr_hits(gt, gt_offsets, pred, pred_offsets, n_videos, hits, static_cast<cudaStream_t>(stream));
   });
 }
+int vcg_op_auc_ap(const float* scores, const int32_t* labels, const int32_t* video_offsets, int32_t n_videos, double* auc,
+                  double* ap, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(scores && labels && video_offsets && auc && ap, "null argument");
+    launch_auc_ap(scores, labels, video_offsets, n_videos, auc, ap, static_cast<cudaStream_t>(stream));
+  });
+}
 int vcg_op_mlp_chain(const float* x0, int32_t dim0, int64_t stride0, const float* x1, int32_t dim1, int64_t stride1,
                      int32_t rows, const vcg_mlp_op* ops, int32_t n_ops, float* out, int64_t out_stride, void* stream) {
   return guarded([&] {

@@ -82,6 +82,9 @@ void launch_cut_points(const float* logits, const int32_t* offsets, int n_videos
 void launch_pr_hits(const int32_t* gt, const int32_t* gt_off, const int32_t* pred, const int32_t* pred_off, int n_videos,
                     int32_t* hits, cudaStream_t s);
 
+void launch_auc_ap(const float* scores, const int32_t* labels, const int32_t* offsets, int n_videos, double* auc, double* ap,
+                   cudaStream_t s);
+
 // window model, post-backbone part (window.cu); parameter structs are those of include/vcg.h
 void launch_mlp_chain(const float* x0, int dim0, long stride0, const float* x1, int dim1, long stride1, int rows,
                       const vcg_mlp_op* ops, int n_ops, float* out, long out_stride, cudaStream_t s);

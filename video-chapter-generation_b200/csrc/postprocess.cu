@@ -7,6 +7,11 @@
 //               Python's round (half to even); a trailing run is dropped
 //   hits        calculate_pr (eval_utils.py:21-92): for every point of list A, is there a point of list B at distance
 //               0 / <= 3 / <= 5 — the six counts the host divides into recall and precision
+//   AUC / AP    sklearn.metrics.roc_curve + auc and average_precision_score per video
+//               (test_video_segment_point.py:253-255, 299-301) without a sort: with TP_i / FP_i = the positives /
+//               negatives scored >= clip i,  AP = 1/P * sum over positives i of TP_i / (TP_i + FP_i)  and
+//               AUC = sum over positives of (negatives scored lower + half the negatives tied) / (P * N)
+//               — the step-wise sums sklearn takes over distinct thresholds, regrouped per positive clip
 // One CTA per video; videos are contiguous clip ranges [offsets[v], offsets[v+1]).
 #include "kernels.cuh"
 #include "launch.cuh"
@@ -92,7 +97,66 @@ __global__ void __launch_bounds__(128) pr_hits_kernel(const int32_t* __restrict_
   if (threadIdx.x < 6) hits[v * 6 + threadIdx.x] = s_hits[threadIdx.x];
 }
 
+// One warp per positive clip (round-robin), lanes stride over the video's clips.  Integer counts are exact; the double
+// sums are taken in a fixed order (clip order per warp, then warp order), so results are run-to-run identical.
+__global__ void __launch_bounds__(256) auc_ap_kernel(const float* __restrict__ scores, const int32_t* __restrict__ labels,
+                                                     const int32_t* __restrict__ offsets, double* __restrict__ auc,
+                                                     double* __restrict__ ap) {
+  pdl_enter();
+  const int v = blockIdx.x;
+  const int lo = offsets[v], n = offsets[v + 1] - lo;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __shared__ double s_ap[8];
+  __shared__ long long s_u2[8];
+  __shared__ int s_pos[8];
+  double ap_sum = 0.0;
+  long long u2 = 0;      // 2 * (negatives below) + (negatives tied), summed over this warp's positives
+  int n_pos = 0;
+  for (int i = warp; i < n; i += nw) {
+    if (labels[lo + i] != 1) continue;          // warp-uniform
+    const float si = scores[lo + i];
+    int tp = 0, fp = 0, eq = 0, lt = 0;
+    for (int j = lane; j < n; j += 32) {
+      const float sj = scores[lo + j];
+      const bool pos = labels[lo + j] == 1;
+      tp += (pos && sj >= si);
+      fp += (!pos && sj >= si);
+      eq += (!pos && sj == si);
+      lt += (!pos && sj < si);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      tp += __shfl_xor_sync(0xffffffffu, tp, d);
+      fp += __shfl_xor_sync(0xffffffffu, fp, d);
+      eq += __shfl_xor_sync(0xffffffffu, eq, d);
+      lt += __shfl_xor_sync(0xffffffffu, lt, d);
+    }
+    ap_sum += static_cast<double>(tp) / static_cast<double>(tp + fp);
+    u2 += 2LL * lt + eq;
+    ++n_pos;
+  }
+  if (lane == 0) { s_ap[warp] = ap_sum; s_u2[warp] = u2; s_pos[warp] = n_pos; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    long long u = 0;
+    int P = 0;
+    for (int w = 0; w < nw; ++w) { a += s_ap[w]; u += s_u2[w]; P += s_pos[w]; }
+    const int N = n - P;
+    // sklearn: no positives -> AP 0.0 (recall defined as 1 everywhere); a single class -> ROC AUC undefined (nan)
+    ap[v] = P > 0 ? a / static_cast<double>(P) : 0.0;
+    auc[v] = (P > 0 && N > 0) ? static_cast<double>(u) / (2.0 * static_cast<double>(P) * static_cast<double>(N))
+                              : __longlong_as_double(0x7ff8000000000000LL);
+  }
+}
+
 }  // namespace
+
+void launch_auc_ap(const float* scores, const int32_t* labels, const int32_t* offsets, int n_videos, double* auc, double* ap,
+                   cudaStream_t s) {
+  if (n_videos == 0) return;
+  launch_pdl(auc_ap_kernel, n_videos, 256, 0, s, scores, labels, offsets, auc, ap);
+}
 
 void launch_cut_points(const float* logits, const int32_t* offsets, int n_videos, int clip_frames, int max_offset, int cap,
                        int32_t* labels_out, int32_t* cuts, int32_t* counts, cudaStream_t s) {
