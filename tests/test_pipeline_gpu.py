@@ -1,0 +1,94 @@
+"""The evaluation of test_video_segment_point.py end to end on a synthetic dataset, two ways that must agree:
+
+  A  the caller's own flow through the mirrored API: InferYoutubeClipDataset -> DataLoader (fp32 CHW clips) ->
+     TwoStream.forward -> topk / prob[:, 1] -> the per-video loop (:250-333) with sklearn metrics and eval_utils
+  B  the B200 flow: clips_u8 per video (every frame decoded once, uint8) -> Engine.score_clips_u8_host ->
+     vcg_op_cut_points / vcg_op_pr_hits / vcg_op_auc_ap on the device
+
+Labels and chapter timestamps (cut points) must be identical; P/R identical; AUC / AP equal to 1e-9.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_point_evaluation_reference_flow_vs_device_flow(tmp_path):
+    sk = pytest.importorskip("sklearn.metrics")
+    from torch.utils.data import DataLoader
+    from torchvision import transforms
+    from transformers import BertTokenizer
+    from data.infer_youtube_video_dataset import InferYoutubeClipDataset
+    from eval_utils.eval_utils import calculate_pr, convert_clip_label2cut_point
+    from oracle import metrics_oracle as mo
+    from oracle import synthetic_dataset as syn
+    from vcg_b200 import postprocess as pp
+    from test_parity_gpu import build_model
+
+    p = syn.build(str(tmp_path))
+    tok = BertTokenizer(vocab_file=p["vocab"], do_lower_case=True)
+    tf = transforms.Compose([transforms.ToTensor(),
+                             transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    T, L = syn.T, 20
+    ds = InferYoutubeClipDataset(p["img_dir"], p["clips_json"], tok, T, L, transform=tf)
+    model, sd = build_model(T, "mlp", "fp32")
+
+    def run_loader():
+        logits, probs = [], []
+        for img, ids, mask, _ in DataLoader(ds, batch_size=5, shuffle=False):
+            lg, pr = model(img.float().to(0), ids.to(0), mask.to(0))
+            logits.append(lg)
+            probs.append(pr)
+        return torch.cat(logits), torch.cat(probs)
+
+    # random weights put every clip on one side: centre the decision so that both labels (and cut points) occur
+    logits, _ = run_loader()
+    shift = float((logits[:, 1] - logits[:, 0]).median())
+    sd["fusion_head.head.bias"] = sd["fusion_head.head.bias"] + torch.tensor([shift, 0.0])
+    model, _ = build_model(T, "mlp", "fp32", sd=sd)
+
+    # ---- A: the caller's flow
+    logits, probs = run_loader()
+    pred_label = logits.data.topk(1, 1, True, True)[1].squeeze(1).cpu().numpy()
+    pred_score = probs[:, 1].cpu().numpy()
+    assert 0 < pred_label.sum() < len(pred_label)
+    vids = [info["vid"] for info in ds.all_clip_infos]
+    gt_label = np.array([info["clip_label"] for info in ds.all_clip_infos])
+    flow_a = {}
+    for g in mo.reference_video_groups(vids):             # first clip of each video twice, like the reference loop
+        vid = vids[g[0]]
+        fpr, tpr, _ = sk.roc_curve(gt_label[g], pred_score[g], pos_label=1)
+        gt_cuts = convert_clip_label2cut_point(gt_label[g].tolist(), T, ds.max_offset)
+        pred_cuts = convert_clip_label2cut_point(pred_label[g].tolist(), T, ds.max_offset)
+        flow_a[vid] = {"auc": sk.auc(fpr, tpr), "ap": sk.average_precision_score(gt_label[g], pred_score[g]),
+                       "gt_cuts": gt_cuts, "pred_cuts": pred_cuts,
+                       "pr": calculate_pr(gt_cuts, pred_cuts) if gt_cuts else None}
+
+    # ---- B: uint8 frames, host entry point, device post-processing
+    eng = model.engine
+    lg_b, pr_b, lo = [], [], 0
+    for vid in dict.fromkeys(vids):
+        n = vids.count(vid)
+        frames, clip_start, ids, mask, _ = ds.clips_u8(lo, lo + n)
+        lg, pr = eng.score_clips_u8_host(frames.pin_memory(), clip_start.pin_memory(), ids.pin_memory(), mask.pin_memory())
+        lg_b.append(lg.clone())
+        pr_b.append(pr.clone())
+        lo += n
+    lg_b, pr_b = torch.cat(lg_b).cuda(), torch.cat(pr_b).cuda()
+    assert float((lg_b - logits).abs().max() / logits.abs().max()) <= 1e-4
+    idx, off = pp.reference_video_groups(vids)
+    labels_dev, pred_cuts_dev = pp.cut_points_device(lg_b[idx.cuda()], off, T, ds.max_offset)
+    gt_logits = torch.stack([1.0 - torch.from_numpy(gt_label).float(), torch.from_numpy(gt_label).float()], 1).cuda()
+    _, gt_cuts_dev = pp.cut_points_device(gt_logits[idx.cuda()], off, T, ds.max_offset)
+    auc, ap = pp.auc_ap_device(pr_b[:, 1][idx.cuda()], torch.from_numpy(gt_label).cuda()[idx.cuda()], off)
+    assert labels_dev.cpu().tolist() == pred_label[idx.numpy()].tolist()
+    scored = [v for v, vid in enumerate(dict.fromkeys(vids)) if flow_a[vid]["gt_cuts"]]
+    pr_dev = pp.pr_hits_device([gt_cuts_dev[v] for v in scored], [pred_cuts_dev[v] for v in scored])
+    for v, vid in enumerate(dict.fromkeys(vids)):
+        a = flow_a[vid]
+        print(vid, a, float(auc[v]), float(ap[v]))
+        assert pred_cuts_dev[v] == a["pred_cuts"] and gt_cuts_dev[v] == a["gt_cuts"]       # identical timestamps
+        assert abs(float(auc[v]) - a["auc"]) <= 1e-9 and abs(float(ap[v]) - a["ap"]) <= 1e-9
+        if v in scored:
+            assert pr_dev[scored.index(v)] == a["pr"]
