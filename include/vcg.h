@@ -211,7 +211,11 @@ VCG_API int vcg_op_pr_hits(const int32_t* gt, const int32_t* gt_offsets, const i
  * All tensors fp32 device memory; weights are the reference's nn.Linear / nn.LayerNorm parameters as they are
  * (Linear weight [out, in] row-major).  The host mirror (model/fusion/two_stream_window.py) strings these together. */
 enum { VCG_MLP_LINEAR = 0, VCG_MLP_LAYERNORM = 1, VCG_MLP_RELU = 2, VCG_MLP_GELU = 3,
-       VCG_MLP_MULHALVES = 4 /* row of 2n -> n: row[i] * row[n+i] ("multiplication" head, two_stream_window.py:277) */ };
+       VCG_MLP_MULHALVES = 4,  /* row of 2n -> n: row[i] * row[n+i] ("multiplication" head, two_stream_window.py:277) */
+       VCG_MLP_MEANGROUPS = 5, /* row of g*out_dim -> out_dim: mean over the g groups (two_stream_domain_specific.py:344) */
+       VCG_MLP_SOFTMAX = 6,    /* softmax over the row */
+       VCG_MLP_SAVE = 7,       /* keep a copy of the row (<= 1024 wide) ...                                        */
+       VCG_MLP_ADDSAVED = 8 }; /* ... and add it back later: residual connections (window_self_attention.py:165-169) */
 typedef struct vcg_mlp_op {
   int32_t type;          /* VCG_MLP_*                                                    */
   int32_t in_dim;        /* LINEAR: input features                                       */
@@ -250,6 +254,26 @@ VCG_API int vcg_op_self_attention_first(const vcg_self_attn_params* p, const flo
  * out[r,o] = bias[o] + sum_i x1[r,i] * y[r, o*in1 + i]. */
 VCG_API int vcg_op_bilinear_contract(const float* y, const float* x1, const float* bias, int32_t rows, int32_t in1,
                              int32_t out_features, float* out, void* stream);
+
+typedef struct vcg_center_attn_params {  /* window attention with the CENTRE clip as the only query, hidden size 128:
+                                          * WindowSelfAttention (two_stream_domain_specific.py:92-135, of whose output
+                                          * only the centre row is used, :354-356) and VideoChapterWindowAttention
+                                          * (window_self_attention.py:80-121) */
+  int32_t num_heads;
+  int32_t bias_head_stride;              /* elements between heads in pos_bias                                      */
+  int32_t bias_offset;                   /* first element of the centre query's row: centre*(2w+1) or 0             */
+  int32_t add_residual;                  /* 1: out += x[:, centre] (the un-normalised input, window_self_attention.py:160-163) */
+  const float *pre_norm_w, *pre_norm_b;  /* LayerNorm BEFORE the positions are added, or NULL                        */
+  const float *post_norm_w, *post_norm_b;/* LayerNorm AFTER the positions are added, or NULL                         */
+  const float *pos_w, *pos_b;            /* position_encoding.0 = Linear(1, 128)                                     */
+  const float *pos_norm_w, *pos_norm_b;  /* position_encoding.1 = LayerNorm(128)                                     */
+  const float *pos_bias;                 /* window_pos_bias                                                          */
+  const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b;
+  const float *o_w, *o_b;                /* single Linear output projection, or NULL (context returned as is)        */
+} vcg_center_attn_params;
+/* x [B,W,128] -> out [B,128]; positions (t - W/2) / (W/2 + 1e-6) */
+VCG_API int vcg_op_center_attention(const vcg_center_attn_params* p, const float* x, int32_t B, int32_t W, float* out,
+                            void* stream);
 
 typedef struct vcg_window_layer {        /* VideoChapterBlock (stacked_window_self_attention.py:99-148) */
   const float *attn_norm_w, *attn_norm_b, *ffn_norm_w, *ffn_norm_b;

@@ -47,7 +47,7 @@ def main():
     _, bert_hugface, resnet50_tsm, _ = load_reference()
     from model.fusion import two_stream_window  # noqa  (reference module)
     torch.set_grad_enabled(False)
-    for name, head_type, T, window, L, B in CASES:
+    for name, head_type, T, window, L, B in ([] if os.environ.get('ONLY_VARIANTS') else CASES):
         print(f"== {name}")
         sd = W.make_window_state_dict(T, window, head_type, seed=123)
         lang = bert_hugface.BertHugface(pretrain_stage=False)
@@ -69,6 +69,44 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN, f"window_{name}.npz"), logits=logits.numpy(), probs=probs.numpy(),
                             labels=logits.topk(1, 1, True, True)[1].view(-1).numpy(), text_ids=ids.numpy(),
                             meta=np.array([T, window, L, B, 77]))
+    # ---- the two unused variants: model/fusion/two_stream_domain_specific.py and model/fusion/window_self_attention.py
+    from model.fusion import two_stream_domain_specific, window_self_attention  # noqa  (reference modules)
+    name, T, window, L, B = "domain_T8_w1_L24_B2", 8, 1, 24, 2
+    print(f"== {name}")
+    sd = W.make_domain_state_dict(T, window, seed=123)
+    lang = bert_hugface.BertHugface(pretrain_stage=False)
+    vision = resnet50_tsm.Resnet50TSM(segments_size=T, shift_div=8, pretrain_stage=False)
+    model = two_stream_domain_specific.TwoStream(lang.base_model, vision.base_model, lang.embed_size, vision.feature_dim,
+                                                 T, 128, window)
+    model.build_chapter_head(output_size=2)
+    print("   load_state_dict(strict=True):", model.load_state_dict(sd, strict=True))
+    model = model.eval()
+    img, ids, mask = make_inputs(T, window, L, B, seed=77)
+    logits, probs = model(img, ids, mask, None)
+    o_logits, o_probs = worc.domain_specific_forward(sd, img, ids, mask, T)
+    errs = {"logits": rel(o_logits, logits), "probs": rel(o_probs, probs)}
+    print("   oracle vs reference (rel):", errs, "logits", logits.tolist())
+    assert max(errs.values()) <= 1e-5, errs
+    np.savez_compressed(os.path.join(GOLDEN, f"window_{name}.npz"), logits=logits.numpy(), probs=probs.numpy(),
+                        labels=logits.topk(1, 1, True, True)[1].view(-1).numpy(), text_ids=ids.numpy(),
+                        meta=np.array([T, window, L, B, 77]))
+    for window in (1, 2):
+        name = f"single_block_w{window}_B5"
+        print(f"== {name}")
+        cfg = type("Config", (), {"hidden_size": 128, "num_attention_heads": 16, "attention_probs_dropout_prob": 0.1,
+                                  "window_size": window})
+        clf = window_self_attention.VideoChapterClassifier(cfg)
+        sd = W.make_single_block_state_dict(window, seed=123)
+        print("   load_state_dict(strict=True):", clf.load_state_dict(sd, strict=True))
+        clf = clf.eval()
+        x = torch.randn(5, 2 * window + 1, 128, generator=torch.Generator().manual_seed(9 + window))
+        logits, probs = clf(x, None)
+        o_logits, o_probs = worc.single_block_classifier(sd, x)
+        errs = {"logits": rel(o_logits, logits), "probs": rel(o_probs, probs)}
+        print("   oracle vs reference (rel):", errs, "logits", logits.tolist())
+        assert max(errs.values()) <= 1e-5, errs
+        np.savez_compressed(os.path.join(GOLDEN, f"window_{name}.npz"), logits=logits.numpy(), probs=probs.numpy(),
+                            x=x.numpy(), meta=np.array([window, 5]))
     try:   # the reference's MemoryManager starts a monitoring thread per model
         model.memory_manager.tracker._tracking = False
     except Exception:

@@ -218,6 +218,76 @@ def make_window_state_dict(clip_frames=8, window_size=1, head_type="cross_attn",
     return sd
 
 
+def _param_factory(sd, g):
+    def u(shape, a):
+        return (torch.rand(shape, generator=g) * 2 - 1) * a
+
+    def linear(prefix, d_in, d_out):
+        sd[prefix + ".weight"] = u((d_out, d_in), 1.5 / d_in ** 0.5)
+        sd[prefix + ".bias"] = u((d_out,), 0.1)
+
+    def norm(prefix, d):
+        sd[prefix + ".weight"] = torch.rand(d, generator=g) + 0.5
+        sd[prefix + ".bias"] = u((d,), 0.1)
+
+    def seq(prefix, dims, step=4):
+        """nn.Sequential(Linear, LayerNorm, act, Dropout, ..., Linear): Linear j at step*j, its LayerNorm at step*j+1"""
+        for j in range(len(dims) - 1):
+            linear(f"{prefix}.{step * j}", dims[j], dims[j + 1])
+            if j < len(dims) - 2:
+                norm(f"{prefix}.{step * j + 1}", dims[j + 1])
+    return u, linear, norm, seq
+
+
+def make_domain_state_dict(clip_frames=8, window_size=1, hidden_size=128, seed=123):
+    """State dict of the reference's model/fusion/two_stream_domain_specific.py TwoStream + build_chapter_head:
+    backbones as in make_state_dict (same seed) plus fusion_head.{lang,vision}_proj_heads, the two WindowSelfAttention
+    blocks, the (unused) cross_attn member and the classifier."""
+    full = make_state_dict(clip_frames, "mlp", hidden_size, seed=seed)
+    sd = {k: v for k, v in full.items() if not k.startswith("fusion_head.")}
+    u, linear, norm, seq = _param_factory(sd, _gen(seed + 701))
+    h, W = hidden_size, 2 * window_size + 1
+    for i in range(W):
+        seq(f"fusion_head.lang_proj_heads.{i}", [768, 384, h])
+        seq(f"fusion_head.vision_proj_heads.{i}", [2048, 8 * h, 4 * h, h])
+    for name in ("lang_window_attn", "vision_window_attn", "cross_attn"):
+        p = f"fusion_head.{name}"
+        for n in ("query_proj", "key_proj", "value_proj"):
+            linear(f"{p}.{n}", h, h)
+        seq(f"{p}.out_proj", [h, 2 * h, 2 * h, 2 * h, h])
+        if name == "cross_attn":
+            norm(p + ".vision_norm", h)
+            norm(p + ".lang_norm", h)
+        else:
+            norm(p + ".norm", h)
+            sd[p + ".window_pos_bias"] = u((1, 16, W, W), 0.5)
+            linear(p + ".position_encoding.0", 1, h)
+            norm(p + ".position_encoding.1", h)
+    seq("fusion_head.classifier", [2 * h, 2 * h, h, h // 2, h // 4, 2])
+    return sd
+
+
+def make_single_block_state_dict(window_size=1, hidden_size=128, seed=123):
+    """State dict of the reference's model/fusion/window_self_attention.py VideoChapterClassifier."""
+    sd = {}
+    u, linear, norm, seq = _param_factory(sd, _gen(seed + 801))
+    h, W = hidden_size, 2 * window_size + 1
+    b = "window_block"
+    norm(b + ".attention_norm", h)
+    norm(b + ".ffn_norm", h)
+    for n in ("query", "key", "value", "out_proj"):
+        linear(f"{b}.attention.{n}", h, h)
+    linear(b + ".attention.position_encoding.0", 1, h)
+    norm(b + ".attention.position_encoding.1", h)
+    sd[b + ".attention.window_pos_bias"] = u((1, 16, 1, W), 0.5)
+    linear(b + ".ffn.1", h, 4 * h)
+    linear(b + ".ffn.4", 4 * h, h)
+    norm("classifier.0", h)
+    linear("classifier.1", h, h // 2)
+    linear("classifier.4", h // 2, 2)
+    return sd
+
+
 def make_text(batch, max_len, seed=123):
     """Synthetic token ids / attention mask: [CLS]=101 first, len ~ U{10..L}, pad id 0."""
     g = _gen(seed + 1)

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE — CPU restatement (plain PyTorch fp32, functional) of the reference's window model:
 model/fusion/two_stream_window.py (ChapterHead :134-290, CrossAttention :11-88, TwoStream.forward :392-445) and
-model/fusion/stacked_window_self_attention.py (:6-224).  Pinned against the unmodified reference by
+model/fusion/stacked_window_self_attention.py (:6-224), plus the two unused variants model/fusion/two_stream_domain_specific.py
+and model/fusion/window_self_attention.py.  Pinned against the unmodified reference by
 oracle/make_golden_window.py.  Only tests may import this."""
 import math
 
@@ -116,3 +117,64 @@ def window_forward(sd, img_clips, text_ids, attention_masks, T, head_type="cross
         vis = orc.resnet50_tsm_forward(sd, x, T, shift_div).view(B, T, -1)
         fused.append(chapter_head(sd, lang_emb, vis, i, T, head_type))
     return window_stack(sd, torch.stack(fused, dim=1))
+
+
+def _center_attention(sd, p, x, q, k, v, bias_row, num_heads=16, pre_norm=None, post_norm=None):
+    """The centre clip queries its window: x [B,W,H] -> context [B,H].  Positions (t - W//2) / (W//2 + 1e-6) go through
+    position_encoding = Sequential(Linear(1,H), LayerNorm(H)) and are added to x."""
+    B, W, H = x.shape
+    hd, mid = H // num_heads, W // 2
+    if pre_norm:
+        x = _ln(sd, pre_norm, x)
+    pos = ((torch.arange(W) - mid).float() / (mid + 1e-6)).unsqueeze(-1)
+    x = x + _ln(sd, p + ".position_encoding.1", _lin(sd, p + ".position_encoding.0", pos))
+    if post_norm:
+        x = _ln(sd, post_norm, x)
+    qh = _lin(sd, q, x[:, mid:mid + 1]).view(B, 1, num_heads, hd).transpose(1, 2)
+    kh = _lin(sd, k, x).view(B, W, num_heads, hd).transpose(1, 2)
+    vh = _lin(sd, v, x).view(B, W, num_heads, hd).transpose(1, 2)
+    att = F.softmax(qh @ kh.transpose(-1, -2) / math.sqrt(hd) + bias_row, dim=-1)
+    return (att @ vh).transpose(1, 2).contiguous().view(B, H)
+
+
+def domain_specific_head(sd, lang_embs, vision_embs, T, H=128):
+    """two_stream_domain_specific.ChapterHead.forward (:318-369): lang_embs [B,W,768], vision_embs [B,W,T,2048]."""
+    B, W = lang_embs.shape[:2]
+    lang, vis = [], []
+    for i in range(W):
+        lang.append(F.relu(_mlp(sd, f"fusion_head.lang_proj_heads.{i}", lang_embs[:, i], 2)))
+        v = F.relu(_mlp(sd, f"fusion_head.vision_proj_heads.{i}", vision_embs[:, i].reshape(-1, vision_embs.shape[-1]), 3))
+        vis.append(v.view(B, T, H).mean(dim=1))
+    centre = []
+    for name, x in (("lang_window_attn", torch.stack(lang, 1)), ("vision_window_attn", torch.stack(vis, 1))):
+        p = f"fusion_head.{name}"
+        bias = sd[p + ".window_pos_bias"][:, :, W // 2:W // 2 + 1, :W]          # the centre query's row
+        ctx = _center_attention(sd, p, x, p + ".query_proj", p + ".key_proj", p + ".value_proj", bias, post_norm=p + ".norm")
+        centre.append(_mlp(sd, p + ".out_proj", ctx, 4))
+    logits = _mlp(sd, "fusion_head.classifier", torch.cat(centre, dim=1), 5)
+    return logits, F.softmax(logits, dim=1)
+
+
+def domain_specific_forward(sd, img_clips, text_ids, attention_masks, T, shift_div=8):
+    """two_stream_domain_specific.TwoStream.forward, :446-482."""
+    B, W, L = text_ids.shape
+    lang, vis = [], []
+    for i in range(W):
+        lang.append(orc.bert_forward(sd, text_ids[:, i], attention_masks[:, i]))
+        x = img_clips[:, i].reshape(B * T, *img_clips.shape[3:]).contiguous()
+        vis.append(orc.resnet50_tsm_forward(sd, x, T, shift_div).view(B, T, -1))
+    return domain_specific_head(sd, torch.stack(lang, 1), torch.stack(vis, 1), T)
+
+
+def single_block_classifier(sd, x):
+    """window_self_attention.VideoChapterClassifier.forward (:201-206) with VideoChapterBlock (:156-170) and
+    VideoChapterWindowAttention (:80-121): x [B,W,H] -> logits, probs."""
+    W, mid = x.shape[1], x.shape[1] // 2
+    a = "window_block.attention"
+    ctx = _center_attention(sd, a, x, a + ".query", a + ".key", a + ".value", sd[a + ".window_pos_bias"][:, :, :, :W],
+                            pre_norm="window_block.attention_norm")
+    y = _lin(sd, a + ".out_proj", ctx) + x[:, mid]
+    n = _ln(sd, "window_block.ffn_norm", y)
+    y = y + _lin(sd, "window_block.ffn.4", F.gelu(_lin(sd, "window_block.ffn.1", n)))
+    logits = _lin(sd, "classifier.4", F.gelu(_lin(sd, "classifier.1", _ln(sd, "classifier.0", y))))
+    return logits, F.softmax(logits, dim=-1)

@@ -160,3 +160,28 @@ def test_metrics_oracle_matches_sklearn():
             assert (np.isnan(want_auc) and np.isnan(got_auc)) or abs(got_auc - want_auc) <= 1e-12, (y, s)
             assert abs(got_ap - want_ap) <= 1e-12, (y, s)
     assert mo.reference_video_groups(["a", "a", "b", "b", "b", "c"]) == [[0, 0, 1], [2, 2, 3, 4], [5, 5]]
+
+
+def test_variant_oracles_match_reference_golden(golden_dir):
+    """The reference's two unused fusion variants (two_stream_domain_specific.py, window_self_attention.py):
+    restatements vs the reference's own outputs (oracle/make_golden_window.py)."""
+    import numpy as np
+    import torch
+    from oracle import weights as W
+    from oracle import window_oracle as worc
+    from oracle.make_golden_window import make_inputs
+    g = np.load(f"{golden_dir}/window_domain_T8_w1_L24_B2.npz")
+    T, window, L, B, seed = [int(x) for x in g["meta"]]
+    sd = W.make_domain_state_dict(T, window, seed=123)
+    img, ids, mask = make_inputs(T, window, L, B, seed)
+    with torch.no_grad():
+        logits, probs = worc.domain_specific_forward(sd, img, ids, mask, T)
+    assert np.abs(logits.numpy() - g["logits"]).max() <= 1e-5 * np.abs(g["logits"]).max()
+    assert np.abs(probs.numpy() - g["probs"]).max() <= 1e-5
+    for window in (1, 2):
+        g = np.load(f"{golden_dir}/window_single_block_w{window}_B5.npz")
+        sd = W.make_single_block_state_dict(window, seed=123)
+        with torch.no_grad():
+            logits, probs = worc.single_block_classifier(sd, torch.from_numpy(g["x"]))
+        assert np.abs(logits.numpy() - g["logits"]).max() <= 1e-5 * np.abs(g["logits"]).max()
+        assert np.abs(probs.numpy() - g["probs"]).max() <= 1e-5

@@ -336,7 +336,7 @@ def test_window_chain_routes_wide_layers_to_the_gemm():
     from model.fusion import two_stream_window as tsw
     torch.manual_seed(0)
     seq = tsw._mlp3(2048, 1024, 512, 128).cuda().eval()
-    model = tsw.TwoStream.__new__(tsw.TwoStream)          # only _run_chain / _mlp_op are used
+    model = tsw.TwoStream.__new__(tsw.TwoStream)          # only _run_chain is used
     for rows in (16, 256):                                 # 16: one chain program; 256: GEMM + chain stretches
         x = torch.randn(rows, 2048, device="cuda")
         with torch.no_grad():
@@ -592,3 +592,50 @@ def test_device_auc_ap_matches_metrics_oracle():
         assert (np.isnan(want_auc) and np.isnan(float(auc[v]))) or abs(float(auc[v]) - want_auc) <= 1e-12, v
         assert abs(float(ap[v]) - want_ap) <= 1e-12, v
     assert np.isnan(float(auc[2])) and float(ap[2]) == 0.0 and np.isnan(float(auc[6])) and float(ap[6]) == 1.0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_domain_specific_model_matches_reference_golden(golden_dir, precision):
+    """two_stream_domain_specific.TwoStream (mean-pooled frames, one centre-query window attention per modality,
+    classifier) through the mirrored module API against the reference's own outputs."""
+    from model.fusion import two_stream_domain_specific as tsd
+    from model.lang import bert_hugface
+    from model.vision import resnet50_tsm
+    from oracle import weights as W
+    from oracle.make_golden_window import make_inputs
+    g = np.load(f"{golden_dir}/window_domain_T8_w1_L24_B2.npz")
+    T, window, L, B, seed = [int(x) for x in g["meta"]]
+    sd = W.make_domain_state_dict(T, window, seed=123)
+    lang = bert_hugface.BertHugface(pretrain_stage=False)
+    vis = resnet50_tsm.Resnet50TSM(segments_size=T, shift_div=8, pretrain_stage=False)
+    model = tsd.TwoStream(lang.base_model, vis.base_model, lang.embed_size, vis.feature_dim, T, 128, window)
+    model.build_chapter_head(output_size=2)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(0).eval()
+    model.precision = precision
+    img, ids, mask = make_inputs(T, window, L, B, seed)
+    logits, probs = model(img.cuda(), ids.cuda(), mask.cuda(), clip_info=None)
+    errs = {"logits": rel(logits, torch.from_numpy(g["logits"])), "probs": rel(probs, torch.from_numpy(g["probs"]))}
+    print(precision, errs, logits.tolist())
+    assert errs["logits"] <= TOL[precision] and errs["probs"] <= TOL[precision], errs
+    assert logits.topk(1, 1, True, True)[1].view(-1).tolist() == g["labels"].tolist()
+
+
+@pytest.mark.parametrize("window", [1, 2])
+def test_single_block_classifier_matches_reference_golden(golden_dir, window):
+    """window_self_attention.VideoChapterClassifier: centre-query attention + residual + FFN + classifier in one
+    attention launch and one chain program, against the reference's own outputs (fp32 operators: 1e-5)."""
+    from model.fusion import window_self_attention as wsa
+    from oracle import weights as W
+    g = np.load(f"{golden_dir}/window_single_block_w{window}_B5.npz")
+    cfg = type("Config", (), {"hidden_size": 128, "num_attention_heads": 16, "attention_probs_dropout_prob": 0.1,
+                              "window_size": window})
+    clf = wsa.VideoChapterClassifier(cfg)
+    clf.load_state_dict(W.make_single_block_state_dict(window, seed=123), strict=True)
+    clf = clf.cuda().eval()
+    logits, probs = clf(torch.from_numpy(g["x"]).cuda(), None)
+    errs = {"logits": rel(logits, torch.from_numpy(g["logits"])), "probs": rel(probs, torch.from_numpy(g["probs"]))}
+    print(window, errs)
+    assert errs["logits"] <= 1e-5 and errs["probs"] <= 1e-5, errs
+    with pytest.raises(RuntimeError):
+        clf(torch.from_numpy(g["x"]), None)

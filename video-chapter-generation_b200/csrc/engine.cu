@@ -1384,6 +1384,12 @@ int vcg_op_bilinear_contract(const float* y, const float* x1, const float* bias,
     launch_bilinear_contract(y, x1, bias, rows, in1, out_features, out, static_cast<cudaStream_t>(stream));
   });
 }
+int vcg_op_center_attention(const vcg_center_attn_params* p, const float* x, int32_t B, int32_t W, float* out, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(p && x && out, "null argument");
+    launch_center_attention(*p, x, B, W, out, static_cast<cudaStream_t>(stream));
+  });
+}
 int vcg_op_window_stack(const vcg_window_stack_params* p, const float* x, int32_t B, int32_t W, float* logits, float* probs,
                         void* stream) {
   return guarded([&] {

@@ -94,6 +94,7 @@ void launch_self_attention_first(const vcg_self_attn_params& p, const float* vis
                                  float* out, cudaStream_t s);
 void launch_bilinear_contract(const float* y, const float* x1, const float* bias, int rows, int in1, int out_features,
                               float* out, cudaStream_t s);
+void launch_center_attention(const vcg_center_attn_params& p, const float* x, int B, int W, float* out, cudaStream_t s);
 void launch_window_stack(const vcg_window_stack_params& p, const float* x, int B, int W, float* logits, float* probs,
                          cudaStream_t s);
 

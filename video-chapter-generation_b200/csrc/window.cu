@@ -16,6 +16,7 @@ namespace vcg {
 
 namespace {
 
+constexpr int kMaxSaved = 1024;  // widest row a SAVE step keeps
 constexpr int kMaxDim = 4352;   // widest row of any step (2 * T*128 with T <= 17 for the "multiplication" head)
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(256) mlp_chain_kernel(const float* __restrict_
                                                         long out_stride) {
   pdl_enter();
   __shared__ float buf[2][kMaxDim];
+  __shared__ float saved[kMaxSaved];
   __shared__ float red[8];
   const long r = blockIdx.x;
   for (int i = threadIdx.x; i < dim0; i += blockDim.x) buf[0][i] = x0[r * stride0 + i];
@@ -95,6 +97,30 @@ __global__ void __launch_bounds__(256) mlp_chain_kernel(const float* __restrict_
     } else if (op.type == VCG_MLP_MULHALVES) {
       dim >>= 1;
       for (int i = threadIdx.x; i < dim; i += blockDim.x) buf[cur][i] *= buf[cur][dim + i];
+      __syncthreads();
+    } else if (op.type == VCG_MLP_MEANGROUPS) {
+      const int g = dim / op.out_dim;
+      for (int i = threadIdx.x; i < op.out_dim; i += blockDim.x) {
+        float a = 0.f;
+        for (int j = 0; j < g; ++j) a += buf[cur][j * op.out_dim + i];
+        buf[cur ^ 1][i] = a / static_cast<float>(g);
+      }
+      cur ^= 1;
+      dim = op.out_dim;
+      __syncthreads();
+    } else if (op.type == VCG_MLP_SOFTMAX) {
+      if (threadIdx.x == 0) {          // rows here are a handful of class logits
+        float m = -INFINITY, sum = 0.f;
+        for (int i = 0; i < dim; ++i) m = fmaxf(m, buf[cur][i]);
+        for (int i = 0; i < dim; ++i) { buf[cur][i] = expf(buf[cur][i] - m); sum += buf[cur][i]; }
+        for (int i = 0; i < dim; ++i) buf[cur][i] /= sum;
+      }
+      __syncthreads();
+    } else if (op.type == VCG_MLP_SAVE) {
+      for (int i = threadIdx.x; i < dim; i += blockDim.x) saved[i] = buf[cur][i];
+      __syncthreads();
+    } else if (op.type == VCG_MLP_ADDSAVED) {
+      for (int i = threadIdx.x; i < dim; i += blockDim.x) buf[cur][i] += saved[i];
       __syncthreads();
     } else {
       for (int i = threadIdx.x; i < dim; i += blockDim.x)
@@ -232,6 +258,61 @@ __global__ void __launch_bounds__(256) bilinear_contract_kernel(const float* __r
   if (lane == 0) out[w] = acc + (bias ? bias[o] : 0.f);
 }
 
+// Window attention with the centre clip as the only query (see vcg_center_attn_params).  One CTA per batch item.
+__global__ void __launch_bounds__(128) center_attention_kernel(const __grid_constant__ vcg_center_attn_params p,
+                                                               const float* __restrict__ x, int W, float* __restrict__ out) {
+  pdl_enter();
+  constexpr int H = 128, kMaxW = 9;
+  __shared__ float sx[kMaxW][H], sk[kMaxW][H], sval[kMaxW][H], spos[H], sq[H], sctx[H], sp[16][kMaxW], red[8];
+  const long b = blockIdx.x;
+  const int nh = p.num_heads, hd = H / nh, mid = W / 2;
+  for (int i = threadIdx.x; i < W * H; i += blockDim.x) sx[i / H][i % H] = x[b * W * H + i];
+  __syncthreads();
+  for (int t = 0; t < W; ++t) {
+    if (p.pre_norm_w) row_layernorm(sx[t], H, p.pre_norm_w, p.pre_norm_b, 1e-5f, red);
+    const float pos = static_cast<float>(t - mid) / (static_cast<float>(mid) + 1e-6f);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) spos[i] = pos * p.pos_w[i] + p.pos_b[i];     // Linear(1, H)
+    __syncthreads();
+    row_layernorm(spos, H, p.pos_norm_w, p.pos_norm_b, 1e-5f, red);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) sx[t][i] += spos[i];
+    __syncthreads();
+    if (p.post_norm_w) row_layernorm(sx[t], H, p.post_norm_w, p.post_norm_b, 1e-5f, red);
+    row_linear(sx[t], H, p.k_w, p.k_b, sk[t], H);
+    row_linear(sx[t], H, p.v_w, p.v_b, sval[t], H);
+  }
+  row_linear(sx[mid], H, p.q_w, p.q_b, sq, H);
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  for (int i = threadIdx.x; i < nh * W; i += blockDim.x) {
+    const int h = i / W, t = i % W;
+    float s = 0.f;
+    for (int d = 0; d < hd; ++d) s = fmaf(sq[h * hd + d], sk[t][h * hd + d], s);
+    sp[h][t] = s * scale + p.pos_bias[h * p.bias_head_stride + p.bias_offset + t];
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < nh) {
+    const int h = threadIdx.x;
+    float m = -INFINITY, sum = 0.f;
+    for (int t = 0; t < W; ++t) m = fmaxf(m, sp[h][t]);
+    for (int t = 0; t < W; ++t) { sp[h][t] = expf(sp[h][t] - m); sum += sp[h][t]; }
+    for (int t = 0; t < W; ++t) sp[h][t] /= sum;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const int h = i / hd;
+    float c = 0.f;
+    for (int t = 0; t < W; ++t) c = fmaf(sp[h][t], sval[t][i], c);
+    sctx[i] = c;
+  }
+  __syncthreads();
+  const float* res = sctx;
+  if (p.o_w) {
+    row_linear(sctx, H, p.o_w, p.o_b, sq, H);
+    res = sq;
+  }
+  for (int i = threadIdx.x; i < H; i += blockDim.x)
+    out[b * H + i] = res[i] + (p.add_residual ? x[(b * W + mid) * H + i] : 0.f);
+}
+
 // StackedVideoChapterAttention.forward: x [B, W, 128] -> logits, probs [B, 2].  One CTA per batch item.
 __global__ void __launch_bounds__(256) window_stack_kernel(const __grid_constant__ vcg_window_stack_params p,
                                                            const float* __restrict__ x, int W, float* __restrict__ logits,
@@ -335,7 +416,7 @@ void launch_mlp_chain(const float* x0, int dim0, long stride0, const float* x1, 
   VCG_REQUIRE(dim0 + dim1 <= kMaxDim, "mlp chain: input row too wide");
   MlpProgram prog{};
   prog.n_ops = n_ops;
-  int dim = dim0 + dim1;
+  int dim = dim0 + dim1, saved_dim = -1;
   for (int i = 0; i < n_ops; ++i) {
     prog.ops[i] = ops[i];
     if (ops[i].type == VCG_MLP_LINEAR) {
@@ -346,6 +427,16 @@ void launch_mlp_chain(const float* x0, int dim0, long stride0, const float* x1, 
     } else if (ops[i].type == VCG_MLP_MULHALVES) {
       VCG_REQUIRE((dim & 1) == 0, "mlp chain: MULHALVES needs an even row");
       dim >>= 1;
+    } else if (ops[i].type == VCG_MLP_MEANGROUPS) {
+      VCG_REQUIRE(ops[i].out_dim >= 1 && dim % ops[i].out_dim == 0, "mlp chain: MEANGROUPS needs a row of g * out_dim");
+      dim = ops[i].out_dim;
+    } else if (ops[i].type == VCG_MLP_SOFTMAX) {
+      VCG_REQUIRE(dim <= 64, "mlp chain: SOFTMAX is for short rows of class logits");
+    } else if (ops[i].type == VCG_MLP_SAVE) {
+      VCG_REQUIRE(dim <= kMaxSaved, "mlp chain: SAVE row too wide");
+      saved_dim = dim;
+    } else if (ops[i].type == VCG_MLP_ADDSAVED) {
+      VCG_REQUIRE(saved_dim == dim, "mlp chain: ADDSAVED needs a saved row of the same width");
     } else {
       VCG_REQUIRE(ops[i].type == VCG_MLP_RELU || ops[i].type == VCG_MLP_GELU, "mlp chain: unknown step");
     }
@@ -388,6 +479,15 @@ void launch_bilinear_contract(const float* y, const float* x1, const float* bias
   const long n_out = static_cast<long>(rows) * out_features;
   const long blocks = (n_out * 32 + 255) / 256;
   launch_pdl(bilinear_contract_kernel, static_cast<unsigned>(blocks), 256, 0, s, y, x1, bias, n_out, in1, out_features, out);
+}
+
+void launch_center_attention(const vcg_center_attn_params& p, const float* x, int B, int W, float* out, cudaStream_t s) {
+  if (B == 0) return;
+  VCG_REQUIRE(W >= 1 && W <= 9 && (W & 1), "centre attention: odd window of at most 9 clips");
+  VCG_REQUIRE(p.num_heads >= 1 && p.num_heads <= 16 && 128 % p.num_heads == 0, "centre attention: bad head count");
+  VCG_REQUIRE(p.pos_w && p.pos_b && p.pos_norm_w && p.pos_norm_b && p.pos_bias && p.q_w && p.k_w && p.v_w,
+              "centre attention: missing parameter");
+  launch_pdl(center_attention_kernel, B, 128, 0, s, p, x, W, out);
 }
 
 void launch_window_stack(const vcg_window_stack_params& p, const float* x, int B, int W, float* logits, float* probs,

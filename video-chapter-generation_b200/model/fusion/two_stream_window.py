@@ -21,6 +21,7 @@ import os
 import torch
 from torch import nn
 
+from model.fusion._chain import MulHalves, run_chain
 from model.fusion.stacked_window_self_attention import StackedVideoChapterAttention, _no_forward
 from ops.temporal_shift import TemporalShift
 
@@ -70,11 +71,6 @@ class SelfAttention(nn.Module):
         self.resid_drop = nn.Dropout(resid_pdrop)
         self.proj = nn.Linear(n_embd, output_size)
 
-    forward = _no_forward
-
-
-class _MulHalves(nn.Module):
-    """Chain-program marker: a row of 2n values becomes row[:n] * row[n:] (VCG_MLP_MULHALVES)."""
     forward = _no_forward
 
 
@@ -182,61 +178,11 @@ class TwoStream(nn.Module):
             self._engine, self._engine_key = eng, key
         return self._engine
 
-    @staticmethod
-    def _mlp_op(m):
-        from vcg_b200 import binding as B
-        if isinstance(m, nn.Linear):
-            return B.VcgMlpOp(B.MLP_LINEAR, m.in_features, m.out_features, 0.0, m.weight.data_ptr(),
-                              m.bias.data_ptr() if m.bias is not None else None)
-        if isinstance(m, nn.LayerNorm):
-            return B.VcgMlpOp(B.MLP_LAYERNORM, 0, 0, m.eps, m.weight.data_ptr(), m.bias.data_ptr())
-        if isinstance(m, nn.ReLU):
-            return B.VcgMlpOp(B.MLP_RELU, 0, 0, 0.0, None, None)
-        if isinstance(m, nn.GELU):
-            return B.VcgMlpOp(B.MLP_GELU, 0, 0, 0.0, None, None)
-        if isinstance(m, _MulHalves):
-            return B.VcgMlpOp(B.MLP_MULHALVES, 0, 0, 0.0, None, None)
-        raise RuntimeError(f"unsupported module in an MLP chain: {type(m).__name__}")
-
     def _run_chain(self, seq, final_relu, x0, x1=None):
         """nn.Sequential of Linear / LayerNorm / ReLU / GELU / Dropout over the rows of x0 (| x1).  Wide Linear layers
         over many rows (the 2048->1024->512 vision projections, B*T rows) go to the tcgen05 GEMM in its fp32 (3xTF32)
-        mode; everything else runs as one vcg_op_mlp_chain program per stretch."""
-        from vcg_b200 import binding as B
-        from vcg_b200 import ops
-        lib = B.load_library()
-        s = torch.cuda.current_stream().cuda_stream
-        mods = [m for m in seq if not isinstance(m, nn.Dropout)] + ([nn.ReLU()] if final_relu else [])
-        pending, cur, cur1 = [], x0, x1
-
-        def flush():
-            nonlocal pending, cur, cur1
-            if not pending:
-                return
-            out_dim = cur.shape[1] + (0 if cur1 is None else cur1.shape[1])
-            for m in pending:
-                out_dim = m.out_features if isinstance(m, nn.Linear) else out_dim // 2 if isinstance(m, _MulHalves) else out_dim
-            ops_arr = (B.VcgMlpOp * len(pending))(*[self._mlp_op(m) for m in pending])
-            out = torch.empty(cur.shape[0], out_dim, dtype=torch.float32, device=cur.device)
-            B.check(lib.vcg_op_mlp_chain(cur.data_ptr(), cur.shape[1], cur.stride(0), 0 if cur1 is None else cur1.data_ptr(),
-                                         0 if cur1 is None else cur1.shape[1], 0 if cur1 is None else cur1.stride(0),
-                                         cur.shape[0], ops_arr, len(pending), out.data_ptr(), out.stride(0), s))
-            pending, cur, cur1 = [], out, None
-
-        for m in mods:
-            if isinstance(m, _MulHalves):     # its own program, so that a wide Linear behind it can take the GEMM
-                pending.append(m)
-                flush()
-                continue
-            big = (isinstance(m, nn.Linear) and cur1 is None and x0.shape[0] >= 128 and m.in_features >= 512
-                   and m.out_features >= 512 and m.in_features % 32 == 0 and m.out_features % 64 == 0)
-            if big:
-                flush()
-                cur = ops.gemm(cur.contiguous(), m.weight.detach(), m.bias.detach(), None, B.ACT_NONE)
-            else:
-                pending.append(m)
-        flush()
-        return cur
+        mode; everything else runs as one vcg_op_mlp_chain program per stretch (model/fusion/_chain.py)."""
+        return run_chain(seq, final_relu, x0, x1)
 
     # ------------------------------------------------------------------ forward
     def _chapter_head(self, i, lang_emb, vis_emb):
@@ -255,7 +201,7 @@ class TwoStream(nn.Module):
             f = self._run_chain(fh.head[i], False, vis_out.view(bs, T * H), lang_out)
         elif fh.head_type == "multiplication":     # head[i](vision_out * lang_expand[i](lang_out))   (:274-279)
             expanded = self._run_chain(fh.lang_expand_layers[i], False, lang_out)              # [bs, T*H]
-            f = self._run_chain([_MulHalves()] + list(fh.head[i]), False, vis_out.view(bs, T * H), expanded)
+            f = self._run_chain([MulHalves()] + list(fh.head[i]), False, vis_out.view(bs, T * H), expanded)
         elif fh.head_type == "bilinear":           # head[i](Bilinear(lang_out, vision_flat))          (:269-272)
             from vcg_b200 import ops
             bl = fh.bilinear_layers[i]

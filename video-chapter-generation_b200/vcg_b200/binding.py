@@ -52,6 +52,12 @@ class VcgSelfAttnParams(ctypes.Structure):
     _fields_ = [("num_heads", ctypes.c_int32)] + [(n, _fp) for n in ("q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "o_w", "o_b")]
 
 
+class VcgCenterAttnParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("num_heads", "bias_head_stride", "bias_offset", "add_residual")] + [
+        (n, _fp) for n in ("pre_norm_w", "pre_norm_b", "post_norm_w", "post_norm_b", "pos_w", "pos_b", "pos_norm_w",
+                           "pos_norm_b", "pos_bias", "q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "o_w", "o_b")]
+
+
 class VcgWindowLayer(ctypes.Structure):
     _fields_ = [(n, _fp) for n in (
         "attn_norm_w", "attn_norm_b", "ffn_norm_w", "ffn_norm_b", "pos_w", "pos_b", "pos_bias",
@@ -65,7 +71,7 @@ class VcgWindowStackParams(ctypes.Structure):
                 ("cls_norm_w", _fp * 4), ("cls_norm_b", _fp * 4)]
 
 
-MLP_LINEAR, MLP_LAYERNORM, MLP_RELU, MLP_GELU, MLP_MULHALVES = 0, 1, 2, 3, 4
+MLP_LINEAR, MLP_LAYERNORM, MLP_RELU, MLP_GELU, MLP_MULHALVES, MLP_MEANGROUPS, MLP_SOFTMAX, MLP_SAVE, MLP_ADDSAVED = range(9)
 
 
 class VcgProfileEntry(ctypes.Structure):
@@ -110,6 +116,7 @@ PROTOTYPES = {
     "vcg_op_cross_attention": (ctypes.c_int, [ctypes.POINTER(VcgCrossAttnParams), _vp, _vp, _i32, _i32, _vp, _vp]),
     "vcg_op_self_attention_first": (ctypes.c_int, [ctypes.POINTER(VcgSelfAttnParams), _vp, _vp, _i32, _i32, _vp, _vp]),
     "vcg_op_bilinear_contract": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "vcg_op_center_attention": (ctypes.c_int, [ctypes.POINTER(VcgCenterAttnParams), _vp, _i32, _i32, _vp, _vp]),
     "vcg_op_window_stack": (ctypes.c_int, [ctypes.POINTER(VcgWindowStackParams), _vp, _i32, _i32, _vp, _vp, _vp]),
     "vcg_op_layernorm": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _vp]),
 }
