@@ -92,3 +92,20 @@ def test_point_evaluation_reference_flow_vs_device_flow(tmp_path):
         assert abs(float(auc[v]) - a["auc"]) <= 1e-9 and abs(float(ap[v]) - a["ap"]) <= 1e-9
         if v in scored:
             assert pr_dev[scored.index(v)] == a["pr"]
+
+    # ---- the same through vcg_b200.evaluate (one call), against the script's averaging (:345-358) of flow A
+    from vcg_b200 import evaluate as ev
+    res = ev.evaluate_flat_clips(eng, ds)
+    order = list(dict.fromkeys(vids))
+    assert res["videos"] == order
+    assert abs(res["mAP"] - np.mean([flow_a[v]["ap"] for v in order])) <= 1e-9
+    prs = [flow_a[v]["pr"] for v in order if flow_a[v]["pr"] is not None]
+    want_recall = np.mean([p_[0] for p_ in prs])
+    want_prec3 = np.mean([p_[4] for p_ in prs if p_[4] is not None])
+    assert abs(res["recall"] - want_recall) <= 1e-12 and abs(res["precision@3"] - want_prec3) <= 1e-12
+    assert res["vid2cut_points"]["vidA"]["second_pred_cut_points"] == flow_a["vidA"]["pred_cuts"]
+    ev.write_results(res, str(tmp_path / "out" / "result.txt"), str(tmp_path / "out" / "vid2cut_points.json"))
+    text = (tmp_path / "out" / "result.txt").read_text()
+    assert text.startswith(f"mAP {res['mAP']}\nrecall ") and "f-score_rand" in text
+    once = ev.evaluate_flat_clips(eng, ds, reference_grouping=False, random_baseline=False)
+    assert len(once["auc_list"]) == 2 and "recall_rand" not in once
