@@ -109,3 +109,14 @@ def test_point_evaluation_reference_flow_vs_device_flow(tmp_path):
     assert text.startswith(f"mAP {res['mAP']}\nrecall ") and "f-score_rand" in text
     once = ev.evaluate_flat_clips(eng, ds, reference_grouping=False, random_baseline=False)
     assert len(once["auc_list"]) == 2 and "recall_rand" not in once
+
+    # ---- the per-video harness (video_segment/test_video_segment_point_per_video.py:104-175)
+    from data.infer_youtube_video_dataset import InferYoutubeVideoDataset
+    vds = InferYoutubeVideoDataset(p["img_dir"], p["data_file"], p["vid_file"], tok, T, L, transform=tf)
+    per_video = ev.infer_videos(eng, vds, list(syn.VIDEOS))
+    assert per_video["total_frames"] == sum(n for n, _ in syn.VIDEOS.values()) and per_video["video_infer_fps"] > 0
+    for vid in syn.VIDEOS:          # the same clips as the flat file -> the same labels; cut points without the duplicate
+        rows = [i for i, v in enumerate(vids) if v == vid]
+        assert per_video["videos"][vid]["pred_labels"] == pred_label[rows].tolist()
+        assert per_video["videos"][vid]["pred_cut_points"] == convert_clip_label2cut_point(pred_label[rows].tolist(), T, 2)
+        assert per_video["videos"][vid]["gt_cut_points"] == convert_clip_label2cut_point(gt_label[rows].tolist(), T, 2)

@@ -108,3 +108,36 @@ def write_results(out, result_file, vid2cut_points_file=None):
             for name in ("recall", "precision", "f-score"):
                 f.write(f"{name}_rand {out[name + '_rand']}, {name}_rand@3 {out[name + '_rand@3']}, "
                         f"{name}_rand@5 {out[name + '_rand@5']}\n")
+
+
+def infer_videos(engine, video_dataset, vids, pin=True):
+    """The per-video harness of video_segment/test_video_segment_point_per_video.py (:104-175) on the B200 path: for
+    every vid choose it, score all its clips through Engine.score_clips_u8_host (frames of the video decoded once),
+    turn ground-truth and predicted labels into cut points, and accumulate the reference's throughput metric
+    ``video infer fps = total_frames / sum(forward time)`` — here the forward time is measured with CUDA events around the
+    host-buffer call (copies included, decode excluded, as in the reference where decode happens in the DataLoader).
+    -> {"videos": {vid: {"duration", "gt_cut_points", "pred_cut_points", "pred_labels", "infer_seconds"}},
+        "total_frames", "total_infer_seconds", "video_infer_fps"}"""
+    from eval_utils.eval_utils import convert_clip_label2cut_point
+    out = {"videos": {}, "total_frames": 0, "total_infer_seconds": 0.0}
+    T, max_offset = video_dataset.clip_frame_num, video_dataset.max_offset
+    for vid in vids:
+        video_dataset.manual_choose_vid(vid)
+        duration = video_dataset.get_duration()
+        frames, clip_start, ids, mask, labels = video_dataset.video_u8()
+        if pin:
+            frames, clip_start, ids, mask = (t.pin_memory() for t in (frames, clip_start, ids, mask))
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        logits, _ = engine.score_clips_u8_host(frames, clip_start, ids, mask)
+        stop.record()
+        stop.synchronize()
+        seconds = start.elapsed_time(stop) / 1e3
+        pred = logits.topk(1, 1, True, True)[1].view(-1).tolist()
+        out["videos"][vid] = {"duration": duration, "pred_labels": pred, "infer_seconds": seconds,
+                              "gt_cut_points": convert_clip_label2cut_point(labels.tolist(), T, max_offset),
+                              "pred_cut_points": convert_clip_label2cut_point(pred, T, max_offset)}
+        out["total_frames"] += duration
+        out["total_infer_seconds"] += seconds
+    out["video_infer_fps"] = out["total_frames"] / out["total_infer_seconds"] if out["total_infer_seconds"] > 0 else 0.0
+    return out
