@@ -93,6 +93,11 @@ VCG_API int vcg_forward_text(vcg_engine* e, const int64_t* text_ids, const int64
  *   vision_emb_out [B,T,2048], lang_emb_out [B,768] (BertPooler output), both fp32. */
 VCG_API int vcg_embed(vcg_engine* e, const float* img_clip, const int64_t* text_ids, const int64_t* attention_mask, int32_t B,
               int32_t L, float* vision_emb_out, float* lang_emb_out, void* stream);
+/* The same from decoded uint8 HWC frames [n_frames,224,224,3] (device): clip b = frames clip_start[b] .. +T-1, or, with
+ * clip_start == NULL, the regular grid first_start + b*clip_stride (the ResNet stem then runs once per distinct frame). */
+VCG_API int vcg_embed_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames, const int32_t* clip_start,
+                 int32_t first_start, int32_t clip_stride, const int64_t* text_ids, const int64_t* attention_mask,
+                 int32_t B, int32_t L, float* vision_emb_out, float* lang_emb_out, void* stream);
 
 /* Sliding-window scoring of one video straight from decoded frames (replaces ToTensor+Normalize at
  * test_video_segment_point.py:142-145, the clip gather of infer_youtube_video_dataset.py:117 and the forward).

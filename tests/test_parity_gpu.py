@@ -462,6 +462,12 @@ def test_window_score_video_equals_materialised_windows():
     torch.cuda.synchronize()
     print("score_video vs forward", rel(logits, ref_logits))
     assert rel(logits, ref_logits) <= 1e-4 and rel(probs, ref_probs) <= 1e-4
+    # straight from the uint8 frames: regular grid (stem once per distinct frame) and explicit clip starts
+    lg_u8, pr_u8 = model.score_video_u8(frames.cuda(), ids.cuda(), mask.cuda(), first_start=0, clip_stride=4)
+    lg_cs, _ = model.score_video_u8(frames.cuda(), ids.cuda(), mask.cuda(),
+                                    clip_start=torch.tensor([4 * n for n in range(N)], dtype=torch.int32))
+    print("score_video_u8 vs forward", rel(lg_u8, ref_logits), rel(lg_cs, ref_logits))
+    assert rel(lg_u8, ref_logits) <= 1e-4 and rel(pr_u8, ref_probs) <= 1e-4 and rel(lg_cs, ref_logits) <= 1e-4
 
 
 def test_flat_clip_reader_end_to_end(tmp_path):

@@ -1090,6 +1090,38 @@ int vcg_embed(vcg_engine* e, const float* img_clip, const int64_t* text_ids, con
   });
 }
 
+int vcg_embed_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames, const int32_t* clip_start, int32_t first_start,
+                 int32_t clip_stride, const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L,
+                 float* vision_emb_out, float* lang_emb_out, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e && frames_u8 && text_ids && attention_mask && vision_emb_out && lang_emb_out, "null argument");
+    VCG_REQUIRE(e->finalized, "vcg_finalize has not been called");
+    VCG_REQUIRE(e->cfg.modality == VCG_MODALITY_EMBED && e->cfg.vision == VCG_VISION_R50TSM, "engine was not created for embeddings");
+    VCG_REQUIRE(B >= 0 && L >= 1 && L <= e->Lmax, "token count exceeds max_tokens of the engine");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    FrameSource src;
+    src.frames_u8 = frames_u8;
+    if (clip_start) {
+      src.clip_start = clip_start;
+    } else {   // regular grid: the stem runs once per distinct frame
+      VCG_REQUIRE(clip_stride >= 1 && first_start >= 0 &&
+                  (B == 0 || first_start + static_cast<long>(clip_stride) * (B - 1) + e->T <= n_frames),
+                  "clip grid exceeds the frame buffer");
+      std::vector<int32_t> starts(B);
+      for (int b = 0; b < B; ++b) starts[b] = first_start + b * clip_stride;
+      e->st_start.ensure(static_cast<size_t>(std::max(B, 1)) * sizeof(int32_t));
+      VCG_CUDA(cudaMemcpyAsync(e->st_start.p, starts.data(), static_cast<size_t>(B) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+      VCG_CUDA(cudaStreamSynchronize(s));   // `starts` is a temporary
+      src.clip_start = e->st_start.as<int32_t>();
+      src.grid_start = first_start;
+      src.grid_stride = clip_stride;
+    }
+    for (int b0 = 0; b0 < B; b0 += e->Bt)
+      run_text(e, text_ids, attention_mask, b0, std::min(e->Bt, B - b0), L, lang_emb_out + static_cast<long>(b0) * kBertHidden, s);
+    for (int g0 = 0; g0 < B; g0 += e->Bv) run_vision(e, src, g0, std::min(e->Bv, B - g0), vision_emb_out, s);
+  });
+}
+
 int vcg_score_clips_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames, const int32_t* clip_start,
                        const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L, float* logits,
                        float* probs, void* stream) {

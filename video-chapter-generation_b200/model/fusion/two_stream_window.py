@@ -310,11 +310,35 @@ class TwoStream(nn.Module):
             ids = torch.cat([text_ids.long(), torch.zeros(1, L, dtype=torch.long, device=dev)])
             mask = torch.cat([attention_masks.long(), torch.zeros(1, L, dtype=torch.long, device=dev)])
             vis_emb, lang_emb = eng.embed(img, ids, mask)                      # [N+1,T,2048], [N+1,768]
-            n = torch.arange(N, device=dev)
-            vis_by_pos, lang_by_pos = [], []
-            for i in range(2 * w + 1):
-                src = n + (i - w) * skip
-                src = torch.where((src >= 0) & (src < N), src, torch.full_like(src, N))     # N = the padding clip
-                vis_by_pos.append(vis_emb[src])
-                lang_by_pos.append(lang_emb[src])
-            return self._fuse_and_classify(vis_by_pos, lang_by_pos)
+            return self._score_from_embeddings(vis_emb, lang_emb, N, skip)
+
+    def score_video_u8(self, frames_u8, text_ids, attention_masks, first_start=0, clip_stride=4, clip_start=None,
+                       skip=None):
+        """score_video() straight from the video's decoded uint8 HWC frames [n,224,224,3] (CUDA): clip n = frames
+        first_start + n*clip_stride .. +T-1 (or clip_start[n]); ToTensor + Normalize run on the device and, on the regular
+        grid, the ResNet stem once per distinct frame.  The dataset's padding clip (all-zero NORMALISED frames, which no
+        uint8 frame can express) is embedded separately through the fp32 entry point.  -> (logits, probs) [N,2]."""
+        self._check(text_ids)
+        N, L = text_ids.shape
+        T = self.segment_size
+        skip = max(1, T // 4) if skip is None else skip
+        eng = self._get_engine(text_ids.device, L)
+        with torch.no_grad():
+            dev = text_ids.device
+            vis, lang = eng.embed_u8(frames_u8, text_ids.long(), attention_masks.long(), clip_start, first_start, clip_stride)
+            pad_vis, pad_lang = eng.embed(torch.zeros(1, T, 3, 224, 224, device=dev),
+                                          torch.zeros(1, L, dtype=torch.long, device=dev),
+                                          torch.zeros(1, L, dtype=torch.long, device=dev))
+            return self._score_from_embeddings(torch.cat([vis, pad_vis]), torch.cat([lang, pad_lang]), N, skip)
+
+    def _score_from_embeddings(self, vis_emb, lang_emb, N, skip):
+        """Row N of the embeddings is the padding clip; target n sees the rows n + (i - w) * skip."""
+        w = self.window_size
+        n = torch.arange(N, device=lang_emb.device)
+        vis_by_pos, lang_by_pos = [], []
+        for i in range(2 * w + 1):
+            src = n + (i - w) * skip
+            src = torch.where((src >= 0) & (src < N), src, torch.full_like(src, N))     # N = the padding clip
+            vis_by_pos.append(vis_emb[src])
+            lang_by_pos.append(lang_emb[src])
+        return self._fuse_and_classify(vis_by_pos, lang_by_pos)

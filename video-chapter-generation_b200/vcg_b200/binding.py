@@ -111,6 +111,7 @@ PROTOTYPES = {
     "vcg_op_cut_points": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "vcg_op_pr_hits": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "vcg_op_auc_ap": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "vcg_embed_u8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vcg_embed": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vcg_op_mlp_chain": (ctypes.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, ctypes.POINTER(VcgMlpOp), _i32, _vp, _i64, _vp]),
     "vcg_op_cross_attention": (ctypes.c_int, [ctypes.POINTER(VcgCrossAttnParams), _vp, _vp, _i32, _i32, _vp, _vp]),

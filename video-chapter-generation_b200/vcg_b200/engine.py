@@ -139,6 +139,25 @@ class Engine:
                                          ve.data_ptr(), le.data_ptr(), _stream()))
         return ve, le
 
+    def embed_u8(self, frames_u8, text_ids, attention_mask, clip_start=None, first_start=0, clip_stride=4):
+        """embed() from device-resident uint8 HWC frames [n,224,224,3]: clip b = frames clip_start[b].. (int32 CUDA), or
+        the regular grid first_start + b*clip_stride when clip_start is None (stem once per distinct frame)."""
+        ids, mask, B, L = self._text(text_ids, attention_mask)
+        assert frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+        dev = ids.device
+        if clip_start is not None:
+            clip_start = clip_start.to(device=dev, dtype=torch.int32).contiguous()
+            assert clip_start.numel() == B
+        ve = torch.empty(B, self.clip_frames, 2048, dtype=torch.float32, device=dev)
+        le = torch.empty(B, 768, dtype=torch.float32, device=dev)
+        if B == 0:
+            return ve, le
+        with torch.cuda.device(dev):
+            _b.check(self._lib.vcg_embed_u8(self._h, frames_u8.data_ptr(), frames_u8.shape[0],
+                                            0 if clip_start is None else clip_start.data_ptr(), first_start, clip_stride,
+                                            ids.data_ptr(), mask.data_ptr(), B, L, ve.data_ptr(), le.data_ptr(), _stream()))
+        return ve, le
+
     def forward_vision(self, img_clip, return_emb=False):
         """Resnet50TSM.forward / Resnet50.forward: img_clip [B,T,3,224,224] fp32 -> (logits, probs)."""
         if not img_clip.is_cuda:
