@@ -645,3 +645,29 @@ def test_single_block_classifier_matches_reference_golden(golden_dir, window):
     assert errs["logits"] <= 1e-5 and errs["probs"] <= 1e-5, errs
     with pytest.raises(RuntimeError):
         clf(torch.from_numpy(g["x"]), None)
+
+
+def test_maximum_sizes_precomputed_embeddings():
+    """The corners of BASELINE.json configs[4]: 1024 clips per call, 512 tokens (BERT's position limit, the mma.sync
+    attention path with online softmax), 32-frame clips, precomputed vision embeddings, bf16.  Size-independent checks:
+    bit-identical reruns, a clip scores the same inside the 1024-clip call as in a call of its own 8 neighbours, and
+    fully padded tails (mask 0) do not influence the result."""
+    from oracle import weights as W
+    T, L, B = 32, 512, 1024
+    model, _ = build_model(T, "mlp", "bf16", vision=False)
+    g = torch.Generator().manual_seed(41)
+    emb = (torch.rand(B, T, 2048, generator=g) * 2.0).cuda().view(B, T, 2048, 1, 1)
+    ids, mask = W.make_text(B, L, seed=41)
+    mask[0] = 1                                                                 # one clip at the full 512 tokens
+    ids, mask = ids.cuda(), mask.cuda()
+    l1, p1 = model(emb, ids, mask)
+    l2, _ = model(emb, ids, mask)
+    assert torch.equal(l1, l2) and torch.isfinite(l1).all()
+    assert torch.allclose(p1.sum(1), torch.ones(B, device="cuda"), atol=1e-5)
+    for lo in (0, 504, 1016):
+        part, _ = model(emb[lo:lo + 8], ids[lo:lo + 8], mask[lo:lo + 8])
+        assert rel(part, l1[lo:lo + 8]) <= 5e-3, lo
+    junk = ids.clone()
+    junk[mask == 0] = 1234                                                      # padded positions hold arbitrary ids
+    l3, _ = model(emb, junk, mask)
+    assert torch.equal(l3, l1)
