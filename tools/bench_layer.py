@@ -56,6 +56,7 @@ CASES = {
     "ds_l2": lambda: conv_case(56, 256, 512, 1, 2, False, False, False, act=B.ACT_NONE),
     "qkv": lambda: gemm_case(GEMM_M, 2304, 768, B.ACT_NONE, False),
     "attn_out": lambda: gemm_case(GEMM_M, 768, 768, B.ACT_NONE, True),
+    "attn_out_nores": lambda: gemm_case(GEMM_M, 768, 768, B.ACT_NONE, False),
     "ffn_in": lambda: gemm_case(GEMM_M, 3072, 768, B.ACT_GELU, False),
     "ffn_out": lambda: gemm_case(GEMM_M, 768, 3072, B.ACT_NONE, True),
     "ffn_in_noact": lambda: gemm_case(GEMM_M, 3072, 768, B.ACT_NONE, False),
