@@ -120,3 +120,24 @@ def test_point_evaluation_reference_flow_vs_device_flow(tmp_path):
         assert per_video["videos"][vid]["pred_labels"] == pred_label[rows].tolist()
         assert per_video["videos"][vid]["pred_cut_points"] == convert_clip_label2cut_point(pred_label[rows].tolist(), T, 2)
         assert per_video["videos"][vid]["gt_cut_points"] == convert_clip_label2cut_point(gt_label[rows].tolist(), T, 2)
+
+
+def test_command_line_counterpart(tmp_path):
+    """video_segment/test_video_segment_point_b200.py — the caller's switches, model construction, evaluation and result
+    files — on the synthetic dataset: --data_mode all (uint8 path, device metrics) and text (DataLoader path)."""
+    import json
+    from oracle import synthetic_dataset as syn
+    from oracle import weights as W
+    from video_segment import test_video_segment_point_b200 as cli
+    p = syn.build(str(tmp_path / "data"))
+    for mode, sd in (("all", W.make_state_dict(syn.T, "mlp", seed=123)), ("text", W.make_unimodal_state_dict("bert", syn.T, seed=123))):
+        ckpt = str(tmp_path / f"ckpt_{mode}.pth")
+        torch.save({"epoch": 1, "best_result": 0.0, "model_state_dict": sd}, ckpt)
+        out = cli.main(["--gpu", "0", "--data_mode", mode, "--clip_frame_num", str(syn.T), "--clips_json", p["clips_json"],
+                        "--img_dir", p["img_dir"], "--ckpt", ckpt, "--vocab", p["vocab"], "--max_text_len", "20",
+                        "--precision", "fp32", "--num_workers", "0", "--batch_size", "5",
+                        "--result_file", str(tmp_path / mode / "result.txt"),
+                        "--vid2cut_points_file", str(tmp_path / mode / "cuts.json")])
+        assert (tmp_path / mode / "result.txt").read_text().startswith(f"mAP {out['mAP']}")
+        cuts = json.loads((tmp_path / mode / "cuts.json").read_text())
+        assert set(cuts) == set(syn.VIDEOS) and 0.0 <= out["mAP"] <= 1.0

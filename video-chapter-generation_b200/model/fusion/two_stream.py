@@ -129,6 +129,12 @@ class TwoStream(nn.Module):
     def engine(self):
         return self._engine
 
+    def get_engine(self, device=None, n_tokens=None):
+        """The vcg_b200.Engine holding this module's weights (built on first use): the way to the uint8 / host-buffer
+        entry points (score_clips_u8_host ...) without a warm-up forward."""
+        device = next(self.parameters()).device if device is None else device
+        return self._get_engine(device, self.max_tokens if n_tokens is None else n_tokens)
+
     # ------------------------------------------------------------------ forward
     def forward(self, img_clip, text_ids, attention_mask, return_emb=False):
         """-> (binary_logits [B,2], binary_prob [B,2]) (+ vision_emb [B,T,2048], lang_emb [B,768])."""
