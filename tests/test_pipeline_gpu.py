@@ -141,3 +141,37 @@ def test_command_line_counterpart(tmp_path):
         assert (tmp_path / mode / "result.txt").read_text().startswith(f"mAP {out['mAP']}")
         cuts = json.loads((tmp_path / mode / "cuts.json").read_text())
         assert set(cuts) == set(syn.VIDEOS) and 0.0 <= out["mAP"] <= 1.0
+
+
+def test_convert2vision_emb_round_trip(tmp_path):
+    """convert2vision_emb.py's job on the uint8 path: the files it writes hold what forward(..., return_emb=True) returns,
+    and feeding them back as precomputed embeddings (Identity vision model, BASELINE.json configs[1]) reproduces the logits."""
+    from torchvision import transforms
+    from transformers import BertTokenizer
+    from data.infer_youtube_video_dataset import InferYoutubeClipDataset
+    from oracle import synthetic_dataset as syn
+    from vcg_b200 import vision_emb_io as vio
+    from test_parity_gpu import build_model, rel
+    p = syn.build(str(tmp_path / "data"))
+    tok = BertTokenizer(vocab_file=p["vocab"], do_lower_case=True)
+    tf = transforms.Compose([transforms.ToTensor(),
+                             transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    T, L = syn.T, 20
+    ds = InferYoutubeClipDataset(p["img_dir"], p["clips_json"], tok, T, L, transform=tf)
+    model, sd = build_model(T, "mlp", "fp32")
+    n = vio.convert_flat_clips(model, ds, str(tmp_path / "emb"))
+    assert n == len(ds)
+    rows = [0, 3, 11]                                                # vidA x2, vidB
+    items = [ds[i] for i in rows]
+    img = torch.stack([it[0] for it in items]).cuda()
+    ids = torch.stack([it[1] for it in items]).cuda()
+    mask = torch.stack([it[2] for it in items]).cuda()
+    logits, _, vis, _ = model(img, ids, mask, return_emb=True)
+    for k, i in enumerate(rows):
+        info = ds.all_clip_infos[i]
+        back = vio.load_vision_embs(str(tmp_path / "emb"), info["vid"], [info["clip_start_end"][0]], T)
+        assert back.shape == (1, T, 2048, 1, 1)
+        assert rel(back.view(T, 2048), vis[k]) <= 1e-5
+        light, _ = build_model(T, "mlp", "fp32", sd=sd, vision=False)
+        lg, _ = light(back.cuda(), ids[k:k + 1], mask[k:k + 1])
+        assert rel(lg, logits[k:k + 1]) <= 1e-4

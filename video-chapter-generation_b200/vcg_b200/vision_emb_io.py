@@ -32,3 +32,32 @@ def load_vision_embs(save_dir, vid, starts, clip_frames=16):
     t = torch.from_numpy(np.stack(embs).astype(np.float32))
     assert t.shape[1:] == (clip_frames, 2048), t.shape
     return t.view(len(starts), clip_frames, 2048, 1, 1)
+
+
+def convert_flat_clips(model, dataset, save_dir, precision=None):
+    """convert2vision_emb.py's loop (:150-206) on the B200 path: the ResNet-50-TSM embeddings [T, 2048] of every clip of
+    an InferYoutubeClipDataset, written as ``<save_dir>/<vid>/vision_emb_{start}_{end}.npy``.
+
+    ``model`` is the two-stream module holding the weights (model.fusion.two_stream.TwoStream); the clips of a video go
+    through ONE backbone-only engine pass from uint8 frames (Engine.embed_u8: every frame decoded and normalised once)
+    instead of fp32 batches through forward(..., return_emb=True).  Returns the number of files written."""
+    from vcg_b200.engine import Engine
+    dev = next(model.parameters()).device
+    _, shift_div = model._vision_kind()
+    eng = Engine(model.segment_size, "mlp", precision or model.precision, True, dataset.max_text_len, model.vision_chunk,
+                 model.hidden_size, shift_div, device=dev, modality="embed")
+    eng.load_state_dict(model.state_dict())
+    infos = dataset.all_clip_infos
+    written, lo = 0, 0
+    try:
+        while lo < len(infos):
+            hi = lo
+            while hi < len(infos) and infos[hi]["vid"] == infos[lo]["vid"]:
+                hi += 1
+            frames, clip_start, ids, mask, _ = dataset.clips_u8(lo, hi)
+            vis, _ = eng.embed_u8(frames.to(dev), ids.to(dev), mask.to(dev), clip_start.to(dev))
+            written += len(save_vision_embs(save_dir, infos[lo:hi], vis))
+            lo = hi
+    finally:
+        eng.close()
+    return written
