@@ -390,6 +390,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       mbar_wait(&tmem_full[acc], TF32X3 ? (it & 1) : ((it >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      [[maybe_unused]] bool released_any = false;   // bf16: this warp already handed its TMEM buffer back
 
       if constexpr (TF32X3) {
         // ---- fp32 verification path: direct row-per-lane accesses
@@ -590,6 +591,14 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
               *reinterpret_cast<uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4)) = o;
             }
           }
+          // this warp's accumulator columns are in registers / shared memory now: hand the TMEM buffer back before the
+          // store chain (barrier, TMA store, TSM scatter, wait) so that the MMA warp can start tile it+2 meanwhile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+          }
+          released_any = true;
           fence_proxy_async_smem();                       // generic-proxy writes -> visible to the TMA store
           // every warp that shares this C tile has finished it
           asm volatile("bar.sync %0, %1;" ::"r"(1 + my_sub), "n"(kGps * 128) : "memory");
@@ -637,10 +646,14 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
         }
         c_it += n_sub;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+      bool need_release = true;
+      if constexpr (!TF32X3) need_release = !released_any;
+      if (need_release) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+        }
       }
     }
     if constexpr (!TF32X3) {
