@@ -27,6 +27,7 @@ struct Conv23Params {
   int P;                   // planes (64 or 128)
   int n2;                  // 4P / 256 output-channel sub-tiles of conv3
   int n_stages, n_cslots;
+  int early_release;       // hand the TMEM buffer back right after the last tcgen05.ld of a B sub-tile (VCG_C23_EARLY)
 };
 
 constexpr int kC23Threads = (kFirstEpiWarp + kEpiWarpsBf16) * 32;
@@ -290,14 +291,24 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23_kernel(const __grid_con
       const int slot = my_it % kCSlots;
       uint8_t* ctile = sC + slot * kCBytes;
       uint8_t* crow = ctile + row * 128;
+      // passes software-pipelined as in conv_gemm.cuh: next tcgen05.ld in flight during the math, TMEM handed back to
+      // the MMA warp right after the last load
+      uint32_t rr[2][16];
+      tmem_ld_32x16(taddr + my_sub * 64, rr[0]);
       mbar_wait(&c_full[slot], (my_it / kCSlots) & 1);
 #pragma unroll
       for (int pass = 0; pass < 4; ++pass) {
         const int cs = pass * 16;
         const int col0 = nb * BLOCK_N + my_sub * 64 + cs;
-        uint32_t r[16];
-        tmem_ld_32x16(taddr + my_sub * 64 + cs, r);
         tmem_ld_wait();
+        if (pass < 3) {
+          tmem_ld_32x16(taddr + my_sub * 64 + cs + 16, rr[(pass + 1) & 1]);
+        } else if (q.early_release) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        const uint32_t (&r)[16] = rr[pass & 1];
         float2 v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
@@ -360,9 +371,11 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23_kernel(const __grid_con
         mbar_arrive(&c_empty[slot]);
       }
       c_it += BLOCK_N / 64;
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (!q.early_release) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
     }
     if (lane == 0) tma_store_wait_all();
   }

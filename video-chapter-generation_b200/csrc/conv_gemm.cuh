@@ -506,14 +506,29 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
           const int slot = my_it % kCSlots;
           uint8_t* ctile = sC + slot * kCBytes;
           uint8_t* crow = ctile + row * 128;
+          // software-pipelined over the 16-column passes: the tcgen05.ld of pass p+1 is in flight during the math of
+          // pass p (the first one during the wait for the C slot), and the TMEM buffer goes back to the MMA warp as soon
+          // as the last load has landed
+          constexpr int kPasses = kCg / 16;
+          uint32_t rr[2][16];
+          tmem_ld_32x16(taddr + my_sub * 64 + col_in_sub, rr[0]);
           mbar_wait(&c_full[slot], (my_it / kCSlots) & 1);    // residual landed / slot free
 #pragma unroll
-          for (int pass = 0; pass < kCg / 16; ++pass) {
+          for (int pass = 0; pass < kPasses; ++pass) {
             const int cs = col_in_sub + pass * 16;            // first column inside the C tile
             const int col0 = n_blk * BLOCK_N + my_sub * 64 + cs;
-            uint32_t r[16];
-            tmem_ld_32x16(taddr + my_sub * 64 + cs, r);
             tmem_ld_wait();
+            if (pass + 1 < kPasses) {
+              tmem_ld_32x16(taddr + my_sub * 64 + cs + 16, rr[(pass + 1) & 1]);
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (CG2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+              }
+              released_any = true;
+            }
+            const uint32_t (&r)[16] = rr[pass & 1];
             float2 v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
@@ -591,14 +606,6 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
               *reinterpret_cast<uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4)) = o;
             }
           }
-          // this warp's accumulator columns are in registers / shared memory now: hand the TMEM buffer back before the
-          // store chain (barrier, TMA store, TSM scatter, wait) so that the MMA warp can start tile it+2 meanwhile
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (CG2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
-          }
-          released_any = true;
           fence_proxy_async_smem();                       // generic-proxy writes -> visible to the TMA store
           // every warp that shares this C tile has finished it
           asm volatile("bar.sync %0, %1;" ::"r"(1 + my_sub), "n"(kGps * 128) : "memory");

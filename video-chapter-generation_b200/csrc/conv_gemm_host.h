@@ -470,6 +470,10 @@ inline Conv23Launch build_conv23(const void* in, int Nimg, int H, int W, int P, 
   }
   L.q.n_stages = std::min(stages, kMaxStages);
   L.q.n_cslots = std::min(cslots, kMaxCSlots);
+  {
+    static const int early = [] { const char* v = getenv("VCG_C23_EARLY"); return v ? atoi(v) : 1; }();
+    L.q.early_release = early;
+  }
   VCG_REQUIRE(L.q.n_stages >= 2 && L.q.n_cslots >= 4, "fused conv2+conv3: shared-memory split failed");
   const long m_tiles = static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n;
   L.grid = static_cast<int>(std::min<long>(m_tiles, sm_count()));
