@@ -107,7 +107,7 @@ class ClockSampler:
 
 
 def make_inputs(batch, seed):
-    from oracle import weights as W
+    from vcg_b200 import synthetic as W
     ids, mask = W.make_text(batch, L, seed=seed)
     g = torch.Generator().manual_seed(seed + 7)
     # precomputed vision embeddings are post-ReLU average-pooled features: non-negative, O(1)
@@ -148,7 +148,7 @@ def timed(fn, steps, warmup, dist_on, drain=None):
 def cpu_port_clips_per_s(n_clips, steps=1, warmup=0, threads=None):
     """The reference's CPU path (oracle restatement) on a bounded sample of the workload."""
     from oracle import two_stream_oracle as orc
-    from oracle import weights as W
+    from vcg_b200 import synthetic as W
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     sd = W.make_state_dict(T, "mlp", seed=123, include_vision=False)
@@ -189,7 +189,7 @@ def run_reference(args):
 
 def pipeline_extra(args, peaks):
     """configs[2]: whole per-video pipeline over a synthetic 1-hour video at 1 fps (3600 frames -> 896 clips)."""
-    from oracle import weights as W
+    from vcg_b200 import synthetic as W
     from vcg_b200.engine import Engine
     n_frames = 3600
     starts = W.clip_starts(n_frames, T)
@@ -277,7 +277,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
 
-    from oracle import weights as W
+    from vcg_b200 import synthetic as W
     from vcg_b200 import distributed as vd
     from vcg_b200.engine import Engine
     peaks = measured_peaks()

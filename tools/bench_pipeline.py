@@ -4,7 +4,7 @@ import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "video-chapter-generation_b200")); sys.path.insert(0, ROOT)
 import torch
-from oracle import weights as W
+from vcg_b200 import synthetic as W
 from vcg_b200.engine import Engine
 T, L = 16, 100
 n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 1200

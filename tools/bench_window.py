@@ -8,7 +8,7 @@ import torch
 from model.fusion import two_stream_window
 from model.lang import bert_hugface
 from model.vision import resnet50_tsm
-from oracle import weights as W
+from vcg_b200 import synthetic as W
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 w = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 head = sys.argv[3] if len(sys.argv) > 3 else "cross_attn"
