@@ -53,6 +53,40 @@ __device__ __forceinline__ void row_linear(const float* x, int K, const float* _
   __syncthreads();
 }
 
+// Several rows against the same weights: y[r][n] = b[n] + sum_k x[r][k] W[n,k] for r < R, rows in shared memory (16-byte
+// aligned, strides xs / ys floats, K % 4 == 0).  One thread per output neuron: it walks its weight row once (float4 loads,
+// the lines stay in L1 between the 8 consecutive k steps that share them) and feeds up to 8 row accumulators from
+// broadcast shared-memory reads — the T frame vectors / W window tokens of one item cost one pass over the weights instead
+// of one latency-bound warp-per-neuron pass per row.
+__device__ __forceinline__ void rows_linear(const float* x, int xs, int R, int K, const float* __restrict__ W,
+                                            const float* __restrict__ b, float* y, int ys, int N) {
+  for (int r0 = 0; r0 < R; r0 += 8) {
+    const int rc = min(8, R - r0);
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      const float4* w4 = reinterpret_cast<const float4*>(W + static_cast<long>(n) * K);
+      for (int k4 = 0; k4 < (K >> 2); ++k4) {
+        const float4 w = __ldg(w4 + k4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < rc) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + (r0 + i) * xs + (k4 << 2));
+            acc[i] = fmaf(xv.x, w.x, acc[i]); acc[i] = fmaf(xv.y, w.y, acc[i]);
+            acc[i] = fmaf(xv.z, w.z, acc[i]); acc[i] = fmaf(xv.w, w.w, acc[i]);
+          }
+        }
+      }
+      const float bb = b ? b[n] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < rc) y[(r0 + i) * ys + n] = acc[i] + bb;
+    }
+  }
+  __syncthreads();
+}
+
 // nn.LayerNorm over a row in shared memory (two-pass statistics, in place)
 __device__ __forceinline__ void row_layernorm(float* x, int N, const float* __restrict__ g, const float* __restrict__ b,
                                               float eps, float* red) {
@@ -138,7 +172,7 @@ __global__ void __launch_bounds__(128) cross_attention_kernel(const __grid_const
                                                               int T, float* __restrict__ out) {
   pdl_enter();
   constexpr int H = 128, kMaxT = 40;
-  extern __shared__ float dyn[];                      // sv | sk | sval, T rows of H each
+  extern __shared__ __align__(16) float dyn[];        // sv | sk | sval, T rows of H each
   float (*sv)[H] = reinterpret_cast<float (*)[H]>(dyn);
   float (*sk)[H] = sv + T;
   float (*sval)[H] = sk + T;
@@ -156,10 +190,8 @@ __global__ void __launch_bounds__(128) cross_attention_kernel(const __grid_const
     __syncthreads();
   }
   row_linear(sl, H, p.q_w, p.q_b, sq, H);
-  for (int t = 0; t < T; ++t) {
-    row_linear(sv[t], H, p.k_w, p.k_b, sk[t], H);
-    row_linear(sv[t], H, p.v_w, p.v_b, sval[t], H);
-  }
+  rows_linear(&sv[0][0], H, T, H, p.k_w, p.k_b, &sk[0][0], H, H);
+  rows_linear(&sv[0][0], H, T, H, p.v_w, p.v_b, &sval[0][0], H, H);
   const float scale = rsqrtf(static_cast<float>(hd));
   for (int i = threadIdx.x; i < nh * T; i += blockDim.x) {
     const int h = i / T, t = i % T;
@@ -195,7 +227,7 @@ __global__ void __launch_bounds__(128) self_attention_first_kernel(const __grid_
                                                                    float* __restrict__ out) {
   pdl_enter();
   constexpr int H = 128, kMaxN = 41;
-  extern __shared__ float dyn[];                      // sx | sk | sval, N = T + 1 rows of H each
+  extern __shared__ __align__(16) float dyn[];        // sx | sk | sval, N = T + 1 rows of H each
   const int N = T + 1;
   float (*sx)[H] = reinterpret_cast<float (*)[H]>(dyn);
   float (*sk)[H] = sx + N;
@@ -207,10 +239,8 @@ __global__ void __launch_bounds__(128) self_attention_first_kernel(const __grid_
   for (int i = threadIdx.x; i < H; i += blockDim.x) sx[T][i] = lang[b * H + i];
   __syncthreads();
   row_linear(sx[0], H, p.q_w, p.q_b, sq, H);
-  for (int t = 0; t < N; ++t) {
-    row_linear(sx[t], H, p.k_w, p.k_b, sk[t], H);
-    row_linear(sx[t], H, p.v_w, p.v_b, sval[t], H);
-  }
+  rows_linear(&sx[0][0], H, N, H, p.k_w, p.k_b, &sk[0][0], H, H);
+  rows_linear(&sx[0][0], H, N, H, p.v_w, p.v_b, &sval[0][0], H, H);
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   for (int i = threadIdx.x; i < nh * N; i += blockDim.x) {
     const int h = i / N, t = i % N;
@@ -263,7 +293,8 @@ __global__ void __launch_bounds__(128) center_attention_kernel(const __grid_cons
                                                                const float* __restrict__ x, int W, float* __restrict__ out) {
   pdl_enter();
   constexpr int H = 128, kMaxW = 9;
-  __shared__ float sx[kMaxW][H], sk[kMaxW][H], sval[kMaxW][H], spos[H], sq[H], sctx[H], sp[16][kMaxW], red[8];
+  __shared__ __align__(16) float sx[kMaxW][H], sk[kMaxW][H], sval[kMaxW][H];
+  __shared__ float spos[H], sq[H], sctx[H], sp[16][kMaxW], red[8];
   const long b = blockIdx.x;
   const int nh = p.num_heads, hd = H / nh, mid = W / 2;
   for (int i = threadIdx.x; i < W * H; i += blockDim.x) sx[i / H][i % H] = x[b * W * H + i];
@@ -277,9 +308,9 @@ __global__ void __launch_bounds__(128) center_attention_kernel(const __grid_cons
     for (int i = threadIdx.x; i < H; i += blockDim.x) sx[t][i] += spos[i];
     __syncthreads();
     if (p.post_norm_w) row_layernorm(sx[t], H, p.post_norm_w, p.post_norm_b, 1e-5f, red);
-    row_linear(sx[t], H, p.k_w, p.k_b, sk[t], H);
-    row_linear(sx[t], H, p.v_w, p.v_b, sval[t], H);
   }
+  rows_linear(&sx[0][0], H, W, H, p.k_w, p.k_b, &sk[0][0], H, H);
+  rows_linear(&sx[0][0], H, W, H, p.v_w, p.v_b, &sval[0][0], H, H);
   row_linear(sx[mid], H, p.q_w, p.q_b, sq, H);
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   for (int i = threadIdx.x; i < nh * W; i += blockDim.x) {
@@ -313,14 +344,24 @@ __global__ void __launch_bounds__(128) center_attention_kernel(const __grid_cons
     out[b * H + i] = res[i] + (p.add_residual ? x[(b * W + mid) * H + i] : 0.f);
 }
 
-// StackedVideoChapterAttention.forward: x [B, W, 128] -> logits, probs [B, 2].  One CTA per batch item.
+// StackedVideoChapterAttention.forward: x [B, W, 128] -> logits, probs [B, 2].  One CTA per batch item; the W tokens go
+// through every Linear together (rows_linear).  Dynamic shared memory: h | n | q | k | v [W][H], f1 | f2 [W][4H],
+// sc [NH][W][W].
 __global__ void __launch_bounds__(256) window_stack_kernel(const __grid_constant__ vcg_window_stack_params p,
                                                            const float* __restrict__ x, int W, float* __restrict__ logits,
                                                            float* __restrict__ probs) {
   pdl_enter();
-  constexpr int H = 128, kMaxW = 9, NH = 16, HD = 8;
-  __shared__ float h[kMaxW][H], n[kMaxW][H], q[kMaxW][H], k[kMaxW][H], v[kMaxW][H], f1[4 * H], f2[4 * H];
-  __shared__ float sc[NH][kMaxW][kMaxW], red[8];
+  constexpr int H = 128, NH = 16, HD = 8;
+  extern __shared__ __align__(16) float dyn[];
+  float (*h)[H] = reinterpret_cast<float (*)[H]>(dyn);
+  float (*n)[H] = h + W;
+  float (*q)[H] = n + W;
+  float (*k)[H] = q + W;
+  float (*v)[H] = k + W;
+  float* f1 = &v[W][0];                   // [W][4H]
+  float* f2 = f1 + W * 4 * H;             // [W][4H]
+  float* sc = f2 + W * 4 * H;             // [NH][W][W]
+  __shared__ float red[8];
   const long b = blockIdx.x;
   for (int i = threadIdx.x; i < W * H; i += blockDim.x) h[i / H][i % H] = x[b * W * H + i];
   __syncthreads();
@@ -335,20 +376,20 @@ __global__ void __launch_bounds__(256) window_stack_kernel(const __grid_constant
       const float pos = static_cast<float>(t - mid) / (static_cast<float>(mid) + 1e-6f);
       for (int i = threadIdx.x; i < H; i += blockDim.x) n[t][i] += pos * L.pos_w[i] + L.pos_b[i];
       __syncthreads();
-      row_linear(n[t], H, L.q_w, L.q_b, q[t], H);
-      row_linear(n[t], H, L.k_w, L.k_b, k[t], H);
-      row_linear(n[t], H, L.v_w, L.v_b, v[t], H);
     }
+    rows_linear(&n[0][0], H, W, H, L.q_w, L.q_b, &q[0][0], H, H);
+    rows_linear(&n[0][0], H, W, H, L.k_w, L.k_b, &k[0][0], H, H);
+    rows_linear(&n[0][0], H, W, H, L.v_w, L.v_b, &v[0][0], H, H);
     for (int i = threadIdx.x; i < NH * W * W; i += blockDim.x) {
       const int hh = i / (W * W), tq = (i / W) % W, tk = i % W;
       float s = 0.f;
 #pragma unroll
       for (int d = 0; d < HD; ++d) s = fmaf(q[tq][hh * HD + d], k[tk][hh * HD + d], s);
-      sc[hh][tq][tk] = s * 0.35355339059327373f + L.pos_bias[hh * p.pos_bias_stride + tk];   // / sqrt(8)
+      sc[i] = s * 0.35355339059327373f + L.pos_bias[hh * p.pos_bias_stride + tk];   // / sqrt(8)
     }
     __syncthreads();
     for (int i = threadIdx.x; i < NH * W; i += blockDim.x) {
-      float* row = sc[i / W][i % W];
+      float* row = sc + i * W;
       float m = -INFINITY, sum = 0.f;
       for (int t = 0; t < W; ++t) m = fmaxf(m, row[t]);
       for (int t = 0; t < W; ++t) { row[t] = expf(row[t] - m); sum += row[t]; }
@@ -358,33 +399,31 @@ __global__ void __launch_bounds__(256) window_stack_kernel(const __grid_constant
     for (int i = threadIdx.x; i < W * H; i += blockDim.x) {     // context, written over n
       const int t = i / H, c = i % H, hh = c / HD;
       float a = 0.f;
-      for (int tk = 0; tk < W; ++tk) a = fmaf(sc[hh][t][tk], v[tk][c], a);
+      for (int tk = 0; tk < W; ++tk) a = fmaf(sc[(hh * W + t) * W + tk], v[tk][c], a);
       n[t][c] = a;
     }
     __syncthreads();
-    for (int t = 0; t < W; ++t) {
-      row_linear(n[t], H, L.o_w, L.o_b, q[t], H);
-      for (int i = threadIdx.x; i < H; i += blockDim.x) h[t][i] += q[t][i];     // residual
-      __syncthreads();
-    }
+    rows_linear(&n[0][0], H, W, H, L.o_w, L.o_b, &q[0][0], H, H);
+    for (int i = threadIdx.x; i < W * H; i += blockDim.x) h[i / H][i % H] += q[i / H][i % H];     // residual
+    __syncthreads();
     // ---- FFN: pre-LN, 128 -> 256 -> 512 -> 256 -> 128 with GELU between, residual
     for (int t = 0; t < W; ++t) {
       for (int i = threadIdx.x; i < H; i += blockDim.x) n[t][i] = h[t][i];
       __syncthreads();
       row_layernorm(n[t], H, L.ffn_norm_w, L.ffn_norm_b, 1e-5f, red);
-      row_linear(n[t], H, L.f0_w, L.f0_b, f1, 2 * H);
-      for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) f1[i] = gelu_erf(f1[i]);
-      __syncthreads();
-      row_linear(f1, 2 * H, L.f1_w, L.f1_b, f2, 4 * H);
-      for (int i = threadIdx.x; i < 4 * H; i += blockDim.x) f2[i] = gelu_erf(f2[i]);
-      __syncthreads();
-      row_linear(f2, 4 * H, L.f2_w, L.f2_b, f1, 2 * H);
-      for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) f1[i] = gelu_erf(f1[i]);
-      __syncthreads();
-      row_linear(f1, 2 * H, L.f3_w, L.f3_b, f2, H);
-      for (int i = threadIdx.x; i < H; i += blockDim.x) h[t][i] += f2[i];
-      __syncthreads();
     }
+    rows_linear(&n[0][0], H, W, H, L.f0_w, L.f0_b, f1, 4 * H, 2 * H);
+    for (int i = threadIdx.x; i < W * 2 * H; i += blockDim.x) { float& e = f1[(i / (2 * H)) * 4 * H + i % (2 * H)]; e = gelu_erf(e); }
+    __syncthreads();
+    rows_linear(f1, 4 * H, W, 2 * H, L.f1_w, L.f1_b, f2, 4 * H, 4 * H);
+    for (int i = threadIdx.x; i < W * 4 * H; i += blockDim.x) f2[i] = gelu_erf(f2[i]);
+    __syncthreads();
+    rows_linear(f2, 4 * H, W, 4 * H, L.f2_w, L.f2_b, f1, 4 * H, 2 * H);
+    for (int i = threadIdx.x; i < W * 2 * H; i += blockDim.x) { float& e = f1[(i / (2 * H)) * 4 * H + i % (2 * H)]; e = gelu_erf(e); }
+    __syncthreads();
+    rows_linear(f1, 4 * H, W, 2 * H, L.f3_w, L.f3_b, f2, 4 * H, H);
+    for (int i = threadIdx.x; i < W * H; i += blockDim.x) h[i / H][i % H] += f2[(i / H) * 4 * H + i % H];
+    __syncthreads();
   }
   // ---- final LayerNorm, middle (target) clip, classifier: 4 x (Linear, LayerNorm, GELU), Linear(32, 2), softmax
   float* t0 = h[mid];
@@ -495,7 +534,13 @@ void launch_window_stack(const vcg_window_stack_params& p, const float* x, int B
   if (B == 0) return;
   VCG_REQUIRE(W >= 1 && W <= 9 && (W & 1), "window stack: odd window of at most 9 clips");
   VCG_REQUIRE(p.num_layers >= 0 && p.num_layers <= 8 && p.pos_bias_stride >= W, "window stack: bad parameters");
-  launch_pdl(window_stack_kernel, B, 256, 0, s, p, x, W, logits, probs);
+  const size_t smem = (static_cast<size_t>(5) * W * 128 + static_cast<size_t>(2) * W * 512 + static_cast<size_t>(16) * W * W) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    VCG_CUDA(cudaFuncSetAttribute(window_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  launch_pdl(window_stack_kernel, B, 256, smem, s, p, x, W, logits, probs);
 }
 
 }  // namespace vcg
