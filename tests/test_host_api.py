@@ -140,3 +140,23 @@ def test_flat_clip_reader(tmp_path):
     assert v.text_ids[0].tolist() == [101, 7592, 2088] + [0] * 9 and v.attention_mask[0].tolist() == [1] * 3 + [0] * 9
     assert v.attention_mask[2].sum() == L and v.text_ids[2, 0] == 101                    # truncated at max_text_len
     assert v.labels.tolist() == [0, 1, 0] and v.cut_points == [6]
+
+
+def test_evaluation_host_logic():
+    """Host-side pieces of vcg_b200.evaluate / postprocess that need no GPU: the reference loop's clip grouping (first
+    clip of every video twice) and the averaging of test_video_segment_point.py:345-358."""
+    import math
+    from oracle import metrics_oracle as mo
+    from vcg_b200 import evaluate as ev
+    from vcg_b200 import postprocess as pp
+    vids = ["a", "a", "a", "b", "c", "c"]
+    idx, off = pp.reference_video_groups(vids)
+    assert idx.tolist() == [0, 0, 1, 2, 3, 3, 4, 4, 5] and off.tolist() == [0, 4, 6, 9]
+    assert [idx[off[v]:off[v + 1]].tolist() for v in range(3)] == mo.reference_video_groups(vids)
+    assert pp.reference_video_groups([])[1].tolist() == [0]
+    out = {}
+    ev._summarise(out, [(1.0, 1.0, 1.0, 0.5, 0.5, 1.0), (0.0, 0.5, 0.5, None, None, None)], "")
+    assert out["recall"] == 0.5 and out["recall@3"] == 0.75 and out["precision"] == 0.5 and out["precision@5"] == 1.0
+    assert out["f-score"] == 0.5 and abs(out["f-score@5"] - 2 * 0.75 * 1.0 / 1.75) < 1e-15
+    ev._summarise(out, [(0.0, 0.0, 0.0, None, None, None)], "_rand")
+    assert out["recall_rand"] == 0.0 and math.isnan(out["precision_rand"]) and math.isnan(out["f-score_rand"])
