@@ -249,6 +249,12 @@ __global__ void layernorm768_kernel(const elem_t<FP32>* __restrict__ x, const fl
   const int row0 = 2 * (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
   if (row0 >= rows) return;                      // `rows` = allocated rows: every load below stays inside the buffer
+  // CTAs beyond the first wave (8 CTAs x 148 SMs) start late anyway: they look at the device-side row count first and
+  // leave without touching memory when their rows do not exist (with token packing that is the usual case)
+  if (rows_dev && blockIdx.x >= 8 * 148) {
+    rows = min(rows, __ldg(rows_dev));
+    if (row0 >= rows) return;
+  }
   const bool two_alloc = row0 + 1 < rows;
   float v[2][3][8];
 #pragma unroll
