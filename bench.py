@@ -7,7 +7,7 @@
 
 Workload (BASELINE.json configs[1]): the two-stream point model (BERT-base text stream + fusion head, mlp head,
 T=16, L=100) on PRECOMPUTED vision embeddings, 256 clips per step per GPU, bf16, synthetic data, random-init weights
-(oracle/weights.py, seed 123).  One step = one pass of TwoStream.forward over one batch of 256 clips.
+(vcg_b200/synthetic.py, seed 123).  One step = one pass of TwoStream.forward over one batch of 256 clips.
   value  : clips/s with inputs resident in HBM (CUDA events, max over ranks, barrier + synchronize both sides)
   e2e    : the same through the host-buffer C-ABI call (vcg_forward_host): pinned host inputs, H2D + D2H inside
   extra  : at N=1 also the whole pipeline of configs[2] (uint8 frames -> preprocess -> ResNet-50-TSM + BERT + head
