@@ -108,7 +108,7 @@ def test_window_dataset_matches_reference(golden_dir, synthetic, w):
 
 
 def test_timestamp_helpers():
-    from data.common_utils import extract_first_timestamp, extract_timestamp
+    from data._timestamps import extract_first_timestamp, extract_timestamp
     assert extract_timestamp("intro 1:02:03 x") == ("1:02:03", 3723, 6, 13)
     assert extract_timestamp("12:34 go") == ("12:34", 754, 0, 5)
     assert extract_timestamp("no stamp") == ("", -1, -1, -1)

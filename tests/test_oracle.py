@@ -185,3 +185,42 @@ def test_variant_oracles_match_reference_golden(golden_dir):
             logits, probs = worc.single_block_classifier(sd, torch.from_numpy(g["x"]))
         assert np.abs(logits.numpy() - g["logits"]).max() <= 1e-5 * np.abs(g["logits"]).max()
         assert np.abs(probs.numpy() - g["probs"]).max() <= 1e-5
+
+
+def test_oracle_reproduces_video_scale_goldens(golden_dir):
+    """Video-scale fixtures (oracle/make_golden_video.py, UNMODIFIED reference): the oracle restatement on a sample of the
+    146 clips of the 10-minute video (first clips, a scene change, the tail) and on all 256 clips of configs[1]; the
+    committed labels / timestamps are what the reference's topk + convert_clip_label2cut_point give."""
+    g = np.load(f"{golden_dir}/video_mlp_T16_L100_600f.npz")
+    T, L, B, seed, _, _, n_frames, _ = [int(x) for x in g["meta"]]
+    sd = W.make_state_dict(T, "mlp", seed=seed)
+    sd["fusion_head.head.bias"] = torch.from_numpy(g["head_bias"]).clone()
+    frames, scenes = W.make_video_u8(n_frames, seed=seed)
+    starts = W.clip_starts(n_frames, T)
+    assert scenes == g["scene_starts"].tolist() and starts == g["clip_starts"].tolist()
+    ids, mask = W.make_video_text(starts, scenes, T, L, seed=seed)
+    ref = torch.from_numpy(g["logits"])
+    sample = [0, 16, 17, B - 1]                      # clip 16/17: the first label change of the video
+    with torch.no_grad():
+        img = orc.gather_clips(orc.preprocess_u8(frames), [starts[i] for i in sample], T)
+        logits = orc.two_stream_forward(sd, img, ids[sample], mask[sample], T, 128, "mlp", 8)[0]
+    assert float((logits - ref[sample]).abs().max() / ref.abs().max()) <= 1e-4
+    assert orc.predict_labels(logits) == g["labels"][sample].tolist()
+    labels = orc.predict_labels(ref)
+    assert labels == g["labels"].tolist() and 0 < sum(labels) < B
+    assert orc.convert_clip_label2cut_point(labels, T, 2) == g["cut_points"].tolist()
+    assert len(g["cut_points"]) >= 3
+    m = ref[:, 1] - ref[:, 0]
+    assert abs(float(m.abs().min()) - float(g["min_abs_margin"])) < 1e-9
+
+    g2 = np.load(f"{golden_dir}/video_emb_mlp_T16_L100_B256.npz")
+    T, L, B, seed = [int(x) for x in g2["meta"][:4]]
+    sd2 = W.make_state_dict(T, "mlp", seed=seed, include_vision=False)
+    sd2["fusion_head.head.bias"] = torch.from_numpy(g2["head_bias"]).clone()
+    emb, ids2, mask2 = W.make_precomputed_inputs(B, T, L, seed=seed)
+    with torch.no_grad():
+        l2 = orc.two_stream_forward(sd2, None, ids2, mask2, T, 128, "mlp", 8, vision_emb=emb)[0]
+    ref2 = torch.from_numpy(g2["logits"])
+    assert float((l2 - ref2).abs().max() / ref2.abs().max()) <= 1e-4
+    assert orc.predict_labels(l2) == g2["labels"].tolist()
+    assert orc.convert_clip_label2cut_point(g2["labels"].tolist(), T, 2) == g2["cut_points"].tolist()

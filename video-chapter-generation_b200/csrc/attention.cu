@@ -284,11 +284,10 @@ void launch_bert_attention(const void* qkv, const int64_t* mask, const int32_t* 
   if (!fp32) {
     const int Lp = (L + 63) / 64 * 64;
     const size_t smem = static_cast<size_t>(2 * Lp + kQBlock) * kRowPad * sizeof(__nv_bfloat16) + Lp * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static PerDeviceMax configured;
+    if (configured.raise(smem)) {
       VCG_CUDA(cudaFuncSetAttribute(bert_attention_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
-      configured = smem;
     }
     dim3 grid(kBertHeads, B, (L + kQBlock - 1) / kQBlock);
     launch_pdl(bert_attention_bf16_kernel, grid, 256, smem, s, static_cast<const __nv_bfloat16*>(qkv), mask, cu, key_ok,

@@ -393,10 +393,9 @@ void launch_attention_items(const int32_t* cu, int B, void* items, int32_t* n_it
 void launch_bert_attention_tc(const void* qkv, const int32_t* cu, const uint8_t* key_ok, void* ctx, int B, long rows,
                               cudaStream_t s, const void* items, const int32_t* n_items) {
   if (B == 0) return;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     VCG_CUDA(cudaFuncSetAttribute(bert_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
   }
   static std::map<std::pair<const void*, long>, CUtensorMap> maps;
   auto key = std::make_pair(qkv, rows);

@@ -4,14 +4,13 @@
 
 namespace vcg {
 
-int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    VCG_CUDA(cudaGetDevice(&dev));
-    VCG_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-  }
-  return n;
+int sm_count() {   // of the CURRENT device (plans are built per engine, i.e. per device)
+  static int n[64] = {};
+  int dev = 0;
+  VCG_CUDA(cudaGetDevice(&dev));
+  const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+  if (!n[slot]) VCG_CUDA(cudaDeviceGetAttribute(&n[slot], cudaDevAttrMultiProcessorCount, dev));
+  return n[slot];
 }
 
 int cg2_policy() {
@@ -34,11 +33,10 @@ int fuse23_policy() {
 
 void launch_conv23(const Conv23Launch& L, cudaStream_t stream) {
   if (L.grid <= 0) return;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     VCG_CUDA(cudaFuncSetAttribute(conv23_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC23SmemBytes));
     VCG_CUDA(cudaFuncSetAttribute(conv23_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC23SmemBytes));
-    configured = true;
   }
   if (L.q.P == 64) launch_pdl(conv23_kernel<64>, L.grid, kC23Threads, kC23SmemBytes, stream, L.q);
   else launch_pdl(conv23_kernel<128>, L.grid, kC23Threads, kC23SmemBytes, stream, L.q);
@@ -47,11 +45,10 @@ void launch_conv23(const Conv23Launch& L, cudaStream_t stream) {
 template <int BLOCK_N, bool LNF = false>
 static void launch_pair_t(const ConvGemmLaunch& L, cudaStream_t stream) {
   using Cfg = ConvGemmCfg<BLOCK_N, false>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     VCG_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BLOCK_N, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
-    configured = true;
   }
   launch_pdl(conv_gemm_pair_kernel<BLOCK_N, LNF>, L.grid, Cfg::kThreads, Cfg::kSmemBytes, stream, L.p);   // __cluster_dims__(2,1,1)
 }
@@ -59,11 +56,10 @@ static void launch_pair_t(const ConvGemmLaunch& L, cudaStream_t stream) {
 template <int BLOCK_N, bool TF32X3, bool LNF = false>
 static void launch_t(const ConvGemmLaunch& L, cudaStream_t stream) {
   using Cfg = ConvGemmCfg<BLOCK_N, TF32X3>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     VCG_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, TF32X3, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
-    configured = true;
   }
   launch_pdl(conv_gemm_kernel<BLOCK_N, TF32X3, LNF>, L.grid, Cfg::kThreads, Cfg::kSmemBytes, stream, L.p);
 }

@@ -132,6 +132,7 @@ struct vcg_engine {
   bool tsm = true;
   // text weights
   DevBuf word, pos, type, emb_g, emb_b;
+  int vocab = 0;
   std::vector<BertLayerW> layers;
   // tail weights (fp32)
   LinearW pooler;                       // [768][768] + bias, activation type (tcgen05 GEMM, tanh epilogue)
@@ -321,7 +322,8 @@ void finalize_vision(vcg_engine* e, cudaStream_t s) {
   e->shifted.clear();
   for (int i = 0; i < 16; ++i) {
     const Bottleneck& bk = e->blocks[i];
-    const int ch = (i == 0) ? 64 : bk.Cin / 4;
+    // two shifted channel groups of `fold = Cin / shift_div` channels each (block 0: the max-pool writes a full copy)
+    const int ch = (i == 0) ? 64 : (e->tsm ? 2 * bk.Cin / e->cfg.shift_div : 0);
     auto buf = std::make_unique<DevBuf>();
     if (e->tsm) buf->alloc(nF * bk.H * bk.H * ch * es, /*zero=*/true);   // never-written edge frames stay zero
     e->shifted.push_back(std::move(buf));
@@ -336,6 +338,7 @@ void finalize_text(vcg_engine* e, cudaStream_t s) {
   VCG_REQUIRE(pos.shape.size() == 2 && pos.shape[1] == kBertHidden && pos.shape[0] >= e->Lmax,
               "position embedding table shorter than max_tokens");
   const RawTensor& type = need(e, lm + "embeddings.token_type_embeddings.weight");
+  e->vocab = static_cast<int>(word.shape[0]);
   convert_to(e->word, word, e->fp32, s);
   convert_to(e->pos, pos, e->fp32, s);
   convert_to(e->type, type, e->fp32, s);
@@ -744,7 +747,15 @@ struct FrameSource {
   const float* img_clip = nullptr;     // [B,T,3,224,224] fp32
   const uint8_t* frames_u8 = nullptr;  // [n_frames,224,224,3]
   const int32_t* clip_start = nullptr; // [B] (device)
-  int grid_start = 0, grid_stride = 0; // clips on a regular grid: clip b starts at grid_start + b*grid_stride (0 = unknown)
+  const int32_t* clip_start_host = nullptr;   // the same on the host when the caller has it (pass planning, bounds checks)
+  int n_frames = 0;                    // frames in frames_u8 (0 = unknown): device-side indices are clamped to it
+};
+
+// One vision pass over clips [g0, g0 + n).  stride > 0: the clips sit on a regular grid (clip g0 + i starts at frame
+// f0 + i*stride, stride < T), so the stem / max-pool / layer1.0 downsample run once per DISTINCT frame.
+struct VisionPass {
+  int n = 0, stride = 0;
+  long f0 = 0;
 };
 
 // Progress of an asynchronous host->device copy of the vision input (side stream): `ready[i]` = (units on the device
@@ -787,7 +798,7 @@ void run_text(vcg_engine* e, const int64_t* ids, const int64_t* mask, int b0, in
   {
     ProfScope ps(e, s, "bert_embed_ln|bert.embed", 0, static_cast<double>(bt) * L * 768 * 4 * e->es(), true);
     launch_bert_embed_ln(ids + static_cast<long>(b0) * L, bt * L, L, e->pk_src.as<int32_t>(), e->pk_total.as<int32_t>(),
-                         e->word.p, e->pos.p, e->type.p, e->emb_g.as<float>(), e->emb_b.as<float>(), e->hid.p, e->fp32, s);
+                         e->vocab, e->word.p, e->pos.p, e->type.p, e->emb_g.as<float>(), e->emb_b.as<float>(), e->hid.p, e->fp32, s);
   }
   BertPlan& bp = bert_plan(e, bt, L);
   run_steps(e, bp.steps, mask + static_cast<long>(b0) * L, s);
@@ -827,25 +838,63 @@ void run_text(vcg_engine* e, const int64_t* ids, const int64_t* mask, int b0, in
   }
 }
 
+// Plans the next vision pass over clips [g0, g0 + remaining).  With the clip starts known on the host, every maximal
+// constant-stride run of >= 8 clips (or the whole rest) becomes a shared-stem pass, and clips that are on no such run
+// (the reference dataset's +1/+3 frame-file offsets at the ends of a video, data/infer_youtube_video_dataset.py:190-193,
+// or arbitrary flat clips) go through the per-clip gather, cut where the next long run starts.
+VisionPass next_vision_pass(const vcg_engine* e, const FrameSource& src, int g0, int remaining) {
+  VisionPass vp;
+  vp.n = std::min(e->Bv, remaining);
+  const int32_t* h = src.clip_start_host;
+  if (!src.frames_u8 || !h || remaining < 2) return vp;
+  const int end = g0 + remaining;
+  auto run_at = [&](int i, int* stride) {
+    if (i + 1 >= end) return 1;
+    const int d = h[i + 1] - h[i];
+    if (!shared_stem_ok(e, d)) return 1;
+    int n = 2;
+    while (i + n < end && n < e->Bv && h[i + n] - h[i + n - 1] == d) ++n;
+    *stride = d;
+    return n;
+  };
+  int d = 0;
+  const int r = run_at(g0, &d);
+  if (r >= 2 && r >= std::min(8, remaining)) {
+    vp.n = r; vp.stride = d; vp.f0 = h[g0];
+    return vp;
+  }
+  int n = 1, d2 = 0;
+  while (n < vp.n && run_at(g0 + n, &d2) < 8) ++n;
+  vp.n = n;
+  return vp;
+}
+
+void check_clip_starts(const int32_t* h, int B, int T, int n_frames) {
+  for (int b = 0; b < B; ++b)
+    if (h[b] < 0 || static_cast<long>(h[b]) + T > n_frames)
+      throw Error("vcg: clip " + std::to_string(b) + " starts at frame " + std::to_string(h[b]) + ": frames [start, start+" +
+                  std::to_string(T) + ") leave the buffer of " + std::to_string(n_frames) + " frames");
+}
+
 // Vision stream for clips [g0, g0 + bv) of the caller's numbering: pre-processing, ResNet-50(-TSM), average pool.
 // Returns the fp32 embeddings [bv*T, 2048] (in the caller's buffer when vision_emb_out is given) and leaves the same
 // values in the activation type at the fixed GEMM-operand address (e->vis_emb / e->vis_emb_act).
-const float* run_vision(vcg_engine* e, const FrameSource& src, int g0, int bv, float* vision_emb_out, cudaStream_t s) {
-  const int T = e->T;
+const float* run_vision(vcg_engine* e, const FrameSource& src, int g0, const VisionPass& vpass, float* vision_emb_out,
+                        cudaStream_t s) {
+  const int T = e->T, bv = vpass.n;
   if (src.img_clip) {
     ProfScope ps(e, s, "nchw_to_stem|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (4 + e->es()));
     launch_nchw_to_stem(src.img_clip + static_cast<long>(g0) * T * 3 * kImg * kImg, bv * T, e->stem_in.p, e->fp32, s);
-  } else if (shared_stem_ok(e, src.grid_stride)) {
+  } else if (vpass.stride > 0) {
     // overlapping clips: every unique frame of this pass is pre-processed (and run through the stem) once
-    const int U = src.grid_stride * (bv - 1) + T;
-    const long f0 = src.grid_start + static_cast<long>(src.grid_stride) * g0;
+    const int U = vpass.stride * (bv - 1) + T;
     ProfScope ps(e, s, "preprocess_u8|preprocess", 0, static_cast<double>(U) * kImg * kImg * 3 * (1 + e->es()));
-    launch_preprocess_u8(src.frames_u8 + f0 * kImg * kImg * 3, nullptr, U, e->stem_in.p, e->fp32, s);
+    launch_preprocess_u8(src.frames_u8 + vpass.f0 * kImg * kImg * 3, nullptr, U, e->stem_in.p, e->fp32, s);
   } else {
     ProfScope ps(e, s, "preprocess_u8|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (1 + e->es()));
-    launch_preprocess_u8_clips(src.frames_u8, src.clip_start + g0, bv, T, e->stem_in.p, e->fp32, s);
+    launch_preprocess_u8_clips(src.frames_u8, src.clip_start + g0, bv, T, e->stem_in.p, e->fp32, s, src.n_frames);
   }
-  VisionPlan& vp = vision_plan(e, bv, (src.frames_u8 && shared_stem_ok(e, src.grid_stride)) ? src.grid_stride : 0);
+  VisionPlan& vp = vision_plan(e, bv, src.frames_u8 ? vpass.stride : 0);
   run_steps(e, vp.steps, nullptr, s);
   // fp32 embeddings go to the caller's buffer when asked for; in fp32 mode they are also the GEMM operand
   float* dst = vision_emb_out ? vision_emb_out + static_cast<long>(g0) * T * kVisionDim : e->vis_emb.as<float>();
@@ -881,13 +930,15 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
     tp.v_w_t = e->v_w_t.as<float>(); tp.v_b = e->v_b.as<float>();
     tp.proj_w = e->proj_w.as<float>(); tp.proj_b = e->proj_b.as<float>();
     // ---- vision stream + head in sub-chunks
-    const int step = have_frames ? e->Bv : bt;
-    for (int c0 = 0; c0 < bt; c0 += step) {
-      const int bv = std::min(step, bt - c0);
+    for (int c0 = 0, bv = 0; c0 < bt; c0 += bv) {
       const int g0 = b0 + c0;   // first clip of this sub-chunk in the caller's numbering
+      VisionPass vpass;
+      vpass.n = bt - c0;
+      if (have_frames) vpass = next_vision_pass(e, src, g0, bt - c0);
+      bv = vpass.n;
       if (feed) feed->wait_for(s, g0, g0 + bv);
       if (have_frames) {
-        run_vision(e, src, g0, bv, vision_emb_out, s);
+        run_vision(e, src, g0, vpass, vision_emb_out, s);
       } else {
         const float* vis = vision_emb_in + static_cast<long>(g0) * T * kVisionDim;
         if (vision_emb_out)
@@ -932,9 +983,10 @@ void score_vision_only(vcg_engine* e, const FrameSource& src, int B, float* logi
                        cudaStream_t s) {
   VCG_REQUIRE(e->finalized, "vcg_finalize has not been called");
   VCG_REQUIRE(e->cfg.modality == VCG_MODALITY_VISION, "engine was not created for the image-only model");
-  for (int g0 = 0; g0 < B; g0 += e->Bv) {
-    const int bv = std::min(e->Bv, B - g0);
-    const float* emb = run_vision(e, src, g0, bv, vision_emb_out, s);
+  for (int g0 = 0, bv = 0; g0 < B; g0 += bv) {
+    const VisionPass vpass = next_vision_pass(e, src, g0, B - g0);
+    bv = vpass.n;
+    const float* emb = run_vision(e, src, g0, vpass, vision_emb_out, s);
     ProfScope ps(e, s, "linear_head2|head.final", 2.0 * bv * e->T * kVisionDim * 2, 0);
     launch_linear_head2(emb, e->head_w.as<float>(), e->head_b.as<float>(), bv, e->T * kVisionDim, logits + g0 * 2L,
                         probs + g0 * 2L, s);
@@ -1086,7 +1138,11 @@ int vcg_embed(vcg_engine* e, const float* img_clip, const int64_t* text_ids, con
       run_text(e, text_ids, attention_mask, b0, std::min(e->Bt, B - b0), L, lang_emb_out + static_cast<long>(b0) * kBertHidden, s);
     FrameSource src;
     src.img_clip = img_clip;
-    for (int g0 = 0; g0 < B; g0 += e->Bv) run_vision(e, src, g0, std::min(e->Bv, B - g0), vision_emb_out, s);
+    for (int g0 = 0; g0 < B;) {
+      const VisionPass vpass = next_vision_pass(e, src, g0, B - g0);
+      run_vision(e, src, g0, vpass, vision_emb_out, s);
+      g0 += vpass.n;
+    }
   });
 }
 
@@ -1101,24 +1157,28 @@ int vcg_embed_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames, cons
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     FrameSource src;
     src.frames_u8 = frames_u8;
+    src.n_frames = n_frames;
+    std::vector<int32_t> starts(B);
     if (clip_start) {
       src.clip_start = clip_start;
     } else {   // regular grid: the stem runs once per distinct frame
       VCG_REQUIRE(clip_stride >= 1 && first_start >= 0 &&
                   (B == 0 || first_start + static_cast<long>(clip_stride) * (B - 1) + e->T <= n_frames),
                   "clip grid exceeds the frame buffer");
-      std::vector<int32_t> starts(B);
       for (int b = 0; b < B; ++b) starts[b] = first_start + b * clip_stride;
       e->st_start.ensure(static_cast<size_t>(std::max(B, 1)) * sizeof(int32_t));
       VCG_CUDA(cudaMemcpyAsync(e->st_start.p, starts.data(), static_cast<size_t>(B) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
       VCG_CUDA(cudaStreamSynchronize(s));   // `starts` is a temporary
       src.clip_start = e->st_start.as<int32_t>();
-      src.grid_start = first_start;
-      src.grid_stride = clip_stride;
+      src.clip_start_host = starts.data();
     }
     for (int b0 = 0; b0 < B; b0 += e->Bt)
       run_text(e, text_ids, attention_mask, b0, std::min(e->Bt, B - b0), L, lang_emb_out + static_cast<long>(b0) * kBertHidden, s);
-    for (int g0 = 0; g0 < B; g0 += e->Bv) run_vision(e, src, g0, std::min(e->Bv, B - g0), vision_emb_out, s);
+    for (int g0 = 0; g0 < B;) {
+      const VisionPass vpass = next_vision_pass(e, src, g0, B - g0);
+      run_vision(e, src, g0, vpass, vision_emb_out, s);
+      g0 += vpass.n;
+    }
   });
 }
 
@@ -1127,10 +1187,11 @@ int vcg_score_clips_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames
                        float* probs, void* stream) {
   return guarded([&] {
     VCG_REQUIRE(e && frames_u8 && clip_start && text_ids && attention_mask && logits && probs, "null argument");
-    (void)n_frames;
+    VCG_REQUIRE(n_frames >= e->T || B == 0, "frame buffer shorter than one clip");
     FrameSource src;
     src.frames_u8 = frames_u8;
-    src.clip_start = clip_start;
+    src.clip_start = clip_start;   // device-side starts: the gather clamps every frame index to [0, n_frames)
+    src.n_frames = n_frames;
     score(e, src, nullptr, text_ids, attention_mask, B, L, logits, probs, nullptr, nullptr,
           static_cast<cudaStream_t>(stream));
   });
@@ -1153,8 +1214,8 @@ int vcg_score_video_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames
     FrameSource src;
     src.frames_u8 = frames_u8;
     src.clip_start = e->st_start.as<int32_t>();
-    src.grid_start = first_start;
-    src.grid_stride = clip_stride;
+    src.clip_start_host = starts.data();
+    src.n_frames = n_frames;
     score(e, src, nullptr, text_ids, attention_mask, B, L, logits, probs, nullptr, nullptr, s);
   });
 }
@@ -1167,6 +1228,8 @@ int vcg_score_clips_u8_host(vcg_engine* e, const uint8_t* frames_u8_host, int32_
     VCG_REQUIRE(e && frames_u8_host && clip_start_host && text_ids_host && attention_mask_host && logits_host && probs_host,
                 "null argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VCG_REQUIRE(e->finalized, "vcg_finalize has not been called");
+    check_clip_starts(clip_start_host, B, e->T, n_frames);   // before anything is enqueued
     const size_t fbytes = static_cast<size_t>(n_frames) * kImg * kImg * 3;
     const size_t tbytes = static_cast<size_t>(B) * L * sizeof(int64_t);
     e->st_frames.ensure(fbytes);
@@ -1196,15 +1259,8 @@ int vcg_score_clips_u8_host(vcg_engine* e, const uint8_t* frames_u8_host, int32_
     FrameSource src;
     src.frames_u8 = e->st_frames.as<uint8_t>();
     src.clip_start = e->st_start.as<int32_t>();
-    if (B >= 2) {   // regular grid of clips (the reference's range(0, n - T, 4)) -> shared-stem path
-      const int stride = clip_start_host[1] - clip_start_host[0];
-      bool regular = stride >= 1;
-      for (int b = 2; b < B && regular; ++b) regular = clip_start_host[b] - clip_start_host[b - 1] == stride;
-      if (regular && clip_start_host[0] >= 0 && clip_start_host[B - 1] + e->T <= n_frames) {
-        src.grid_start = clip_start_host[0];
-        src.grid_stride = stride;
-      }
-    }
+    src.clip_start_host = clip_start_host;   // regular runs (the reference's range(0, n - T, 4)) share the stem, pass by pass
+    src.n_frames = n_frames;
     score(e, src, nullptr, e->st_ids.as<int64_t>(), e->st_mask.as<int64_t>(), B, L, e->st_logits.as<float>(),
           e->st_probs.as<float>(), nullptr, nullptr, s, &feed);
     VCG_CUDA(cudaMemcpyAsync(logits_host, e->st_logits.p, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -67,43 +67,72 @@ __device__ __forceinline__ long stem_offset(long n, int hp, int wp) {
 
 // ------------------------------------------------------------------------------------------------ preprocess
 // ToTensor + Normalize (test_video_segment_point.py:142-145): (u8/255 - mean)/std, HWC -> zero-padded NHWC4.
-// One thread = 4 pixels: 12 bytes in (three aligned 32-bit loads), 4 pixel stores out.
+// HBM-bound: 150 528 B read + 401 408 B written per frame (bf16).  One CTA = kPrePairs padded row pairs of one frame:
+//   1. the 2*kPrePairs source rows (672 B each, 16-byte aligned) come in as coalesced 16-byte loads into shared memory;
+//   2. (x/255 - mean)/std is a 3 x 256 table in shared memory, computed with exactly the expression above;
+//   3. bf16: the stem input interleaves each padded row pair per pixel ([n][Hp/2][Wp][2][4], stem_offset), so one thread
+//      = one pixel column of a pair = ONE 16-byte store, consecutive threads on consecutive addresses (512 B per warp);
+//      fp32: two float4 stores per thread, each a 512-byte run per warp.
+// Rows of the pair outside the image are the zero border (bf16: written as zeros, which they already are).
 __constant__ float c_mean[3] = {0.485f, 0.456f, 0.406f};
 __constant__ float c_std[3] = {0.229f, 0.224f, 0.225f};
+constexpr int kPrePairs = 4;                                   // padded row pairs per CTA
+constexpr int kPreChunks = (kImg / 2 + 1 + kPrePairs - 1) / kPrePairs;   // 113 pairs hold image rows -> 29 CTAs per frame
+constexpr int kPreRowBytes = kImg * 3;                         // 672
 
 template <bool FP32>
-__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ frame_index,
-                                     const int32_t* __restrict__ clip_start, int T, long total,
-                                     elem_t<FP32>* __restrict__ out) {
-  pdl_enter();
-  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
-  if (idx >= total) return;
-  constexpr int W4 = kImg / 4;
-  const int w4 = static_cast<int>(idx % W4);
-  const int h = static_cast<int>((idx / W4) % kImg);
-  const long n = idx / (W4 * kImg);
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __restrict__ frames,
+                                                            const int32_t* __restrict__ frame_index,
+                                                            const int32_t* __restrict__ clip_start, int T, int n_frames,
+                                                            elem_t<FP32>* __restrict__ out) {
+  __shared__ __align__(16) uint8_t s_rows[kPrePairs * 2][kPreRowBytes];
+  __shared__ float s_lut[3][256];
+  pdl_launch_dependents();
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 768; i += 256) {
+    const int c = i >> 8, v = i & 255;
+    s_lut[c][v] = (static_cast<float>(v) / 255.0f - c_mean[c]) / c_std[c];
+  }
+  const long n = blockIdx.x / kPreChunks;                       // destination image
+  const int q0 = 1 + (blockIdx.x % kPreChunks) * kPrePairs;     // first padded row pair (pair q = padded rows 2q, 2q+1)
+  pdl_wait();
   long f = n;
-  if (clip_start) f = clip_start[n / T] + (n % T);
-  else if (frame_index) f = frame_index[n];
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(frames + (f * kImg + h) * (kImg * 3L) + w4 * 12);
-  const uint32_t u0 = __ldg(src), u1 = __ldg(src + 1), u2 = __ldg(src + 2);
-  uint8_t b[12];
-  *reinterpret_cast<uint32_t*>(b) = u0;
-  *reinterpret_cast<uint32_t*>(b + 4) = u1;
-  *reinterpret_cast<uint32_t*>(b + 8) = u2;
+  if (clip_start) f = static_cast<long>(__ldg(clip_start + n / T)) + (n % T);
+  else if (frame_index) f = __ldg(frame_index + n);
+  if (n_frames > 0) f = min(max(f, 0L), static_cast<long>(n_frames) - 1);   // never read outside the frame buffer
+  const uint8_t* src = frames + f * (static_cast<long>(kImg) * kPreRowBytes);
+  constexpr int V = kPreRowBytes / 16;                          // 42 16-byte vectors per row
+  for (int i = tid; i < kPrePairs * 2 * V; i += 256) {
+    const int r = i / V, v = i % V;
+    const int h = 2 * (q0 + (r >> 1)) + (r & 1) - kStemPad;     // image row of padded row 2q + (r & 1)
+    if (h >= 0 && h < kImg)
+      *reinterpret_cast<uint4*>(&s_rows[r][v * 16]) = __ldg(reinterpret_cast<const uint4*>(src + h * kPreRowBytes) + v);
+  }
+  __syncthreads();
+  for (int i = tid; i < kPrePairs * kImg; i += 256) {
+    const int pr = i / kImg, w = i % kImg;
+    const int q = q0 + pr;
+    if (q > kImg / 2 + 1) break;                                // past the last pair that holds an image row
+    float v[2][3];
 #pragma unroll
-  for (int px = 0; px < 4; ++px) {
-    float v[3];
+    for (int r = 0; r < 2; ++r) {
+      const int h = 2 * q + r - kStemPad;
+      const bool in = h >= 0 && h < kImg;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = (static_cast<float>(b[px * 3 + c]) / 255.0f - c_mean[c]) / c_std[c];
-    elem_t<FP32>* dst = out + stem_offset<FP32>(n, h + kStemPad, w4 * 4 + px + kStemPad);
+      for (int c = 0; c < 3; ++c) v[r][c] = in ? s_lut[c][s_rows[pr * 2 + r][w * 3 + c]] : 0.f;
+    }
     if constexpr (FP32) {
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], 0.f);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int h = 2 * q + r - kStemPad;
+        if (h >= 0 && h < kImg)
+          *reinterpret_cast<float4*>(out + stem_offset<true>(n, 2 * q + r, w + kStemPad)) = make_float4(v[r][0], v[r][1], v[r][2], 0.f);
+      }
     } else {
-      uint2 q;
-      q.x = pack_bf16x2(v[0], v[1]);
-      q.y = pack_bf16x2(v[2], 0.f);
-      *reinterpret_cast<uint2*>(dst) = q;
+      uint4 o;
+      o.x = pack_bf16x2(v[0][0], v[0][1]); o.y = pack_bf16x2(v[0][2], 0.f);
+      o.z = pack_bf16x2(v[1][0], v[1][1]); o.w = pack_bf16x2(v[1][2], 0.f);
+      *reinterpret_cast<uint4*>(out + stem_offset<false>(n, 2 * q, w + kStemPad)) = o;
     }
   }
 }
@@ -322,7 +351,7 @@ __global__ void layernorm768_kernel(const elem_t<FP32>* __restrict__ x, const fl
 // BertEmbeddings (modeling_bert.py:72-113): word[id] + position[pos] + token_type[0], LayerNorm(eps 1e-12)
 template <bool FP32>
 __global__ void bert_embed_ln_kernel(const int64_t* __restrict__ ids, int rows, int L,
-                                     const int32_t* __restrict__ tok_src, const int32_t* __restrict__ rows_dev,
+                                     const int32_t* __restrict__ tok_src, const int32_t* __restrict__ rows_dev, int vocab,
                                      const elem_t<FP32>* __restrict__ word, const elem_t<FP32>* __restrict__ pos,
                                      const elem_t<FP32>* __restrict__ type, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, elem_t<FP32>* __restrict__ out) {
@@ -332,7 +361,7 @@ __global__ void bert_embed_ln_kernel(const int64_t* __restrict__ ids, int rows, 
   if (rows_dev) rows = min(rows, *rows_dev);
   if (row >= rows) return;
   const int src = tok_src ? tok_src[row] : row;   // packed row -> b*L + j
-  const long id = ids[src];
+  const long id = min(max(ids[src], 0L), static_cast<long>(vocab) - 1);   // never index outside the embedding table
   const int p = src % L;
   float v[3][8];
 #pragma unroll
@@ -583,17 +612,17 @@ inline unsigned blocks_for(long total, int threads) { return static_cast<unsigne
   } while (0)
 
 void launch_preprocess_u8(const uint8_t* frames, const int32_t* frame_index, int n, void* out, bool fp32,
-                          cudaStream_t s) {
-  const long total = static_cast<long>(n) * kImg * (kImg / 4);
-  if (total == 0) return;
-  VCG_DISPATCH(fp32, (launch_pdl(preprocess_u8_kernel<FP>, blocks_for(total, 256), 256, 0, s, frames, frame_index, nullptr, 1, total, static_cast<elem_t<FP>*>(out))));
+                          cudaStream_t s, int n_frames) {
+  if (n == 0) return;
+  VCG_DISPATCH(fp32, (launch_pdl(preprocess_u8_kernel<FP>, static_cast<unsigned>(n) * kPreChunks, 256, 0, s, frames, frame_index,
+                                 nullptr, 1, n_frames, static_cast<elem_t<FP>*>(out))));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_preprocess_u8_clips(const uint8_t* frames, const int32_t* clip_start, int B, int T, void* out, bool fp32,
-                                cudaStream_t s) {
-  const long total = static_cast<long>(B) * T * kImg * (kImg / 4);
-  if (total == 0) return;
-  VCG_DISPATCH(fp32, (launch_pdl(preprocess_u8_kernel<FP>, blocks_for(total, 256), 256, 0, s, frames, nullptr, clip_start, T, total, static_cast<elem_t<FP>*>(out))));
+                                cudaStream_t s, int n_frames) {
+  if (B * T == 0) return;
+  VCG_DISPATCH(fp32, (launch_pdl(preprocess_u8_kernel<FP>, static_cast<unsigned>(B * T) * kPreChunks, 256, 0, s, frames, nullptr,
+                                 clip_start, T, n_frames, static_cast<elem_t<FP>*>(out))));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_nchw_to_stem(const float* img, int n, void* out, bool fp32, cudaStream_t s) {
@@ -628,11 +657,11 @@ void launch_gather_rows768(const void* x, const int32_t* row_of, int stride, int
   VCG_DISPATCH(fp32, (launch_pdl(gather_rows768_kernel<FP>, blocks_for(B, 8), 256, 0, s, static_cast<const elem_t<FP>*>(x), row_of, stride, B, static_cast<elem_t<FP>*>(out))));
   VCG_CUDA(cudaGetLastError());
 }
-void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const int32_t* tok_src, const int32_t* rows_dev,
+void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const int32_t* tok_src, const int32_t* rows_dev, int vocab,
                           const void* word, const void* pos, const void* type, const float* gamma, const float* beta,
                           void* out, bool fp32, cudaStream_t s) {
   if (rows == 0) return;
-  VCG_DISPATCH(fp32, (launch_pdl(bert_embed_ln_kernel<FP>, blocks_for(rows, 8), 256, 0, s, ids, rows, L, tok_src, rows_dev, static_cast<const elem_t<FP>*>(word), static_cast<const elem_t<FP>*>(pos),
+  VCG_DISPATCH(fp32, (launch_pdl(bert_embed_ln_kernel<FP>, blocks_for(rows, 8), 256, 0, s, ids, rows, L, tok_src, rows_dev, vocab, static_cast<const elem_t<FP>*>(word), static_cast<const elem_t<FP>*>(pos),
                          static_cast<const elem_t<FP>*>(type), gamma, beta, static_cast<elem_t<FP>*>(out))));
   VCG_CUDA(cudaGetLastError());
 }

@@ -18,11 +18,12 @@ constexpr int kBertHeads = 12;
 constexpr int kBertFfn = 3072;
 constexpr int kVisionDim = 2048;
 
+// n_frames > 0: source frame indices are clamped to [0, n_frames) (the kernel never reads outside the frame buffer)
 void launch_preprocess_u8(const uint8_t* frames, const int32_t* frame_index, int n, void* out, bool fp32,
-                          cudaStream_t s);
+                          cudaStream_t s, int n_frames = 0);
 // clip-structured gather: image i = (b, t) reads frame clip_start[b] + t
 void launch_preprocess_u8_clips(const uint8_t* frames, const int32_t* clip_start, int B, int T, void* out, bool fp32,
-                                cudaStream_t s);
+                                cudaStream_t s, int n_frames = 0);
 void launch_nchw_to_stem(const float* img, int n, void* out, bool fp32, cudaStream_t s);
 void launch_maxpool_tsm(const void* in, int n, void* out, void* out_shifted, int T, int fold, bool fp32,
                         cudaStream_t s);
@@ -34,7 +35,8 @@ void launch_bert_pack(const int64_t* mask, int B, int L, int32_t* cu, int32_t* t
 // out[b] = x[row_of ? row_of[b] : b*stride]  (rows of 768)
 void launch_gather_rows768(const void* x, const int32_t* row_of, int stride, int B, void* out, bool fp32, cudaStream_t s);
 // tok_src / rows_dev are nullptr in the un-packed layout (row m = token m of the [B, L] matrix)
-void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const int32_t* tok_src, const int32_t* rows_dev,
+// token ids are clamped to [0, vocab)
+void launch_bert_embed_ln(const int64_t* ids, int rows, int L, const int32_t* tok_src, const int32_t* rows_dev, int vocab,
                           const void* word, const void* pos, const void* type, const float* gamma, const float* beta,
                           void* out, bool fp32, cudaStream_t s);
 // bf16 path, LayerNorm folded into the GEMMs: out[b] = LayerNorm(x[row_of[b]]) for the B pooled rows

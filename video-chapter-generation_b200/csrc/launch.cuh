@@ -21,6 +21,32 @@ __device__ __forceinline__ void pdl_enter() {
   pdl_wait();
 }
 
+// Function attributes (dynamic shared memory opt-in) and the SM count are PER DEVICE: a process may hold engines on several
+// GPUs (Engine(device=...)), so one-time setup is keyed by the current device, not by the process.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    VCG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || done[dev]) return dev < 0 || dev >= 64;
+    done[dev] = true;
+    return true;
+  }
+};
+
+// the same for a dynamic-shared-memory limit that grows with the problem: true when `bytes` exceeds what was set so far
+struct PerDeviceMax {
+  size_t cur[64] = {};
+  bool raise(size_t bytes) {
+    int dev = 0;
+    VCG_CUDA(cudaGetDevice(&dev));
+    const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+    if (bytes <= cur[slot]) return false;
+    cur[slot] = bytes;
+    return true;
+  }
+};
+
 inline bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {

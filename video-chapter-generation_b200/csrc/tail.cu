@@ -158,11 +158,10 @@ void launch_head_final(const TailParams& p, int B, bool fp32, cudaStream_t s) {
   VCG_REQUIRE(p.T + 1 <= kMaxTok, "clip_frame_num + 1 must be <= 40");
   const int ntok = p.T + 1;
   const size_t smem = sizeof(float) * ((p.head_type == 0 ? 1 : 3) * ntok * p.H + p.H + 4 * ntok);
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[fp32]) {
+  static PerDeviceMax configured[2];
+  if (configured[fp32].raise(smem)) {
     if (fp32) VCG_CUDA(cudaFuncSetAttribute(head_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     else VCG_CUDA(cudaFuncSetAttribute(head_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured[fp32] = smem;
   }
   if (fp32) launch_pdl(head_final_kernel<true>, B, 128, smem, s, p);
   else launch_pdl(head_final_kernel<false>, B, 128, smem, s, p);

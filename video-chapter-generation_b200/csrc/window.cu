@@ -489,10 +489,9 @@ void launch_cross_attention(const vcg_cross_attn_params& p, const float* lang, c
   VCG_REQUIRE(T >= 2 && T <= 40, "cross attention: 2..40 frames per clip");
   VCG_REQUIRE(p.num_heads >= 1 && p.num_heads <= 16 && 128 % p.num_heads == 0, "cross attention: bad head count");
   const size_t smem = static_cast<size_t>(3) * T * 128 * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static PerDeviceMax configured;
+  if (configured.raise(smem)) {
     VCG_CUDA(cudaFuncSetAttribute(cross_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
   }
   launch_pdl(cross_attention_kernel, B, 128, smem, s, p, lang, vision, T, out);
 }
@@ -503,10 +502,9 @@ void launch_self_attention_first(const vcg_self_attn_params& p, const float* vis
   VCG_REQUIRE(T >= 1 && T <= 40, "self attention: 1..40 frames per clip");
   VCG_REQUIRE(p.num_heads >= 1 && p.num_heads <= 16 && 128 % p.num_heads == 0, "self attention: bad head count");
   const size_t smem = static_cast<size_t>(3) * (T + 1) * 128 * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static PerDeviceMax configured;
+  if (configured.raise(smem)) {
     VCG_CUDA(cudaFuncSetAttribute(self_attention_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
   }
   launch_pdl(self_attention_first_kernel, B, 128, smem, s, p, vision, lang, T, out);
 }
@@ -535,10 +533,9 @@ void launch_window_stack(const vcg_window_stack_params& p, const float* x, int B
   VCG_REQUIRE(W >= 1 && W <= 9 && (W & 1), "window stack: odd window of at most 9 clips");
   VCG_REQUIRE(p.num_layers >= 0 && p.num_layers <= 8 && p.pos_bias_stride >= W, "window stack: bad parameters");
   const size_t smem = (static_cast<size_t>(5) * W * 128 + static_cast<size_t>(2) * W * 512 + static_cast<size_t>(16) * W * W) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static PerDeviceMax configured;
+  if (configured.raise(smem)) {
     VCG_CUDA(cudaFuncSetAttribute(window_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
   }
   launch_pdl(window_stack_kernel, B, 256, smem, s, p, x, W, logits, probs);
 }

@@ -24,7 +24,7 @@ import numpy as np
 import torch
 from PIL import Image
 
-from data.common_utils import extract_first_timestamp, parse_csv_to_list
+from data._timestamps import extract_first_timestamp, parse_csv_to_list
 
 X_PAD = 0
 Y_PAD = -1

@@ -202,6 +202,8 @@ class Engine:
             probs = torch.empty(B, 2, dtype=torch.float32, device=dev)
         else:
             logits, probs = out
+        if B == 0:      # nothing to score (empty tensors have no device pointer to hand over)
+            return logits, probs
         with torch.cuda.device(dev):
             _b.check(self._lib.vcg_score_clips_u8(self._h, frames_u8.data_ptr(), frames_u8.shape[0],
                                                   clip_start.data_ptr(), ids.data_ptr(), mask.data_ptr(), B, L,
@@ -219,6 +221,8 @@ class Engine:
             probs = torch.empty(B, 2, dtype=torch.float32, device=dev)
         else:
             logits, probs = out
+        if B == 0:
+            return logits, probs
         with torch.cuda.device(dev):
             _b.check(self._lib.vcg_score_video_u8(self._h, frames_u8.data_ptr(), frames_u8.shape[0], first_start,
                                                   clip_stride, ids.data_ptr(), mask.data_ptr(), B, L,
@@ -237,6 +241,8 @@ class Engine:
             probs = torch.empty(B, 2, dtype=torch.float32).pin_memory()
         else:
             logits, probs = out
+        if B == 0:
+            return logits, probs
         with torch.cuda.device(self.device):
             _b.check(self._lib.vcg_score_clips_u8_host(self._h, frames_u8.data_ptr(), frames_u8.shape[0],
                                                        clip_start.data_ptr(), text_ids.data_ptr(),
@@ -256,6 +262,8 @@ class Engine:
             probs = torch.empty(B, 2, dtype=torch.float32).pin_memory()
         else:
             logits, probs = out
+        if B == 0:
+            return logits, probs
         with torch.cuda.device(self.device):
             _b.check(self._lib.vcg_forward_host(self._h, 0 if img_clip is None else img_clip.data_ptr(),
                                                 0 if img_clip is not None else vision_emb.data_ptr(),

@@ -302,10 +302,61 @@ def make_text(batch, max_len, seed=123):
     return ids, mask
 
 
+def make_precomputed_inputs(batch, clip_frames, max_len, seed=123, full_length=False):
+    """BASELINE.json configs[1] inputs: precomputed vision embeddings (post-ReLU average-pooled features are
+    non-negative and O(1): uniform [0,2)) + text.  full_length=True: every attention mask is all ones."""
+    ids, mask = make_text(batch, max_len, seed=seed)
+    if full_length:
+        g2 = _gen(seed + 11)
+        ids = torch.randint(1000, VOCAB, (batch, max_len), generator=g2)
+        ids[:, 0] = 101
+        mask = torch.ones_like(mask)
+    g = _gen(seed + 7)
+    emb = torch.rand(batch, clip_frames, 2048, generator=g) * 2.0
+    return emb, ids, mask
+
+
 def make_frames_u8(n_frames, seed=123):
     """uint8 HWC frames [n,224,224,3], uniform in [0,255]."""
     g = _gen(seed + 2)
     return torch.randint(0, 256, (n_frames, 224, 224, 3), generator=g, dtype=torch.uint8)
+
+
+def make_video_u8(n_frames, seed=123, scene_min=24, scene_max=72, noise=16):
+    """A synthetic VIDEO (not i.i.d. noise): scenes of U{scene_min..scene_max} frames.  A scene has its own base colour
+    (uniform over the frame, U{0..255} per channel: scenes differ in brightness and hue the way shots do) and its own
+    7x7 mosaic of 32-pixel cells (+-48 grey levels around the base); every frame adds uniform noise of +-``noise``.
+    Neighbouring clips therefore see related frames and a scene change moves the vision embeddings, so that the scores
+    of a video form RUNS of labels (what the reference's peak picker, eval_utils/eval_utils.py:3-18, turns into
+    timestamps).  Integer arithmetic only -> identical on every machine.
+    -> (frames [n,224,224,3] uint8, scene start indices)."""
+    g = _gen(seed + 3)
+    frames = torch.empty(n_frames, 224, 224, 3, dtype=torch.uint8)
+    starts, f = [], 0
+    while f < n_frames:
+        n = int(torch.randint(scene_min, scene_max + 1, (1,), generator=g))
+        n = min(n, n_frames - f)
+        colour = torch.randint(0, 256, (1, 1, 3), generator=g, dtype=torch.int16)
+        mosaic = torch.randint(-48, 49, (7, 7, 3), generator=g, dtype=torch.int16) + colour
+        base = mosaic.repeat_interleave(32, 0).repeat_interleave(32, 1)                       # [224,224,3]
+        jitter = torch.randint(-noise, noise + 1, (n, 224, 224, 3), generator=g, dtype=torch.int16)
+        frames[f:f + n] = (base[None] + jitter).clamp_(0, 255).to(torch.uint8)
+        starts.append(f)
+        f += n
+    return frames, starts
+
+
+def make_video_text(starts, scene_starts, clip_frames, max_len, seed=123):
+    """Subtitle tokens of the clips of a synthetic video: the subtitles of a real video change with its shots, and
+    neighbouring clips (stride 4 s, window T s) see mostly the same words.  Every scene of make_video_u8 gets one token
+    sequence of U{10..max_len} tokens ([CLS] first, pad id 0); a clip carries the text of the scene its centre frame
+    lies in.  -> (ids [B,L] int64, attention_mask [B,L] int64)."""
+    import bisect
+    n_scenes = len(scene_starts)
+    s_ids, s_mask = make_text(n_scenes, max_len, seed=seed + 5)
+    which = [max(0, bisect.bisect_right(scene_starts, st + clip_frames // 2) - 1) for st in starts]
+    idx = torch.tensor(which, dtype=torch.long)
+    return s_ids[idx].contiguous(), s_mask[idx].contiguous()
 
 
 def clip_starts(n_frames, clip_frames, stride=4):
