@@ -108,6 +108,14 @@ VCG_API int vcg_score_clips_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t 
                        const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L, float* logits,
                        float* probs, void* stream);
 
+/* Same with the clip starts ALSO given on the host (clip_start_host [B] int32, same values as the device array): the
+ * engine plans its vision passes from them, so every run of overlapping clips on a regular grid (each video of a
+ * video-major clip list: infer_youtube_video_dataset.py:117) shares pre-processing / stem / max-pool between its clips,
+ * and the starts are bounds-checked before anything is enqueued.  Everything else stays on the device. */
+VCG_API int vcg_score_clips_u8_planned(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames, const int32_t* clip_start,
+                               const int32_t* clip_start_host, const int64_t* text_ids, const int64_t* attention_mask,
+                               int32_t B, int32_t L, float* logits, float* probs, void* stream);
+
 /* Same for clips on a regular grid — clip b = frames first_start + b*clip_stride .. +T-1, the reference's
  * range(0, n_frames - T, 4) (infer_youtube_video_dataset.py:117).  Overlapping clips share frames, so pre-processing,
  * the ResNet stem, the max-pool and layer1.0's downsample run once per UNIQUE frame (TSM makes everything after

@@ -15,7 +15,9 @@ Resnet50TSM, eval_utils.convert_clip_label2cut_point), exactly as the callers dr
 Random-init weights give every clip of a video nearly the same margin l1 - l0, i.e. one label and no timestamps.  So
 that BOTH labels (and real runs of them) occur, the two entries of ``fusion_head.head.bias`` are re-centred: the
 common mode of the logits goes to zero and the decision threshold goes to the middle of the WIDEST GAP between sorted
-margins in the central 25-75 % of the clips.  The adjusted bias is part of the fixture (``head_bias``); logits are
+margins in the central 10-90 % of the clips that still yields >= 3 chapter timestamps.  ``raw_logit_absmax`` keeps the
+magnitude of the reference's logits BEFORE that shift (the scale the relative tolerances of BASELINE.json refer to: the
+shift is one additive constant per logit, applied identically to the reference and to the CUDA path).  The adjusted bias is part of the fixture (``head_bias``); logits are
 the reference's with that bias (the head is re-run through the reference's own ``model.fusion_head`` on the reference's
 embeddings, and a full reference forward of the first batch confirms it is the same computation bit for bit).
 ``min_abs_margin`` / ``margin_gap`` record how far every clip is from a label flip: the GPU tests assert the CUDA
@@ -40,15 +42,25 @@ SEED = 123
 CACHE = "/tmp/vcg_video_golden_cache.pt"
 
 
-def recentre(logits, bias):
-    """-> (new bias, threshold gap).  See the module docstring."""
+def recentre(logits, bias, T, convert):
+    """-> (new bias, threshold gap).  See the module docstring.  Among the gaps between neighbouring sorted margins in
+    the central 10-90 % of the clips, takes the WIDEST one whose threshold still yields >= 3 chapter timestamps
+    (``convert`` = the reference's convert_clip_label2cut_point)."""
     l = logits.double()
-    m = (l[:, 1] - l[:, 0]).sort().values
+    mm = l[:, 1] - l[:, 0]
+    m = mm.sort().values
     n = len(m)
-    lo, hi = int(0.25 * n), int(0.75 * n)
+    lo, hi = int(0.10 * n), int(0.90 * n)
     gaps = m[lo + 1:hi + 1] - m[lo:hi]
-    j = int(gaps.argmax())
-    theta = float((m[lo + j] + m[lo + j + 1]) / 2)
+    best = None
+    for j in gaps.argsort(descending=True).tolist():
+        theta = float((m[lo + j] + m[lo + j + 1]) / 2)
+        labels = (mm > theta).long().tolist()
+        if len(convert(labels, T, 2)) >= 3:
+            best = (j, theta)
+            break
+    assert best is not None, "no threshold gives three chapter timestamps"
+    j, theta = best
     common = float(((l[:, 0] + l[:, 1]) / 2).mean())
     nb = bias.double().clone()
     nb[0] += theta / 2 - common
@@ -103,7 +115,7 @@ def main():
             print(f"   reference forward: clips {b0}..{sl.stop} of {B}  ({time.time() - t0:.0f} s)", flush=True)
         vis_emb, lang_emb, logits0 = torch.cat(vis_emb), torch.cat(lang_emb), torch.cat(logits0)
         torch.save({"vis": vis_emb, "lang": lang_emb, "logits": logits0}, CACHE)
-    bias, gap = recentre(logits0, sd["fusion_head.head.bias"])
+    bias, gap = recentre(logits0, sd["fusion_head.head.bias"], T, eval_utils.convert_clip_label2cut_point)
     sd["fusion_head.head.bias"] = bias
     model.fusion_head.head.bias.copy_(bias)
     logits = torch.cat([model.fusion_head(lang_emb[b0:b0 + batch], vis_emb[b0:b0 + batch]) for b0 in range(0, B, batch)])
@@ -127,7 +139,7 @@ def main():
         logits=logits.numpy(), probs=probs.numpy(), labels=np.array(labels), cut_points=np.array(cuts, dtype=np.int64),
         head_bias=bias.numpy(), clip_starts=np.array(starts), scene_starts=np.array(scenes),
         lang_emb_f16=lang_emb.half().numpy(), vision_emb_clipmean=vis_emb.mean(dim=(1, 2)).numpy(),
-        min_abs_margin=float(margin.abs().min()), margin_gap=gap,
+        min_abs_margin=float(margin.abs().min()), margin_gap=gap, raw_logit_absmax=float(logits0.abs().max()),
         meta=np.array([T, L, B, SEED, 8, 128, n_frames, batch]))
 
     # ------------------------------------------------------------------ configs[1]: precomputed embeddings, B = 256
@@ -136,7 +148,7 @@ def main():
     emb, ids2, mask2 = W.make_precomputed_inputs(Bq, T, L, seed=SEED)
     model2 = build_model(two_stream, bert_hugface, resnet50_tsm, sd2, T, identity_vision=True)
     lg0 = model2(emb.view(Bq, T, 2048, 1, 1), ids2, mask2)[0]
-    bias2, gap2 = recentre(lg0, sd2["fusion_head.head.bias"])
+    bias2, gap2 = recentre(lg0, sd2["fusion_head.head.bias"], T, eval_utils.convert_clip_label2cut_point)
     sd2["fusion_head.head.bias"] = bias2
     model2.fusion_head.head.bias.copy_(bias2)
     logits2, probs2 = model2(emb.view(Bq, T, 2048, 1, 1), ids2, mask2)
@@ -151,7 +163,7 @@ def main():
         os.path.join(GOLDEN, "video_emb_mlp_T16_L100_B256.npz"),
         logits=logits2.numpy(), probs=probs2.numpy(), labels=np.array(labels2), cut_points=np.array(cuts2, dtype=np.int64),
         head_bias=bias2.numpy(), min_abs_margin=float(m2.abs().min()), margin_gap=gap2,
-        meta=np.array([T, L, Bq, SEED, 8, 128]))
+        raw_logit_absmax=float(lg0.abs().max()), meta=np.array([T, L, Bq, SEED, 8, 128]))
 
 
 if __name__ == "__main__":

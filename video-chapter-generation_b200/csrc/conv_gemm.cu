@@ -31,8 +31,24 @@ int fuse23_policy() {
   return pol;
 }
 
+int c23h_policy() {
+  static int pol = -2;
+  if (pol == -2) {
+    const char* v = getenv("VCG_C23H");
+    pol = v ? atoi(v) : -1;
+  }
+  return pol;
+}
+
 void launch_conv23(const Conv23Launch& L, cudaStream_t stream) {
   if (L.grid <= 0) return;
+  if (L.halo) {
+    static PerDeviceOnce configured_h;
+    if (configured_h.first())
+      VCG_CUDA(cudaFuncSetAttribute(conv23h_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC23hSmemBytes));
+    launch_pdl(conv23h_kernel<0>, L.grid, kC23Threads, kC23hSmemBytes, stream, L.q);
+    return;
+  }
   static PerDeviceOnce configured;
   if (configured.first()) {
     VCG_CUDA(cudaFuncSetAttribute(conv23_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC23SmemBytes));

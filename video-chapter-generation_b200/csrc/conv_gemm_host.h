@@ -2,6 +2,7 @@
 #pragma once
 #include "conv_gemm.cuh"
 #include "conv23.cuh"
+#include "conv23h.cuh"
 #include "tensormap.h"
 #include <algorithm>
 #include <cstdlib>
@@ -420,6 +421,7 @@ void launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream);   // conv_g
 // ---- fused conv2 (3x3) + conv3 (1x1 + residual) of a bottleneck, planes P = 64 / 128 (conv23.cuh) -------------------
 struct Conv23Launch {
   Conv23Params q;
+  bool halo = false;   // conv23h_kernel (weights + halo patch resident in shared memory)
   int grid = 0;
   double flops = 0;
   const char* name = "";
@@ -485,5 +487,64 @@ inline Conv23Launch build_conv23(const void* in, int Nimg, int H, int W, int P, 
 }
 
 void launch_conv23(const Conv23Launch& L, cudaStream_t stream);   // conv_gemm.cu
+
+// ---- the same for layer1 (P = 64, stride 1) with the weights and the conv2 halo patch resident in shared memory
+//      (conv23h.cuh).  VCG_C23H=0 falls back to conv23_kernel.
+int c23h_policy();   // conv_gemm.cu
+inline bool conv23h_ok(int P, int stride, int H, int W, bool fp32) {
+  return !fp32 && P == 64 && stride == 1 && W % 8 == 0 && H >= 16 && c23h_policy() != 0;
+}
+
+inline Conv23Launch build_conv23h(const void* in, int Nimg, int H, int W, const void* W2, const float* bias2, const void* W3,
+                                  void* out, const Epilogue& e3, const char* name) {
+  constexpr int P = 64, Cout = 256;
+  Conv23Launch L;
+  memset(&L.q, 0, sizeof L.q);
+  L.name = name;
+  L.halo = true;
+  ConvGemmParams& p = L.q.g;
+  p.bw = 8; p.bh = 16; p.nf = 1;
+  p.Wo = W; p.Ho = H; p.Nimg = Nimg; p.N = Cout;
+  p.tiles_w = (W + p.bw - 1) / p.bw;
+  p.tiles_h = (H + p.bh - 1) / p.bh;
+  p.tiles_n = Nimg;
+  p.n_tiles = 1;
+  p.n_taps = 9; p.cpt = 1;
+  {   // conv2 input [Nimg, H, W, 64] as (C, W, H, 1, N); one box = the (8+2) x (16+2) halo patch of a tile
+    const uint64_t img = static_cast<uint64_t>(H) * W * P * 2;
+    const uint64_t dims[5] = {P, static_cast<uint64_t>(W), static_cast<uint64_t>(H), 1, static_cast<uint64_t>(Nimg)};
+    const uint64_t str[4] = {static_cast<uint64_t>(P) * 2, static_cast<uint64_t>(W) * P * 2, img, img};
+    const uint32_t box[5] = {P, kC23hHaloW, kC23hHaloH, 1, 1};
+    p.a_map[0] = make_tensor_map(in, false, 5, dims, str, box);
+    for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+  }
+  p.a_bytes = kC23hHaloBytes;
+  p.b_map = weight_map(W2, P, 9 * P, P, false);
+  p.b_bytes = static_cast<uint32_t>(P) * 128u;
+  p.out = out; p.ld_out = Cout;
+  p.bias = e3.bias; p.residual = e3.residual; p.ld_res = Cout; p.act = e3.act;
+  p.tsm_out = e3.tsm_out; p.tsm_ld = e3.tsm_ld; p.tsm_fold = e3.tsm_fold; p.T = e3.T > 0 ? e3.T : 1;
+  if (e3.tsm_out) VCG_REQUIRE(e3.tsm_fold % 32 == 0, "TSM fold must be a multiple of 32 channels");
+  p.out_map = c_tile_map(out, Cout, p);
+  p.res_map = e3.residual ? c_tile_map(e3.residual, Cout, p) : p.out_map;
+  p.res_clip_T = 0;
+  if (e3.residual && e3.res_clip_T > 0) {
+    VCG_REQUIRE(p.Nimg % e3.res_clip_T == 0, "clip-view residual: whole clips only");
+    p.res_map = clip_view_map(e3.residual, Cout, p.Wo, p.Ho, e3.res_clip_T, p.Nimg / e3.res_clip_T, e3.res_clip_stride, 64, p.bw,
+                              p.bh, p.nf, false);
+    p.res_clip_T = e3.res_clip_T;
+  }
+  L.q.w3_map = weight_map(W3, Cout, P, 256, false);
+  L.q.bias2 = bias2;
+  L.q.P = P;
+  L.q.n2 = 1;
+  L.q.n_stages = kC23hHaloStages;
+  L.q.n_cslots = kC23hCSlots;
+  L.q.early_release = 1;
+  const long m_tiles = static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n;
+  L.grid = static_cast<int>(std::min<long>(m_tiles, sm_count()));
+  L.flops = 2.0 * Nimg * H * W * (static_cast<double>(P) * 9 * P + static_cast<double>(Cout) * P);
+  return L;
+}
 
 }  // namespace vcg

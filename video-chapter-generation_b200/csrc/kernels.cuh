@@ -60,7 +60,7 @@ struct TailParams {
   // inputs
   int T, H;                // frames per clip, head hidden size (128)
   const void* lang_out;    // [B, H]    relu(W_l lang_emb)       activation type (bf16 / fp32), written by a GEMM
-  const void* vis_out;     // [B*T, H]  relu(W_v vision_emb[t])  activation type, written by a GEMM
+  const void* vis_out;     // [B*T, H]  relu(W_v vision_emb[t])  fp32, written by a 3xTF32 GEMM
   int head_type;           // 0 mlp, 1 attn
   // head weights (fp32; *_t are transposed to [in][out])
   const float* head_w;     // mlp: [2][(T+1)*H]

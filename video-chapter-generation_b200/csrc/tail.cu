@@ -30,9 +30,9 @@ __global__ void __launch_bounds__(128) head_final_kernel(const TailParams p) {
   float* s_q = s_v + ntok * H;             // [H]
   float* s_att = s_q + H;                  // [4][ntok]
   __shared__ float s_red[8];
-  const in_t* vis_out = static_cast<const in_t*>(p.vis_out);
+  const float* vis_out = static_cast<const float*>(p.vis_out);   // fp32 in both precisions (3xTF32 projection)
   const in_t* lang_out = static_cast<const in_t*>(p.lang_out);
-  for (int i = tid; i < T * H; i += 128) s_tok[i] = static_cast<float>(vis_out[static_cast<long>(b) * T * H + i]);
+  for (int i = tid; i < T * H; i += 128) s_tok[i] = vis_out[static_cast<long>(b) * T * H + i];
   for (int i = tid; i < H; i += 128) s_tok[T * H + i] = static_cast<float>(lang_out[static_cast<long>(b) * H + i]);
   __syncthreads();
   float logit[2] = {0.f, 0.f};

@@ -93,6 +93,7 @@ PROTOTYPES = {
     "vcg_forward_vision": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "vcg_forward_text": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "vcg_score_clips_u8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "vcg_score_clips_u8_planned": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vcg_score_video_u8": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vcg_score_clips_u8_host": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vcg_forward_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),

@@ -190,12 +190,17 @@ class Engine:
                                                 probs.data_ptr(), 0 if le is None else le.data_ptr(), _stream()))
         return (logits, probs, le) if return_emb else (logits, probs)
 
-    def score_clips_u8(self, frames_u8, clip_start, text_ids, attention_mask, out=None):
-        """Device-resident uint8 HWC frames [n,224,224,3] + int32 clip starts [B] -> (logits, probs)."""
+    def score_clips_u8(self, frames_u8, clip_start, text_ids, attention_mask, out=None, clip_start_host=None):
+        """Device-resident uint8 HWC frames [n,224,224,3] + int32 clip starts [B] -> (logits, probs).
+        clip_start_host (the same starts as a CPU int32 tensor) lets the engine plan shared-stem vision passes over
+        every regular run of overlapping clips (vcg_score_clips_u8_planned)."""
         ids, mask, B, L = self._text(text_ids, attention_mask)
         assert frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
         clip_start = clip_start.to(torch.int32).contiguous()
         assert clip_start.is_cuda and clip_start.numel() == B
+        if clip_start_host is not None:
+            assert (not clip_start_host.is_cuda and clip_start_host.dtype == torch.int32 and
+                    clip_start_host.is_contiguous() and clip_start_host.numel() == B)
         dev = ids.device
         if out is None:
             logits = torch.empty(B, 2, dtype=torch.float32, device=dev)
@@ -205,9 +210,15 @@ class Engine:
         if B == 0:      # nothing to score (empty tensors have no device pointer to hand over)
             return logits, probs
         with torch.cuda.device(dev):
-            _b.check(self._lib.vcg_score_clips_u8(self._h, frames_u8.data_ptr(), frames_u8.shape[0],
-                                                  clip_start.data_ptr(), ids.data_ptr(), mask.data_ptr(), B, L,
-                                                  logits.data_ptr(), probs.data_ptr(), _stream()))
+            if clip_start_host is not None:
+                _b.check(self._lib.vcg_score_clips_u8_planned(self._h, frames_u8.data_ptr(), frames_u8.shape[0],
+                                                              clip_start.data_ptr(), clip_start_host.data_ptr(),
+                                                              ids.data_ptr(), mask.data_ptr(), B, L,
+                                                              logits.data_ptr(), probs.data_ptr(), _stream()))
+            else:
+                _b.check(self._lib.vcg_score_clips_u8(self._h, frames_u8.data_ptr(), frames_u8.shape[0],
+                                                      clip_start.data_ptr(), ids.data_ptr(), mask.data_ptr(), B, L,
+                                                      logits.data_ptr(), probs.data_ptr(), _stream()))
         return logits, probs
 
     def score_video_u8(self, frames_u8, first_start, clip_stride, text_ids, attention_mask, out=None):
