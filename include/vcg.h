@@ -183,6 +183,15 @@ VCG_API int vcg_op_conv2d_nhwc(const void* in, int32_t n, int32_t H, int32_t W, 
 
 /* ResNet stem conv (7x7/2, folded BN, ReLU) over the padded stem input; weight bf16 [64][4 row pairs][8 px][2 rows][4 ch],
  * fp32 [64][7 rows][8 px][4 ch] (zero for row 7, pixel 7, channel 3); out NHWC [n,112,112,64]. */
+/* Fused tail of a ResNet bottleneck (layer1 / layer2, bf16): relu(conv3x3(in, w2) + bias2) -> relu(conv1x1(., w3) + bias3
+ * + residual), optionally scattering the next bottleneck's temporally shifted channels (as vcg_op_conv2d_nhwc).
+ *   in [n,H,W,P], w2 [P,3,3,P], w3 [4P,P] bf16; bias2 [P], bias3 [4P] fp32; residual / out [n,H/stride,W/stride,4P] bf16
+ *   variant 0: per-tap TMA boxes (conv23.cuh, P = 64 / 128); 1: halo patch resident in shared memory (conv23h.cuh,
+ *   P = 64, stride 1). */
+VCG_API int vcg_op_bottleneck_tail(const void* in, int32_t n, int32_t H, int32_t W, int32_t P, int32_t stride, const void* w2,
+                           const float* bias2, const void* w3, const float* bias3, const void* residual, void* out,
+                           void* tsm_out, int32_t tsm_fold, int32_t clip_frames, int32_t variant, void* stream);
+
 VCG_API int vcg_op_stem_conv(const void* in_padded, int32_t n, const void* weight, const float* bias, void* out,
                      int32_t precision, void* stream);
 

@@ -28,6 +28,8 @@ struct Conv23Params {
   int n2;                  // 4P / 256 output-channel sub-tiles of conv3
   int n_stages, n_cslots;
   int early_release;       // hand the TMEM buffer back right after the last tcgen05.ld of a B sub-tile (VCG_C23_EARLY)
+  int prefetch_tiles;      // conv23h: tiles of L2 prefetch distance (VCG_C23H_PF, default 1; 0 = off)
+  uint32_t magic_tpi, magic_tw;   // conv23h: floor(2^32 / d) + 1 for d = tiles per image, tiles per row (exact __umulhi division)
 };
 
 constexpr int kC23Threads = (kFirstEpiWarp + kEpiWarpsBf16) * 32;

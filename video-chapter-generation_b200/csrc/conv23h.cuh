@@ -4,7 +4,16 @@
 // conv23_kernel (conv23.cuh) feeds conv2 as an implicit GEMM with one TMA box per filter tap: every 128-pixel tile pulls
 // its input patch NINE times and both weight matrices once through L2 -> shared memory (312 KB per tile; ncu: L2 -> SM
 // traffic 2.0x the DRAM bytes, tensor pipe 17 % busy).  Here
-//   * W2 [64][9*64] (72 KB) and W3 [256][64] (32 KB) are loaded ONCE per CTA and stay in shared memory,
+//   * W3 [256][64] (32 KB) is loaded ONCE per CTA and stays in shared memory; W2 streams through a ring of four 8 KB
+//     tap tiles (72 KB per tile out of L2, which is not the bottleneck; keeping W2 resident as well was measured: it
+//     leaves room for only three C slots and the epilogue then serialises on them, 7.1 us per tile instead of 5.8),
+//   * the RESIDUAL ADD runs on the tensor core: the bf16 residual tile TMA drops into a C slot is exactly a K-major
+//     A operand, so D[:, 64 g ..] += R_g * I_64 (four N = 64 MMAs per slot, exact: 1.0 * r in fp32) replaces the
+//     epilogue's shared-memory reads, bf16 unpacking and adds.  ncu on the first version of this kernel: 54 % of the
+//     issue slots busy, ~1100 instructions per warp and tile in the conv3 epilogue, tensor pipe 20 % busy, HBM at 63 %
+//     and L2 -> SM traffic down to 1.17x the DRAM bytes without any gain in time - the bottleneck was instruction issue
+//     in the epilogue, not memory.  The epilogue is now tcgen05.ld -> + bias (shared memory) -> cvt.bf16x2 -> max.bf16x2
+//     -> st.shared through 32-bit shared addresses: ~35 instructions per 16-column pass.
 //   * the conv2 input of a tile is ONE TMA box: the (8+2) x (16+2) pixel halo patch of the 8 x 16 output tile (23 KB,
 //     zero-filled outside the image = conv padding), double buffered,
 //   * the nine taps are nine VIEWS of that patch: a tile row is 8 consecutive pixels = 8 consecutive 128-byte rows of
@@ -12,7 +21,8 @@
 //     (10 pixels = 1280 B) apart = the descriptor's stride byte offset, and tap (kh, kw) just moves the start address
 //     by (kh*10 + kw) * 128 B.  The 128-byte swizzle is a function of the shared-memory address bits, TMA wrote the
 //     patch with the same function, so any 128-byte-aligned start inside the 1024-byte-aligned patch reads back right.
-// Per tile that leaves 23 KB (patch) + 64 KB (residual) of loads and 64 + 16 KB of stores: the kernel sits on HBM.
+// Per tile that leaves 23 KB (patch) + 64 KB (residual) + 72 KB (W2, L2 hits) of loads and 64 + 16 KB of stores, and
+// six 16 KB C slots keep ~100 KB of residual loads / output stores in flight per SM: the kernel sits on HBM.
 // Tile = 8 x 16 pixels of ONE frame (56 = 3.5 x 16: the last tile row of a frame is half empty, TMA clips / zero-fills).
 #pragma once
 #include "conv23.cuh"
@@ -23,11 +33,15 @@ constexpr int kC23hHaloW = 10, kC23hHaloH = 18;
 constexpr int kC23hHaloBytes = kC23hHaloW * kC23hHaloH * 128;        // 23 040 B delivered by TMA
 constexpr int kC23hHaloStride = 23 * 1024;                            // stage pitch (1024-byte aligned)
 constexpr int kC23hHaloStages = 2;
-constexpr int kC23hW2Bytes = 9 * 64 * 128;                            // 73 728
+constexpr int kC23hW2Stages = 4;
+constexpr int kC23hTapBytes = 64 * 128;                               // one tap of W2: 64 rows x 64 channels
+constexpr int kC23hW2Bytes = kC23hW2Stages * kC23hTapBytes;           // 32 768
 constexpr int kC23hW3Bytes = 256 * 128;                               // 32 768
-constexpr int kC23hCSlots = 3;
+constexpr int kC23hIdentBytes = 64 * 128;                             // 64 x 64 identity (residual add on the tensor core)
+constexpr int kC23hCSlots = 5;
+constexpr int kC23hBiasBytes = (256 + 64) * 4;
 constexpr int kC23hSmemBytes = kC23hW2Bytes + kC23hW3Bytes + kC23hHaloStages * kC23hHaloStride + kCBytes /*A2*/ +
-                               kC23hCSlots * kCBytes + 1024 /*align*/ + 512 /*barriers*/;
+                               kC23hIdentBytes + kC23hCSlots * kCBytes + kC23hBiasBytes + 1024 /*align*/ + 512 /*barriers*/;
 static_assert(kC23hSmemBytes <= 232448, "shared memory budget exceeded");
 
 // K-major SW128 operand whose 8-row groups are `sbo` bytes apart (a view into the halo patch)
@@ -41,19 +55,54 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
   return d;
 }
 
+// shared-memory accesses through 32-bit shared-window addresses (the generic-pointer forms cost a 64-bit address chain each)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// two fp32 -> packed bf16x2 (round to nearest even) -> ReLU on the packed pair: 2 instructions for 2 elements
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("{\n\t.reg .b32 t;\n\tcvt.rn.bf16x2.f32 t, %2, %1;\n\tmax.bf16x2 %0, t, %3;\n\t}" : "=r"(r) : "f"(lo), "f"(hi), "r"(0u));
+  return r;
+}
+// wait with a suspend-time hint: the waiting warp sleeps in hardware instead of spinning through the issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+  } while (!ok);
+}
+
 template <int kDummy = 0>
 __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_constant__ Conv23Params q) {
   const ConvGemmParams& p = q.g;
-  constexpr int P = 64, BLOCK_N = 256, kCSlots = kC23hCSlots, kHS = kC23hHaloStages;
+  constexpr int P = 64, BLOCK_N = 256, kCSlots = kC23hCSlots, kHS = kC23hHaloStages, kW2S = kC23hW2Stages;
+  constexpr int kBw = 8, kBh = 16;                          // tile: 8 x 16 pixels of one frame
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sW2 = smem;                                      // [9 taps][64 rows][128 B]
+  uint8_t* sW2 = smem;                                      // [kW2S tap stages][64 rows][128 B]
   uint8_t* sW3 = sW2 + kC23hW2Bytes;                        // [256 rows][128 B]
   uint8_t* sHalo = sW3 + kC23hW3Bytes;                      // [kHS][18][10][128 B]
   uint8_t* sA2 = sHalo + kHS * kC23hHaloStride;             // [128 rows][128 B]
-  uint8_t* sC = sA2 + kCBytes;                              // [kCSlots][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + kCSlots * kCBytes);
+  uint8_t* sIdent = sA2 + kCBytes;                          // [64 rows][128 B]: I_64 as a K-major SW128 B operand
+  uint8_t* sC = sIdent + kC23hIdentBytes;                   // [kCSlots][128 rows][128 B]
+  float* sBias3 = reinterpret_cast<float*>(sC + kCSlots * kCBytes);   // [256] conv3 bias, then [64] conv2 bias
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias3) + kC23hBiasBytes);
   uint64_t* w_full = bars;                       // [1]
   uint64_t* halo_full = bars + 1;                // [kHS]
   uint64_t* halo_empty = halo_full + kHS;        // [kHS]
@@ -61,9 +110,11 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint64_t* a2_full = tmem_empty + 2;            // [1] epilogue A -> MMA
   uint64_t* a2_empty = a2_full + 1;              // [1] MMA (conv3 retired) -> epilogue A
-  uint64_t* c_full = a2_empty + 1;               // [kCSlots]
-  uint64_t* c_empty = c_full + kCSlots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_empty + kCSlots);
+  uint64_t* c_full = a2_empty + 1;               // [kCSlots] residual landed -> MMA
+  uint64_t* c_empty = c_full + kCSlots;          // [kCSlots] output store has read the slot -> C producer
+  uint64_t* w2_full = c_empty + kCSlots;         // [kW2S]
+  uint64_t* w2_empty = w2_full + kW2S;           // [kW2S]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w2_empty + kW2S);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -81,12 +132,23 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
     mbar_init(a2_full, kEpiWarpsBf16);
     mbar_init(a2_empty, 1);
     for (int i = 0; i < kCSlots; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 4); }
+    for (int i = 0; i < kW2S; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
     fence_mbar_init();
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  // constants of the forward pass (written once at load time): identity operand and the two bias vectors
+  for (int i = threadIdx.x; i < kC23hIdentBytes / 16; i += blockDim.x) {
+    const int n = i >> 3, chunk = i & 7;                    // physical 16-byte chunk `chunk` of row n holds logical chunk chunk ^ (n & 7)
+    const int lc = chunk ^ (n & 7);
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (lc == (n >> 3)) w[(n & 7) >> 1] = (n & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 at column n
+    sts128(smem_u32(sIdent) + i * 16, w[0], w[1], w[2], w[3]);
+  }
+  for (int i = threadIdx.x; i < 256 + 64; i += blockDim.x) sBias3[i] = i < 256 ? __ldg(p.bias + i) : __ldg(q.bias2 + (i - 256));
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -106,33 +168,52 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
       j = nM - 1; is_a = false;
     }
   };
-  auto m_blk_of = [&](int j) { return static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x); };
+  // tile j of this CTA -> (iw, ih, frame); exact magic-number division (m_blk < 2^24, divisors < 2^8)
+  const uint32_t tpi = static_cast<uint32_t>(p.tiles_w * p.tiles_h);
+  auto tile_at = [&](int j, int& iw, int& ih, int& in) {
+    const uint32_t m_blk = blockIdx.x + static_cast<uint32_t>(j) * gridDim.x;
+    const uint32_t n = __umulhi(m_blk, q.magic_tpi);
+    const uint32_t rem = m_blk - n * tpi;
+    const uint32_t h = __umulhi(rem, q.magic_tw);
+    in = static_cast<int>(n); ih = static_cast<int>(h); iw = static_cast<int>(rem - h * static_cast<uint32_t>(p.tiles_w));
+  };
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer: weights once, then one halo patch per tile
+    // ------------------------------------------------------------ TMA producer: W3 once, then per tile one halo patch + 9 taps of W2
     if (elect_one()) {
       // the weights are constants of the forward pass: they may be fetched before the previous kernel has finished
-      mbar_expect_tx(w_full, kC23hW2Bytes + kC23hW3Bytes);
-      for (int t = 0; t < 9; ++t) tma_load_2d(sW2 + t * 64 * 128, &p.b_map, w_full, t * 64, 0);
+      mbar_expect_tx(w_full, kC23hW3Bytes);
       tma_load_2d(sW3, &q.w3_map, w_full, 0, 0);
       pdl_wait();
+      int ws = 0;
+      uint32_t wphase = 0;
       for (int j = 0; j < nM; ++j) {
         const int st = j % kHS;
-        const int m_blk = m_blk_of(j);
-        const int iw = m_blk % p.tiles_w, ih = (m_blk / p.tiles_w) % p.tiles_h, in = m_blk / (p.tiles_w * p.tiles_h);
+        int iw, ih, in;
+        tile_at(j, iw, ih, in);
         mbar_wait(&halo_empty[st], ((j / kHS) & 1) ^ 1);
         mbar_expect_tx(&halo_full[st], kC23hHaloBytes);
-        tma_load_5d(sHalo + st * kC23hHaloStride, &p.a_map[0], &halo_full[st], 0, iw * p.bw - 1, ih * p.bh - 1, 0, in);
+        tma_load_5d(sHalo + st * kC23hHaloStride, &p.a_map[0], &halo_full[st], 0, iw * kBw - 1, ih * kBh - 1, 0, in);
+        for (int t = 0; t < 9; ++t) {
+          mbar_wait(&w2_empty[ws], wphase ^ 1);
+          mbar_expect_tx(&w2_full[ws], kC23hTapBytes);
+          tma_load_2d(sW2 + ws * kC23hTapBytes, &p.b_map, &w2_full[ws], t * 64, 0);
+          if (++ws == kW2S) { ws = 0; wphase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc1 = umma_idesc(1u, kBlockM, P);
+      constexpr uint32_t idesc1 = umma_idesc(1u, kBlockM, P);          // conv2 and the residual add: N = 64
       constexpr uint32_t idesc2 = umma_idesc(1u, kBlockM, BLOCK_N);
+      const bool has_res = p.residual != nullptr;
       mbar_wait(w_full, 0);
       tc_fence_after();
-      const uint32_t w2_addr = smem_u32(sW2), w3_addr = smem_u32(sW3), a2_addr = smem_u32(sA2);
+      const uint32_t w2_addr = smem_u32(sW2), w3_addr = smem_u32(sW3), a2_addr = smem_u32(sA2), id_addr = smem_u32(sIdent);
+      const uint32_t c_addr = smem_u32(sC);
+      int ws = 0, c_it = 0;
+      uint32_t wphase = 0;
       for (int s = 0; s < n_sub; ++s) {
         int j;
         bool is_a;
@@ -148,12 +229,16 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
           const uint32_t h_addr = smem_u32(sHalo + st * kC23hHaloStride);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&w2_full[ws], wphase);
+            tc_fence_after();
             const uint32_t a_addr = h_addr + ((tap / 3) * kC23hHaloW + (tap % 3)) * 128;
-            const uint32_t b_addr = w2_addr + tap * 64 * 128;
+            const uint32_t b_addr = w2_addr + ws * kC23hTapBytes;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(d_tmem, umma_desc_sw128_sbo(a_addr + k * 32, kC23hHaloW * 128), umma_desc_sw128(b_addr + k * 32), idesc1,
                         (tap | k) != 0);
+            umma_commit(&w2_empty[ws]);
+            if (++ws == kW2S) { ws = 0; wphase ^= 1; }
           }
           umma_commit(&halo_empty[st]);
         } else {
@@ -163,8 +248,21 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
           for (int k = 0; k < 4; ++k)
             umma_bf16(d_tmem, umma_desc_sw128(a2_addr + k * 32), umma_desc_sw128(w3_addr + k * 32), idesc2, k != 0);
           umma_commit(a2_empty);                            // A2 may be overwritten once these MMAs retire
+          // residual add on the tensor core: D[:, 64 g .. 64 g + 63] += R_g * I  (R_g = the bf16 residual tile TMA put into
+          // C slot g, exactly an A operand; 1.0 * r accumulates exactly in fp32).  Four N = 64 MMAs per slot.
+          for (int g = 0; g < BLOCK_N / 64; ++g, ++c_it) {
+            const int slot = c_it % kCSlots;
+            mbar_wait(&c_full[slot], (c_it / kCSlots) & 1);
+            tc_fence_after();
+            if (has_res) {
+              const uint32_t r_addr = c_addr + slot * kCBytes;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem + g * 64, umma_desc_sw128(r_addr + k * 32), umma_desc_sw128(id_addr + k * 32), idesc1, 1u);
+            }
+          }
         }
-        umma_commit(&tmem_full[acc]);
+        umma_commit(&tmem_full[acc]);                       // also: the residual slots of this tile have been read
       }
     }
   } else if (warp == 3) {
@@ -172,21 +270,38 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
     if (elect_one()) {
       pdl_wait();
       const bool has_res = p.residual != nullptr;
+      // DRAM latency is hidden in L2, not in shared memory: the residual boxes and the halo patch of tile j + kPF are
+      // prefetched into L2 (no smem destination) while tile j is in flight; the five C slots then only have to cover
+      // the L2 -> SM latency
+      const int kPF = q.prefetch_tiles;
+      auto prefetch_tile = [&](int j2) {
+        if (j2 >= nM) return;
+        int iw, ih, in;
+        tile_at(j2, iw, ih, in);
+        tma_prefetch_l2_5d(&p.a_map[0], 0, iw * kBw - 1, ih * kBh - 1, 0, in);
+        if (has_res) {
+          for (int jj = 0; jj < BLOCK_N / 64; ++jj) {
+            if (p.res_clip_T == 0) tma_prefetch_l2_5d(&p.res_map, jj * 64, iw * kBw, ih * kBh, 0, in);
+            else tma_prefetch_l2_5d(&p.res_map, jj * 64, iw * kBw, ih * kBh, in % p.res_clip_T, in / p.res_clip_T);
+          }
+        }
+      };
+      if (kPF > 0) for (int j2 = 0; j2 < kPF; ++j2) prefetch_tile(j2);
       int c_it = 0;
       for (int j = 0; j < nM; ++j) {
-        const int m_blk = m_blk_of(j);
-        const int iw = m_blk % p.tiles_w, ih = (m_blk / p.tiles_w) % p.tiles_h, in = m_blk / (p.tiles_w * p.tiles_h);
+        int iw, ih, in;
+        tile_at(j, iw, ih, in);
+        if (kPF > 0) prefetch_tile(j + kPF);
         for (int jj = 0; jj < BLOCK_N / 64; ++jj, ++c_it) {
           const int slot = c_it % kCSlots;
           mbar_wait(&c_empty[slot], ((c_it / kCSlots) & 1) ^ 1);
           if (has_res) {
             mbar_expect_tx(&c_full[slot], kCBytes);
-            const int n0 = in * p.nf;
             if (p.res_clip_T == 0)
-              tma_load_5d(sC + slot * kCBytes, &p.res_map, &c_full[slot], jj * 64, iw * p.bw, ih * p.bh, 0, n0);
+              tma_load_5d(sC + slot * kCBytes, &p.res_map, &c_full[slot], jj * 64, iw * kBw, ih * kBh, 0, in);
             else
-              tma_load_5d(sC + slot * kCBytes, &p.res_map, &c_full[slot], jj * 64, iw * p.bw, ih * p.bh, n0 % p.res_clip_T,
-                          n0 / p.res_clip_T);
+              tma_load_5d(sC + slot * kCBytes, &p.res_map, &c_full[slot], jj * 64, iw * kBw, ih * kBh, in % p.res_clip_T,
+                          in / p.res_clip_T);
           } else {
             mbar_arrive(&c_full[slot]);
           }
@@ -199,48 +314,38 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
     const int quarter = warp & 3;
     const int group = (warp - kFirstEpiWarp) >> 2;
     const int row = quarter * 32 + lane;
-    const int dw = row % p.bw, dh = (row / p.bw) % p.bh, dn = row / (p.bw * p.bh);
-    const int HW = p.Ho * p.Wo;
     __nv_bfloat16* tsm = reinterpret_cast<__nv_bfloat16*>(p.tsm_out);
-    const bool has_res = p.residual != nullptr;
     const int srow = lane >> 1, spiece = lane & 1;
+    const uint32_t rsw = static_cast<uint32_t>(row & 7);
+    const uint32_t a2_row = smem_u32(sA2) + row * 128;
+    const uint32_t bias3_addr = smem_u32(sBias3) + group * 64 * 4;
+    const uint32_t bias2_addr = smem_u32(sBias3) + (256 + group * 16) * 4;
+    const uint32_t c_addr = smem_u32(sC);
     int c_it = 0;
     for (int s = 0; s < n_sub; ++s) {
       int j;
       bool is_a;
       sub_at(s, j, is_a);
       const int acc = s & 1;
-      mbar_wait(&tmem_full[acc], (s >> 1) & 1);
+      mbar_wait_sleep(&tmem_full[acc], (s >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
       if (is_a) {
-        // ---- A: conv2 accumulator -> + bias2 -> ReLU -> bf16 -> A2 (K-major, 128-byte swizzle); group g takes columns
+        // ---- A: conv2 accumulator -> + bias2 -> bf16 -> ReLU -> A2 (K-major, 128-byte swizzle); group g takes columns
         //      [16 g, 16 g + 16)
-        mbar_wait(a2_empty, (j & 1) ^ 1);
-        const int c0 = group * 16;
         uint32_t r[16];
-        tmem_ld_32x16(taddr + c0, r);
+        tmem_ld_32x16(taddr + group * 16, r);
+        mbar_wait(a2_empty, (j & 1) ^ 1);
         tmem_ld_wait();
-        float2 v[8];
+        uint32_t o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
-#pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(q.bias2 + c0 + 2 * e));
-          v[e] = __fadd2_rn(v[e], make_float2(b4.x, b4.y));
-          v[e + 1] = __fadd2_rn(v[e + 1], make_float2(b4.z, b4.w));
+        for (int e = 0; e < 4; ++e) {
+          const float4 b4 = lds128f(bias2_addr + e * 16);
+          o[2 * e] = pack_relu_bf16x2(__uint_as_float(r[4 * e]) + b4.x, __uint_as_float(r[4 * e + 1]) + b4.y);
+          o[2 * e + 1] = pack_relu_bf16x2(__uint_as_float(r[4 * e + 2]) + b4.z, __uint_as_float(r[4 * e + 3]) + b4.w);
         }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = make_float2(fmaxf(v[e].x, 0.f), fmaxf(v[e].y, 0.f));
-        uint8_t* arow = sA2 + row * 128;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint4 o;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) h2[e] = __float22bfloat162_rn(v[c * 4 + e]);
-          *reinterpret_cast<uint4*>(arow + ((((c0 >> 3) + c) ^ (row & 7)) << 4)) = o;
-        }
+        sts128(a2_row + (((2u * group) ^ rsw) << 4), o[0], o[1], o[2], o[3]);
+        sts128(a2_row + (((2u * group + 1u) ^ rsw) << 4), o[4], o[5], o[6], o[7]);
         fence_proxy_async_smem();                              // generic-proxy writes -> visible to the MMA operand fetch
         tc_fence_before();
         __syncwarp();
@@ -250,93 +355,61 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
         }
         continue;
       }
-      // ---- B: the conv3 epilogue (group g drains the g-th 64-column C tile)
-      const int m_blk = m_blk_of(j);
-      const int iw = m_blk % p.tiles_w, ih = (m_blk / p.tiles_w) % p.tiles_h, in = m_blk / (p.tiles_w * p.tiles_h);
-      const int w = iw * p.bw + dw, h = ih * p.bh + dh, n = in * p.nf + dn;
-      const bool row_ok = (dn < p.nf) && (w < p.Wo) && (h < p.Ho) && (n < p.Nimg);
-      const long grow = row_ok ? (static_cast<long>(n) * p.Ho + h) * p.Wo + w : -1;
-      long g_i[2];
-      int t_i[2];
-      if (tsm) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          g_i[i] = __shfl_sync(0xffffffffu, grow, srow + 16 * i);
-          t_i[i] = g_i[i] >= 0 ? static_cast<int>((g_i[i] / HW) % p.T) : 0;
-        }
-      }
-      const int my_sub = group;
-      const int my_it = c_it + my_sub;
+      // ---- B: conv3 + residual are in the accumulator; group g drains the g-th 64-column C tile:
+      //      + bias -> bf16 -> ReLU -> slot (the residual the slot held has been consumed by the tensor core) -> TMA store
+      int iw, ih, in;
+      tile_at(j, iw, ih, in);
+      const int my_it = c_it + group;
       const int slot = my_it % kCSlots;
-      uint8_t* ctile = sC + slot * kCBytes;
-      uint8_t* crow = ctile + row * 128;
+      const uint32_t ctile = c_addr + slot * kCBytes;
+      const uint32_t crow = ctile + row * 128;
       uint32_t rr[2][16];
-      tmem_ld_32x16(taddr + my_sub * 64, rr[0]);
-      mbar_wait(&c_full[slot], (my_it / kCSlots) & 1);
+      tmem_ld_32x16(taddr + group * 64, rr[0]);
 #pragma unroll
       for (int pass = 0; pass < 4; ++pass) {
-        const int cs = pass * 16;
-        const int col0 = my_sub * 64 + cs;
         tmem_ld_wait();
         if (pass < 3) {
-          tmem_ld_32x16(taddr + my_sub * 64 + cs + 16, rr[(pass + 1) & 1]);
+          tmem_ld_32x16(taddr + group * 64 + (pass + 1) * 16, rr[(pass + 1) & 1]);
         } else {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);      // accumulator handed back right after the last tcgen05.ld
         }
         const uint32_t (&r)[16] = rr[pass & 1];
-        float2 v[8];
+        uint32_t o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
-#pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 2 * e));
-          v[e] = __fadd2_rn(v[e], make_float2(b4.x, b4.y));
-          v[e + 1] = __fadd2_rn(v[e + 1], make_float2(b4.z, b4.w));
+        for (int e = 0; e < 4; ++e) {
+          const float4 b4 = lds128f(bias3_addr + (pass * 16 + e * 4) * 4);
+          o[2 * e] = pack_relu_bf16x2(__uint_as_float(r[4 * e]) + b4.x, __uint_as_float(r[4 * e + 1]) + b4.y);
+          o[2 * e + 1] = pack_relu_bf16x2(__uint_as_float(r[4 * e + 2]) + b4.z, __uint_as_float(r[4 * e + 3]) + b4.w);
         }
-        if (has_res) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint4 qq = *reinterpret_cast<const uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4));
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&qq);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[c * 4 + e] = __fadd2_rn(v[c * 4 + e], __bfloat1622float2(h2[e]));
-          }
-        }
-        apply_act8x2(v, p.act);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint4 o;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) h2[e] = __float22bfloat162_rn(v[c * 4 + e]);
-          *reinterpret_cast<uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4)) = o;
-        }
+        sts128(crow + (((2u * pass) ^ rsw) << 4), o[0], o[1], o[2], o[3]);
+        sts128(crow + (((2u * pass + 1u) ^ rsw) << 4), o[4], o[5], o[6], o[7]);
       }
       fence_proxy_async_smem();
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + my_sub), "n"(128) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(128) : "memory");
       if (quarter == 0 && lane == 0) {
-        tma_store_5d(ctile, &p.out_map, my_sub * 64, iw * p.bw, ih * p.bh, 0, in * p.nf);
+        tma_store_5d(reinterpret_cast<const void*>(sC + slot * kCBytes), &p.out_map, group * 64, iw * kBw, ih * kBh, 0, in);
         tma_store_commit();
       }
-      if (tsm) {
+      if (tsm != nullptr && group == 0) {
+        // next bottleneck's temporally shifted input: channels [0, fold) of frame t -> frame t-1, [fold, 2 fold) -> t+1
+        // (ops/temporal_shift.py:34-51).  A tile lies in ONE frame, so t is uniform; 2 lanes per row, 16 bytes each.
+        const int t = in % p.T;
 #pragma unroll
         for (int pass = 0; pass < 4; ++pass) {
-          const int cs = pass * 16;
-          const int col0 = my_sub * 64 + cs;
+          const int col0 = pass * 16;
           const bool zone_a = col0 < p.tsm_fold;
           const bool zone_b = !zone_a && col0 < 2 * p.tsm_fold;
-          if (zone_a || zone_b) {
+          if ((zone_a && t >= 1) || (zone_b && t + 1 < p.T)) {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const int r2 = quarter * 32 + srow + 16 * i;
-              if (g_i[i] >= 0) {
-                const uint4 o = *reinterpret_cast<const uint4*>(ctile + r2 * 128 + ((((cs >> 3) + spiece) ^ (r2 & 7)) << 4));
-                if (zone_a && t_i[i] >= 1)
-                  *reinterpret_cast<uint4*>(tsm + (g_i[i] - HW) * p.tsm_ld + col0 + spiece * 8) = o;
-                if (zone_b && t_i[i] + 1 < p.T)
-                  *reinterpret_cast<uint4*>(tsm + (g_i[i] + HW) * p.tsm_ld + col0 + spiece * 8) = o;
+              const int w = iw * kBw + (r2 & (kBw - 1)), h = ih * kBh + (r2 >> 3);
+              if (w < p.Wo && h < p.Ho) {
+                const uint4 o = lds128(ctile + r2 * 128 + ((((col0 >> 3) + spiece) ^ (r2 & 7)) << 4));
+                const long g = (static_cast<long>(in + (zone_a ? -1 : 1)) * p.Ho + h) * p.Wo + w;
+                *reinterpret_cast<uint4*>(tsm + g * p.tsm_ld + col0 + spiece * 8) = o;
               }
             }
           }

@@ -492,7 +492,7 @@ void launch_conv23(const Conv23Launch& L, cudaStream_t stream);   // conv_gemm.c
 //      (conv23h.cuh).  VCG_C23H=0 falls back to conv23_kernel.
 int c23h_policy();   // conv_gemm.cu
 inline bool conv23h_ok(int P, int stride, int H, int W, bool fp32) {
-  return !fp32 && P == 64 && stride == 1 && W % 8 == 0 && H >= 16 && c23h_policy() != 0;
+  return !fp32 && P == 64 && stride == 1 && W % 8 == 0 && W >= 16 && H >= 16 && c23h_policy() != 0;
 }
 
 inline Conv23Launch build_conv23h(const void* in, int Nimg, int H, int W, const void* W2, const float* bias2, const void* W3,
@@ -540,6 +540,13 @@ inline Conv23Launch build_conv23h(const void* in, int Nimg, int H, int W, const 
   L.q.n2 = 1;
   L.q.n_stages = kC23hHaloStages;
   L.q.n_cslots = kC23hCSlots;
+  VCG_REQUIRE(e3.act == ACT_RELU, "halo variant: ReLU epilogue only");
+  {
+    static const int pf = [] { const char* v = getenv("VCG_C23H_PF"); return v ? atoi(v) : 1; }();
+    L.q.prefetch_tiles = pf;
+  }
+  L.q.magic_tpi = static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(p.tiles_w * p.tiles_h)) + 1u;
+  L.q.magic_tw = static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(p.tiles_w)) + 1u;
   L.q.early_release = 1;
   const long m_tiles = static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n;
   L.grid = static_cast<int>(std::min<long>(m_tiles, sm_count()));

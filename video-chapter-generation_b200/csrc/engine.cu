@@ -1415,6 +1415,24 @@ int vcg_op_conv2d_nhwc(const void* in, int32_t n, int32_t H, int32_t W, int32_t 
     launch_conv_gemm(L, static_cast<cudaStream_t>(stream));
   });
 }
+int vcg_op_bottleneck_tail(const void* in, int32_t n, int32_t H, int32_t W, int32_t P, int32_t stride, const void* w2,
+                           const float* bias2, const void* w3, const float* bias3, const void* residual, void* out,
+                           void* tsm_out, int32_t tsm_fold, int32_t clip_frames, int32_t variant, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(in && w2 && bias2 && w3 && bias3 && out, "null argument");
+    Epilogue ep;
+    ep.bias = bias3; ep.residual = residual; ep.ld_res = 4 * P; ep.act = ACT_RELU;
+    ep.tsm_out = tsm_out; ep.tsm_fold = tsm_fold; ep.tsm_ld = 2 * tsm_fold; ep.T = clip_frames;
+    Conv23Launch L;
+    if (variant == 1) {
+      VCG_REQUIRE(conv23h_ok(P, stride, H, W, false) || c23h_policy() == 0, "halo variant: P = 64, stride 1, W % 8 == 0, W, H >= 16");
+      L = build_conv23h(in, n, H, W, w2, bias2, w3, out, ep, "op.tail_h");
+    } else {
+      L = build_conv23(in, n, H, W, P, stride, w2, bias2, w3, out, ep, "op.tail");
+    }
+    launch_conv23(L, static_cast<cudaStream_t>(stream));
+  });
+}
 int vcg_op_stem_conv(const void* in_padded, int32_t n, const void* weight, const float* bias, void* out,
                      int32_t precision, void* stream) {
   return guarded([&] {

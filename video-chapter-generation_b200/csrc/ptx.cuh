@@ -141,6 +141,13 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
   tma_load_5d<CG2>(smem_dst, m, smem_u32(bar), c0, c1, c2, c3, c4);
 }
 
+// global -> L2 only (no shared-memory destination, no barrier): hides DRAM latency for a box that will be loaded later
+__device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+
 // smem tile -> global (bulk async group); out-of-bounds parts of the box are clipped
 __device__ __forceinline__ void tma_store_5d(const void* smem_src, const CUtensorMap* m, int c0, int c1, int c2, int c3,
                                              int c4) {

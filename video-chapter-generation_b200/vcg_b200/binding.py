@@ -105,6 +105,8 @@ PROTOTYPES = {
     "vcg_op_gemm": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "vcg_op_conv2d_nhwc": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
                                           _i32, _vp, _i32, _vp, _i32, _i32, _vp]),
+    "vcg_op_bottleneck_tail": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+                                               _i32, _vp]),
     "vcg_op_stem_conv": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "vcg_op_maxpool_tsm": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
     "vcg_op_bert_attention": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),

@@ -63,6 +63,21 @@ def conv2d_nhwc(x, w, bias=None, residual=None, stride=1, act=_b.ACT_NONE, tsm_i
     return out
 
 
+def bottleneck_tail(x, w2, bias2, w3, bias3, residual=None, stride=1, tsm_out=None, tsm_fold=0, clip_frames=1, variant=0):
+    """Fused conv2 (3x3) + conv3 (1x1, residual, ReLU) of a bottleneck, bf16: x [n,H,W,P], w2 [P,3,3,P], w3 [4P,P]
+    -> [n,H/stride,W/stride,4P].  variant 0 = conv23_kernel, 1 = conv23h_kernel (P = 64, stride 1)."""
+    _need_cuda(x, w2, bias2, w3, bias3, residual, tsm_out)
+    n, H, W, P = x.shape
+    assert x.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16 and w3.dtype == torch.bfloat16
+    assert x.is_contiguous() and w2.is_contiguous() and w3.is_contiguous()
+    out = torch.empty(n, H // stride, W // stride, 4 * P, dtype=x.dtype, device=x.device)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_bottleneck_tail(x.data_ptr(), n, H, W, P, stride, w2.data_ptr(), bias2.data_ptr(), w3.data_ptr(),
+                                        bias3.data_ptr(), _ptr(residual), out.data_ptr(), _ptr(tsm_out), tsm_fold,
+                                        clip_frames, variant, _stream()))
+    return out
+
+
 def preprocess_u8(frames, frame_index=None, dtype=torch.bfloat16):
     """uint8 [n,224,224,3] -> normalised, zero-padded stem input (fp32: NHWC4 [n,230,240,4]; bf16: the same bytes
     count with row pairs interleaved per pixel, i.e. [n,115,240,2,4] viewed as [n,230,240,4])."""
