@@ -55,26 +55,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
   return d;
 }
 
-// shared-memory accesses through 32-bit shared-window addresses (the generic-pointer forms cost a 64-bit address chain each)
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 lds128f(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-// two fp32 -> packed bf16x2 (round to nearest even) -> ReLU on the packed pair: 2 instructions for 2 elements
-__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("{\n\t.reg .b32 t;\n\tcvt.rn.bf16x2.f32 t, %2, %1;\n\tmax.bf16x2 %0, t, %3;\n\t}" : "=r"(r) : "f"(lo), "f"(hi), "r"(0u));
-  return r;
-}
 // wait with a suspend-time hint: the waiting warp sleeps in hardware instead of spinning through the issue slots
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

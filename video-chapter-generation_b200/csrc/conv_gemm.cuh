@@ -172,6 +172,36 @@ __device__ __forceinline__ void apply_act8x2(float2 (&v)[8], int act) {
   }
 }
 
+// shared-memory accesses through 32-bit shared-window addresses (the generic-pointer forms cost a 64-bit address chain each)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// two fp32 -> packed bf16x2 (round to nearest even), and the same followed by ReLU on the packed pair
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("{\n\t.reg .b32 t;\n\tcvt.rn.bf16x2.f32 t, %2, %1;\n\tmax.bf16x2 %0, t, %3;\n\t}" : "=r"(r) : "f"(lo), "f"(hi), "r"(0u));
+  return r;
+}
+// bf16x2 -> two fp32 (exact)
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+}
+
 // CG2 = CTA-pair mode (bf16 only): the two CTAs of a (2,1,1) cluster compute one 256 x BLOCK_N output tile with
 // tcgen05.mma.cta_group::2.  Each CTA loads its own 128-row A patch and HALF of the B tile (BLOCK_N/2 weight rows), the
 // leader CTA's MMA thread issues for both, and every CTA drains the 128 accumulator rows that live in its own TMEM.
@@ -505,7 +535,10 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
           const int my_it = c_it + my_sub;
           const int slot = my_it % kCSlots;
           uint8_t* ctile = sC + slot * kCBytes;
-          uint8_t* crow = ctile + row * 128;
+          const uint32_t ctile_s = smem_u32(ctile);
+          const uint32_t crow_s = ctile_s + row * 128;
+          bool relu_fast = p.act == ACT_RELU;
+          if constexpr (LNF) relu_fast = false;             // (the row statistics are taken from the activated fp32 values)
           // software-pipelined over the 16-column passes: the tcgen05.ld of pass p+1 is in flight during the math of
           // pass p (the first one during the wait for the C slot), and the TMEM buffer goes back to the MMA warp as soon
           // as the last load has landed
@@ -559,7 +592,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                   const float2 nm = make_float2(-mean_r, -mean_r), rs = make_float2(rstd_r, rstd_r);
 #pragma unroll
                   for (int c = 0; c < 2; ++c) {
-                    const uint4 q = *reinterpret_cast<const uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4));
+                    const uint4 q = lds128(crow_s + ((((cs >> 3) + c) ^ (row & 7)) << 4));
                     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
                     const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.res_gamma + col0 + c * 8));
                     const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.res_gamma + col0 + c * 8 + 4));
@@ -578,14 +611,15 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                 } else {
 #pragma unroll
                   for (int c = 0; c < 2; ++c) {      // logical 16-byte chunk cs/8 + c, XOR-swizzled with row % 8
-                    const uint4 q = *reinterpret_cast<const uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4));
-                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) v[c * 4 + e] = __fadd2_rn(v[c * 4 + e], __bfloat1622float2(h2[e]));
+                    const uint4 q = lds128(crow_s + ((((cs >> 3) + c) ^ (row & 7)) << 4));
+                    v[c * 4 + 0] = __fadd2_rn(v[c * 4 + 0], unpack_bf16x2(q.x));
+                    v[c * 4 + 1] = __fadd2_rn(v[c * 4 + 1], unpack_bf16x2(q.y));
+                    v[c * 4 + 2] = __fadd2_rn(v[c * 4 + 2], unpack_bf16x2(q.z));
+                    v[c * 4 + 3] = __fadd2_rn(v[c * 4 + 3], unpack_bf16x2(q.w));
                   }
                 }
               }
-              apply_act8x2(v, p.act);
+              if (!relu_fast) apply_act8x2(v, p.act);   // ReLU is applied on the packed bf16 pairs below
               if constexpr (LNF) {
                 if (p.out_stats) {   // statistics of what the consumers will read: the bf16-rounded values
 #pragma unroll
@@ -597,13 +631,18 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                 }
               }
             }
+            if (relu_fast) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint4 o;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+              for (int c = 0; c < 2; ++c)
+                sts128(crow_s + ((((cs >> 3) + c) ^ (row & 7)) << 4), pack_relu_bf16x2(v[c * 4].x, v[c * 4].y),
+                       pack_relu_bf16x2(v[c * 4 + 1].x, v[c * 4 + 1].y), pack_relu_bf16x2(v[c * 4 + 2].x, v[c * 4 + 2].y),
+                       pack_relu_bf16x2(v[c * 4 + 3].x, v[c * 4 + 3].y));
+            } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) h2[e] = __float22bfloat162_rn(v[c * 4 + e]);
-              *reinterpret_cast<uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4)) = o;
+              for (int c = 0; c < 2; ++c)
+                sts128(crow_s + ((((cs >> 3) + c) ^ (row & 7)) << 4), pack_bf16x2(v[c * 4].x, v[c * 4].y),
+                       pack_bf16x2(v[c * 4 + 1].x, v[c * 4 + 1].y), pack_bf16x2(v[c * 4 + 2].x, v[c * 4 + 2].y),
+                       pack_bf16x2(v[c * 4 + 3].x, v[c * 4 + 3].y));
             }
           }
           fence_proxy_async_smem();                       // generic-proxy writes -> visible to the TMA store
@@ -626,7 +665,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                 for (int i = 0; i < 2; ++i) {
                   const int rr = quarter * 32 + srow + 16 * i;
                   if (g_i[i] >= 0) {
-                    const uint4 o = *reinterpret_cast<const uint4*>(ctile + rr * 128 + ((((cs >> 3) + spiece) ^ (rr & 7)) << 4));
+                    const uint4 o = lds128(ctile_s + rr * 128 + ((((cs >> 3) + spiece) ^ (rr & 7)) << 4));
                     if (zone_a && t_i[i] >= 1)           // out[t-1, c] = x[t, c]   (shift left in time)
                       *reinterpret_cast<uint4*>(tsm + (g_i[i] - HW) * p.tsm_ld + col0 + spiece * 8) = o;
                     if (zone_b && t_i[i] + 1 < p.T)      // out[t+1, c] = x[t, c]   (shift right in time)
