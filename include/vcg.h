@@ -108,6 +108,13 @@ VCG_API int vcg_score_clips_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t 
                        const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L, float* logits,
                        float* probs, void* stream);
 
+/* Source frame size of every uint8 entry point of this engine (vcg_score_*_u8*, vcg_embed_u8): frames_u8 is then
+ * [n_frames, src_h, src_w, 3] and every frame is resized to 224 x 224 inside the pre-processing kernel with the bilinear
+ * filter the reference applies to PIL frames (GroupScale, data/transforms.py:79-92 = torchvision Resize(BILINEAR) =
+ * PIL.Image.resize, bit-identical on the uint8 result).  Default 224 x 224 = no resize (the frames ffmpeg -s 224x224
+ * produced, video_chapter_youtube_dataset/extract_video_to_frames.py:28). */
+VCG_API int vcg_set_frame_size(vcg_engine* e, int32_t src_h, int32_t src_w, void* stream);
+
 /* Same with the clip starts ALSO given on the host (clip_start_host [B] int32, same values as the device array): the
  * engine plans its vision passes from them, so every run of overlapping clips on a regular grid (each video of a
  * video-major clip list: infer_youtube_video_dataset.py:117) shares pre-processing / stem / max-pool between its clips,
@@ -164,6 +171,10 @@ VCG_API int64_t vcg_launch_count(const vcg_engine* e);
 VCG_API int vcg_op_preprocess_u8(const uint8_t* frames_u8, const int32_t* frame_index, int32_t n, void* out_padded,
                          int32_t precision, void* stream);
 /* fp32 NCHW [n,3,224,224] -> the same padded NHWC4 layout. */
+/* Stand-alone resize: uint8 HWC [n,src_h,src_w,3] -> 224 x 224, written as uint8 HWC [n,224,224,3] (out_u8) and / or as
+ * the normalised zero-padded stem input (out_padded, as vcg_op_preprocess_u8); either may be NULL. */
+VCG_API int vcg_op_resize_u8(const uint8_t* frames_u8, int32_t n, int32_t src_h, int32_t src_w, uint8_t* out_u8, void* out_padded,
+                     int32_t precision, void* stream);
 VCG_API int vcg_op_nchw_to_stem(const float* img, int32_t n, void* out_padded, int32_t precision, void* stream);
 
 /* out[M,N] = act(A[M,K] W[N,K]^T + bias (+ residual)) on tcgen05 tensor cores; element type bf16 (precision 0) or

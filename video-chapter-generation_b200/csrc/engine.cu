@@ -151,6 +151,11 @@ struct vcg_engine {
   DevBuf ln_stats;
   size_t ln_stats_rows = 0;
   int last_bert_rows = 0;   // bt*L of the most recent BERT pass (profile scaling)
+  // source frame size of the uint8 entry points (224 x 224 = no resize) and the resize coefficient tables
+  int src_h = kImg, src_w = kImg;
+  DevBuf rs_xb, rs_xk, rs_yb, rs_yk;
+  bool resizing() const { return src_h != kImg || src_w != kImg; }
+  size_t frame_bytes() const { return static_cast<size_t>(src_h) * src_w * 3; }
   // host-call staging
   DevBuf st_frames, st_ids, st_mask, st_start, st_logits, st_probs;
 
@@ -893,6 +898,16 @@ const float* run_vision(vcg_engine* e, const FrameSource& src, int g0, const Vis
   if (src.img_clip) {
     ProfScope ps(e, s, "nchw_to_stem|preprocess", 0, static_cast<double>(bv) * T * kImg * kImg * 3 * (4 + e->es()));
     launch_nchw_to_stem(src.img_clip + static_cast<long>(g0) * T * 3 * kImg * kImg, bv * T, e->stem_in.p, e->fp32, s);
+  } else if (e->resizing()) {
+    // frames of another size: bilinear resize fused into the pre-processing (resize.cu)
+    const bool shared = vpass.stride > 0;
+    const int n_img = shared ? vpass.stride * (bv - 1) + T : bv * T;
+    ProfScope ps(e, s, "resize_preprocess_u8|preprocess", 0,
+                 static_cast<double>(n_img) * (static_cast<double>(e->frame_bytes()) + kImg * kImg * 3.0 * e->es()));
+    launch_resize_preprocess_u8(src.frames_u8 + (shared ? vpass.f0 * static_cast<long>(e->frame_bytes()) : 0), nullptr,
+                                shared ? nullptr : src.clip_start + g0, T, n_img, shared ? 0 : src.n_frames, e->src_h, e->src_w,
+                                e->rs_xb.as<int32_t>(), e->rs_xk.as<int32_t>(), e->rs_yb.as<int32_t>(), e->rs_yk.as<int32_t>(),
+                                e->stem_in.p, nullptr, e->fp32, s);
   } else if (vpass.stride > 0) {
     // overlapping clips: every unique frame of this pass is pre-processed (and run through the stem) once
     const int U = vpass.stride * (bv - 1) + T;
@@ -1187,6 +1202,24 @@ int vcg_embed_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames, cons
   });
 }
 
+int vcg_set_frame_size(vcg_engine* e, int32_t src_h, int32_t src_w, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e, "null engine");
+    VCG_REQUIRE(src_h >= 1 && src_w >= 1 && src_h <= 15 * kImg && src_w <= 15 * kImg, "source frame size out of range");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    e->src_h = src_h; e->src_w = src_w;
+    if (e->resizing()) {
+      e->rs_xb.alloc(kImg * 2 * sizeof(int32_t));
+      e->rs_yb.alloc(kImg * 2 * sizeof(int32_t));
+      e->rs_xk.alloc(static_cast<size_t>(kImg) * resize_ksize(src_w, kImg) * sizeof(int32_t));
+      e->rs_yk.alloc(static_cast<size_t>(kImg) * resize_ksize(src_h, kImg) * sizeof(int32_t));
+      launch_resize_coeffs(src_w, kImg, e->rs_xb.as<int32_t>(), e->rs_xk.as<int32_t>(), s);
+      launch_resize_coeffs(src_h, kImg, e->rs_yb.as<int32_t>(), e->rs_yk.as<int32_t>(), s);
+      VCG_CUDA(cudaStreamSynchronize(s));
+    }
+  });
+}
+
 int vcg_score_clips_u8(vcg_engine* e, const uint8_t* frames_u8, int32_t n_frames, const int32_t* clip_start,
                        const int64_t* text_ids, const int64_t* attention_mask, int32_t B, int32_t L, float* logits,
                        float* probs, void* stream) {
@@ -1252,7 +1285,7 @@ int vcg_score_clips_u8_host(vcg_engine* e, const uint8_t* frames_u8_host, int32_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     VCG_REQUIRE(e->finalized, "vcg_finalize has not been called");
     check_clip_starts(clip_start_host, B, e->T, n_frames);   // before anything is enqueued
-    const size_t fbytes = static_cast<size_t>(n_frames) * kImg * kImg * 3;
+    const size_t fbytes = static_cast<size_t>(n_frames) * e->frame_bytes();
     const size_t tbytes = static_cast<size_t>(B) * L * sizeof(int64_t);
     e->st_frames.ensure(fbytes);
     e->st_ids.ensure(tbytes);
@@ -1268,10 +1301,11 @@ int vcg_score_clips_u8_host(vcg_engine* e, const uint8_t* frames_u8_host, int32_
     HostFeed feed;
     feed.clip_start_host = clip_start_host;
     feed.T = e->T;
-    const size_t frame_bytes = static_cast<size_t>(kImg) * kImg * 3;
+    const size_t frame_bytes = e->frame_bytes();
+    const int piece = std::max(1, static_cast<int>((128ull * kImg * kImg * 3) / frame_bytes));   // ~19 MB per copy
     size_t ev_i = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += 128, ++ev_i) {
-      const int n = std::min(128, n_frames - f0);
+    for (int f0 = 0; f0 < n_frames; f0 += piece, ++ev_i) {
+      const int n = std::min(piece, n_frames - f0);
       VCG_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(e->st_frames.p) + f0 * frame_bytes, frames_u8_host + f0 * frame_bytes,
                                n * frame_bytes, cudaMemcpyHostToDevice, cs));
       cudaEvent_t ev = e->copy_event(ev_i);
@@ -1388,6 +1422,33 @@ int vcg_op_preprocess_u8(const uint8_t* frames_u8, const int32_t* frame_index, i
                          int32_t precision, void* stream) {
   return guarded([&] {
     launch_preprocess_u8(frames_u8, frame_index, n, out_padded, precision == VCG_PREC_FP32, static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_resize_u8(const uint8_t* frames_u8, int32_t n, int32_t src_h, int32_t src_w, uint8_t* out_u8, void* out_padded,
+                     int32_t precision, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(frames_u8 && (out_u8 || out_padded), "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // coefficient tables per (device, source extent), built once and kept for the life of the process
+    struct Axis { DevBuf b, k; };
+    static std::map<std::pair<int, int>, std::unique_ptr<Axis>> cache;
+    int dev = 0;
+    VCG_CUDA(cudaGetDevice(&dev));
+    auto axis = [&](int in_size) -> Axis& {
+      auto& slot = cache[{dev, in_size}];
+      if (!slot) {
+        slot = std::make_unique<Axis>();
+        slot->b.alloc(kImg * 2 * sizeof(int32_t));
+        slot->k.alloc(static_cast<size_t>(kImg) * resize_ksize(in_size, kImg) * sizeof(int32_t));
+        launch_resize_coeffs(in_size, kImg, slot->b.as<int32_t>(), slot->k.as<int32_t>(), s);
+        VCG_CUDA(cudaStreamSynchronize(s));
+      }
+      return *slot;
+    };
+    Axis& ax = axis(src_w);
+    Axis& ay = axis(src_h);
+    launch_resize_preprocess_u8(frames_u8, nullptr, nullptr, 1, n, 0, src_h, src_w, ax.b.as<int32_t>(), ax.k.as<int32_t>(),
+                                ay.b.as<int32_t>(), ay.k.as<int32_t>(), out_padded, out_u8, precision == VCG_PREC_FP32, s);
   });
 }
 int vcg_op_nchw_to_stem(const float* img, int32_t n, void* out_padded, int32_t precision, void* stream) {

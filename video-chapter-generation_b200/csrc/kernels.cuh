@@ -22,6 +22,12 @@ constexpr int kVisionDim = 2048;
 void launch_preprocess_u8(const uint8_t* frames, const int32_t* frame_index, int n, void* out, bool fp32,
                           cudaStream_t s, int n_frames = 0);
 // clip-structured gather: image i = (b, t) reads frame clip_start[b] + t
+// resize.cu: bilinear resize (PIL / torchvision BILINEAR, bit-identical) fused with the pre-processing
+int resize_ksize(int in_size, int out_size);
+void launch_resize_coeffs(int in_size, int out_size, int32_t* bounds, int32_t* kk, cudaStream_t s);
+void launch_resize_preprocess_u8(const uint8_t* frames, const int32_t* frame_index, const int32_t* clip_start, int T, int n,
+                                 int n_frames, int Hs, int Ws, const int32_t* xb, const int32_t* xk, const int32_t* yb,
+                                 const int32_t* yk, void* out_stem, uint8_t* out_u8, bool fp32, cudaStream_t s);
 void launch_preprocess_u8_clips(const uint8_t* frames, const int32_t* clip_start, int B, int T, void* out, bool fp32,
                                 cudaStream_t s, int n_frames = 0);
 void launch_nchw_to_stem(const float* img, int n, void* out, bool fp32, cudaStream_t s);

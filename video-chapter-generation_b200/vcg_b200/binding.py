@@ -93,6 +93,7 @@ PROTOTYPES = {
     "vcg_forward_vision": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "vcg_forward_text": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "vcg_score_clips_u8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "vcg_set_frame_size": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
     "vcg_score_clips_u8_planned": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vcg_score_video_u8": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vcg_score_clips_u8_host": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
@@ -101,6 +102,7 @@ PROTOTYPES = {
     "vcg_profile_end": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(VcgProfileEntry), _i32, ctypes.POINTER(_i32)]),
     "vcg_launch_count": (_i64, [_vp]),
     "vcg_op_preprocess_u8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),
+    "vcg_op_resize_u8": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
     "vcg_op_nchw_to_stem": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp]),
     "vcg_op_gemm": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "vcg_op_conv2d_nhwc": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,

@@ -43,6 +43,7 @@ class Engine:
             _b.check(self._lib.vcg_create(ctypes.byref(cfg), ctypes.byref(handle)))
         self._h = handle
         self._keep = []   # pinned staging tensors etc.
+        self._frame_size = (224, 224)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -82,6 +83,16 @@ class Engine:
             _b.check(self._lib.vcg_finalize(self._h, _stream()))
 
     # ------------------------------------------------------------------ scoring
+    def _frames(self, frames_u8):
+        """uint8 HWC frames [n,Hs,Ws,3]: frames of another size than 224 x 224 are resized (PIL BILINEAR, bit-identical)
+        inside the pre-processing kernel (vcg_set_frame_size)."""
+        assert frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous() and frames_u8.dim() == 4 and frames_u8.shape[3] == 3
+        size = (int(frames_u8.shape[1]), int(frames_u8.shape[2]))
+        if size != self._frame_size:
+            with torch.cuda.device(self.device):
+                _b.check(self._lib.vcg_set_frame_size(self._h, size[0], size[1], _stream()))
+            self._frame_size = size
+
     def _text(self, text_ids, attention_mask):
         if not (text_ids.is_cuda and attention_mask.is_cuda):
             raise RuntimeError("vcg_b200: inputs must be CUDA tensors (no CPU fallback)")
@@ -143,7 +154,8 @@ class Engine:
         """embed() from device-resident uint8 HWC frames [n,224,224,3]: clip b = frames clip_start[b].. (int32 CUDA), or
         the regular grid first_start + b*clip_stride when clip_start is None (stem once per distinct frame)."""
         ids, mask, B, L = self._text(text_ids, attention_mask)
-        assert frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+        assert frames_u8.is_cuda
+        self._frames(frames_u8)
         dev = ids.device
         if clip_start is not None:
             clip_start = clip_start.to(device=dev, dtype=torch.int32).contiguous()
@@ -195,7 +207,8 @@ class Engine:
         clip_start_host (the same starts as a CPU int32 tensor) lets the engine plan shared-stem vision passes over
         every regular run of overlapping clips (vcg_score_clips_u8_planned)."""
         ids, mask, B, L = self._text(text_ids, attention_mask)
-        assert frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+        assert frames_u8.is_cuda
+        self._frames(frames_u8)
         clip_start = clip_start.to(torch.int32).contiguous()
         assert clip_start.is_cuda and clip_start.numel() == B
         if clip_start_host is not None:
@@ -225,7 +238,8 @@ class Engine:
         """Clips on a regular grid (clip b = frames first_start + b*clip_stride ..): shares the stem between
         overlapping clips.  Device-resident uint8 HWC frames -> (logits, probs)."""
         ids, mask, B, L = self._text(text_ids, attention_mask)
-        assert frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+        assert frames_u8.is_cuda
+        self._frames(frames_u8)
         dev = ids.device
         if out is None:
             logits = torch.empty(B, 2, dtype=torch.float32, device=dev)
@@ -244,7 +258,8 @@ class Engine:
         """HOST tensors in (pinned for full speed), host tensors out; H2D/D2H copies happen inside the call."""
         for t in (frames_u8, clip_start, text_ids, attention_mask):
             assert not t.is_cuda and t.is_contiguous()
-        assert frames_u8.dtype == torch.uint8 and clip_start.dtype == torch.int32
+        assert clip_start.dtype == torch.int32
+        self._frames(frames_u8)
         assert text_ids.dtype == torch.int64 and attention_mask.dtype == torch.int64
         B, L = text_ids.shape
         if out is None:

@@ -89,6 +89,20 @@ def preprocess_u8(frames, frame_index=None, dtype=torch.bfloat16):
     return out
 
 
+def resize_u8(frames, want_u8=True, stem_dtype=None):
+    """uint8 [n,Hs,Ws,3] -> bilinear resize to 224 x 224 (PIL / torchvision BILINEAR, bit-identical): returns
+    (uint8 [n,224,224,3] or None, normalised padded stem input in ``stem_dtype`` or None)."""
+    _need_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames.dim() == 4 and frames.shape[3] == 3
+    n, Hs, Ws = frames.shape[:3]
+    out_u8 = torch.empty(n, 224, 224, 3, dtype=torch.uint8, device=frames.device) if want_u8 else None
+    out_st = torch.zeros(n, STEM_HP, STEM_WP, 4, dtype=stem_dtype, device=frames.device) if stem_dtype is not None else None
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_resize_u8(frames.data_ptr(), n, Hs, Ws, _ptr(out_u8), _ptr(out_st),
+                                  _b.PREC_FP32 if stem_dtype == torch.float32 else _b.PREC_BF16, _stream()))
+    return out_u8, out_st
+
+
 def nchw_to_stem(img, dtype=torch.bfloat16):
     """fp32 [n,3,224,224] (normalised) -> zero-padded NHWC4 [n,230,240,4]."""
     _need_cuda(img)
