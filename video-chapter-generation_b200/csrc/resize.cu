@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) resize_preprocess_u8_kernel(
     s_yb[tid] = (h >= 0 && h < kImg) ? __ldg(yb + 2 * h + (tid & 1)) : 0;
   }
   for (int i = tid; i < 2 * 64; i += 256) s_src[(i >> 6) * src_pitch + (src_pitch - 64) + (i & 63)] = 0;
+  __syncthreads();                                                  // tables visible to every thread
   pdl_wait();
   if (h_first > h_last) return;
   long f = n;
