@@ -33,9 +33,9 @@ constexpr int kC23hHaloW = 10, kC23hHaloH = 18;
 constexpr int kC23hHaloBytes = kC23hHaloW * kC23hHaloH * 128;        // 23 040 B delivered by TMA
 constexpr int kC23hHaloStride = 23 * 1024;                            // stage pitch (1024-byte aligned)
 constexpr int kC23hHaloStages = 2;
-constexpr int kC23hW2Stages = 4;
+constexpr int kC23hW2Stages = 5;
 constexpr int kC23hTapBytes = 64 * 128;                               // one tap of W2: 64 rows x 64 channels
-constexpr int kC23hW2Bytes = kC23hW2Stages * kC23hTapBytes;           // 32 768
+constexpr int kC23hW2Bytes = kC23hW2Stages * kC23hTapBytes;           // 40 960
 constexpr int kC23hW3Bytes = 256 * 128;                               // 32 768
 constexpr int kC23hIdentBytes = 64 * 128;                             // 64 x 64 identity (residual add on the tensor core)
 constexpr int kC23hCSlots = 5;
@@ -137,17 +137,6 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int nM = m_tiles > static_cast<int>(blockIdx.x)
                      ? (m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
-  const int n_sub = 2 * nM;
-  // s-th sub-tile of this CTA: A(0), A(1), B(0), A(2), B(1), ..., B(nM-1)   (A = conv2, B = conv3 of a tile)
-  auto sub_at = [&](int s, int& j, bool& is_a) {
-    if (s == 0) { j = 0; is_a = true; return; }
-    const int t = s - 1, blk = t >> 1;
-    if (blk < nM - 1) {
-      if ((t & 1) == 0) { j = blk + 1; is_a = true; } else { j = blk; is_a = false; }
-    } else {
-      j = nM - 1; is_a = false;
-    }
-  };
   // tile j of this CTA -> (iw, ih, frame); exact magic-number division (m_blk < 2^24, divisors < 2^8)
   const uint32_t tpi = static_cast<uint32_t>(p.tiles_w * p.tiles_h);
   auto tile_at = [&](int j, int& iw, int& ih, int& in) {
@@ -194,56 +183,60 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
       const uint32_t c_addr = smem_u32(sC);
       int ws = 0, c_it = 0;
       uint32_t wphase = 0;
-      for (int s = 0; s < n_sub; ++s) {
-        int j;
-        bool is_a;
-        sub_at(s, j, is_a);
-        const int acc = s & 1;
-        mbar_wait(&tmem_empty[acc], ((s >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        if (is_a) {
-          const int st = j % kHS;
-          mbar_wait(&halo_full[st], (j / kHS) & 1);
+      // conv2 of tile j into accumulator 0, conv3 (+ residual) of tile j into accumulator 1.  The W2 tap ring refills at L2
+      // latency, so conv3 of the PREVIOUS tile is issued in the middle of a tile's nine taps: taps 0-4 come out of the
+      // ring as prefetched, the ~0.7 us of conv3 + residual MMAs cover the refill, taps 5-8 follow.
+      auto issue_taps = [&](uint32_t h_addr, int t0, int t1) {
+        for (int tap = t0; tap < t1; ++tap) {
+          mbar_wait(&w2_full[ws], wphase);
           tc_fence_after();
-          const uint32_t h_addr = smem_u32(sHalo + st * kC23hHaloStride);
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&w2_full[ws], wphase);
-            tc_fence_after();
-            const uint32_t a_addr = h_addr + ((tap / 3) * kC23hHaloW + (tap % 3)) * 128;
-            const uint32_t b_addr = w2_addr + ws * kC23hTapBytes;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, umma_desc_sw128_sbo(a_addr + k * 32, kC23hHaloW * 128), umma_desc_sw128(b_addr + k * 32), idesc1,
-                        (tap | k) != 0);
-            umma_commit(&w2_empty[ws]);
-            if (++ws == kW2S) { ws = 0; wphase ^= 1; }
-          }
-          umma_commit(&halo_empty[st]);
-        } else {
-          mbar_wait(a2_full, j & 1);                        // the conv3 operand of tile j has been written
-          tc_fence_after();
+          const uint32_t a_addr = h_addr + ((tap / 3) * kC23hHaloW + (tap % 3)) * 128;
+          const uint32_t b_addr = w2_addr + ws * kC23hTapBytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, umma_desc_sw128(a2_addr + k * 32), umma_desc_sw128(w3_addr + k * 32), idesc2, k != 0);
-          umma_commit(a2_empty);                            // A2 may be overwritten once these MMAs retire
-          // residual add on the tensor core: D[:, 64 g .. 64 g + 63] += R_g * I  (R_g = the bf16 residual tile TMA put into
-          // C slot g, exactly an A operand; 1.0 * r accumulates exactly in fp32).  Four N = 64 MMAs per slot.
-          for (int g = 0; g < BLOCK_N / 64; ++g, ++c_it) {
-            const int slot = c_it % kCSlots;
-            mbar_wait(&c_full[slot], (c_it / kCSlots) & 1);
-            tc_fence_after();
-            if (has_res) {
-              const uint32_t r_addr = c_addr + slot * kCBytes;
+            umma_bf16(tmem_base, umma_desc_sw128_sbo(a_addr + k * 32, kC23hHaloW * 128), umma_desc_sw128(b_addr + k * 32), idesc1,
+                      (tap | k) != 0);
+          umma_commit(&w2_empty[ws]);
+          if (++ws == kW2S) { ws = 0; wphase ^= 1; }
+        }
+      };
+      auto issue_conv3 = [&](int j) {
+        mbar_wait(&tmem_empty[1], (j & 1) ^ 1);
+        mbar_wait(a2_full, j & 1);                          // the conv3 operand of tile j has been written
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + BLOCK_N;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem + g * 64, umma_desc_sw128(r_addr + k * 32), umma_desc_sw128(id_addr + k * 32), idesc1, 1u);
-            }
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(d_tmem, umma_desc_sw128(a2_addr + k * 32), umma_desc_sw128(w3_addr + k * 32), idesc2, k != 0);
+        umma_commit(a2_empty);                              // A2 may be overwritten once these MMAs retire
+        // residual add on the tensor core: D[:, 64 g .. 64 g + 63] += R_g * I  (R_g = the bf16 residual tile TMA put into
+        // C slot g, exactly an A operand; 1.0 * r accumulates exactly in fp32).  Four N = 64 MMAs per slot.
+        for (int g = 0; g < BLOCK_N / 64; ++g, ++c_it) {
+          const int slot = c_it % kCSlots;
+          mbar_wait(&c_full[slot], (c_it / kCSlots) & 1);
+          tc_fence_after();
+          if (has_res) {
+            const uint32_t r_addr = c_addr + slot * kCBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem + g * 64, umma_desc_sw128(r_addr + k * 32), umma_desc_sw128(id_addr + k * 32), idesc1, 1u);
           }
         }
-        umma_commit(&tmem_full[acc]);                       // also: the residual slots of this tile have been read
+        umma_commit(&tmem_full[1]);                         // also: the residual slots of this tile have been read
+      };
+      for (int j = 0; j < nM; ++j) {
+        const int st = j % kHS;
+        mbar_wait(&tmem_empty[0], (j & 1) ^ 1);
+        mbar_wait(&halo_full[st], (j / kHS) & 1);
+        tc_fence_after();
+        const uint32_t h_addr = smem_u32(sHalo + st * kC23hHaloStride);
+        issue_taps(h_addr, 0, 5);
+        if (j > 0) issue_conv3(j - 1);
+        issue_taps(h_addr, 5, 9);
+        umma_commit(&halo_empty[st]);
+        umma_commit(&tmem_full[0]);
       }
+      if (nM > 0) issue_conv3(nM - 1);
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------ C producer: residual prefetch for the conv3 sub-tiles
@@ -302,12 +295,11 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
     const uint32_t bias2_addr = smem_u32(sBias3) + (256 + group * 16) * 4;
     const uint32_t c_addr = smem_u32(sC);
     int c_it = 0;
-    for (int s = 0; s < n_sub; ++s) {
-      int j;
-      bool is_a;
-      sub_at(s, j, is_a);
+    for (int s = 0; s < 2 * nM; ++s) {
+      const int j = s >> 1;
+      const bool is_a = (s & 1) == 0;                        // A(j): conv2 accumulator 0, B(j): conv3 accumulator 1
       const int acc = s & 1;
-      mbar_wait_sleep(&tmem_full[acc], (s >> 1) & 1);
+      mbar_wait_sleep(&tmem_full[acc], j & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
       if (is_a) {
