@@ -424,6 +424,7 @@ struct Conv23Launch {
   bool halo = false;   // conv23h_kernel (weights + halo patch resident in shared memory)
   int grid = 0;
   double flops = 0;
+  double bytes = 0;    // algorithmic HBM bytes: conv2 input + residual + output + shifted copy (bf16)
   const char* name = "";
 };
 
@@ -483,6 +484,8 @@ inline Conv23Launch build_conv23(const void* in, int Nimg, int H, int W, int P, 
   const long m_tiles = static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n;
   L.grid = static_cast<int>(std::min<long>(m_tiles, sm_count()));
   L.flops = 2.0 * Nimg * p.Ho * p.Wo * (static_cast<double>(P) * 9 * P + static_cast<double>(Cout) * P);
+  L.bytes = 2.0 * Nimg * (static_cast<double>(H) * W * P + static_cast<double>(p.Ho) * p.Wo * (Cout * (e3.residual ? 2.0 : 1.0) +
+                                                                                          (e3.tsm_out ? 2.0 * e3.tsm_fold : 0.0)));
   return L;
 }
 
@@ -551,6 +554,7 @@ inline Conv23Launch build_conv23h(const void* in, int Nimg, int H, int W, const 
   const long m_tiles = static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n;
   L.grid = static_cast<int>(std::min<long>(m_tiles, sm_count()));
   L.flops = 2.0 * Nimg * H * W * (static_cast<double>(P) * 9 * P + static_cast<double>(Cout) * P);
+  L.bytes = 2.0 * Nimg * H * W * (P + Cout * (e3.residual ? 2.0 : 1.0) + (e3.tsm_out ? 2.0 * e3.tsm_fold : 0.0));
   return L;
 }
 

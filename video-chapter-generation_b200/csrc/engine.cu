@@ -723,7 +723,7 @@ void run_steps(vcg_engine* e, const std::vector<Step>& steps, const int64_t* mas
         break;
       }
       case Step::CONV23: {
-        ProfScope ps(e, s, std::string(st.c23.halo ? "conv23h_bf16|" : "conv23_bf16|") + st.c23.name, st.c23.flops, 0);
+        ProfScope ps(e, s, std::string(st.c23.halo ? "conv23h_bf16|" : "conv23_bf16|") + st.c23.name, st.c23.flops, st.c23.bytes);
         launch_conv23(st.c23, s);
         break;
       }
