@@ -671,3 +671,31 @@ def test_maximum_sizes_precomputed_embeddings():
     junk[mask == 0] = 1234                                                      # padded positions hold arbitrary ids
     l3, _ = model(emb, junk, mask)
     assert torch.equal(l3, l1)
+
+
+@pytest.mark.parametrize("shift_div,precision", [(4, "bf16"), (4, "fp32")])
+def test_other_shift_divisors_vs_oracle(shift_div, precision):
+    """TemporalShift with fold_div = 4 (twice as many shifted channels: other buffer sizes, other TMA tap tables, the
+    Cin = 256 blocks take the direct-coordinate path), through every vision entry point, against the oracle's temporal_shift
+    (ops/temporal_shift.py:34-51 restated).  (No shift at all = the plain Resnet50 model: tests/golden/unimodal_r50_*.)"""
+    from oracle import two_stream_oracle as orc
+    from oracle import weights as W
+    from vcg_b200.engine import Engine
+    T, L, B = 8, 24, 5
+    sd = W.make_state_dict(T, "mlp", seed=123)
+    frames = W.make_frames_u8(4 * (B - 1) + T, seed=shift_div + 40)
+    starts = [4 * b for b in range(B)]
+    ids, mask = W.make_text(B, L, seed=9)
+    img = orc.gather_clips(orc.preprocess_u8(frames), starts, T)
+    with torch.no_grad():
+        ref = orc.two_stream_forward(sd, img, ids, mask, T, 128, "mlp", shift_div)[0]
+    eng = Engine(T, "mlp", precision, vision=True, max_tokens=L, max_batch=4, shift_div=shift_div)
+    eng.load_state_dict(sd)
+    a, _ = eng.forward(img.cuda(), ids.cuda(), mask.cuda())
+    b, _ = eng.score_video_u8(frames.cuda(), 0, 4, ids.cuda(), mask.cuda())
+    c, _ = eng.score_clips_u8(frames.cuda(), torch.tensor(starts, dtype=torch.int32).cuda(), ids.cuda(), mask.cuda())
+    torch.cuda.synchronize()
+    errs = [rel(x, ref) for x in (a, b, c)]
+    print(shift_div, precision, errs)
+    assert max(errs) <= TOL[precision], errs
+    eng.close()

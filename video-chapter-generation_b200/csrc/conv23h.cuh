@@ -55,18 +55,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
   return d;
 }
 
-// wait with a suspend-time hint: the waiting warp sleeps in hardware instead of spinning through the issue slots
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
-        : "memory");
-  } while (!ok);
-}
-
 template <int kDummy = 0>
 __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_constant__ Conv23Params q) {
   const ConvGemmParams& p = q.g;
@@ -299,7 +287,7 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
       const int j = s >> 1;
       const bool is_a = (s & 1) == 0;                        // A(j): conv2 accumulator 0, B(j): conv3 accumulator 1
       const int acc = s & 1;
-      mbar_wait_sleep(&tmem_full[acc], j & 1);
+      mbar_wait(&tmem_full[acc], j & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
       if (is_a) {

@@ -64,9 +64,31 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: a waiting thread sleeps in hardware until the phase completes (or the hint elapses)
+// instead of spinning through the issue slots - with 20 warps per CTA mostly waiting, the spin loops were 40 % of the
+// issued instructions of the layer1 tail kernel (profiles/r2) and cost power the capped GEMMs could use.  VCG_SPIN=1 at
+// build time restores the plain spin loop.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef VCG_SPIN
   while (!mbar_try_wait(bar, parity)) {
   }
+#else
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  }
+#endif
 }
 
 // ---------------------------------------------------------------- clusters (CTA pairs)
