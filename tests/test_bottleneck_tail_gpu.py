@@ -19,7 +19,8 @@ def _reference(x, w2, b2, w3, b3, res, stride):
 
 
 @pytest.mark.parametrize("variant,P,H,stride,n", [(0, 64, 56, 1, 6), (1, 64, 56, 1, 6), (1, 64, 56, 1, 1), (1, 64, 56, 1, 37),
-                                                   (1, 64, 24, 1, 5), (0, 128, 28, 1, 8), (0, 128, 56, 2, 4)])
+                                                   (1, 64, 24, 1, 5), (0, 128, 28, 1, 8), (0, 128, 56, 2, 4), (1, 128, 28, 1, 9), (1, 128, 28, 1, 1),
+                                                   (1, 128, 40, 1, 3)])
 def test_bottleneck_tail_matches_torch(variant, P, H, stride, n):
     from vcg_b200 import ops
     g = torch.Generator().manual_seed(7 + n + P)
@@ -31,7 +32,7 @@ def test_bottleneck_tail_matches_torch(variant, P, H, stride, n):
     b3 = torch.randn(4 * P, generator=g).to(dev) * 0.1
     Ho = H // stride
     res = torch.randn(n, Ho, Ho, 4 * P, generator=g).to(dev).to(torch.bfloat16)
-    T = 4 if n % 4 == 0 else 1
+    T = 4 if (n % 4 == 0 and not (variant == 1 and P == 128)) else 1   # the P = 128 halo kernel has no TSM scatter
     fold = 4 * P // 8
     tsm = torch.zeros(n, Ho, Ho, 2 * fold, device=dev, dtype=torch.bfloat16) if T > 1 else None
     out = ops.bottleneck_tail(x, w2, b2, w3, b3, res, stride, tsm_out=tsm, tsm_fold=fold if T > 1 else 0, clip_frames=T,

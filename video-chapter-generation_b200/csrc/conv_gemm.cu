@@ -40,8 +40,24 @@ int c23h_policy() {
   return pol;
 }
 
+int c23h2_policy() {
+  static int pol = -2;
+  if (pol == -2) {
+    const char* v = getenv("VCG_C23H2");
+    pol = v ? atoi(v) : -1;
+  }
+  return pol;
+}
+
 void launch_conv23(const Conv23Launch& L, cudaStream_t stream) {
   if (L.grid <= 0) return;
+  if (L.halo == 2) {
+    static PerDeviceOnce configured_h2;
+    if (configured_h2.first())
+      VCG_CUDA(cudaFuncSetAttribute(conv23h2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC23h2SmemBytes));
+    launch_pdl(conv23h2_kernel<0>, L.grid, kC23Threads, kC23h2SmemBytes, stream, L.q);
+    return;
+  }
   if (L.halo) {
     static PerDeviceOnce configured_h;
     if (configured_h.first())

@@ -3,6 +3,7 @@
 #include "conv_gemm.cuh"
 #include "conv23.cuh"
 #include "conv23h.cuh"
+#include "conv23h2.cuh"
 #include "tensormap.h"
 #include <algorithm>
 #include <cstdlib>
@@ -421,7 +422,7 @@ void launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream);   // conv_g
 // ---- fused conv2 (3x3) + conv3 (1x1 + residual) of a bottleneck, planes P = 64 / 128 (conv23.cuh) -------------------
 struct Conv23Launch {
   Conv23Params q;
-  bool halo = false;   // conv23h_kernel (weights + halo patch resident in shared memory)
+  int halo = 0;        // 1: conv23h_kernel (P = 64), 2: conv23h2_kernel (P = 128): conv2 input as one halo patch per tile
   int grid = 0;
   double flops = 0;
   double bytes = 0;    // algorithmic HBM bytes: conv2 input + residual + output + shifted copy (bf16)
@@ -498,13 +499,22 @@ inline bool conv23h_ok(int P, int stride, int H, int W, bool fp32) {
   return !fp32 && P == 64 && stride == 1 && W % 8 == 0 && W >= 16 && H >= 16 && c23h_policy() != 0;
 }
 
+// layer2 (P = 128, stride 1, no TSM scatter): conv23h2.cuh.  OPT-IN (VCG_C23H2=1): measured 3 % SLOWER than
+// conv23_kernel<128> on the 28 x 28 maps (8-pixel-wide tile rows cover 28 = 3.5 x 8 pixels: 8 tiles per frame instead of
+// 6.125, and with N = 128 MMAs the tensor / shared-memory pipe is already 50 % busy), see DESIGN.md.
+int c23h2_policy();   // conv_gemm.cu
+inline bool conv23h2_ok(int P, int stride, int H, int W, bool fp32, const void* tsm_out) {
+  return !fp32 && P == 128 && stride == 1 && W >= 16 && H >= 16 && tsm_out == nullptr && c23h2_policy() == 1;
+}
+
 inline Conv23Launch build_conv23h(const void* in, int Nimg, int H, int W, const void* W2, const float* bias2, const void* W3,
-                                  void* out, const Epilogue& e3, const char* name) {
-  constexpr int P = 64, Cout = 256;
+                                  void* out, const Epilogue& e3, const char* name, int P = 64) {
+  const int Cout = 4 * P;
+  VCG_REQUIRE(P == 64 || P == 128, "halo variant: planes must be 64 or 128");
   Conv23Launch L;
   memset(&L.q, 0, sizeof L.q);
   L.name = name;
-  L.halo = true;
+  L.halo = P == 64 ? 1 : 2;
   ConvGemmParams& p = L.q.g;
   p.bw = 8; p.bh = 16; p.nf = 1;
   p.Wo = W; p.Ho = H; p.Nimg = Nimg; p.N = Cout;
@@ -515,9 +525,10 @@ inline Conv23Launch build_conv23h(const void* in, int Nimg, int H, int W, const 
   p.n_taps = 9; p.cpt = 1;
   {   // conv2 input [Nimg, H, W, 64] as (C, W, H, 1, N); one box = the (8+2) x (16+2) halo patch of a tile
     const uint64_t img = static_cast<uint64_t>(H) * W * P * 2;
-    const uint64_t dims[5] = {P, static_cast<uint64_t>(W), static_cast<uint64_t>(H), 1, static_cast<uint64_t>(Nimg)};
+    const uint64_t dims[5] = {static_cast<uint64_t>(P), static_cast<uint64_t>(W), static_cast<uint64_t>(H), 1,
+                              static_cast<uint64_t>(Nimg)};
     const uint64_t str[4] = {static_cast<uint64_t>(P) * 2, static_cast<uint64_t>(W) * P * 2, img, img};
-    const uint32_t box[5] = {P, kC23hHaloW, kC23hHaloH, 1, 1};
+    const uint32_t box[5] = {64, kC23hHaloW, kC23hHaloH, 1, 1};
     p.a_map[0] = make_tensor_map(in, false, 5, dims, str, box);
     for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
   }
@@ -537,12 +548,13 @@ inline Conv23Launch build_conv23h(const void* in, int Nimg, int H, int W, const 
                               p.bh, p.nf, false);
     p.res_clip_T = e3.res_clip_T;
   }
-  L.q.w3_map = weight_map(W3, Cout, P, 256, false);
+  L.q.w3_map = weight_map(W3, Cout, P, P == 64 ? 256 : 128, false);
   L.q.bias2 = bias2;
   L.q.P = P;
-  L.q.n2 = 1;
+  L.q.n2 = Cout / 256;
   L.q.n_stages = kC23hHaloStages;
   L.q.n_cslots = kC23hCSlots;
+  if (P == 128) VCG_REQUIRE(e3.tsm_out == nullptr, "halo variant, P = 128: no TSM scatter");
   VCG_REQUIRE(e3.act == ACT_RELU, "halo variant: ReLU epilogue only");
   {
     static const int pf = [] { const char* v = getenv("VCG_C23H_PF"); return v ? atoi(v) : 1; }();

@@ -592,6 +592,9 @@ VisionPlan& vision_plan(vcg_engine* e, int B, int clip_stride = 0) {
       if (fuse23 && conv23h_ok(bk.planes, bk.stride, H, H, fp)) {
         st.kind = Step::CONV23;
         st.c23 = build_conv23h(e->mid1.p, N, H, H, bk.c2.w.p, bk.c2.bias.as<float>(), bk.c3.w.p, xnext, ep, kNames[stage][2]);
+      } else if (fuse23 && conv23h2_ok(bk.planes, bk.stride, H, H, fp, ep.tsm_out)) {
+        st.kind = Step::CONV23;
+        st.c23 = build_conv23h(e->mid1.p, N, H, H, bk.c2.w.p, bk.c2.bias.as<float>(), bk.c3.w.p, xnext, ep, kNames[stage][2], 128);
       } else if (fuse23) {
         st.kind = Step::CONV23;
         st.c23 = build_conv23(e->mid1.p, N, H, H, bk.planes, bk.stride, bk.c2.w.p, bk.c2.bias.as<float>(), bk.c3.w.p, xnext, ep,
@@ -723,7 +726,7 @@ void run_steps(vcg_engine* e, const std::vector<Step>& steps, const int64_t* mas
         break;
       }
       case Step::CONV23: {
-        ProfScope ps(e, s, std::string(st.c23.halo ? "conv23h_bf16|" : "conv23_bf16|") + st.c23.name, st.c23.flops, st.c23.bytes);
+        ProfScope ps(e, s, std::string(st.c23.halo == 2 ? "conv23h2_bf16|" : st.c23.halo ? "conv23h_bf16|" : "conv23_bf16|") + st.c23.name, st.c23.flops, st.c23.bytes);
         launch_conv23(st.c23, s);
         break;
       }
@@ -1485,7 +1488,10 @@ int vcg_op_bottleneck_tail(const void* in, int32_t n, int32_t H, int32_t W, int3
     ep.bias = bias3; ep.residual = residual; ep.ld_res = 4 * P; ep.act = ACT_RELU;
     ep.tsm_out = tsm_out; ep.tsm_fold = tsm_fold; ep.tsm_ld = 2 * tsm_fold; ep.T = clip_frames;
     Conv23Launch L;
-    if (variant == 1) {
+    if (variant == 1 && P == 128) {
+      VCG_REQUIRE(stride == 1 && W >= 16 && H >= 16 && tsm_out == nullptr, "halo variant, P = 128: stride 1, W, H >= 16, no TSM scatter");
+      L = build_conv23h(in, n, H, W, w2, bias2, w3, out, ep, "op.tail_h2", 128);
+    } else if (variant == 1) {
       VCG_REQUIRE(conv23h_ok(P, stride, H, W, false) || c23h_policy() == 0, "halo variant: P = 64, stride 1, W % 8 == 0, W, H >= 16");
       L = build_conv23h(in, n, H, W, w2, bias2, w3, out, ep, "op.tail_h");
     } else {
