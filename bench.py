@@ -415,7 +415,12 @@ def main():
         traffic = tr["dram_bytes"] * per_launch / tr["algorithmic_per_launch"]
     elif tr is not None:
         traffic = tr
-    hbm_bound = dom["bytes"] > 0 and dom_kernel.startswith("conv23")
+    # a pair is HBM-bound when its algorithmic intensity (FLOPs per HBM byte) is below the machine balance
+    balance = peaks["tf_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+
+    def is_hbm(v):
+        return v["bytes"] > 0 and (v["flops"] == 0 or v["flops"] / v["bytes"] < balance)
+    hbm_bound = is_hbm(dom)
     if hbm_bound:
         achieved = dom["bytes"] / dom["ms"] / 1e6   # GB/s
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -423,7 +428,8 @@ def main():
                     "peak_source": peaks["source"] + ", HBM copy bandwidth",
                     "share_of_step": dom["ms"] / tot_ms, "launches_per_step": dom["launches"],
                     "tflops": dom["flops"] / dom["ms"] / 1e9,
-                    "how": "algorithmic bytes (conv2 input + residual + output + shifted copy, bf16) of every launch of this "
+                    "intensity_flop_per_byte": dom["flops"] / dom["bytes"], "machine_balance": balance,
+                    "how": "algorithmic bytes (activations in + weights + residual + output + shifted copy, bf16) of every launch of this "
                            "kernel in one step / its CUDA-event time; traffic = dram bytes of one ncu launch (profiles/traffic.json) "
                            "scaled to the mean launch size"}
     else:
@@ -434,9 +440,9 @@ def main():
                     "share_of_step": dom["ms"] / tot_ms, "launches_per_step": dom["launches"],
                     "how": "algorithmic 2*M*N*K FLOPs of every launch of this kernel in one step / its CUDA-event time"}
     # the largest tensor-bound pair next to it, for the tensor-pipe fraction the metric asks for
-    tens = {k: v for k, v in pairs.items() if v["flops"] > 0 and not k[0].startswith("conv23")}
+    tens = {k: v for k, v in pairs.items() if v["flops"] > 0 and not is_hbm(v)}
     (tk, tl), tv = max(tens.items(), key=lambda kv: kv[1]["ms"])
-    roofline_tensor = {"kernel": f"{tk}|{tl}", "achieved": tv["flops"] / tv["ms"] / 1e9, "peak": peaks["tf_sustained"],
+    roofline_tensor = {"kernel": f"{tk}|{tl}", "intensity_flop_per_byte": (tv["flops"] / tv["bytes"]) if tv["bytes"] else None, "achieved": tv["flops"] / tv["ms"] / 1e9, "peak": peaks["tf_sustained"],
                        "unit": "TFLOP/s", "frac": tv["flops"] / tv["ms"] / 1e9 / peaks["tf_sustained"],
                        "share_of_step": tv["ms"] / tot_ms, "launches_per_step": tv["launches"]}
 

@@ -237,32 +237,23 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23_kernel(const __grid_con
         // ---- A: conv2 accumulator -> + bias2 -> ReLU -> bf16 -> A2[j & 1] (K-major, 128-byte swizzle); the 16 warps split
         //      the P columns (P/4 per group)
         mbar_wait(&a2_empty[j & 1], ((j >> 1) & 1) ^ 1);
-        uint8_t* a2 = sA2 + (j & 1) * a2_bytes;
+        const uint32_t a2 = smem_u32(sA2 + (j & 1) * a2_bytes);
         constexpr int cpg = P / 4;                               // 16 or 32 columns per group
         for (int c0 = group * cpg; c0 < (group + 1) * cpg; c0 += 16) {
           uint32_t r[16];
           tmem_ld_32x16(taddr + c0, r);
           tmem_ld_wait();
-          float2 v[8];
+          uint32_t o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
-#pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(q.bias2 + c0 + 2 * e));
-            v[e] = __fadd2_rn(v[e], make_float2(b4.x, b4.y));
-            v[e + 1] = __fadd2_rn(v[e + 1], make_float2(b4.z, b4.w));
+          for (int e = 0; e < 4; ++e) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(q.bias2 + c0 + 4 * e));
+            o[2 * e] = pack_relu_bf16x2(__uint_as_float(r[4 * e]) + b4.x, __uint_as_float(r[4 * e + 1]) + b4.y);
+            o[2 * e + 1] = pack_relu_bf16x2(__uint_as_float(r[4 * e + 2]) + b4.z, __uint_as_float(r[4 * e + 3]) + b4.w);
           }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = make_float2(fmaxf(v[e].x, 0.f), fmaxf(v[e].y, 0.f));
-          uint8_t* arow = a2 + (c0 >> 6) * kCBytes + row * 128;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint4 o;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __float22bfloat162_rn(v[c * 4 + e]);
-            *reinterpret_cast<uint4*>(arow + (((((c0 & 63) >> 3) + c) ^ (row & 7)) << 4)) = o;
-          }
+          const uint32_t arow = a2 + (c0 >> 6) * kCBytes + row * 128;
+          const uint32_t ch = static_cast<uint32_t>((c0 & 63) >> 3);
+          sts128(arow + (((ch) ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
+          sts128(arow + (((ch + 1u) ^ (row & 7)) << 4), o[4], o[5], o[6], o[7]);
         }
         fence_proxy_async_smem();                              // generic-proxy writes -> visible to the MMA operand fetch
         tc_fence_before();
@@ -292,7 +283,9 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23_kernel(const __grid_con
       const int my_it = c_it + my_sub;
       const int slot = my_it % kCSlots;
       uint8_t* ctile = sC + slot * kCBytes;
-      uint8_t* crow = ctile + row * 128;
+      const uint32_t ctile_s = smem_u32(ctile);
+      const uint32_t crow_s = ctile_s + row * 128;
+      const bool relu_fast = p.act == ACT_RELU;
       // passes software-pipelined as in conv_gemm.cuh: next tcgen05.ld in flight during the math, TMEM handed back to
       // the MMA warp right after the last load
       uint32_t rr[2][16];
@@ -323,20 +316,26 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23_kernel(const __grid_con
         if (has_res) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            const uint4 qq = *reinterpret_cast<const uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4));
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&qq);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[c * 4 + e] = __fadd2_rn(v[c * 4 + e], __bfloat1622float2(h2[e]));
+            const uint4 qq = lds128(crow_s + ((((cs >> 3) + c) ^ (row & 7)) << 4));
+            v[c * 4 + 0] = __fadd2_rn(v[c * 4 + 0], unpack_bf16x2(qq.x));
+            v[c * 4 + 1] = __fadd2_rn(v[c * 4 + 1], unpack_bf16x2(qq.y));
+            v[c * 4 + 2] = __fadd2_rn(v[c * 4 + 2], unpack_bf16x2(qq.z));
+            v[c * 4 + 3] = __fadd2_rn(v[c * 4 + 3], unpack_bf16x2(qq.w));
           }
         }
-        apply_act8x2(v, p.act);
+        if (relu_fast) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint4 o;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+          for (int c = 0; c < 2; ++c)
+            sts128(crow_s + ((((cs >> 3) + c) ^ (row & 7)) << 4), pack_relu_bf16x2(v[c * 4].x, v[c * 4].y),
+                   pack_relu_bf16x2(v[c * 4 + 1].x, v[c * 4 + 1].y), pack_relu_bf16x2(v[c * 4 + 2].x, v[c * 4 + 2].y),
+                   pack_relu_bf16x2(v[c * 4 + 3].x, v[c * 4 + 3].y));
+        } else {
+          apply_act8x2(v, p.act);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) h2[e] = __float22bfloat162_rn(v[c * 4 + e]);
-          *reinterpret_cast<uint4*>(crow + ((((cs >> 3) + c) ^ (row & 7)) << 4)) = o;
+          for (int c = 0; c < 2; ++c)
+            sts128(crow_s + ((((cs >> 3) + c) ^ (row & 7)) << 4), pack_bf16x2(v[c * 4].x, v[c * 4].y),
+                   pack_bf16x2(v[c * 4 + 1].x, v[c * 4 + 1].y), pack_bf16x2(v[c * 4 + 2].x, v[c * 4 + 2].y),
+                   pack_bf16x2(v[c * 4 + 3].x, v[c * 4 + 3].y));
         }
       }
       fence_proxy_async_smem();
@@ -357,7 +356,7 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23_kernel(const __grid_con
             for (int i = 0; i < 2; ++i) {
               const int rr = quarter * 32 + srow + 16 * i;
               if (g_i[i] >= 0) {
-                const uint4 o = *reinterpret_cast<const uint4*>(ctile + rr * 128 + ((((cs >> 3) + spiece) ^ (rr & 7)) << 4));
+                const uint4 o = lds128(ctile_s + rr * 128 + ((((cs >> 3) + spiece) ^ (rr & 7)) << 4));
                 if (zone_a && t_i[i] >= 1)
                   *reinterpret_cast<uint4*>(tsm + (g_i[i] - HW) * p.tsm_ld + col0 + spiece * 8) = o;
                 if (zone_b && t_i[i] + 1 < p.T)

@@ -19,6 +19,7 @@ struct ConvGemmLaunch {
   bool lnf = false;   // epilogue with the LayerNorm terms
   int grid = 0;
   double flops = 0;   // 2*M*N*K of useful work (for reporting)
+  double bytes = 0;   // algorithmic HBM bytes: activations in + weights + out (+ residual, + shifted copy)
   const char* name = "";
 };
 
@@ -219,6 +220,8 @@ inline ConvGemmLaunch build_gemm(const void* A, long lda, const void* W, void* o
   p.b_map = weight_map(W, N, K, L.cg2 ? L.block_n / 2 : L.block_n, fp32);
   set_epilogue(L, out, ld_out, e);
   L.flops = 2.0 * M * N * K;
+  L.bytes = static_cast<double>(es) * (static_cast<double>(M) * K + static_cast<double>(N) * K +
+                                       static_cast<double>(M) * N * (e.residual ? 2.0 : 1.0));
   return L;
 }
 
@@ -293,6 +296,11 @@ inline ConvGemmLaunch build_conv(const void* in, int Nimg, int H, int W, int Cin
   p.b_map = weight_map(Wp, Cout, k * k * Cin, L.cg2 ? L.block_n / 2 : L.block_n, fp32);
   set_epilogue(L, out, Cout, e);
   L.flops = 2.0 * Nimg * Ho * Wo * static_cast<double>(Cout) * k * k * Cin;
+  // a stride-2 1x1 conv touches only the pixels it keeps
+  const double in_px = (k == 1) ? static_cast<double>(Ho) * Wo : static_cast<double>(H) * W;
+  L.bytes = static_cast<double>(es) * (Nimg * in_px * Cin + static_cast<double>(Cout) * k * k * Cin +
+                                       static_cast<double>(Nimg) * Ho * Wo * (Cout * (e.residual ? 2.0 : 1.0) +
+                                                                              (e.tsm_out ? 2.0 * e.tsm_fold : 0.0)));
   return L;
 }
 
@@ -344,6 +352,7 @@ inline ConvGemmLaunch build_stem(const void* in_padded, int Nimg, int Hp, int Wp
   p.b_map = weight_map(Wp_packed, Cout, fp32 ? 7 * 32 : 4 * 64, L.cg2 ? L.block_n / 2 : L.block_n, fp32);
   set_epilogue(L, out, Cout, e);
   L.flops = 2.0 * Nimg * Ho * Wo * static_cast<double>(Cout) * 147;
+  L.bytes = static_cast<double>(elem_size(fp32)) * Nimg * (static_cast<double>(Hp) * Wp * 4 + static_cast<double>(Ho) * Wo * Cout);
   return L;
 }
 
@@ -383,6 +392,7 @@ inline ConvGemmLaunch build_conv1_tsm_direct(const void* x, int Nimg, int T, int
   p.b_map = weight_map(Wp, Cout, Cin, L.cg2 ? L.block_n / 2 : L.block_n, false);
   set_epilogue(L, out, Cout, e);
   L.flops = 2.0 * Nimg * H * W * static_cast<double>(Cout) * Cin;
+  L.bytes = 2.0 * (static_cast<double>(Nimg) * H * W * (Cin + Cout) + static_cast<double>(Cout) * Cin);
   return L;
 }
 
@@ -414,6 +424,7 @@ inline ConvGemmLaunch build_conv1_shared(const void* x0u, int n_clips, int T, in
   p.b_map = weight_map(Wp, Cout, 3 * Cin, L.cg2 ? L.block_n / 2 : L.block_n, false);
   set_epilogue(L, out, Cout, e);
   L.flops = 2.0 * Nimg * H * W * static_cast<double>(Cout) * Cin;
+  L.bytes = 2.0 * (static_cast<double>(Nimg) * H * W * (Cin + Cout) + 3.0 * Cout * Cin);
   return L;
 }
 

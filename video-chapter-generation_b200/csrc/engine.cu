@@ -721,7 +721,7 @@ void run_steps(vcg_engine* e, const std::vector<Step>& steps, const int64_t* mas
   for (const Step& st : steps) {
     switch (st.kind) {
       case Step::CONV_GEMM: {
-        ProfScope ps(e, s, gemm_kernel_name(st.gemm), st.gemm.flops, 0, st.gemm.p.m_dev != nullptr);
+        ProfScope ps(e, s, gemm_kernel_name(st.gemm), st.gemm.flops, st.gemm.bytes, st.gemm.p.m_dev != nullptr);
         launch_conv_gemm(st.gemm, s);
         break;
       }
@@ -842,7 +842,7 @@ void run_text(vcg_engine* e, const int64_t* ids, const int64_t* mask, int b0, in
     }
   }
   for (const ConvGemmLaunch& g : it->second) {
-    ProfScope ps(e, s, gemm_kernel_name(g), g.flops, 0);
+    ProfScope ps(e, s, gemm_kernel_name(g), g.flops, g.bytes);
     launch_conv_gemm(g, s);
   }
   if (lang_emb_out) {
@@ -983,7 +983,7 @@ void score(vcg_engine* e, const FrameSource& src, const float* vision_emb_in, co
           it = e->vis_proj_plans.emplace(bv * T, build_gemm(e->vis_emb.p, kVisionDim, e->vis_w.p, e->vis_out.p, e->H, bv * T, e->H,
                                                             kVisionDim, /*fp32=*/true, ep, "head.vision_proj")).first;
         }
-        ProfScope ps(e, s, gemm_kernel_name(it->second), it->second.flops, 0);
+        ProfScope ps(e, s, gemm_kernel_name(it->second), it->second.flops, it->second.bytes);
         launch_conv_gemm(it->second, s);
       }
       TailParams hp = tp;
