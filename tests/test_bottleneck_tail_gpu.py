@@ -20,7 +20,10 @@ def _reference(x, w2, b2, w3, b3, res, stride):
 
 @pytest.mark.parametrize("variant,P,H,stride,n", [(0, 64, 56, 1, 6), (1, 64, 56, 1, 6), (1, 64, 56, 1, 1), (1, 64, 56, 1, 37),
                                                    (1, 64, 24, 1, 5), (0, 128, 28, 1, 8), (0, 128, 56, 2, 4), (1, 128, 28, 1, 9), (1, 128, 28, 1, 1),
-                                                   (1, 128, 40, 1, 3)])
+                                                   (1, 128, 40, 1, 3),
+                                                   # P = 128 without a TSM scatter (n % 4 != 0 below): conv23t_kernel, the
+                                                   # conv3 operand in tensor memory; stride 1 and 2, ragged frame counts
+                                                   (0, 128, 28, 1, 9), (0, 128, 56, 2, 5), (0, 128, 28, 1, 1), (0, 128, 28, 1, 37)])
 def test_bottleneck_tail_matches_torch(variant, P, H, stride, n):
     from vcg_b200 import ops
     g = torch.Generator().manual_seed(7 + n + P)

@@ -65,6 +65,15 @@ void launch_conv23(const Conv23Launch& L, cudaStream_t stream) {
     launch_pdl(conv23h_kernel<0>, L.grid, kC23Threads, kC23hSmemBytes, stream, L.q);
     return;
   }
+  // P = 128 without a TSM scatter: conv3 operand in tensor memory, five ring stages (conv23t.cuh); VCG_C23T=0 -> conv23_kernel
+  static const bool c23t_on = !(getenv("VCG_C23T") && atoi(getenv("VCG_C23T")) == 0);
+  if (c23t_on && L.q.P == 128 && L.q.g.tsm_out == nullptr && L.q.g.act == ACT_RELU && L.q.g.n_taps * L.q.g.cpt == 18) {
+    static PerDeviceOnce configured_t;
+    if (configured_t.first())
+      VCG_CUDA(cudaFuncSetAttribute(conv23t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC23tSmemBytes));
+    launch_pdl(conv23t_kernel<0>, L.grid, kC23Threads, kC23tSmemBytes, stream, L.q);
+    return;
+  }
   static PerDeviceOnce configured;
   if (configured.first()) {
     VCG_CUDA(cudaFuncSetAttribute(conv23_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC23SmemBytes));

@@ -4,6 +4,7 @@
 #include "conv23.cuh"
 #include "conv23h.cuh"
 #include "conv23h2.cuh"
+#include "conv23t.cuh"
 #include "tensormap.h"
 #include <algorithm>
 #include <cstdlib>
