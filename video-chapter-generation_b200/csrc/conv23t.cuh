@@ -186,8 +186,24 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23t_kernel(const __grid_co
     // ------------------------------------------------------------ C producer: residual prefetch for the conv3 sub-tiles
     if (elect_one()) {
       const bool has_res = p.residual != nullptr;
+      // the residual boxes of the NEXT tile are prefetched into L2 (no shared-memory destination): a C slot only frees up
+      // when the previous sub-tile has been stored, so without it every sub-tile exposes a full DRAM round trip while the
+      // epilogue holds the conv3 accumulator
+      const int kPF = q.prefetch_tiles;
+      auto prefetch_tile = [&](int j2) {
+        if (!has_res || j2 >= nM) return;
+        const int m_blk = m_blk_of(j2);
+        const int iw = m_blk % p.tiles_w, ih = (m_blk / p.tiles_w) % p.tiles_h, in = m_blk / (p.tiles_w * p.tiles_h);
+        const int n0 = in * p.nf;
+        for (int jj = 0; jj < 8; ++jj) {
+          if (p.res_clip_T == 0) tma_prefetch_l2_5d(&p.res_map, jj * 64, iw * p.bw, ih * p.bh, 0, n0);
+          else tma_prefetch_l2_5d(&p.res_map, jj * 64, iw * p.bw, ih * p.bh, n0 % p.res_clip_T, n0 / p.res_clip_T);
+        }
+      };
+      for (int j2 = 0; j2 < kPF; ++j2) prefetch_tile(j2);
       int c_it = 0;
       for (int j = 0; j < nM; ++j) {
+        if (kPF > 0) prefetch_tile(j + kPF);
         const int m_blk = m_blk_of(j);
         const int iw = m_blk % p.tiles_w, ih = (m_blk / p.tiles_w) % p.tiles_h, in = m_blk / (p.tiles_w * p.tiles_h);
         for (int jj = 0; jj < 8; ++jj, ++c_it) {            // nb = jj / 4, 64-column C tile jj % 4
