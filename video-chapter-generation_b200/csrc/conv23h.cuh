@@ -38,9 +38,9 @@ constexpr int kC23hTapBytes = 64 * 128;                               // one tap
 constexpr int kC23hW2Bytes = kC23hW2Stages * kC23hTapBytes;           // 40 960
 constexpr int kC23hW3Bytes = 256 * 128;                               // 32 768
 constexpr int kC23hIdentBytes = 64 * 128;                             // 64 x 64 identity (residual add on the tensor core)
-constexpr int kC23hCSlots = 5;
+constexpr int kC23hCSlots = 6;
 constexpr int kC23hBiasBytes = (256 + 64) * 4;
-constexpr int kC23hSmemBytes = kC23hW2Bytes + kC23hW3Bytes + kC23hHaloStages * kC23hHaloStride + kCBytes /*A2*/ +
+constexpr int kC23hSmemBytes = kC23hW2Bytes + kC23hW3Bytes + kC23hHaloStages * kC23hHaloStride +
                                kC23hIdentBytes + kC23hCSlots * kCBytes + kC23hBiasBytes + 1024 /*align*/ + 512 /*barriers*/;
 static_assert(kC23hSmemBytes <= 232448, "shared memory budget exceeded");
 
@@ -60,14 +60,14 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
   const ConvGemmParams& p = q.g;
   constexpr int P = 64, BLOCK_N = 256, kCSlots = kC23hCSlots, kHS = kC23hHaloStages, kW2S = kC23hW2Stages;
   constexpr int kBw = 8, kBh = 16;                          // tile: 8 x 16 pixels of one frame
+  constexpr uint32_t kA2Col = 128;                          // TMEM columns [128, 160): conv2's output tile as conv3's A operand
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW2 = smem;                                      // [kW2S tap stages][64 rows][128 B]
   uint8_t* sW3 = sW2 + kC23hW2Bytes;                        // [256 rows][128 B]
   uint8_t* sHalo = sW3 + kC23hW3Bytes;                      // [kHS][18][10][128 B]
-  uint8_t* sA2 = sHalo + kHS * kC23hHaloStride;             // [128 rows][128 B]
-  uint8_t* sIdent = sA2 + kCBytes;                          // [64 rows][128 B]: I_64 as a K-major SW128 B operand
+  uint8_t* sIdent = sHalo + kHS * kC23hHaloStride;          // [64 rows][128 B]: I_64 as a K-major SW128 B operand
   uint8_t* sC = sIdent + kC23hIdentBytes;                   // [kCSlots][128 rows][128 B]
   float* sBias3 = reinterpret_cast<float*>(sC + kCSlots * kCBytes);   // [256] conv3 bias, then [64] conv2 bias
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias3) + kC23hBiasBytes);
@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
       const bool has_res = p.residual != nullptr;
       mbar_wait(w_full, 0);
       tc_fence_after();
-      const uint32_t w2_addr = smem_u32(sW2), w3_addr = smem_u32(sW3), a2_addr = smem_u32(sA2), id_addr = smem_u32(sIdent);
+      const uint32_t w2_addr = smem_u32(sW2), w3_addr = smem_u32(sW3), id_addr = smem_u32(sIdent);
+      const uint32_t a2_tmem = tmem_base + kA2Col;          // conv3's A operand lives in tensor memory
       const uint32_t c_addr = smem_u32(sC);
       int ws = 0, c_it = 0;
       uint32_t wphase = 0;
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
         const uint32_t d_tmem = tmem_base + BLOCK_N;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(d_tmem, umma_desc_sw128(a2_addr + k * 32), umma_desc_sw128(w3_addr + k * 32), idesc2, k != 0);
+          umma_bf16_ts(d_tmem, a2_tmem + k * 8, umma_desc_sw128(w3_addr + k * 32), idesc2, k != 0);
         umma_commit(a2_empty);                              // A2 may be overwritten once these MMAs retire
         // residual add on the tensor core: D[:, 64 g .. 64 g + 63] += R_g * I  (R_g = the bf16 residual tile TMA put into
         // C slot g, exactly an A operand; 1.0 * r accumulates exactly in fp32).  Four N = 64 MMAs per slot.
@@ -278,7 +279,6 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
     __nv_bfloat16* tsm = reinterpret_cast<__nv_bfloat16*>(p.tsm_out);
     const int srow = lane >> 1, spiece = lane & 1;
     const uint32_t rsw = static_cast<uint32_t>(row & 7);
-    const uint32_t a2_row = smem_u32(sA2) + row * 128;
     const uint32_t bias3_addr = smem_u32(sBias3) + group * 64 * 4;
     const uint32_t bias2_addr = smem_u32(sBias3) + (256 + group * 16) * 4;
     const uint32_t c_addr = smem_u32(sC);
@@ -291,8 +291,7 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
       if (is_a) {
-        // ---- A: conv2 accumulator -> + bias2 -> bf16 -> ReLU -> A2 (K-major, 128-byte swizzle); group g takes columns
-        //      [16 g, 16 g + 16)
+        // ---- A: conv2 accumulator -> + bias2 -> bf16 -> ReLU -> A2 in tensor memory; group g takes channels [16 g, 16 g + 16)
         uint32_t r[16];
         tmem_ld_32x16(taddr + group * 16, r);
         mbar_wait(a2_empty, (j & 1) ^ 1);
@@ -304,9 +303,9 @@ __global__ void __launch_bounds__(kC23Threads, 1) conv23h_kernel(const __grid_co
           o[2 * e] = pack_relu_bf16x2(__uint_as_float(r[4 * e]) + b4.x, __uint_as_float(r[4 * e + 1]) + b4.y);
           o[2 * e + 1] = pack_relu_bf16x2(__uint_as_float(r[4 * e + 2]) + b4.z, __uint_as_float(r[4 * e + 3]) + b4.w);
         }
-        sts128(a2_row + (((2u * group) ^ rsw) << 4), o[0], o[1], o[2], o[3]);
-        sts128(a2_row + (((2u * group + 1u) ^ rsw) << 4), o[4], o[5], o[6], o[7]);
-        fence_proxy_async_smem();                              // generic-proxy writes -> visible to the MMA operand fetch
+        // conv3's A operand goes back into TENSOR memory (row = lane, 2 bf16 per column): no shared memory, no proxy fence
+        tmem_st_32x8(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + kA2Col + group * 8, o);
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
