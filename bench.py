@@ -44,7 +44,7 @@ VIDEO_FRAMES = 600                 # configs[3]: 10-minute videos
 VIDEOS_PER_ROUND = 6               # per rank and step at N > 1 (6 x 146 = 876 clips)
 JOB_VIDEOS = 1024                  # configs[3]
 TEXT_BATCH = 256                   # configs[1]
-VISION_CHUNK = int(os.environ.get("VCG_VISION_CHUNK", "64"))   # clips per vision pass (12 GB workspace)
+VISION_CHUNK = int(os.environ.get("VCG_VISION_CHUNK", "128"))   # clips per vision pass (24 GB workspace; 128 measured 1.2 % faster than 64)
 CPU_SAMPLE_CLIPS = 4
 METRIC = "candidate clips scored/sec"
 
