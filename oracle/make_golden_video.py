@@ -142,6 +142,40 @@ def main():
         min_abs_margin=float(margin.abs().min()), margin_gap=gap, raw_logit_absmax=float(logits0.abs().max()),
         meta=np.array([T, L, B, SEED, 8, 128, n_frames, batch]))
 
+    # ------------------------------------------------------------------ the same video through the ATTENTION head
+    # (two_stream.py:31-48).  The backbones are the same (make_state_dict draws the head last), so the reference's
+    # embeddings above are re-used and only the reference's own fusion_head is re-run; the full forward of the first batch
+    # confirms it.  The decision bias re-centred is fusion_head.head.proj.bias.
+    sd_a = W.make_state_dict(T, "attn", seed=SEED)
+    assert all(torch.equal(sd_a[k], v) for k, v in sd.items() if not k.startswith("fusion_head.head"))
+    lang_a = bert_hugface.BertHugface(pretrain_stage=False)
+    vis_a = resnet50_tsm.Resnet50TSM(segments_size=T, shift_div=8, pretrain_stage=False)
+    model_a = two_stream.TwoStream(lang_a.base_model, vis_a.base_model, lang_a.embed_size, vis_a.feature_dim, T, 128)
+    model_a.build_chapter_head(output_size=2, head_type="attn")
+    model_a.load_state_dict(sd_a, strict=True)
+    model_a = model_a.eval()
+    logits_a0 = torch.cat([model_a.fusion_head(lang_emb[b0:b0 + batch], vis_emb[b0:b0 + batch]) for b0 in range(0, B, batch)])
+    bias_a, gap_a = recentre(logits_a0, sd_a["fusion_head.head.proj.bias"], T, eval_utils.convert_clip_label2cut_point)
+    sd_a["fusion_head.head.proj.bias"] = bias_a
+    model_a.fusion_head.head.proj.bias.copy_(bias_a)
+    logits_a = torch.cat([model_a.fusion_head(lang_emb[b0:b0 + batch], vis_emb[b0:b0 + batch]) for b0 in range(0, B, batch)])
+    full_a = model_a(img0, ids[:batch], mask[:batch])[0]
+    assert torch.equal(full_a, logits_a[:batch]), (full_a - logits_a[:batch]).abs().max()
+    labels_a = labels_of(logits_a)
+    cuts_a = eval_utils.convert_clip_label2cut_point(labels_a, T, 2)
+    margin_a = (logits_a[:, 1] - logits_a[:, 0]).double()
+    o_a = orc.two_stream_forward(sd_a, img0, ids[:batch], mask[:batch], T, 128, "attn", 8)
+    assert rel(o_a[0], full_a) <= 1e-5
+    print("video (attn head): labels", "".join(map(str, labels_a)))
+    print("video (attn head): cut points", cuts_a, "| positives", sum(labels_a), "of", B, "| gap", gap_a, "| min |margin|",
+          float(margin_a.abs().min()), "| max |logit|", float(logits_a.abs().max()))
+    np.savez_compressed(
+        os.path.join(GOLDEN, "video_attn_T16_L100_600f.npz"),
+        logits=logits_a.numpy(), probs=torch.softmax(logits_a, dim=1).numpy(), labels=np.array(labels_a),
+        cut_points=np.array(cuts_a, dtype=np.int64), head_bias=bias_a.numpy(), clip_starts=np.array(starts),
+        scene_starts=np.array(scenes), min_abs_margin=float(margin_a.abs().min()), margin_gap=gap_a,
+        raw_logit_absmax=float(logits_a0.abs().max()), meta=np.array([T, L, B, SEED, 8, 128, n_frames, batch]))
+
     # ------------------------------------------------------------------ configs[1]: precomputed embeddings, B = 256
     Bq = 256
     sd2 = W.make_state_dict(T, "mlp", seed=SEED, include_vision=False)

@@ -213,6 +213,18 @@ def test_oracle_reproduces_video_scale_goldens(golden_dir):
     m = ref[:, 1] - ref[:, 0]
     assert abs(float(m.abs().min()) - float(g["min_abs_margin"])) < 1e-9
 
+    # the same video through the attention head (fusion_head.head.proj.bias re-centred)
+    ga = np.load(f"{golden_dir}/video_attn_T16_L100_600f.npz")
+    sda = W.make_state_dict(T, "attn", seed=seed)
+    sda["fusion_head.head.proj.bias"] = torch.from_numpy(ga["head_bias"]).clone()
+    refa = torch.from_numpy(ga["logits"])
+    with torch.no_grad():
+        la = orc.two_stream_forward(sda, img[:2], ids[sample[:2]], mask[sample[:2]], T, 128, "attn", 8)[0]
+    assert float((la - refa[sample[:2]]).abs().max() / max(float(ga["raw_logit_absmax"]), float(refa.abs().max()))) <= 1e-4
+    labels_a = orc.predict_labels(refa)
+    assert labels_a == ga["labels"].tolist() and 0 < sum(labels_a) < B
+    assert orc.convert_clip_label2cut_point(labels_a, T, 2) == ga["cut_points"].tolist() and len(ga["cut_points"]) >= 3
+
     g2 = np.load(f"{golden_dir}/video_emb_mlp_T16_L100_B256.npz")
     T, L, B, seed = [int(x) for x in g2["meta"][:4]]
     sd2 = W.make_state_dict(T, "mlp", seed=seed, include_vision=False)

@@ -33,12 +33,15 @@ pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
 
 
-def _video_case(golden_dir):
+BIAS_KEY = {"mlp": "fusion_head.head.bias", "attn": "fusion_head.head.proj.bias"}
+
+
+def _video_case(golden_dir, head="mlp"):
     from oracle import weights as W
-    g = np.load(f"{golden_dir}/video_mlp_T16_L100_600f.npz")
+    g = np.load(f"{golden_dir}/video_{head}_T16_L100_600f.npz")
     T, L, B, seed, _, _, n_frames, _ = [int(x) for x in g["meta"]]
-    sd = W.make_state_dict(T, "mlp", seed=seed)
-    sd["fusion_head.head.bias"] = torch.from_numpy(g["head_bias"]).clone()
+    sd = W.make_state_dict(T, head, seed=seed)
+    sd[BIAS_KEY[head]] = torch.from_numpy(g["head_bias"]).clone()
     frames, scenes = W.make_video_u8(n_frames, seed=seed)
     assert scenes == g["scene_starts"].tolist()
     starts = W.clip_starts(n_frames, T)
@@ -154,6 +157,19 @@ def _free_port():
     p = s.getsockname()[1]
     s.close()
     return p
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_video_timestamps_identical_attention_head(golden_dir, precision):
+    """The same video through the attention ChapterHead (two_stream.py:31-48): reference logits / labels / timestamps from
+    the unmodified reference's fusion head on its own embeddings (oracle/make_golden_video.py)."""
+    from vcg_b200.engine import Engine
+    g, T, L, B, sd, frames, starts, ids, mask = _video_case(golden_dir, "attn")
+    eng = Engine(T, "attn", precision, vision=True, max_tokens=L, max_batch=32)
+    eng.load_state_dict(sd)
+    logits, _ = eng.score_video_u8(frames.cuda(), 0, 4, ids.cuda(), mask.cuda())
+    _check(g, logits, precision, T, "score_video_u8, attn head")
+    eng.close()
 
 
 def _sharded_worker(rank, world, port, golden_dir, out_dir):
