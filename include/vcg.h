@@ -161,6 +161,11 @@ VCG_API int vcg_profile_end(vcg_engine* e, void* stream, vcg_profile_entry* out,
 /* Number of kernel launches issued by this engine since creation (bench.py's gpu_launches). */
 VCG_API int64_t vcg_launch_count(const vcg_engine* e);
 
+/* Debugging aid (engines created while VCG_DEBUG_CHECKSUM=1 is set): 64-bit checksums of the stem input and of every
+ * vision-stream kernel's output (and shifted copy) of the LAST vision pass, in launch order - tools/stress_checksums.py
+ * uses them to find the first kernel whose output differs between two runs on identical inputs. */
+VCG_API int vcg_debug_checksums(vcg_engine* e, uint64_t* out_host, int32_t max_n, int32_t* n_out, void* stream);
+
 /* Stand-alone operators (what the engine is built from; used by the parity tests) ------------------------- */
 
 /* uint8 HWC frames -> normalised, zero-padded stem input (4 channels per pixel, channel 3 = 0; pixel (0,0) of the

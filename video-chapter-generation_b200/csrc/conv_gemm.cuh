@@ -379,10 +379,15 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
         const int ih = (m_blk / p.tiles_w) % p.tiles_h;
         const int in = m_blk / (p.tiles_w * p.tiles_h);
         const int n_sub = min(BLOCK_N / 64, (p.N - n_blk * BLOCK_N + 63) / 64);
-        for (int j = 0; j < n_sub; ++j, ++c_it) {
+        // EVERY tile takes BLOCK_N / 64 consecutive ring positions, and the host makes the ring a multiple of that: slot s
+        // is then always consumed by the same epilogue group, in tile order.  (With a ring of 5 slots and 4 groups a fast
+        // group could wait for use u of a slot whose use u-1 - another group's, one tile back - had not completed yet; the
+        // parity wait then returns at once and the group works on the wrong residual: a rare, timing-dependent glitch of a
+        // few rows of layer3's conv3, found with tools/stress_checksums.py.)
+        for (int j = 0; j < BLOCK_N / 64; ++j, ++c_it) {
           const int slot = c_it % kCSlots;
           mbar_wait(&c_empty[slot], ((c_it / kCSlots) & 1) ^ 1);
-          if (has_res) {
+          if (has_res && j < n_sub) {
             mbar_expect_tx(&c_full[slot], p.a_bytes);   // same box extents as the A patch: rows x 128 B
             const int n0 = in * p.nf;
             if (p.res_clip_T == 0)
@@ -690,7 +695,14 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
             mbar_arrive(&c_empty[slot]);
           }
         }
-        c_it += n_sub;
+        else if (my_sub < kSub) {   // N-edge tile without this group's sub-tile: hand the ring position straight back
+          const int my_it = c_it + my_sub;
+          const int slot = my_it % kCSlots;
+          mbar_wait(&c_full[slot], (my_it / kCSlots) & 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&c_empty[slot]);
+        }
+        c_it += kSub;
       }
       bool need_release = true;
       if constexpr (!TF32X3) need_release = !released_any;

@@ -160,10 +160,13 @@ inline void set_epilogue(ConvGemmLaunch& L, void* out, int ld_out, const Epilogu
     // smem split: residual layers are HBM-bound -> short K loops get few A/B stages and a deep residual-prefetch ring
     const int stage_bytes = kBlockM * 128 + static_cast<int>(p.b_bytes);
     const int budget = 224 * 1024;
-    // C ring: one slot per concurrently draining 64-column sub-tile; layers with a residual keep one more so that the
-    // next tile's residual prefetch can start early.  Everything else goes to A/B stages: deeper rings are what the
-    // long-K GEMMs need (measured at 14 k rows: 3 / 4 / 5 stages -> FFN-out 69 / 62 / 57 us)
-    const int min_slots = std::max(kMinCSlots, L.block_n / 64 + (e.residual ? 1 : 0));
+    // C ring: a multiple of the sub-tiles per output tile (k_sub = BLOCK_N / 64), so that ring slot s always belongs to the
+    // same epilogue group (conv_gemm.cuh, C producer) - a ring of e.g. 5 slots for 4 groups lets a fast group run past
+    // another group's use of its slot.  Layers with a residual want a second round of slots so that the next tile's
+    // residual prefetch starts early; everything else goes to A/B stages: deeper rings are what the long-K GEMMs need
+    // (measured at 14 k rows: 3 / 4 / 5 stages -> FFN-out 69 / 62 / 57 us)
+    const int k_sub = L.block_n / 64;
+    const int min_slots = std::max(kMinCSlots, k_sub) + ((std::max(kMinCSlots, k_sub) % k_sub) ? k_sub - std::max(kMinCSlots, k_sub) % k_sub : 0);
     const int max_stages = std::min(kMaxStages, (budget - min_slots * kCBytes) / stage_bytes);
     const int num_kb = p.n_taps * p.cpt;
     p.n_stages = e.residual ? std::max(2, std::min(max_stages, num_kb + 1)) : max_stages;
@@ -172,10 +175,11 @@ inline void set_epilogue(ConvGemmLaunch& L, void* out, int ld_out, const Epilogu
     if (!e.residual && e.act == ACT_GELU && p.n_stages > 4) p.n_stages -= 1;
     if (const char* v = getenv("VCG_STAGES")) {   // tuning knob (tools/bench_layer.py)
       const int forced = atoi(v);
-      if (forced >= 2 && (budget - forced * stage_bytes) / kCBytes >= kMinCSlots) p.n_stages = std::min(forced, kMaxStages);
+      if (forced >= 2 && (budget - forced * stage_bytes) / kCBytes >= min_slots) p.n_stages = std::min(forced, kMaxStages);
     }
     p.n_cslots = std::min(kMaxCSlots, (budget - p.n_stages * stage_bytes) / kCBytes);
-    VCG_REQUIRE(p.n_stages >= 2 && p.n_cslots >= min_slots, "shared-memory split failed");
+    p.n_cslots -= p.n_cslots % k_sub;
+    VCG_REQUIRE(p.n_stages >= 2 && p.n_cslots >= min_slots && p.n_cslots % k_sub == 0, "shared-memory split failed");
     VCG_REQUIRE(p.N % 32 == 0, "bf16 path: output channels must be a multiple of 32");
     VCG_REQUIRE(ld_out % 8 == 0 && (e.residual == nullptr || e.ld_res % 8 == 0), "row strides must be multiples of 16 bytes");
     p.out_map = c_tile_map(out, ld_out, p);
@@ -489,6 +493,7 @@ inline Conv23Launch build_conv23(const void* in, int Nimg, int H, int W, int P, 
   }
   L.q.n_stages = std::min(stages, kMaxStages);
   L.q.n_cslots = std::min(cslots, kMaxCSlots);
+  L.q.n_cslots -= L.q.n_cslots % 4;   // four epilogue groups per sub-tile: a ring slot must always come back to the same group
   {
     static const int early = [] { const char* v = getenv("VCG_C23_EARLY"); return v ? atoi(v) : 1; }();
     L.q.early_release = early;

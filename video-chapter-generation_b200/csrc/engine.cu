@@ -181,6 +181,10 @@ struct vcg_engine {
     return copy_stream;
   }
 
+  // debug (VCG_DEBUG_CHECKSUM=1): checksum of every vision step's output, read back by vcg_debug_checksums
+  bool debug_checksum = false;
+  DevBuf dbg;
+  int dbg_n = 0;
   // profiling
   bool profiling = false;
   std::vector<ProfRec> prof;
@@ -718,7 +722,36 @@ std::string gemm_kernel_name(const ConvGemmLaunch& L) {
 
 void run_steps(vcg_engine* e, const std::vector<Step>& steps, const int64_t* mask, cudaStream_t s) {
   const double es = e->es();
+  auto checksum = [&](const void* ptr, double bytes) {
+    if (!e->debug_checksum || e->dbg_n >= 250) return;
+    launch_checksum(ptr, static_cast<size_t>(bytes), e->dbg.as<unsigned long long>() + e->dbg_n++, s);
+  };
   for (const Step& st : steps) {
+    if (e->debug_checksum && mask == nullptr) {   // vision plans only
+      if (st.kind == Step::CONV_GEMM) {
+        const ConvGemmParams& p = st.gemm.p;
+        launch_conv_gemm(st.gemm, s);
+        ++e->launches;
+        checksum(p.out, static_cast<double>(p.Nimg) * p.Ho * p.Wo * p.ld_out * es);
+        if (p.tsm_out) checksum(p.tsm_out, static_cast<double>(p.Nimg) * p.Ho * p.Wo * p.tsm_ld * es);
+        continue;
+      }
+      if (st.kind == Step::CONV23) {
+        const ConvGemmParams& p = st.c23.q.g;
+        launch_conv23(st.c23, s);
+        ++e->launches;
+        checksum(p.out, static_cast<double>(p.Nimg) * p.Ho * p.Wo * p.ld_out * es);
+        if (p.tsm_out) checksum(p.tsm_out, static_cast<double>(p.Nimg) * p.Ho * p.Wo * p.tsm_ld * es);
+        continue;
+      }
+      if (st.kind == Step::MAXPOOL) {
+        launch_maxpool_tsm(st.in, st.n, st.out, st.out2, st.a, st.c, e->fp32, s);
+        ++e->launches;
+        checksum(st.out, st.n * 56.0 * 56 * 64 * es);
+        if (st.out2) checksum(st.out2, st.n * 56.0 * 56 * 64 * es);
+        continue;
+      }
+    }
     switch (st.kind) {
       case Step::CONV_GEMM: {
         ProfScope ps(e, s, gemm_kernel_name(st.gemm), st.gemm.flops, st.gemm.bytes, st.gemm.p.m_dev != nullptr);
@@ -921,6 +954,10 @@ const float* run_vision(vcg_engine* e, const FrameSource& src, int g0, const Vis
     launch_preprocess_u8_clips(src.frames_u8, src.clip_start + g0, bv, T, e->stem_in.p, e->fp32, s, src.n_frames);
   }
   VisionPlan& vp = vision_plan(e, bv, src.frames_u8 ? vpass.stride : 0);
+  if (e->debug_checksum) {
+    e->dbg_n = 0;
+    launch_checksum(e->stem_in.p, e->stem_in.bytes, e->dbg.as<unsigned long long>() + e->dbg_n++, s);
+  }
   run_steps(e, vp.steps, nullptr, s);
   // fp32 embeddings go to the caller's buffer when asked for; in fp32 mode they are also the GEMM operand
   float* dst = vision_emb_out ? vision_emb_out + static_cast<long>(g0) * T * kVisionDim : e->vis_emb.as<float>();
@@ -1079,6 +1116,10 @@ int vcg_create(const vcg_config* cfg, vcg_engine** out) {
     e->Bv = cfg->max_batch;
     e->Bt = std::max(cfg->max_batch, 256);
     e->tsm = cfg->shift_div != 0;
+    if (const char* v = getenv("VCG_DEBUG_CHECKSUM")) {
+      e->debug_checksum = atoi(v) != 0;
+      if (e->debug_checksum) e->dbg.alloc(256 * sizeof(unsigned long long), /*zero=*/true);
+    }
     *out = e.release();
   });
 }
@@ -1372,6 +1413,17 @@ int vcg_forward_host(vcg_engine* e, const float* img_clip_host, const float* vis
 }
 
 int64_t vcg_launch_count(const vcg_engine* e) { return e ? e->launches : 0; }
+
+int vcg_debug_checksums(vcg_engine* e, uint64_t* out_host, int32_t max_n, int32_t* n_out, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(e && out_host && n_out, "null argument");
+    VCG_REQUIRE(e->debug_checksum, "engine was not created with VCG_DEBUG_CHECKSUM=1");
+    VCG_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    const int n = std::min(e->dbg_n, max_n);
+    VCG_CUDA(cudaMemcpy(out_host, e->dbg.p, static_cast<size_t>(n) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    *n_out = n;
+  });
+}
 
 int vcg_profile_begin(vcg_engine* e) {
   return guarded([&] {

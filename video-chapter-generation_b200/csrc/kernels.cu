@@ -706,6 +706,20 @@ void launch_pack_stem(const float* w, const float* bn_w, const float* bn_b, cons
                          w, bn_w, bn_b, bn_mean, bn_var, eps, static_cast<elem_t<FP>*>(w_out), bias_out)));
   VCG_CUDA(cudaGetLastError());
 }
+// debug: order-independent 64-bit checksum of a buffer (sum of word * position weight), accumulated into *out
+__global__ void checksum_kernel(const uint32_t* __restrict__ p, long n_words, unsigned long long* out) {
+  unsigned long long s = 0;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n_words; i += static_cast<long>(gridDim.x) * blockDim.x)
+    s += static_cast<unsigned long long>(p[i]) * static_cast<unsigned long long>((i & 1023) + 1);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+void launch_checksum(const void* p, size_t bytes, unsigned long long* out, cudaStream_t s) {
+  VCG_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned long long), s));
+  if (bytes < 4) return;
+  checksum_kernel<<<592, 256, 0, s>>>(static_cast<const uint32_t*>(p), static_cast<long>(bytes / 4), out);
+  VCG_CUDA(cudaGetLastError());
+}
 void launch_convert(const float* in, void* out, long n, bool fp32, cudaStream_t s) {
   if (n == 0) return;
   VCG_DISPATCH(fp32, (launch_pdl(convert_kernel<FP>, blocks_for((n + 7) / 8, 256), 256, 0, s, in, static_cast<elem_t<FP>*>(out), n)));

@@ -118,6 +118,7 @@ void launch_pack_stem(const float* w /*[64,3,7,7]*/, const float* bn_w, const fl
                       cudaStream_t s);
 void launch_convert(const float* in, void* out, long n, bool fp32, cudaStream_t s);       // fp32 -> T copy
 void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t s);    // [r][c] -> [c][r]
+void launch_checksum(const void* p, size_t bytes, unsigned long long* out, cudaStream_t s);   // debug
 void launch_cast_to_f32(const void* in, float* out, long n, bool fp32, cudaStream_t s);
 
 }  // namespace vcg

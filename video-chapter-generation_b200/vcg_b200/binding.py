@@ -101,6 +101,7 @@ PROTOTYPES = {
     "vcg_profile_begin": (ctypes.c_int, [_vp]),
     "vcg_profile_end": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(VcgProfileEntry), _i32, ctypes.POINTER(_i32)]),
     "vcg_launch_count": (_i64, [_vp]),
+    "vcg_debug_checksums": (ctypes.c_int, [_vp, _vp, _i32, ctypes.POINTER(_i32), _vp]),
     "vcg_op_preprocess_u8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),
     "vcg_op_resize_u8": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
     "vcg_op_nchw_to_stem": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp]),

@@ -313,6 +313,14 @@ class Engine:
                         "flops": buf[i].flops, "bytes": buf[i].bytes})
         return out
 
+    def debug_checksums(self):
+        """Checksums of the last vision pass's kernel outputs (engine created under VCG_DEBUG_CHECKSUM=1)."""
+        buf = (ctypes.c_uint64 * 256)()
+        n = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            _b.check(self._lib.vcg_debug_checksums(self._h, buf, 256, ctypes.byref(n), _stream()))
+        return [int(buf[i]) for i in range(n.value)]
+
     @property
     def launch_count(self):
         return int(self._lib.vcg_launch_count(self._h))
