@@ -164,6 +164,9 @@ VCG_API int64_t vcg_launch_count(const vcg_engine* e);
 /* Debugging aid (engines created while VCG_DEBUG_CHECKSUM=1 is set): 64-bit checksums of the stem input and of every
  * vision-stream kernel's output (and shifted copy) of the LAST vision pass, in launch order - tools/stress_checksums.py
  * uses them to find the first kernel whose output differs between two runs on identical inputs. */
+/* Debug: the launches number [from, to) counted from this call go out without the programmatic-dependent-launch attribute
+ * (ordinary stream order), to bisect an ordering problem to one kernel boundary; (0, 0) switches the window off. */
+VCG_API int vcg_debug_pdl_window(int32_t from, int32_t to);
 VCG_API int vcg_debug_checksums(vcg_engine* e, uint64_t* out_host, int32_t max_n, int32_t* n_out, void* stream);
 
 /* Stand-alone operators (what the engine is built from; used by the parity tests) ------------------------- */
@@ -214,6 +217,28 @@ VCG_API int vcg_op_stem_conv(const void* in_padded, int32_t n, const void* weigh
 /* 3x3/2 max-pool NHWC [n,112,112,64] -> x [n,56,56,64] and its temporally shifted copy (fold = 64/shift_div). */
 VCG_API int vcg_op_maxpool_tsm(const void* in, int32_t n, void* out, void* out_shifted, int32_t clip_frames,
                        int32_t shift_div, int32_t precision, void* stream);
+
+/* ---- Batch-statistics BatchNorm mode (opt-in; reference caller #1 nulls the running statistics of every BatchNorm2d after
+ * .eval(), test_video_segment_point.py:116-122, so F.batch_norm normalises with the statistics of the batch it is given).
+ * The mirror composes the vision stream of ONE forward call from these operators (vcg_b200/bn_batch.py); all pointers are
+ * device pointers, activations NHWC in the given precision. */
+/* conv 7x7/2 of the padded stem input with an explicit activation (VCG_ACT_*) and an optional bias (may be NULL). */
+VCG_API int vcg_op_stem_conv_act(const void* in_padded, int32_t n, const void* weight, const float* bias, void* out,
+                                 int32_t act, int32_t precision, void* stream);
+/* Rows of the workspace vcg_op_bn_batch_stats needs: partial is [rows_of_partial][2][C] doubles. */
+VCG_API int32_t vcg_op_bn_partials(int64_t rows, int32_t C);
+/* Per-channel mean and 1 / sqrt(biased variance + eps) of x [rows, C] (C = 64 * 2^k <= 2048), deterministic. */
+VCG_API int vcg_op_bn_batch_stats(const void* x, int64_t rows, int32_t C, float eps, double* partial, float* mean,
+                                  float* rstd, int32_t precision, void* stream);
+/* out = relu?((x - mean) * rstd * gamma + beta (+ residual)) over x [rows, C]. */
+VCG_API int vcg_op_bn_apply(const void* x, int64_t rows, int32_t C, const float* mean, const float* rstd,
+                            const float* gamma, const float* beta, const void* residual, int32_t relu, void* out,
+                            int32_t precision, void* stream);
+/* TemporalShift.shift (ops/temporal_shift.py:34-51) of x [n, hw, C], n = clips * clip_frames, fold = C / shift_div. */
+VCG_API int vcg_op_tsm_shift(const void* x, int64_t n, int32_t hw, int32_t C, int32_t clip_frames, int32_t fold, void* out,
+                             int32_t precision, void* stream);
+/* AdaptiveAvgPool2d(1) of x [n, hw, C] -> fp32 [n, C]. */
+VCG_API int vcg_op_avgpool(const void* x, int32_t n, int32_t hw, int32_t C, float* out, int32_t precision, void* stream);
 
 /* softmax(Q K^T / 8 + key mask) V for BERT: qkv [B*L, 2304] (Q|K|V, 12 heads x 64) -> ctx [B*L, 768]. */
 VCG_API int vcg_op_bert_attention(const void* qkv, const int64_t* attention_mask, void* ctx, int32_t B, int32_t L,

@@ -93,8 +93,28 @@ def temporal_shift(x, n_segment, fold_div=8):
     return out.view(nt, c, h, w)
 
 
+BN_BATCH_STATS = False   # set by batch_stat_bn(): restates caller #1's quirk, test_video_segment_point.py:116-122
+
+
+class batch_stat_bn:
+    """Context manager: BatchNorm2d normalises with the statistics of the batch it is given — what an eval-mode
+    nn.BatchNorm2d does once running_mean / running_var are None and track_running_stats is False
+    (torch.nn.modules.batchnorm._BatchNorm.forward: bn_training = running_mean is None and running_var is None)."""
+
+    def __enter__(self):
+        global BN_BATCH_STATS
+        self.prev, BN_BATCH_STATS = BN_BATCH_STATS, True
+
+    def __exit__(self, *exc):
+        global BN_BATCH_STATS
+        BN_BATCH_STATS = self.prev
+
+
 def _bn(sd, prefix, x):
-    """BatchNorm2d in eval mode with running statistics (standard .eval(): test_whole_pipeline_per_video.py:105)."""
+    """BatchNorm2d in eval mode with running statistics (standard .eval(): test_whole_pipeline_per_video.py:105), or with
+    batch statistics under batch_stat_bn()."""
+    if BN_BATCH_STATS:
+        return F.batch_norm(x, None, None, sd[prefix + ".weight"], sd[prefix + ".bias"], True, 0.0, 1e-5)
     return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
                         sd[prefix + ".bias"], False, 0.0, 1e-5)
 

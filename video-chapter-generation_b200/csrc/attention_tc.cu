@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1) bert_attention_tc_kernel(const __
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
-  const int n_items = __ldg(p.n_items);
+  const int n_items = ld_chain_i32(p.n_items);   // written by attn_items_kernel: not before the wait (launch.cuh)
   const int n_my = n_items > static_cast<int>(blockIdx.x)
                        ? (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
 

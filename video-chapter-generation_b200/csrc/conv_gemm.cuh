@@ -287,7 +287,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
 
   const int num_kb = p.n_taps * p.cpt;
   // rows beyond *m_dev are never needed: only the M tiles that hold valid rows are computed
-  const int m_tiles = p.m_dev ? (min(__ldg(p.m_dev), p.Wo) + kBlockM - 1) / kBlockM : p.tiles_w * p.tiles_h * p.tiles_n;
+  const int m_tiles = p.m_dev ? (min(ld_chain_i32(p.m_dev), p.Wo) + kBlockM - 1) / kBlockM : p.tiles_w * p.tiles_h * p.tiles_n;
   // CG2: a unit tile is (pair of M tiles, N tile); the odd CTA of a last, half-empty pair works on an M tile past the
   // end (its image coordinate is out of range: TMA zero-fills the loads and clips the stores)
   const int total_tiles = (CG2 ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles;

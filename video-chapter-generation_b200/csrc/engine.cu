@@ -17,6 +17,13 @@
 
 using namespace vcg;
 
+namespace vcg {
+PdlDebugWindow& pdl_debug_window() {
+  static PdlDebugWindow w;
+  return w;
+}
+}  // namespace vcg
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -1414,6 +1421,11 @@ int vcg_forward_host(vcg_engine* e, const float* img_clip_host, const float* vis
 
 int64_t vcg_launch_count(const vcg_engine* e) { return e ? e->launches : 0; }
 
+int vcg_debug_pdl_window(int32_t from, int32_t to) {
+  vcg::PdlDebugWindow& w = vcg::pdl_debug_window();
+  w.idx = 0; w.from = from; w.to = to;
+  return w.idx;
+}
 int vcg_debug_checksums(vcg_engine* e, uint64_t* out_host, int32_t max_n, int32_t* n_out, void* stream) {
   return guarded([&] {
     VCG_REQUIRE(e && out_host && n_out, "null argument");
@@ -1559,6 +1571,48 @@ int vcg_op_stem_conv(const void* in_padded, int32_t n, const void* weight, const
     ep.bias = bias; ep.act = ACT_RELU;
     ConvGemmLaunch L = build_stem(in_padded, n, kStemHp, kStemWp, kStemOut, kStemOut, weight, 64, out, precision == VCG_PREC_FP32, ep);
     launch_conv_gemm(L, static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_stem_conv_act(const void* in_padded, int32_t n, const void* weight, const float* bias, void* out, int32_t act,
+                         int32_t precision, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(in_padded && weight && out, "null argument");
+    Epilogue ep;
+    ep.bias = bias; ep.act = act;
+    ConvGemmLaunch L = build_stem(in_padded, n, kStemHp, kStemWp, kStemOut, kStemOut, weight, 64, out, precision == VCG_PREC_FP32, ep);
+    launch_conv_gemm(L, static_cast<cudaStream_t>(stream));
+  });
+}
+int32_t vcg_op_bn_partials(int64_t rows, int32_t C) {
+  if (rows < 1 || C < 64 || C > 2048 || C % 8 != 0) return 0;
+  return bn_stats_partials(rows, C);
+}
+int vcg_op_bn_batch_stats(const void* x, int64_t rows, int32_t C, float eps, double* partial, float* mean, float* rstd,
+                          int32_t precision, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(x && partial && mean && rstd, "null argument");
+    launch_bn_batch_stats(x, rows, C, eps, partial, mean, rstd, precision == VCG_PREC_FP32, static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_bn_apply(const void* x, int64_t rows, int32_t C, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, const void* residual, int32_t relu, void* out, int32_t precision, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(x && mean && rstd && gamma && beta && out, "null argument");
+    launch_bn_apply(x, rows, C, mean, rstd, gamma, beta, residual, relu != 0, out, precision == VCG_PREC_FP32,
+                    static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_tsm_shift(const void* x, int64_t n, int32_t hw, int32_t C, int32_t clip_frames, int32_t fold, void* out,
+                     int32_t precision, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(x && out, "null argument");
+    launch_tsm_shift(x, n, hw, C, clip_frames, fold, out, precision == VCG_PREC_FP32, static_cast<cudaStream_t>(stream));
+  });
+}
+int vcg_op_avgpool(const void* x, int32_t n, int32_t hw, int32_t C, float* out, int32_t precision, void* stream) {
+  return guarded([&] {
+    VCG_REQUIRE(x && out && C % 8 == 0 && hw >= 1, "bad argument");
+    launch_avgpool(x, n, hw, C, out, nullptr, static_cast<cudaStream_t>(stream), precision == VCG_PREC_FP32);
   });
 }
 int vcg_op_maxpool_tsm(const void* in, int32_t n, void* out, void* out_shifted, int32_t clip_frames,

@@ -281,7 +281,7 @@ __global__ void layernorm768_kernel(const elem_t<FP32>* __restrict__ x, const fl
   // CTAs beyond the first wave (8 CTAs x 148 SMs) start late anyway: they look at the device-side row count first and
   // leave without touching memory when their rows do not exist (with token packing that is the usual case)
   if (rows_dev && blockIdx.x >= 8 * 148) {
-    rows = min(rows, __ldg(rows_dev));
+    rows = min(rows, ld_chain_i32(rows_dev));
     if (row0 >= rows) return;
   }
   const bool two_alloc = row0 + 1 < rows;
@@ -297,7 +297,7 @@ __global__ void layernorm768_kernel(const elem_t<FP32>* __restrict__ x, const fl
     }
   // token-packed BERT: only the packed rows exist.  Read the device-side count AFTER issuing the row loads (it is a
   // dependent L2 round trip that would otherwise sit in front of them).
-  if (rows_dev) rows = min(rows, __ldg(rows_dev));
+  if (rows_dev) rows = min(rows, ld_chain_i32(rows_dev));
   if (row0 >= rows) return;
   const bool two = row0 + 1 < rows;
   float s[2] = {0.f, 0.f};
@@ -358,7 +358,7 @@ __global__ void bert_embed_ln_kernel(const int64_t* __restrict__ ids, int rows, 
   pdl_enter();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (rows_dev) rows = min(rows, *rows_dev);
+  if (rows_dev) rows = min(rows, ld_chain_i32(rows_dev));
   if (row >= rows) return;
   const int src = tok_src ? tok_src[row] : row;   // packed row -> b*L + j
   const long id = min(max(ids[src], 0L), static_cast<long>(vocab) - 1);   // never index outside the embedding table
@@ -707,6 +707,91 @@ void launch_pack_stem(const float* w, const float* bn_w, const float* bn_b, cons
   VCG_CUDA(cudaGetLastError());
 }
 // debug: order-independent 64-bit checksum of a buffer (sum of word * position weight), accumulated into *out
+// ------------------------------------------------------------------------------------------------ batch-statistics BatchNorm
+// Opt-in compatibility mode for reference caller #1, which nulls the running statistics of every BatchNorm2d after
+// .eval() (test_video_segment_point.py:116-122): F.batch_norm then normalises with the statistics of the batch it is
+// given.  Three small HBM-bound kernels over NHWC [rows, C] activations (rows = frames * H * W of ONE forward call):
+//   bn_partial_stats: per-CTA double sums of x and x^2 per channel (fixed grid, fixed order -> deterministic)
+//   bn_finish_stats : mean and 1/sqrt(biased var + eps) per channel
+//   bn_apply        : (x - mean) * rstd * gamma + beta (+ residual) (ReLU)
+constexpr int kBnThreads = 256;
+template <bool FP32>
+__global__ void __launch_bounds__(kBnThreads) bn_partial_stats_kernel(const elem_t<FP32>* __restrict__ x, long rows, int C,
+                                                                      double* __restrict__ partial /*[grid][2][C]*/) {
+  __shared__ double sh[kBnThreads][17];                    // 16 sums per thread (+1: bank spread)
+  const int groups = C / 8;                                // 8 .. 256 channel groups of 8
+  const int lanes = kBnThreads / groups;                   // rows in flight per CTA
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
+  double sum[8], sq[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sum[e] = sq[e] = 0.0;
+  for (long r = static_cast<long>(blockIdx.x) * lanes + lane; r < rows; r += static_cast<long>(gridDim.x) * lanes) {
+    float v[8];
+    load8<FP32>(x + r * C + g * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sum[e] += v[e]; sq[e] += static_cast<double>(v[e]) * v[e]; }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sh[threadIdx.x][e] = sum[e]; sh[threadIdx.x][8 + e] = sq[e]; }
+  __syncthreads();
+  if (lane == 0) {
+    for (int l = 1; l < lanes; ++l)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sum[e] += sh[l * groups + g][e]; sq[e] += sh[l * groups + g][8 + e]; }
+    double* o = partial + static_cast<long>(blockIdx.x) * 2 * C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { o[g * 8 + e] = sum[e]; o[C + g * 8 + e] = sq[e]; }
+  }
+}
+__global__ void bn_finish_stats_kernel(const double* __restrict__ partial, int n_partial, int C, long rows, float eps,
+                                       float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < n_partial; ++b) { s += partial[static_cast<long>(b) * 2 * C + c]; q += partial[static_cast<long>(b) * 2 * C + C + c]; }
+  const double m = s / static_cast<double>(rows);
+  double var = q / static_cast<double>(rows) - m * m;      // biased variance, as F.batch_norm normalises with
+  if (var < 0.0) var = 0.0;
+  mean[c] = static_cast<float>(m);
+  rstd[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+template <bool FP32>
+__global__ void bn_apply_kernel(const elem_t<FP32>* __restrict__ x, long total /*rows * C / 8*/, int C,
+                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const elem_t<FP32>* __restrict__ residual, int relu, elem_t<FP32>* __restrict__ out) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = static_cast<int>(idx % (C / 8)) * 8;
+  float v[8], r[8];
+  load8<FP32>(x + idx * 8, v);
+  if (residual) load8<FP32>(residual + idx * 8, r);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float y = (v[e] - __ldg(mean + c0 + e)) * __ldg(rstd + c0 + e) * __ldg(gamma + c0 + e) + __ldg(beta + c0 + e);
+    if (residual) y += r[e];
+    v[e] = relu ? fmaxf(y, 0.0f) : y;
+  }
+  store8<FP32>(out + idx * 8, v);
+}
+// TemporalShift.shift (ops/temporal_shift.py:34-51) as a stand-alone gather: frame t takes channels [0, fold) from frame
+// t + 1 and [fold, 2 fold) from frame t - 1 of its own clip (zeros at the clip ends), the rest from itself.
+template <bool FP32>
+__global__ void tsm_shift_kernel(const elem_t<FP32>* __restrict__ x, long total /*n * hw * C / 8*/, int hw, int C, int T,
+                                 int fold, elem_t<FP32>* __restrict__ out) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = static_cast<int>(idx % (C / 8)) * 8;
+  const long row = idx / (C / 8);
+  const int t = static_cast<int>((row / hw) % T);
+  long src = row;
+  bool ok = true;
+  if (c0 < fold) { ok = t + 1 < T; src = row + hw; }
+  else if (c0 < 2 * fold) { ok = t >= 1; src = row - hw; }
+  float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (ok) load8<FP32>(x + src * C + c0, v);
+  store8<FP32>(out + idx * 8, v);
+}
 __global__ void checksum_kernel(const uint32_t* __restrict__ p, long n_words, unsigned long long* out) {
   unsigned long long s = 0;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n_words; i += static_cast<long>(gridDim.x) * blockDim.x)
@@ -718,6 +803,38 @@ void launch_checksum(const void* p, size_t bytes, unsigned long long* out, cudaS
   VCG_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned long long), s));
   if (bytes < 4) return;
   checksum_kernel<<<592, 256, 0, s>>>(static_cast<const uint32_t*>(p), static_cast<long>(bytes / 4), out);
+  VCG_CUDA(cudaGetLastError());
+}
+int bn_stats_partials(long rows, int C) {
+  const long per_cta = kBnThreads / (C / 8);
+  return static_cast<int>(std::min<long>(592, (rows + per_cta - 1) / per_cta));
+}
+void launch_bn_batch_stats(const void* x, long rows, int C, float eps, double* partial, float* mean, float* rstd, bool fp32,
+                           cudaStream_t s) {
+  VCG_REQUIRE(C % 8 == 0 && C >= 64 && C <= 2048 && kBnThreads % (C / 8) == 0, "BatchNorm statistics: C must be 64 * 2^k, at most 2048");
+  VCG_REQUIRE(rows >= 1, "BatchNorm statistics of an empty batch");
+  const int grid = bn_stats_partials(rows, C);
+  VCG_DISPATCH(fp32, (bn_partial_stats_kernel<FP><<<grid, kBnThreads, 0, s>>>(static_cast<const elem_t<FP>*>(x), rows, C, partial)));
+  VCG_CUDA(cudaGetLastError());
+  bn_finish_stats_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, grid, C, rows, eps, mean, rstd);
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_bn_apply(const void* x, long rows, int C, const float* mean, const float* rstd, const float* gamma,
+                     const float* beta, const void* residual, bool relu, void* out, bool fp32, cudaStream_t s) {
+  VCG_REQUIRE(C % 8 == 0, "BatchNorm: C must be a multiple of 8");
+  const long total = rows * (C / 8);
+  if (total == 0) return;
+  VCG_DISPATCH(fp32, (bn_apply_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const elem_t<FP>*>(x), total, C, mean, rstd, gamma, beta,
+                                                                                static_cast<const elem_t<FP>*>(residual), relu ? 1 : 0,
+                                                                                static_cast<elem_t<FP>*>(out))));
+  VCG_CUDA(cudaGetLastError());
+}
+void launch_tsm_shift(const void* x, long n, int hw, int C, int T, int fold, void* out, bool fp32, cudaStream_t s) {
+  VCG_REQUIRE(C % 8 == 0 && fold % 8 == 0 && fold >= 0 && 2 * fold <= C && T >= 1 && n % T == 0, "temporal shift: bad shape");
+  const long total = n * hw * (C / 8);
+  if (total == 0) return;
+  VCG_DISPATCH(fp32, (tsm_shift_kernel<FP><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const elem_t<FP>*>(x), total, hw, C, T, fold,
+                                                                                 static_cast<elem_t<FP>*>(out))));
   VCG_CUDA(cudaGetLastError());
 }
 void launch_convert(const float* in, void* out, long n, bool fp32, cudaStream_t s) {

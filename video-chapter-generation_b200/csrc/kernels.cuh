@@ -120,5 +120,12 @@ void launch_convert(const float* in, void* out, long n, bool fp32, cudaStream_t 
 void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t s);    // [r][c] -> [c][r]
 void launch_checksum(const void* p, size_t bytes, unsigned long long* out, cudaStream_t s);   // debug
 void launch_cast_to_f32(const void* in, float* out, long n, bool fp32, cudaStream_t s);
+// batch-statistics BatchNorm (opt-in mode of reference caller #1) and the stand-alone temporal shift
+int bn_stats_partials(long rows, int C);       // CTAs of the statistics pass = rows of `partial` ([n][2][C] doubles)
+void launch_bn_batch_stats(const void* x, long rows, int C, float eps, double* partial, float* mean, float* rstd, bool fp32,
+                           cudaStream_t s);
+void launch_bn_apply(const void* x, long rows, int C, const float* mean, const float* rstd, const float* gamma,
+                     const float* beta, const void* residual, bool relu, void* out, bool fp32, cudaStream_t s);
+void launch_tsm_shift(const void* x, long n, int hw, int C, int T, int fold, void* out, bool fp32, cudaStream_t s);
 
 }  // namespace vcg

@@ -21,6 +21,17 @@ __device__ __forceinline__ void pdl_enter() {
   pdl_wait();
 }
 
+// A value that an EARLIER KERNEL OF THE CHAIN wrote (device-side row / item counts) must be loaded after griddepcontrol.wait.
+// __ldg and loads through const __restrict__ pointers are invariant loads to the compiler, which is free to hoist them
+// above the wait's asm statement: the tcgen05 attention kernel read its item count before the wait (LDG.E.CONSTANT ahead of
+// ACQBULK in the SASS), i.e. possibly before attn_items_kernel had written it, and used the count of the PREVIOUS pass (zero
+// on a fresh engine) whenever its CTAs became resident early enough.  A volatile asm load keeps its place behind the wait.
+__device__ __forceinline__ int ld_chain_i32(const int* p) {
+  int v;
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // Function attributes (dynamic shared memory opt-in) and the SM count are PER DEVICE: a process may hold engines on several
 // GPUs (Engine(device=...)), so one-time setup is keyed by the current device, not by the process.
 struct PerDeviceOnce {
@@ -56,6 +67,11 @@ inline bool pdl_enabled() {
   return on != 0;
 }
 
+// debug (vcg_debug_pdl_window): launches number [from, to) since the window was set go out WITHOUT the attribute, to bisect
+// an ordering problem to one kernel boundary
+struct PdlDebugWindow { int idx = 0, from = 0, to = 0; };
+PdlDebugWindow& pdl_debug_window();   // defined in engine.cu
+
 template <class... KArgs, class... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg{};
@@ -65,7 +81,10 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  PdlDebugWindow& dw = pdl_debug_window();
+  const bool windowed_off = dw.idx >= dw.from && dw.idx < dw.to;
+  ++dw.idx;
+  attr[0].val.programmaticStreamSerializationAllowed = (pdl_enabled() && !windowed_off) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   VCG_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));

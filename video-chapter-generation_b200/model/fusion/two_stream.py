@@ -9,9 +9,11 @@ kernels behind the C ABI of include/vcg.h) on first use and whenever they change
 BERT text stream, ResNet-50-TSM vision stream, ChapterHead, softmax — inside the library on the current CUDA
 stream.  There is no eager/CPU fallback: without a Blackwell GPU or without the built library ``forward`` raises.
 
-Deviation (documented in DESIGN.md): BatchNorm always uses its running statistics (standard ``.eval()``), i.e. the
-semantics of test_whole_pipeline_per_video.py:105; caller #1's batch-statistics quirk is not
-reproduced.  Extra knobs (attributes, not constructor arguments, so the reference call sites stay unchanged):
+BatchNorm uses its running statistics (standard ``.eval()``, the semantics of test_whole_pipeline_per_video.py:105)
+unless ``bn_batch_stats`` is set (attribute, or env VCG_BN_BATCH_STATS=1): then every BatchNorm2d normalises with the
+statistics of the B*T frames of the call, which is what caller #1 computes after nulling the running statistics
+(test_video_segment_point.py:116-122) — slower, layer by layer (vcg_b200/bn_batch.py), with the vision
+stream in the fp32 (3xTF32) arithmetic unless ``bn_batch_precision = "bf16"``.  Extra knobs (attributes, not constructor arguments, so the reference call sites stay unchanged):
 ``precision`` ("bf16" default, or "fp32" = 3xTF32 verification mode; env VCG_PRECISION), ``vision_chunk`` (clips per
 internal pass, env VCG_VISION_CHUNK) and ``max_tokens``.
 """
@@ -77,8 +79,14 @@ class TwoStream(nn.Module):
         self.precision = os.environ.get("VCG_PRECISION", "bf16")
         self.vision_chunk = int(os.environ.get("VCG_VISION_CHUNK", "32"))
         self.max_tokens = 128
+        self.bn_batch_stats = os.environ.get("VCG_BN_BATCH_STATS", "0") == "1"
+        # the mode exists to reproduce caller #1's numbers: its vision stream defaults to the fp32 arithmetic (1e-4); in
+        # bf16 the per-layer rounding is not damped by folded running statistics and the logits land at ~3e-2
+        self.bn_batch_precision = os.environ.get("VCG_BN_BATCH_PRECISION", "fp32")
         self._engine = None
         self._engine_key = None
+        self._bn_vision = None
+        self._bn_vision_key = None
 
     def build_chapter_head(self, output_size, head_type="mlp"):
         """head_type: mlp or attn (reference :118-124)."""
@@ -109,17 +117,18 @@ class TwoStream(nn.Module):
             v += t._version + (t.data_ptr() % 1000003)
         return v
 
-    def _get_engine(self, device, n_tokens):
+    def _get_engine(self, device, n_tokens, precision=None):
         from vcg_b200.engine import Engine
         has_backbone, shift_div = self._vision_kind()
         max_tokens = max(self.max_tokens, n_tokens)
-        key = (str(device), self.precision, self.vision_chunk, max_tokens, has_backbone, shift_div,
+        precision = self.precision if precision is None else precision
+        key = (str(device), precision, self.vision_chunk, max_tokens, has_backbone, shift_div,
                self.fusion_head.head_type, self._weights_version())
         if self._engine is None or key != self._engine_key:
             if self._engine is not None:
                 self._engine.close()
             self.max_tokens = max_tokens
-            eng = Engine(self.segment_size, self.fusion_head.head_type, self.precision, has_backbone, max_tokens,
+            eng = Engine(self.segment_size, self.fusion_head.head_type, precision, has_backbone, max_tokens,
                          self.vision_chunk, self.hidden_size, shift_div, device=device)
             eng.load_state_dict(self.state_dict())
             self._engine, self._engine_key = eng, key
@@ -135,6 +144,16 @@ class TwoStream(nn.Module):
         device = next(self.parameters()).device if device is None else device
         return self._get_engine(device, self.max_tokens if n_tokens is None else n_tokens)
 
+    def _batch_stat_vision(self, device, shift_div):
+        """Layer-by-layer vision stream with batch-statistics BatchNorm (vcg_b200.bn_batch), rebuilt when weights change."""
+        from vcg_b200.bn_batch import BatchStatVision
+        key = (str(device), self.bn_batch_precision, shift_div, self._weights_version())
+        if self._bn_vision is None or key != self._bn_vision_key:
+            self._bn_vision = BatchStatVision(self.state_dict(), self.segment_size, shift_div, self.bn_batch_precision,
+                                              device)
+            self._bn_vision_key = key
+        return self._bn_vision
+
     # ------------------------------------------------------------------ forward
     def forward(self, img_clip, text_ids, attention_mask, return_emb=False):
         """-> (binary_logits [B,2], binary_prob [B,2]) (+ vision_emb [B,T,2048], lang_emb [B,768])."""
@@ -142,8 +161,13 @@ class TwoStream(nn.Module):
             raise RuntimeError("TwoStream.forward needs CUDA inputs: the B200 implementation has no CPU fallback")
         if self.training:
             raise RuntimeError("TwoStream is inference-only here: call .eval() first")
-        eng = self._get_engine(text_ids.device, text_ids.shape[1])
+        batch_stat = self.bn_batch_stats and self._vision_kind()[0]
+        # the batch-statistics mode runs the WHOLE forward (text stream and head too) in bn_batch_precision
+        eng = self._get_engine(text_ids.device, text_ids.shape[1], self.bn_batch_precision if batch_stat else None)
         with torch.no_grad():
+            if eng.vision and batch_stat:
+                emb = self._batch_stat_vision(text_ids.device, self._vision_kind()[1]).embed(img_clip)
+                return eng.forward(None, text_ids, attention_mask, return_emb=return_emb, vision_emb=emb)
             if eng.vision:
                 return eng.forward(img_clip, text_ids, attention_mask, return_emb=return_emb)
             # precomputed vision embeddings: [B,T,2048,1,1] (what rearrange + Identity + view yields)

@@ -101,6 +101,7 @@ PROTOTYPES = {
     "vcg_profile_begin": (ctypes.c_int, [_vp]),
     "vcg_profile_end": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(VcgProfileEntry), _i32, ctypes.POINTER(_i32)]),
     "vcg_launch_count": (_i64, [_vp]),
+    "vcg_debug_pdl_window": (ctypes.c_int, [_i32, _i32]),
     "vcg_debug_checksums": (ctypes.c_int, [_vp, _vp, _i32, ctypes.POINTER(_i32), _vp]),
     "vcg_op_preprocess_u8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),
     "vcg_op_resize_u8": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
@@ -112,6 +113,12 @@ PROTOTYPES = {
                                                _i32, _vp]),
     "vcg_op_stem_conv": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "vcg_op_maxpool_tsm": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "vcg_op_stem_conv_act": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "vcg_op_bn_partials": (ctypes.c_int32, [ctypes.c_int64, _i32]),
+    "vcg_op_bn_batch_stats": (ctypes.c_int, [_vp, ctypes.c_int64, _i32, ctypes.c_float, _vp, _vp, _vp, _i32, _vp]),
+    "vcg_op_bn_apply": (ctypes.c_int, [_vp, ctypes.c_int64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp]),
+    "vcg_op_tsm_shift": (ctypes.c_int, [_vp, ctypes.c_int64, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "vcg_op_avgpool": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _vp]),
     "vcg_op_bert_attention": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "vcg_op_bert_attention_packed": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, ctypes.c_int64, _vp]),
     "vcg_op_cut_points": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),

@@ -125,15 +125,80 @@ def stem_conv(x_padded, w_packed, bias):
 
 
 def maxpool_tsm(x, clip_frames, shift_div=8):
-    """[n,112,112,64] -> (pooled [n,56,56,64], temporally shifted copy [n,56,56,64])."""
+    """[n,112,112,64] -> (pooled [n,56,56,64], temporally shifted copy [n,56,56,64]; None when shift_div == 0)."""
     _need_cuda(x)
     n = x.shape[0]
     out = torch.empty(n, 56, 56, 64, dtype=x.dtype, device=x.device)
-    shifted = torch.zeros_like(out)
+    shifted = torch.zeros_like(out) if shift_div > 0 else None
     lib = _b.load_library()
-    _b.check(lib.vcg_op_maxpool_tsm(x.data_ptr(), n, out.data_ptr(), shifted.data_ptr(), clip_frames, shift_div,
+    _b.check(lib.vcg_op_maxpool_tsm(x.data_ptr(), n, out.data_ptr(), _ptr(shifted), clip_frames, shift_div,
                                     _prec(x), _stream()))
     return out, shifted
+
+
+def stem_conv_act(x_padded, w_packed, bias=None, act=_b.ACT_NONE):
+    """stem_conv with an explicit activation and an optional bias (batch-statistics BatchNorm mode wants the raw conv)."""
+    _need_cuda(x_padded, w_packed, bias)
+    n = x_padded.shape[0]
+    out = torch.empty(n, 112, 112, 64, dtype=x_padded.dtype, device=x_padded.device)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_stem_conv_act(x_padded.data_ptr(), n, w_packed.data_ptr(), _ptr(bias), out.data_ptr(), act,
+                                      _prec(x_padded), _stream()))
+    return out
+
+
+def bn_batch_stats(x, eps=1e-5):
+    """Per-channel (mean, 1/sqrt(biased var + eps)) over every row of the NHWC activation x [..., C]: the statistics
+    F.batch_norm uses when a BatchNorm2d has no running statistics (test_video_segment_point.py:116-122)."""
+    _need_cuda(x)
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    lib = _b.load_library()
+    n_partial = lib.vcg_op_bn_partials(rows, C)
+    if n_partial <= 0:
+        raise RuntimeError(f"vcg_b200: batch statistics need C = 64 * 2^k <= 2048 and at least one row (C={C}, rows={rows})")
+    partial = torch.empty(n_partial, 2, C, dtype=torch.float64, device=x.device)
+    mean = torch.empty(C, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(C, dtype=torch.float32, device=x.device)
+    _b.check(lib.vcg_op_bn_batch_stats(x.data_ptr(), rows, C, eps, partial.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                       _prec(x), _stream()))
+    return mean, rstd
+
+
+def bn_apply(x, mean, rstd, gamma, beta, residual=None, relu=True):
+    """relu?((x - mean) * rstd * gamma + beta (+ residual)) over the NHWC activation x [..., C]."""
+    _need_cuda(x, mean, rstd, gamma, beta, residual)
+    assert x.is_contiguous() and (residual is None or (residual.is_contiguous() and residual.shape == x.shape
+                                                       and residual.dtype == x.dtype))
+    C = x.shape[-1]
+    out = torch.empty_like(x)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_bn_apply(x.data_ptr(), x.numel() // C, C, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                 beta.data_ptr(), _ptr(residual), 1 if relu else 0, out.data_ptr(), _prec(x), _stream()))
+    return out
+
+
+def tsm_shift(x, clip_frames, fold):
+    """TemporalShift.shift (ops/temporal_shift.py:34-51) of the NHWC activation x [n,H,W,C], n = clips * clip_frames."""
+    _need_cuda(x)
+    assert x.is_contiguous() and x.dim() == 4
+    n, H, W, C = x.shape
+    out = torch.empty_like(x)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_tsm_shift(x.data_ptr(), n, H * W, C, clip_frames, fold, out.data_ptr(), _prec(x), _stream()))
+    return out
+
+
+def avgpool(x):
+    """AdaptiveAvgPool2d(1): NHWC [n,H,W,C] -> fp32 [n,C]."""
+    _need_cuda(x)
+    assert x.is_contiguous() and x.dim() == 4
+    n, H, W, C = x.shape
+    out = torch.empty(n, C, dtype=torch.float32, device=x.device)
+    lib = _b.load_library()
+    _b.check(lib.vcg_op_avgpool(x.data_ptr(), n, H * W, C, out.data_ptr(), _prec(x), _stream()))
+    return out
 
 
 def bert_attention(qkv, attention_mask, B, L):
