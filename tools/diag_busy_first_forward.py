@@ -1,3 +1,6 @@
+"""Fresh bf16 engines whose FIRST forward is queued behind other GPU work (torch matmuls, or the operator launches of the
+batch-statistics BatchNorm mode): lang_emb / logits against the reference golden.  This is the flow that exposed the attention
+kernel reading its item count ahead of the dependent-launch wait; run with VCG_PDL=0 for the contrast."""
 import sys, torch
 sys.path.insert(0,'/root/repo/tests'); sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/video-chapter-generation_b200')
 from test_bn_batch import golden_case, rel
