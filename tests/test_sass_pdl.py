@@ -44,3 +44,27 @@ def test_no_global_load_ahead_of_the_pdl_wait():
         if "ACQBULK" in body and not any(name in f for name in CONSTANT_PROLOGUE):
             real[f] = lines[:3]
     assert not real, f"global memory access ahead of griddepcontrol.wait: {real}"
+
+
+def test_every_kernel_launched_with_the_attribute_waits():
+    """A kernel launched with programmatic stream serialization that never executes griddepcontrol.wait could finish
+    before its predecessor and break the chain for everything behind it: every kernel handed to launch_pdl must wait."""
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(LIB):
+        pytest.skip("cuobjdump or the built library is not available")
+    csrc = os.path.join(PKG, "csrc")
+    names = set()
+    for f in os.listdir(csrc):
+        if f.endswith((".cu", ".cuh", ".h")):
+            text = open(os.path.join(csrc, f)).read()
+            names.update(re.findall(r"launch_pdl\(\s*([A-Za-z_0-9]+_kernel)\b", text))
+    assert len(names) >= 30, names
+    sass = subprocess.run([cuobjdump, "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    bodies = sass.split("Function : ")[1:]
+    checked = 0
+    for body in bodies:
+        fn = body.split("\n", 1)[0].strip()
+        if any(re.search(r"\d+" + n + r"(I|E|P|v)", fn) for n in names):   # Itanium mangling: <len><name>
+            checked += 1
+            assert "ACQBULK" in body, f"{fn} is launched with the dependent-launch attribute but never waits"
+    assert checked >= len(names), (checked, len(names))
