@@ -4,7 +4,8 @@ They only HOLD parameters (same names, shapes and default initialisation as torc
 kaiming-normal convs, unit BatchNorm); all arithmetic happens in libvcg_b200.so.  BatchNorm is deliberately NOT an
 ``nn.BatchNorm2d`` subclass: reference caller #1 nulls the running statistics of every ``nn.BatchNorm2d`` it finds
 (test_video_segment_point.py:116-122); the engine folds eval-mode statistics into the convolutions, so the running
-statistics must survive that loop (DESIGN.md "BatchNorm mode").
+statistics must survive that loop (DESIGN.md "BatchNorm mode").  What that loop does to the reference —
+batch statistics at inference — is available as the opt-in mode ``TwoStream.bn_batch_stats`` (vcg_b200/bn_batch.py).
 """
 import torch
 import torch.nn as nn
