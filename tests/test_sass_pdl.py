@@ -17,11 +17,15 @@ LIB = os.path.join(PKG, "lib", "libvcg_b200.so")
 CONSTANT_PROLOGUE = ("conv23h_kernel", "conv23h2_kernel", "resize_preprocess_u8_kernel")
 
 
-def test_no_global_load_ahead_of_the_pdl_wait():
+@pytest.fixture(scope="module")
+def sass():
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     if not os.path.exists(cuobjdump) or not os.path.exists(LIB):
         pytest.skip("cuobjdump or the built library is not available")
-    sass = subprocess.run([cuobjdump, "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    return subprocess.run([cuobjdump, "-sass", LIB], capture_output=True, text=True, check=True).stdout
+
+
+def test_no_global_load_ahead_of_the_pdl_wait(sass):
     fn, waited, offenders, with_wait = None, False, {}, 0
     for line in sass.splitlines():
         m = re.search(r"Function : (\S+)", line)
@@ -46,12 +50,9 @@ def test_no_global_load_ahead_of_the_pdl_wait():
     assert not real, f"global memory access ahead of griddepcontrol.wait: {real}"
 
 
-def test_every_kernel_launched_with_the_attribute_waits():
+def test_every_kernel_launched_with_the_attribute_waits(sass):
     """A kernel launched with programmatic stream serialization that never executes griddepcontrol.wait could finish
     before its predecessor and break the chain for everything behind it: every kernel handed to launch_pdl must wait."""
-    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
-    if not os.path.exists(cuobjdump) or not os.path.exists(LIB):
-        pytest.skip("cuobjdump or the built library is not available")
     csrc = os.path.join(PKG, "csrc")
     names = set()
     for f in os.listdir(csrc):
@@ -59,7 +60,6 @@ def test_every_kernel_launched_with_the_attribute_waits():
             text = open(os.path.join(csrc, f)).read()
             names.update(re.findall(r"launch_pdl\(\s*([A-Za-z_0-9]+_kernel)\b", text))
     assert len(names) >= 30, names
-    sass = subprocess.run([cuobjdump, "-sass", LIB], capture_output=True, text=True, check=True).stdout
     bodies = sass.split("Function : ")[1:]
     checked = 0
     for body in bodies:
@@ -68,3 +68,11 @@ def test_every_kernel_launched_with_the_attribute_waits():
             checked += 1
             assert "ACQBULK" in body, f"{fn} is launched with the dependent-launch attribute but never waits"
     assert checked >= len(names), (checked, len(names))
+
+
+def test_library_carries_tcgen05_and_tma_code(sass):
+    """The hot kernels are tcgen05 / TMEM / TMA code for sm_100a, not recompiled mma.sync: the mnemonics must be there."""
+    assert "arch = sm_100a" in sass
+    for mnemonic, at_least in (("UTCHMMA", 50), ("LDTM", 30), ("STTM", 2), ("UTMALDG", 50), ("UTMASTG", 5), ("UTCBAR", 10)):
+        n = len(re.findall(r"\b" + mnemonic + r"\b", sass))
+        assert n >= at_least, f"{mnemonic}: {n} occurrences"
